@@ -1,0 +1,103 @@
+// Parameter block of the tcgen05 implicit-GEMM 3x3 convolution kernel (conv_tc.cu).
+// Shared between the kernel and the host-side planner (engine.cpp).
+#pragma once
+#include <cuda.h>
+#include <stdint.h>
+
+namespace ss4k {
+
+constexpr int kTileW = 128;        // output pixels per tile row == UMMA M
+constexpr int kBoxW = 130;         // halo row: kTileW + 2 pixels, one TMA box
+constexpr int kRowBytes = 128;     // 64 channels * 2 bytes == one swizzle-128B row
+constexpr int kMaxKBlocks = 12;
+constexpr int kMaxTaps = 16;
+constexpr int kMaxASlots = 8;
+constexpr int kTmemCols = 512;
+constexpr int kAccStageCols = 256; // two accumulator stages of 256 columns
+constexpr int kSmemBytes = 232448; // 227 KB opt-in dynamic shared memory
+constexpr int kConvThreads = 192;  // warp0 TMA, warp1 MMA, warps2-5 epilogue
+
+// convolution "mode" == MMA schedule
+enum ConvMode : int {
+  kModeConv3 = 0,  // 3x3 stride 1 pad 1: 9 taps
+  kModeUp2 = 1,    // nearest-x2 upsample fused: 4 output phases x 4 pre-summed taps
+  kModeS2 = 2      // 3x3 stride 2 pad 1 read through a (2C, W/2, 2, H/2, N) view: 4 taps, k-step masks
+};
+
+enum OutMode : int {
+  kOutNHWC = 0,       // fp16/bf16 NHWC at (oy, ox), channel offset out_coff
+  kOutNCHWF32 = 1,    // float NCHW, first `cout` channels (final conv)
+  kOutPSNCHWF32 = 2,  // PixelShuffle(ps_r) into float NCHW (+ nearest-upsampled base image)  [SRVGG tail]
+  kOutPS2NHWC = 3,    // PixelShuffle(2) into NHWC (weights' output channels pre-permuted to (a,b,c))
+  kOutScatterNHWC = 4,// BSVD temporal shift: channel slices go to the t-1 / t+1 / t ring slots
+  kOutNCHWF16 = 5,
+  kOutU8NHWC = 6      // clamp [0,1], *255, truncate or round, uint8 NHWC (3 channels)
+};
+
+enum ActKind : int { kActNone = 0, kActPRelu = 1, kActRelu6 = 2 };
+
+struct KBlock {
+  int32_t tmap;   // which activation tensor map (0: hi / only, 1: lo half of a split tensor)
+  int32_t c0;     // first channel of this 64-channel block inside the source tensor
+  int32_t p;      // coordinate in the "row phase" dimension (stride-2 view), else 0
+  int32_t pad;
+};
+
+struct Tap {
+  int8_t dr;      // input row of the tile this tap reads, relative to the output row (0..2)
+  int8_t shift;   // pixel shift inside the halo row (0..2)
+  int8_t sub;     // accumulator sub-index (output phase for kModeUp2), else 0
+  int8_t pad;
+};
+
+struct Epilogue {
+  const float* bias;     // [npad_total]
+  const float* slope;    // [npad_total] negative-side slope (PReLU / LeakyReLU), or nullptr
+  int32_t act;           // ActKind
+  int32_t out_mode;      // OutMode
+  float alpha;           // out = alpha*act(acc+bias) + beta1*res1 + beta2*res2
+  float beta1, beta2;
+  int32_t is_bf16;
+  const void* res1;      // NHWC 16-bit, indexed at the OUTPUT pixel
+  const void* res2;
+  int32_t res1_pitch, res1_coff, res2_pitch, res2_coff;
+  void* out;             // destination (see OutMode)
+  void* out_lo;          // split mode: low halves (NHWC), or nullptr
+  void* out2;            // scatter: slot receiving channels [0, fold)      (frame t-1's view)
+  void* out3;            // scatter: slot receiving channels [fold, 2 fold) (frame t+1's view)
+  int32_t out_pitch, out_coff;
+  int32_t out_h, out_w;  // output image size (pixels)
+  int32_t cout;          // real output channels of the whole conv
+  int32_t ps_r;          // PixelShuffle factor for kOutPSNCHWF32
+  int32_t fold;          // scatter fold (C/8)
+  int32_t round_u8;      // kOutU8NHWC: 1 = round to nearest, 0 = truncate (fsrcnn_upscaler.py:233)
+  const void* base;      // kOutPSNCHWF32: NHWC 16-bit base image (input of the net), pitch base_pitch
+  int32_t base_pitch;
+  int32_t res_sub;       // 1: residuals are indexed at output pixel, 0 same (kept for clarity)
+};
+
+struct ConvParams {
+  CUtensorMap tmA[2];    // activations, 5-D (C, W, P, H, N), box (64, box_w, 1, 1, 1), swizzle 128B
+  CUtensorMap tmW;       // packed weights, 3-D (64, npad_total, nkb*ntaps), box (64, n_cta, ntaps)
+  Epilogue ep;
+  KBlock kb[kMaxKBlocks];
+  Tap taps[kMaxTaps];
+  uint8_t ksmask[kMaxKBlocks][kMaxTaps];  // 4-bit mask of the 16-channel k-steps to issue
+  int32_t nkb, ntaps, nsub, max_dr;
+  int32_t mode;
+  int32_t n_img, H, W;   // tile-grid space ("A space": output grid, or the low-res grid for kModeUp2)
+  int32_t R;             // output rows (of A space) per tile
+  int32_t tiles_x, tiles_y, n_chunks, n_tiles;  // n_tiles = n_img*tiles_y*tiles_x*n_chunks
+  int32_t n_cta;         // accumulator width N of one CTA tile (<= 64... multiple of 16)
+  int32_t acc_stride;    // TMEM columns between accumulators (multiple of 32)
+  int32_t a_slots, a_slot_bytes, a_sub_bytes;
+  int32_t w_slots, w_slot_bytes, w_tile_bytes;
+  int32_t w_resident;    // weights loaded once per CTA
+  int32_t desc_mode;     // 0: shifted start; 1: shifted start + base_offset; 2: one box per tap shift
+  uint32_t idesc;        // tcgen05 instruction descriptor
+  uint32_t a_row_tx;     // bytes one halo row load delivers (all TMA boxes)
+  uint32_t w_tx;         // bytes one weight block load delivers
+  int32_t* err;          // device int[4]: watchdog diagnostics (tag, block, ...)
+};
+
+}  // namespace ss4k

@@ -1,0 +1,211 @@
+// HBM-bound layout / colour kernels around the convolution stack, plus the naive direct
+// convolution used ONLY by the start-up self-probe (ss4k_create) to validate the tcgen05 path.
+//
+//   prep_*   : frame at the boundary (float NCHW / half NCHW / uint8 NHWC / NV12) -> 16-bit NHWC,
+//              channel-padded, optional pixel_unshuffle(2) (RRDBNet x2 head) and the [0,1]
+//              normalisation  (reference: fsrcnn_upscaler.py:170-176,237-241; basicsr pixel_unshuffle)
+//   unprep_* : 16-bit NHWC -> float NCHW (operator-level tests)
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "elementwise.h"
+
+namespace ss4k {
+
+namespace {
+
+__device__ __forceinline__ uint16_t to16(float f, bool bf16) {
+  if (bf16) {
+    __nv_bfloat16 h = __float2bfloat16_rn(f);
+    return *reinterpret_cast<uint16_t*>(&h);
+  }
+  __half h = __float2half_rn(f);
+  return *reinterpret_cast<uint16_t*>(&h);
+}
+__device__ __forceinline__ float from16(uint16_t u, bool bf16) {
+  if (bf16) return __bfloat162float(*reinterpret_cast<__nv_bfloat16*>(&u));
+  return __half2float(*reinterpret_cast<__half*>(&u));
+}
+
+// BT.709 limited-range YCbCr -> RGB in [0,1] (the reference moves rgb24 through ffmpeg pipes,
+// twitchgrabber.py:97-98, so the matrix is this repo's own definition)
+__device__ __forceinline__ float3 yuv709_to_rgb(float y, float u, float v) {
+  const float yy = (y - 16.f) * (1.f / 219.f);
+  const float cb = (u - 128.f) * (1.f / 224.f);
+  const float cr = (v - 128.f) * (1.f / 224.f);
+  float3 rgb;
+  rgb.x = yy + 1.5748f * cr;
+  rgb.y = yy - 0.187324f * cb - 0.468124f * cr;
+  rgb.z = yy + 1.8556f * cb;
+  rgb.x = fminf(fmaxf(rgb.x, 0.f), 1.f);
+  rgb.y = fminf(fmaxf(rgb.y, 0.f), 1.f);
+  rgb.z = fminf(fmaxf(rgb.z, 0.f), 1.f);
+  return rgb;
+}
+
+// value of source channel c at source pixel (n, y, x); channel >= C reads `fill`
+struct SrcF32NCHW {
+  const float* p; int C, H, W;
+  __device__ float operator()(int n, int c, int y, int x) const {
+    return __ldg(p + ((static_cast<size_t>(n) * C + c) * H + y) * W + x);
+  }
+};
+struct SrcF16NCHW {
+  const __half* p; int C, H, W;
+  __device__ float operator()(int n, int c, int y, int x) const {
+    return __half2float(p[((static_cast<size_t>(n) * C + c) * H + y) * W + x]);
+  }
+};
+struct SrcU8NHWC {
+  const uint8_t* p; int C, H, W;
+  __device__ float operator()(int n, int c, int y, int x) const {
+    return static_cast<float>(__ldg(p + ((static_cast<size_t>(n) * H + y) * W + x) * C + c)) / 255.0f;
+  }
+};
+struct SrcNV12 {
+  const uint8_t* p; int C, H, W;  // C == 3
+  __device__ float operator()(int n, int c, int y, int x) const {
+    const uint8_t* frame = p + static_cast<size_t>(n) * (static_cast<size_t>(H) * W * 3 / 2);
+    const float Y = static_cast<float>(__ldg(frame + static_cast<size_t>(y) * W + x));
+    const uint8_t* uv = frame + static_cast<size_t>(H) * W + static_cast<size_t>(y >> 1) * W + (x & ~1);
+    const float3 rgb = yuv709_to_rgb(Y, static_cast<float>(__ldg(uv)), static_cast<float>(__ldg(uv + 1)));
+    return c == 0 ? rgb.x : (c == 1 ? rgb.y : rgb.z);
+  }
+};
+
+// one thread per OUTPUT pixel; out is [N, H/us, W/us, pitch] 16-bit; channels [0, C*us*us) real,
+// channel `fill_ch` (if >= 0) = fill_val (BSVD noise map), the rest zero.
+template <class Src>
+__global__ void prep_kernel(Src src, uint16_t* __restrict__ out, uint16_t* __restrict__ out_lo, int N,
+                            int pitch, int us, int fill_ch, float fill_val, int bf16) {
+  const int OH = src.H / us, OW = src.W / us;
+  const size_t total = static_cast<size_t>(N) * OH * OW;
+  const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int ox = static_cast<int>(idx % OW);
+  const int oy = static_cast<int>((idx / OW) % OH);
+  const int n = static_cast<int>(idx / (static_cast<size_t>(OW) * OH));
+  const int creal = src.C * us * us;
+  uint16_t* o = out + idx * pitch;
+  uint16_t* ol = out_lo != nullptr ? out_lo + idx * pitch : nullptr;
+  for (int c8 = 0; c8 < pitch; c8 += 8) {
+    uint16_t v[8], vl[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int ch = c8 + i;
+      float f = 0.f;
+      if (ch < creal) {
+        // torch pixel_unshuffle: ch = c*us*us + i_row*us + j_col
+        const int c = ch / (us * us);
+        const int rem = ch - c * us * us;
+        const int iy = rem / us, jx = rem - iy * us;
+        f = src(n, c, oy * us + iy, ox * us + jx);
+      } else if (ch == fill_ch) {
+        f = fill_val;
+      }
+      v[i] = to16(f, bf16 != 0);
+      vl[i] = to16(f - from16(v[i], bf16 != 0), bf16 != 0);
+    }
+    *reinterpret_cast<uint4*>(o + c8) = *reinterpret_cast<uint4*>(v);
+    if (ol != nullptr) *reinterpret_cast<uint4*>(ol + c8) = *reinterpret_cast<uint4*>(vl);
+  }
+}
+
+__global__ void unprep_kernel(const uint16_t* __restrict__ in, const uint16_t* __restrict__ in_lo,
+                              float* __restrict__ out, int N, int C, int H, int W, int pitch, int coff,
+                              int bf16) {
+  const size_t total = static_cast<size_t>(N) * C * H * W;
+  const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int x = static_cast<int>(idx % W);
+  const int y = static_cast<int>((idx / W) % H);
+  const int c = static_cast<int>((idx / (static_cast<size_t>(W) * H)) % C);
+  const int n = static_cast<int>(idx / (static_cast<size_t>(W) * H * C));
+  const size_t off = ((static_cast<size_t>(n) * H + y) * W + x) * pitch + coff + c;
+  float f = from16(in[off], bf16 != 0);
+  if (in_lo != nullptr) f += from16(in_lo[off], bf16 != 0);
+  out[idx] = f;
+}
+
+// naive direct conv (self-probe only): NHWC 16-bit in, packed-order-agnostic OIHW float weights that
+// were already rounded to the operand type by the host; fp32 accumulate; float NCHW out.
+__global__ void ref_conv3x3_kernel(const uint16_t* __restrict__ in, const float* __restrict__ w,
+                                   const float* __restrict__ bias, float* __restrict__ out, int N, int H,
+                                   int W, int pitch, int cin, int cout, int bf16) {
+  const size_t total = static_cast<size_t>(N) * cout * H * W;
+  const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int x = static_cast<int>(idx % W);
+  const int y = static_cast<int>((idx / W) % H);
+  const int co = static_cast<int>((idx / (static_cast<size_t>(W) * H)) % cout);
+  const int n = static_cast<int>(idx / (static_cast<size_t>(W) * H * cout));
+  float acc = bias != nullptr ? bias[co] : 0.f;
+  for (int ky = 0; ky < 3; ++ky) {
+    const int iy = y + ky - 1;
+    if (iy < 0 || iy >= H) continue;
+    for (int kx = 0; kx < 3; ++kx) {
+      const int ix = x + kx - 1;
+      if (ix < 0 || ix >= W) continue;
+      const uint16_t* px = in + ((static_cast<size_t>(n) * H + iy) * W + ix) * pitch;
+      for (int ci = 0; ci < cin; ++ci)
+        acc = fmaf(from16(px[ci], bf16 != 0), w[((static_cast<size_t>(co) * cin + ci) * 3 + ky) * 3 + kx], acc);
+    }
+  }
+  out[idx] = acc;
+}
+
+template <class Src>
+cudaError_t launch_prep(Src src, void* out, void* out_lo, int N, int pitch, int us, int fill_ch,
+                        float fill_val, int bf16, cudaStream_t s) {
+  const size_t total = static_cast<size_t>(N) * (src.H / us) * (src.W / us);
+  const int threads = 256;
+  const unsigned blocks = static_cast<unsigned>((total + threads - 1) / threads);
+  prep_kernel<Src><<<blocks, threads, 0, s>>>(src, reinterpret_cast<uint16_t*>(out),
+                                              reinterpret_cast<uint16_t*>(out_lo), N, pitch, us, fill_ch,
+                                              fill_val, bf16);
+  return cudaGetLastError();
+}
+
+}  // namespace
+
+cudaError_t prep_launch(int in_fmt, const void* in, void* out, void* out_lo, int N, int C, int H, int W,
+                        int pitch, int unshuffle, int fill_ch, float fill_val, int bf16, cudaStream_t s) {
+  const int us = unshuffle > 1 ? unshuffle : 1;
+  switch (in_fmt) {
+    case 0:
+      return launch_prep(SrcF32NCHW{reinterpret_cast<const float*>(in), C, H, W}, out, out_lo, N, pitch, us, fill_ch, fill_val, bf16, s);
+    case 1:
+      return launch_prep(SrcF16NCHW{reinterpret_cast<const __half*>(in), C, H, W}, out, out_lo, N, pitch, us, fill_ch, fill_val, bf16, s);
+    case 2:
+      return launch_prep(SrcU8NHWC{reinterpret_cast<const uint8_t*>(in), C, H, W}, out, out_lo, N, pitch, us, fill_ch, fill_val, bf16, s);
+    case 3:
+      return launch_prep(SrcNV12{reinterpret_cast<const uint8_t*>(in), 3, H, W}, out, out_lo, N, pitch, us, fill_ch, fill_val, bf16, s);
+    default:
+      return cudaErrorInvalidValue;
+  }
+}
+
+cudaError_t unprep_launch(const void* in, const void* in_lo, float* out, int N, int C, int H, int W,
+                          int pitch, int coff, int bf16, cudaStream_t s) {
+  const size_t total = static_cast<size_t>(N) * C * H * W;
+  const int threads = 256;
+  const unsigned blocks = static_cast<unsigned>((total + threads - 1) / threads);
+  unprep_kernel<<<blocks, threads, 0, s>>>(reinterpret_cast<const uint16_t*>(in),
+                                           reinterpret_cast<const uint16_t*>(in_lo), out, N, C, H, W, pitch,
+                                           coff, bf16);
+  return cudaGetLastError();
+}
+
+cudaError_t ref_conv3x3_launch(const void* in, const float* w, const float* bias, float* out, int N, int H,
+                               int W, int pitch, int cin, int cout, int bf16, cudaStream_t s) {
+  const size_t total = static_cast<size_t>(N) * cout * H * W;
+  const int threads = 128;
+  const unsigned blocks = static_cast<unsigned>((total + threads - 1) / threads);
+  ref_conv3x3_kernel<<<blocks, threads, 0, s>>>(reinterpret_cast<const uint16_t*>(in), w, bias, out, N, H, W,
+                                                pitch, cin, cout, bf16);
+  return cudaGetLastError();
+}
+
+}  // namespace ss4k

@@ -1,0 +1,21 @@
+#pragma once
+#include <cuda_runtime.h>
+
+#include "conv_params.h"
+
+namespace ss4k {
+
+// conv_tc.cu
+cudaError_t conv_tc_prepare();
+cudaError_t conv_tc_launch(const ConvParams& p, int grid, cudaStream_t stream);
+
+// elementwise.cu
+// in_fmt: SS4K_FMT_* ; out: [N, H/us, W/us, pitch] 16-bit NHWC (out_lo: low halves for split mode or null)
+cudaError_t prep_launch(int in_fmt, const void* in, void* out, void* out_lo, int N, int C, int H, int W,
+                        int pitch, int unshuffle, int fill_ch, float fill_val, int bf16, cudaStream_t s);
+cudaError_t unprep_launch(const void* in, const void* in_lo, float* out, int N, int C, int H, int W,
+                          int pitch, int coff, int bf16, cudaStream_t s);
+cudaError_t ref_conv3x3_launch(const void* in, const float* w, const float* bias, float* out, int N, int H,
+                               int W, int pitch, int cin, int cout, int bf16, cudaStream_t s);
+
+}  // namespace ss4k

@@ -1,0 +1,933 @@
+// Engine: context, weight store, weight packing, plan materialisation (buffers, TMA tensor maps,
+// tile configuration, CUDA graph) and the C ABI of include/ss4k.h.
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <cmath>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/ss4k.h"
+#include "conv_params.h"
+#include "elementwise.h"
+#include "program.h"
+
+using namespace ss4k;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+std::string fmt(const char* f, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, f);
+  vsnprintf(buf, sizeof(buf), f, ap);
+  va_end(ap);
+  return buf;
+}
+
+struct HostTensor {
+  std::vector<float> data;
+  std::vector<int64_t> shape;
+};
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+}  // namespace
+
+struct ss4k_ctx {
+  int device = 0;
+  int nsm = 148;
+  int desc_mode = 0;
+  std::string err;
+  std::map<int, std::map<std::string, HostTensor>> weights;
+  EncodeTiledFn encode = nullptr;
+  int32_t* err_host = nullptr;  // mapped pinned int[4]: watchdog diagnostics
+  int32_t* err_dev = nullptr;
+  int64_t launches = 0;
+  cudaStream_t stream = nullptr;  // internal stream (ss4k_run_host, graph capture)
+};
+
+namespace {
+
+int fail(ss4k_ctx* ctx, int code, const std::string& msg) {
+  g_last_error = msg;
+  if (ctx) ctx->err = msg;
+  return code;
+}
+
+#define CK(ctx, call)                                                                              \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess)                                                                         \
+      return fail(ctx, SS4K_E_CUDA, fmt("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__)); \
+  } while (0)
+
+uint16_t f2h(float f, bool bf16) {
+  if (bf16) {
+    __nv_bfloat16 h = __float2bfloat16_rn(f);
+    uint16_t u;
+    memcpy(&u, &h, 2);
+    return u;
+  }
+  __half h = __float2half_rn(f);
+  uint16_t u;
+  memcpy(&u, &h, 2);
+  return u;
+}
+float h2f(uint16_t u, bool bf16) {
+  if (bf16) {
+    __nv_bfloat16 h;
+    memcpy(&h, &u, 2);
+    return __bfloat162float(h);
+  }
+  __half h;
+  memcpy(&h, &u, 2);
+  return __half2float(h);
+}
+
+int round_up(int a, int b) { return (a + b - 1) / b * b; }
+
+// ------------------------------------------------------------------------------------------------
+// A materialised convolution: packed weights on the device + kernel parameter block + grid.
+struct ConvExec {
+  ConvParams p;
+  int grid = 0;
+  void* d_w = nullptr;
+  float* d_bias = nullptr;
+  float* d_slope = nullptr;
+  bool ext_out = false;  // ep.out is the caller's output pointer (patched per run)
+  std::string name;
+};
+
+struct PackedWeights {
+  std::vector<uint16_t> w;  // [(nkb*ntaps)][npad_total][64]
+  std::vector<float> bias, slope;
+  std::vector<KBlock> kb;
+  std::vector<Tap> taps;
+  std::vector<uint8_t> mask;  // [nkb][kMaxTaps]
+  int nkb = 0, ntaps = 0, nsub = 1, max_dr = 2, npad_total = 0;
+};
+
+// effective weight of tap t for (out channel n, in channel c); see DESIGN.md section 4.3
+struct TapGeom {
+  int ntaps, nsub, max_dr;
+};
+
+// Lower OIHW fp32 weights to the kernel's packed K-block/tap layout.
+//   W: [cout][cin][3][3]; in_coff/in_pitch describe where the cin channels sit in the source tensor.
+std::string pack_weights(const ConvSpec& cs, const HostTensor& W, const HostTensor* B, const HostTensor* S,
+                         bool bf16, PackedWeights* out) {
+  if (W.shape.size() != 4 || W.shape[0] != cs.cout || W.shape[1] != cs.cin || W.shape[2] != 3 || W.shape[3] != 3)
+    return fmt("weight %s has shape [%lld,%lld,..], expected [%d,%d,3,3]", cs.wname.c_str(),
+               (long long)(W.shape.size() > 0 ? W.shape[0] : -1), (long long)(W.shape.size() > 1 ? W.shape[1] : -1),
+               cs.cout, cs.cin);
+  if (B && (int)B->data.size() != cs.cout) return fmt("bias %s has wrong size", cs.bname.c_str());
+  if (S && (int)S->data.size() != cs.cout) return fmt("slope %s has wrong size", cs.sname.c_str());
+  const int npad = round_up(cs.cout, 16);
+  out->npad_total = npad;
+  auto w_at = [&](int n, int c, int ky, int kx) -> float {
+    return W.data[((static_cast<size_t>(n) * cs.cin + c) * 3 + ky) * 3 + kx];
+  };
+  // output-channel permutation (PixelShuffle(2) fused store): packed row (a*2+b)*Cq + c  <-  c*4 + a*2 + b
+  std::vector<int> orow(npad, -1);
+  for (int n = 0; n < cs.cout; ++n) {
+    if (cs.wperm == 1) {
+      const int cq = cs.cout / 4;
+      const int c = n / 4, ab = n % 4;
+      orow[ab * cq + c] = n;
+    } else {
+      orow[n] = n;
+    }
+  }
+  // taps
+  out->taps.clear();
+  if (cs.mode == kModeConv3) {
+    out->nsub = 1; out->max_dr = 2;
+    for (int ky = 0; ky < 3; ++ky)
+      for (int kx = 0; kx < 3; ++kx) out->taps.push_back(Tap{(int8_t)ky, (int8_t)kx, 0, 0});
+  } else if (cs.mode == kModeUp2) {
+    out->nsub = 4; out->max_dr = 2;
+    for (int a = 0; a < 2; ++a)
+      for (int b = 0; b < 2; ++b)
+        for (int tr = 0; tr < 2; ++tr)
+          for (int tc = 0; tc < 2; ++tc)
+            out->taps.push_back(Tap{(int8_t)(a + tr), (int8_t)(b + tc), (int8_t)(a * 2 + b), 0});
+  } else if (cs.mode == kModeS2) {
+    out->nsub = 1; out->max_dr = 1;
+    for (int dy = 0; dy < 2; ++dy)
+      for (int dx = 0; dx < 2; ++dx) out->taps.push_back(Tap{(int8_t)dy, (int8_t)dx, 0, 0});
+  } else {
+    return "unknown conv mode";
+  }
+  out->ntaps = (int)out->taps.size();
+  // K blocks: (tmap, c0, p) + which weight half (hi/lo) they multiply with
+  struct KB { KBlock kb; int whalf; int cbase; int pa; };  // cbase: channel of W that kb channel 0 maps to
+  std::vector<KB> kbs;
+  const int nsplit = cs.split ? 3 : 1;
+  if (cs.mode == kModeS2) {
+    if (cs.in_coff != 0 || cs.in_pitch % 16) return "stride-2 conv needs in_coff == 0 and pitch % 16 == 0";
+    const int merged = 2 * cs.in_pitch;
+    for (int pa = 0; pa < 2; ++pa)
+      for (int c0 = 0; c0 < merged; c0 += 64)
+        for (int sp = 0; sp < nsplit; ++sp)
+          kbs.push_back(KB{KBlock{sp == 2 ? 1 : 0, c0, pa, 0}, sp == 1 ? 1 : 0, c0, pa});
+  } else {
+    for (int c0 = 0; c0 < cs.cin; c0 += 64)
+      for (int sp = 0; sp < nsplit; ++sp)
+        kbs.push_back(KB{KBlock{sp == 2 ? 1 : 0, cs.in_coff + c0, 0, 0}, sp == 1 ? 1 : 0, c0, 0});
+  }
+  out->nkb = (int)kbs.size();
+  if (out->nkb > kMaxKBlocks) return fmt("conv %s needs %d K blocks (max %d)", cs.name.c_str(), out->nkb, kMaxKBlocks);
+  out->kb.clear();
+  for (auto& k : kbs) out->kb.push_back(k.kb);
+  out->mask.assign(static_cast<size_t>(out->nkb) * kMaxTaps, 0);
+  out->w.assign(static_cast<size_t>(out->nkb) * out->ntaps * npad * 64, 0);
+
+  static const int up_sets[2][2][3] = {{{0, -1, -1}, {1, 2, -1}}, {{0, 1, -1}, {2, -1, -1}}};
+  for (int kbi = 0; kbi < out->nkb; ++kbi) {
+    const KB& K = kbs[kbi];
+    for (int t = 0; t < out->ntaps; ++t) {
+      uint8_t m = 0;
+      for (int cc = 0; cc < 64; ++cc) {
+        // which weight taps / channel does (kb channel cc, tap t) correspond to
+        int wc = -1;
+        int kys[3] = {-1, -1, -1}, kxs[3] = {-1, -1, -1};
+        if (cs.mode == kModeConv3) {
+          wc = K.cbase + cc;
+          kys[0] = out->taps[t].dr; kxs[0] = out->taps[t].shift;
+        } else if (cs.mode == kModeUp2) {
+          wc = K.cbase + cc;
+          const int a = out->taps[t].sub >> 1, b = out->taps[t].sub & 1;
+          const int tr = out->taps[t].dr - a, tc = out->taps[t].shift - b;
+          for (int i = 0; i < 3; ++i) { kys[i] = up_sets[a][tr][i]; kxs[i] = up_sets[b][tc][i]; }
+        } else {  // kModeS2: merged channel = pb*pitch + c
+          const int mch = K.cbase + cc;
+          const int pb = mch / cs.in_pitch;
+          const int c = mch - pb * cs.in_pitch;
+          const int dy = out->taps[t].dr - 1, dx = out->taps[t].shift - 1;
+          const int ky = 2 * dy + K.pa + 1, kx = 2 * dx + pb + 1;
+          if (pb < 2 && ky >= 0 && kx >= 0) { wc = c; kys[0] = ky; kxs[0] = kx; }
+        }
+        if (wc < 0 || wc >= cs.cin) continue;
+        bool any = false;
+        for (int row = 0; row < npad; ++row) {
+          const int n = orow[row];
+          if (n < 0) continue;
+          float sum = 0.f;
+          for (int i = 0; i < 3 && kys[i] >= 0; ++i)
+            for (int j = 0; j < 3 && kxs[j] >= 0; ++j) sum += w_at(n, wc, kys[i], kxs[j]);
+          const uint16_t hi = f2h(sum, bf16);
+          uint16_t val = hi;
+          if (K.whalf == 1) val = f2h(sum - h2f(hi, bf16), bf16);
+          out->w[((static_cast<size_t>(kbi) * out->ntaps + t) * npad + row) * 64 + cc] = val;
+          any = true;
+        }
+        if (any) m |= static_cast<uint8_t>(1u << (cc / 16));
+      }
+      out->mask[static_cast<size_t>(kbi) * kMaxTaps + t] = m;
+    }
+  }
+  out->bias.assign(npad, 0.f);
+  out->slope.assign(npad, 1.f);
+  for (int row = 0; row < npad; ++row) {
+    const int n = orow[row];
+    if (n < 0) continue;
+    if (B) out->bias[row] = B->data[n];
+    out->slope[row] = S ? S->data[n] : cs.const_slope;
+  }
+  return "";
+}
+
+// ------------------------------------------------------------------------------------------------
+struct TileCfg {
+  int R, n_cta, n_chunks, acc_stride, tiles_x, tiles_y, n_tiles;
+  int a_slots, a_slot_bytes, a_sub_bytes, w_slots, w_slot_bytes, w_tile_bytes, w_resident;
+};
+
+std::string configure_tiles(int desc_mode, int nsm, int n_img, int H, int W, int npad_total, int ntaps,
+                            int nsub, int max_dr, int nkb, TileCfg* t) {
+  t->n_chunks = (npad_total + 63) / 64;
+  if (npad_total % t->n_chunks) return "output channels not divisible into equal chunks";
+  t->n_cta = npad_total / t->n_chunks;
+  if (t->n_cta % 16) return "chunk width must be a multiple of 16";
+  t->acc_stride = round_up(t->n_cta, 32);
+  const int max_acc = kAccStageCols / t->acc_stride;
+  int rmax = std::min(8, max_acc / nsub);
+  if (rmax < 1) return "accumulators do not fit one TMEM stage";
+  t->tiles_x = (W + kTileW - 1) / kTileW;
+  double best = 1e30;
+  int bestR = 1;
+  for (int R = 1; R <= rmax; ++R) {
+    const int ty = (H + R - 1) / R;
+    const long tiles = static_cast<long>(n_img) * ty * t->tiles_x * t->n_chunks;
+    const long waves = (tiles + nsm - 1) / nsm;
+    const double cost = static_cast<double>(waves) * (R + 0.3 * max_dr + 0.2);
+    if (cost < best - 1e-9) { best = cost; bestR = R; }
+  }
+  t->R = bestR;
+  t->tiles_y = (H + t->R - 1) / t->R;
+  t->n_tiles = n_img * t->tiles_y * t->tiles_x * t->n_chunks;
+  t->w_tile_bytes = t->n_cta * kRowBytes;
+  t->w_slot_bytes = ntaps * t->w_tile_bytes;
+  t->w_resident = (nkb == 1 && t->n_chunks == 1) ? 1 : 0;
+  t->a_sub_bytes = kTileW * kRowBytes;
+  t->a_slot_bytes = desc_mode == 2 ? 3 * t->a_sub_bytes : round_up(kBoxW * kRowBytes, 1024);
+  const int avail = kSmemBytes - 1024 - 512;
+  t->w_slots = t->w_resident ? 1 : 2;
+  if (t->w_slots * t->w_slot_bytes + 2 * t->a_slot_bytes > avail) t->w_slots = 1;
+  const int left = avail - t->w_slots * t->w_slot_bytes;
+  t->a_slots = std::min(kMaxASlots, left / t->a_slot_bytes);
+  if (t->a_slots < 2) return "shared memory budget exceeded";
+  return "";
+}
+
+std::string encode_act_map(ss4k_ctx* ctx, CUtensorMap* tm, void* ptr, int n, int h, int w, int pitch, int mode,
+                           bool bf16, int box_w) {
+  cuuint64_t dims[5];
+  cuuint64_t strides[4];
+  const cuuint64_t eb = 2;
+  if (mode == kModeS2) {
+    if (h % 2 || w % 2) return "stride-2 conv needs even H and W";
+    dims[0] = 2 * pitch; dims[1] = w / 2; dims[2] = 2; dims[3] = h / 2; dims[4] = n;
+    strides[0] = 2 * pitch * eb;
+    strides[1] = static_cast<cuuint64_t>(w) * pitch * eb;
+    strides[2] = 2 * static_cast<cuuint64_t>(w) * pitch * eb;
+    strides[3] = static_cast<cuuint64_t>(h) * w * pitch * eb;
+  } else {
+    dims[0] = pitch; dims[1] = w; dims[2] = 1; dims[3] = h; dims[4] = n;
+    strides[0] = pitch * eb;
+    strides[1] = static_cast<cuuint64_t>(w) * pitch * eb;
+    strides[2] = static_cast<cuuint64_t>(w) * pitch * eb;
+    strides[3] = static_cast<cuuint64_t>(h) * w * pitch * eb;
+  }
+  cuuint32_t box[5] = {64, static_cast<cuuint32_t>(box_w), 1, 1, 1};
+  cuuint32_t es[5] = {1, 1, 1, 1, 1};
+  CUresult r = ctx->encode(tm, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, ptr,
+                           dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fmt("cuTensorMapEncodeTiled(activation) failed: %d", (int)r);
+  return "";
+}
+
+std::string encode_w_map(ss4k_ctx* ctx, CUtensorMap* tm, void* ptr, int npad_total, int ntiles, int n_cta,
+                         int ntaps, bool bf16) {
+  cuuint64_t dims[3] = {64, static_cast<cuuint64_t>(npad_total), static_cast<cuuint64_t>(ntiles)};
+  cuuint64_t strides[2] = {128, static_cast<cuuint64_t>(npad_total) * 128};
+  cuuint32_t box[3] = {64, static_cast<cuuint32_t>(n_cta), static_cast<cuuint32_t>(ntaps)};
+  cuuint32_t es[3] = {1, 1, 1};
+  CUresult r = ctx->encode(tm, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, ptr,
+                           dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fmt("cuTensorMapEncodeTiled(weights) failed: %d", (int)r);
+  return "";
+}
+
+void free_conv(ConvExec& c) {
+  if (c.d_w) cudaFree(c.d_w);
+  if (c.d_bias) cudaFree(c.d_bias);
+  if (c.d_slope) cudaFree(c.d_slope);
+  c.d_w = nullptr; c.d_bias = nullptr; c.d_slope = nullptr;
+}
+
+// Build the kernel parameter block of one conv.  bufptr(id) resolves program buffer ids.
+template <class BufPtr>
+int materialize_conv(ss4k_ctx* ctx, const ConvSpec& cs, const HostTensor& W, const HostTensor* B,
+                     const HostTensor* S, int act_mode, BufPtr bufptr, ConvExec* ex) {
+  const bool bf16 = act_mode == SS4K_ACT_BF16;
+  PackedWeights pw;
+  std::string e = pack_weights(cs, W, B, S, bf16, &pw);
+  if (!e.empty()) return fail(ctx, SS4K_E_WEIGHTS, e);
+  ConvParams& p = ex->p;
+  memset(&p, 0, sizeof(p));
+  ex->name = cs.name;
+  // A-space geometry
+  int AH = cs.in_h, AW = cs.in_w;
+  if (cs.mode == kModeS2) { AH = cs.in_h / 2; AW = cs.in_w / 2; }
+  TileCfg t;
+  e = configure_tiles(ctx->desc_mode, ctx->nsm, cs.n, AH, AW, pw.npad_total, pw.ntaps, pw.nsub, pw.max_dr, pw.nkb, &t);
+  if (!e.empty()) return fail(ctx, SS4K_E_INVALID, "conv " + cs.name + ": " + e);
+  // upload weights
+  CK(ctx, cudaMalloc(&ex->d_w, pw.w.size() * 2));
+  CK(ctx, cudaMemcpy(ex->d_w, pw.w.data(), pw.w.size() * 2, cudaMemcpyHostToDevice));
+  CK(ctx, cudaMalloc(&ex->d_bias, pw.bias.size() * 4));
+  CK(ctx, cudaMemcpy(ex->d_bias, pw.bias.data(), pw.bias.size() * 4, cudaMemcpyHostToDevice));
+  CK(ctx, cudaMalloc(&ex->d_slope, pw.slope.size() * 4));
+  CK(ctx, cudaMemcpy(ex->d_slope, pw.slope.data(), pw.slope.size() * 4, cudaMemcpyHostToDevice));
+  // tensor maps
+  const int box_w = ctx->desc_mode == 2 ? kTileW : kBoxW;
+  e = encode_act_map(ctx, &p.tmA[0], bufptr(cs.in_buf), cs.n, cs.in_h, cs.in_w, cs.in_pitch, cs.mode, bf16, box_w);
+  if (!e.empty()) return fail(ctx, SS4K_E_CUDA, e);
+  if (cs.split) {
+    e = encode_act_map(ctx, &p.tmA[1], bufptr(cs.in_lo_buf), cs.n, cs.in_h, cs.in_w, cs.in_pitch, cs.mode, bf16, box_w);
+    if (!e.empty()) return fail(ctx, SS4K_E_CUDA, e);
+  } else {
+    p.tmA[1] = p.tmA[0];
+  }
+  e = encode_w_map(ctx, &p.tmW, ex->d_w, pw.npad_total, pw.nkb * pw.ntaps, t.n_cta, pw.ntaps, bf16);
+  if (!e.empty()) return fail(ctx, SS4K_E_CUDA, e);
+  // schedule tables
+  p.nkb = pw.nkb; p.ntaps = pw.ntaps; p.nsub = pw.nsub; p.max_dr = pw.max_dr; p.mode = cs.mode;
+  for (int i = 0; i < pw.nkb; ++i) p.kb[i] = pw.kb[i];
+  for (int i = 0; i < pw.ntaps; ++i) p.taps[i] = pw.taps[i];
+  for (int i = 0; i < pw.nkb; ++i)
+    for (int j = 0; j < kMaxTaps; ++j) p.ksmask[i][j] = pw.mask[static_cast<size_t>(i) * kMaxTaps + j];
+  p.n_img = cs.n; p.H = AH; p.W = AW; p.R = t.R;
+  p.tiles_x = t.tiles_x; p.tiles_y = t.tiles_y; p.n_chunks = t.n_chunks; p.n_tiles = t.n_tiles;
+  p.n_cta = t.n_cta; p.acc_stride = t.acc_stride;
+  p.a_slots = t.a_slots; p.a_slot_bytes = t.a_slot_bytes; p.a_sub_bytes = t.a_sub_bytes;
+  p.w_slots = t.w_slots; p.w_slot_bytes = t.w_slot_bytes; p.w_tile_bytes = t.w_tile_bytes;
+  p.w_resident = t.w_resident;
+  p.desc_mode = ctx->desc_mode;
+  const uint32_t f = bf16 ? 1u : 0u;
+  p.idesc = (1u << 4) | (f << 7) | (f << 10) | (static_cast<uint32_t>(t.n_cta >> 3) << 17) | (static_cast<uint32_t>(128 >> 4) << 24);
+  p.a_row_tx = ctx->desc_mode == 2 ? 3u * kTileW * kRowBytes : static_cast<uint32_t>(kBoxW) * kRowBytes;
+  p.w_tx = static_cast<uint32_t>(t.w_slot_bytes);
+  p.err = ctx->err_dev;
+  // epilogue
+  Epilogue& E = p.ep;
+  E.bias = ex->d_bias;
+  E.slope = ex->d_slope;
+  E.act = cs.act; E.out_mode = cs.out_mode;
+  E.alpha = cs.alpha; E.beta1 = cs.beta1; E.beta2 = cs.beta2;
+  E.is_bf16 = bf16 ? 1 : 0;
+  E.res1 = cs.res1_buf >= 0 ? bufptr(cs.res1_buf) : nullptr;
+  E.res2 = cs.res2_buf >= 0 ? bufptr(cs.res2_buf) : nullptr;
+  E.res1_pitch = cs.res1_pitch; E.res1_coff = cs.res1_coff;
+  E.res2_pitch = cs.res2_pitch; E.res2_coff = cs.res2_coff;
+  ex->ext_out = cs.out_buf == kBufExternalOut;
+  E.out = cs.out_buf >= 0 ? bufptr(cs.out_buf) : nullptr;
+  E.out_lo = cs.out_lo_buf >= 0 ? bufptr(cs.out_lo_buf) : nullptr;
+  E.out2 = cs.out2_buf >= 0 ? bufptr(cs.out2_buf) : nullptr;
+  E.out3 = cs.out3_buf >= 0 ? bufptr(cs.out3_buf) : nullptr;
+  E.out_pitch = cs.out_pitch; E.out_coff = cs.out_coff;
+  E.out_h = cs.out_h; E.out_w = cs.out_w;
+  E.cout = cs.cout; E.ps_r = cs.ps_r; E.fold = cs.fold; E.round_u8 = cs.round_u8;
+  E.base = cs.base_buf >= 0 ? bufptr(cs.base_buf) : nullptr;
+  E.base_pitch = cs.base_pitch;
+  ex->grid = std::min(t.n_tiles, ctx->nsm);
+  return SS4K_OK;
+}
+
+int check_kernel_health(ss4k_ctx* ctx, cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return SS4K_OK;
+  std::string msg = fmt("%s: %s", what, cudaGetErrorString(e));
+  if (ctx && ctx->err_host && ctx->err_host[0] != 0)
+    msg += fmt(" [pipeline watchdog: wait tag %d block %d thread %d parity %d]", ctx->err_host[0], ctx->err_host[1],
+               ctx->err_host[2], ctx->err_host[3]);
+  return fail(ctx, SS4K_E_CUDA, msg);
+}
+
+}  // namespace
+
+// ================================================================================================
+struct ss4k_plan {
+  ss4k_ctx* ctx = nullptr;
+  ss4k_plan_cfg cfg;
+  Program prog;
+  std::vector<void*> bufs;
+  std::vector<ConvExec> convs;  // one per conv step, in step order
+  std::vector<int> step_conv;   // step index -> conv index (or -1)
+  cudaGraphExec_t graph = nullptr;
+  int graph_first = -1, graph_last = -1;  // [first, last] step range inside the graph
+  void* stage_in = nullptr;   // device staging for ss4k_run_host
+  void* stage_out = nullptr;
+  int64_t in_bytes = 0, out_bytes = 0;
+};
+
+namespace {
+
+int64_t fmt_bytes(int fmtid, int n, int c, int h, int w) {
+  switch (fmtid) {
+    case SS4K_FMT_F32_NCHW: return static_cast<int64_t>(n) * c * h * w * 4;
+    case SS4K_FMT_F16_NCHW: return static_cast<int64_t>(n) * c * h * w * 2;
+    case SS4K_FMT_U8_NHWC: return static_cast<int64_t>(n) * c * h * w;
+    case SS4K_FMT_NV12: return static_cast<int64_t>(n) * h * w * 3 / 2;
+    default: return 0;
+  }
+}
+
+int run_step(ss4k_plan* pl, int si, const void* in_dev, void* out_dev, cudaStream_t st) {
+  ss4k_ctx* ctx = pl->ctx;
+  const Step& s = pl->prog.steps[si];
+  if (s.kind == 0) {
+    const PrepSpec& p = s.prep;
+    const bool bf16 = pl->cfg.act_mode == SS4K_ACT_BF16;
+    CK(ctx, prep_launch(p.in_fmt, in_dev, pl->bufs[p.out_buf], p.out_lo_buf >= 0 ? pl->bufs[p.out_lo_buf] : nullptr,
+                        p.n, p.c, p.h, p.w, pl->prog.bufs[p.out_buf].pitch, p.unshuffle, p.fill_ch, p.fill_val,
+                        bf16 ? 1 : 0, st));
+    ctx->launches++;
+  } else {
+    ConvExec& c = pl->convs[pl->step_conv[si]];
+    if (c.ext_out) {
+      ConvParams p = c.p;
+      p.ep.out = out_dev;
+      CK(ctx, conv_tc_launch(p, c.grid, st));
+    } else {
+      CK(ctx, conv_tc_launch(c.p, c.grid, st));
+    }
+    ctx->launches++;
+  }
+  return SS4K_OK;
+}
+
+bool step_is_external(const Step& s) {
+  if (s.kind == 0) return true;  // prep reads the caller's pointer
+  return s.conv.out_buf == kBufExternalOut;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ss4k_abi_version(void) { return SS4K_ABI_VERSION; }
+
+const char* ss4k_last_error(ss4k_ctx* ctx) {
+  if (ctx) return ctx->err.c_str();
+  return g_last_error.c_str();
+}
+
+void ss4k_free(void* p) { free(p); }
+
+static int self_probe(ss4k_ctx* ctx);
+
+int ss4k_create(int device_id, ss4k_ctx** out_ctx) {
+  if (!out_ctx) return fail(nullptr, SS4K_E_INVALID, "out_ctx is null");
+  *out_ctx = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(nullptr, SS4K_E_NODEVICE,
+                fmt("no CUDA device (%s); this engine has no CPU path", e == cudaSuccess ? "count 0" : cudaGetErrorString(e)));
+  if (device_id < 0 || device_id >= ndev) return fail(nullptr, SS4K_E_INVALID, "device_id out of range");
+  cudaDeviceProp prop;
+  CK(nullptr, cudaGetDeviceProperties(&prop, device_id));
+  if (prop.major != 10)
+    return fail(nullptr, SS4K_E_NODEVICE, fmt("device %d is sm_%d%d; this engine is written for sm_100a (B200)", device_id, prop.major, prop.minor));
+  CK(nullptr, cudaSetDevice(device_id));
+  std::unique_ptr<ss4k_ctx> ctx(new ss4k_ctx());
+  ctx->device = device_id;
+  ctx->nsm = prop.multiProcessorCount;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  CK(nullptr, cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+  if (!fn || qres != cudaDriverEntryPointSuccess) return fail(nullptr, SS4K_E_NODEVICE, "cuTensorMapEncodeTiled not available in this driver");
+  ctx->encode = reinterpret_cast<EncodeTiledFn>(fn);
+  CK(nullptr, cudaHostAlloc(reinterpret_cast<void**>(&ctx->err_host), 16, cudaHostAllocMapped));
+  memset(ctx->err_host, 0, 16);
+  CK(nullptr, cudaHostGetDevicePointer(reinterpret_cast<void**>(&ctx->err_dev), ctx->err_host, 0));
+  CK(nullptr, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  CK(nullptr, conv_tc_prepare());
+  const char* force = getenv("SS4K_DESC_MODE");
+  if (force && *force) {
+    ctx->desc_mode = atoi(force);
+    if (getenv("SS4K_SKIP_PROBE") == nullptr) {
+      int rc = self_probe(ctx.get());
+      if (rc != SS4K_OK) { g_last_error = ctx->err; return rc; }
+    }
+  } else {
+    int rc = SS4K_E_SELFTEST;
+    std::string log;
+    for (int mode = 0; mode < 3; ++mode) {
+      ctx->desc_mode = mode;
+      rc = self_probe(ctx.get());
+      if (rc == SS4K_OK) break;
+      log += fmt("[mode %d: %s] ", mode, ctx->err.c_str());
+      if (rc != SS4K_E_SELFTEST) break;  // CUDA error: context is likely poisoned
+    }
+    if (rc != SS4K_OK) return fail(nullptr, rc, "tcgen05 self-probe failed: " + log);
+  }
+  *out_ctx = ctx.release();
+  return SS4K_OK;
+}
+
+int ss4k_destroy(ss4k_ctx* ctx) {
+  if (!ctx) return SS4K_OK;
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  if (ctx->err_host) cudaFreeHost(ctx->err_host);
+  delete ctx;
+  return SS4K_OK;
+}
+
+int ss4k_desc_mode(ss4k_ctx* ctx) { return ctx ? ctx->desc_mode : -1; }
+int ss4k_set_desc_mode(ss4k_ctx* ctx, int mode) {
+  if (!ctx || mode < 0 || mode > 2) return fail(ctx, SS4K_E_INVALID, "bad desc mode");
+  ctx->desc_mode = mode;
+  return SS4K_OK;
+}
+int64_t ss4k_launch_count(ss4k_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int ss4k_load_weights(ss4k_ctx* ctx, int net_id, const char* name, const void* host_ptr, int dtype,
+                      const int64_t* shape, int ndim) {
+  if (!ctx || !name || !host_ptr || !shape || ndim < 1 || ndim > 4) return fail(ctx, SS4K_E_INVALID, "bad argument to ss4k_load_weights");
+  HostTensor t;
+  size_t count = 1;
+  for (int i = 0; i < ndim; ++i) { t.shape.push_back(shape[i]); count *= static_cast<size_t>(shape[i]); }
+  t.data.resize(count);
+  if (dtype == SS4K_DT_F32) {
+    memcpy(t.data.data(), host_ptr, count * 4);
+  } else if (dtype == SS4K_DT_F16) {
+    const uint16_t* h = reinterpret_cast<const uint16_t*>(host_ptr);
+    for (size_t i = 0; i < count; ++i) t.data[i] = h2f(h[i], false);
+  } else {
+    return fail(ctx, SS4K_E_INVALID, "unsupported weight dtype");
+  }
+  ctx->weights[net_id][name] = std::move(t);
+  return SS4K_OK;
+}
+
+int ss4k_clear_weights(ss4k_ctx* ctx, int net_id) {
+  if (!ctx) return SS4K_E_INVALID;
+  ctx->weights.erase(net_id);
+  return SS4K_OK;
+}
+
+static PlanCfgLite lite(const ss4k_plan_cfg* c) {
+  PlanCfgLite l;
+  l.arch = c->arch; l.n = c->n; l.h = c->h; l.w = c->w; l.scale = c->scale; l.depth = c->depth;
+  l.tile = c->tile; l.tile_pad = c->tile_pad; l.act_mode = c->act_mode; l.in_fmt = c->in_fmt; l.out_fmt = c->out_fmt;
+  return l;
+}
+
+int ss4k_plan_dry(const ss4k_plan_cfg* cfg, char** out_json) {
+  if (!cfg || !out_json) return fail(nullptr, SS4K_E_INVALID, "null argument");
+  Program prog;
+  std::string e = build_program(lite(cfg), &prog);
+  if (!e.empty()) return fail(nullptr, SS4K_E_INVALID, e);
+  std::string js = prog.to_json();
+  *out_json = static_cast<char*>(malloc(js.size() + 1));
+  memcpy(*out_json, js.c_str(), js.size() + 1);
+  return SS4K_OK;
+}
+
+int ss4k_plan_destroy(ss4k_plan* pl) {
+  if (!pl) return SS4K_OK;
+  if (pl->graph) cudaGraphExecDestroy(pl->graph);
+  for (auto& c : pl->convs) free_conv(c);
+  for (void* b : pl->bufs) if (b) cudaFree(b);
+  if (pl->stage_in) cudaFree(pl->stage_in);
+  if (pl->stage_out) cudaFree(pl->stage_out);
+  delete pl;
+  return SS4K_OK;
+}
+
+int ss4k_plan_create(ss4k_ctx* ctx, const ss4k_plan_cfg* cfg, ss4k_plan** out_plan) {
+  if (!ctx || !cfg || !out_plan) return fail(ctx, SS4K_E_INVALID, "null argument");
+  *out_plan = nullptr;
+  CK(ctx, cudaSetDevice(ctx->device));
+  std::unique_ptr<ss4k_plan> pl(new ss4k_plan());
+  pl->ctx = ctx;
+  pl->cfg = *cfg;
+  std::string e = build_program(lite(cfg), &pl->prog);
+  if (!e.empty()) return fail(ctx, SS4K_E_INVALID, e);
+  auto wit = ctx->weights.find(cfg->net_id);
+  if (wit == ctx->weights.end()) return fail(ctx, SS4K_E_WEIGHTS, fmt("no weights loaded for net_id %d", cfg->net_id));
+  const auto& wmap = wit->second;
+  Program& P = pl->prog;
+  // buffers
+  pl->bufs.assign(P.bufs.size(), nullptr);
+  for (size_t i = 0; i < P.bufs.size(); ++i) {
+    cudaError_t ce = cudaMalloc(&pl->bufs[i], P.bufs[i].bytes());
+    if (ce != cudaSuccess) {
+      int rc = fail(ctx, SS4K_E_NOMEM, fmt("cudaMalloc(%zu bytes) for buffer %s failed: %s", P.bufs[i].bytes(), P.bufs[i].name.c_str(), cudaGetErrorString(ce)));
+      ss4k_plan_destroy(pl.release());
+      return rc;
+    }
+    cudaMemset(pl->bufs[i], 0, P.bufs[i].bytes());
+  }
+  auto bufptr = [&](int id) -> void* { return id >= 0 ? pl->bufs[id] : nullptr; };
+  // convs
+  pl->step_conv.assign(P.steps.size(), -1);
+  pl->convs.reserve(P.steps.size());
+  for (size_t si = 0; si < P.steps.size(); ++si) {
+    if (P.steps[si].kind != 1) continue;
+    const ConvSpec& cs = P.steps[si].conv;
+    auto w = wmap.find(cs.wname);
+    if (w == wmap.end()) { int rc = fail(ctx, SS4K_E_WEIGHTS, "missing weight " + cs.wname); ss4k_plan_destroy(pl.release()); return rc; }
+    const HostTensor* B = nullptr;
+    const HostTensor* S = nullptr;
+    if (!cs.bname.empty()) {
+      auto b = wmap.find(cs.bname);
+      if (b == wmap.end()) { int rc = fail(ctx, SS4K_E_WEIGHTS, "missing bias " + cs.bname); ss4k_plan_destroy(pl.release()); return rc; }
+      B = &b->second;
+    }
+    if (!cs.sname.empty()) {
+      auto s = wmap.find(cs.sname);
+      if (s == wmap.end()) { int rc = fail(ctx, SS4K_E_WEIGHTS, "missing PReLU slope " + cs.sname); ss4k_plan_destroy(pl.release()); return rc; }
+      S = &s->second;
+    }
+    pl->convs.emplace_back();
+    pl->step_conv[si] = static_cast<int>(pl->convs.size()) - 1;
+    int rc = materialize_conv(ctx, cs, w->second, B, S, cfg->act_mode, bufptr, &pl->convs.back());
+    if (rc != SS4K_OK) { ss4k_plan_destroy(pl.release()); return rc; }
+  }
+  pl->in_bytes = fmt_bytes(P.in_fmt, P.in_n, P.in_c, P.in_h, P.in_w);
+  pl->out_bytes = fmt_bytes(P.out_fmt, P.out_n, P.out_c, P.out_h, P.out_w);
+  // CUDA graph over the internal (non-external) middle of the program
+  if (cfg->use_graph) {
+    int first = -1, last = -1;
+    for (size_t si = 0; si < P.steps.size(); ++si) {
+      if (!step_is_external(P.steps[si])) { if (first < 0) first = (int)si; last = (int)si; }
+    }
+    bool contiguous = first >= 0;
+    for (int si = first; contiguous && si <= last; ++si) if (step_is_external(P.steps[si])) contiguous = false;
+    if (contiguous && last - first >= 1) {
+      cudaGraph_t g = nullptr;
+      int64_t saved = ctx->launches;
+      cudaError_t ce = cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal);
+      int rc = SS4K_OK;
+      if (ce == cudaSuccess) {
+        for (int si = first; si <= last && rc == SS4K_OK; ++si) rc = run_step(pl.get(), si, nullptr, nullptr, ctx->stream);
+        ce = cudaStreamEndCapture(ctx->stream, &g);
+      }
+      ctx->launches = saved;
+      if (ce == cudaSuccess && rc == SS4K_OK && g) {
+        ce = cudaGraphInstantiate(&pl->graph, g, 0);
+        if (ce == cudaSuccess) { pl->graph_first = first; pl->graph_last = last; }
+        else pl->graph = nullptr;
+      }
+      if (g) cudaGraphDestroy(g);
+      cudaGetLastError();
+    }
+  }
+  *out_plan = pl.release();
+  return SS4K_OK;
+}
+
+int ss4k_plan_out_shape(const ss4k_plan* pl, int32_t out_nchw[4]) {
+  if (!pl || !out_nchw) return SS4K_E_INVALID;
+  out_nchw[0] = pl->prog.out_n; out_nchw[1] = pl->prog.out_c; out_nchw[2] = pl->prog.out_h; out_nchw[3] = pl->prog.out_w;
+  return SS4K_OK;
+}
+double ss4k_plan_flops(const ss4k_plan* pl) { return pl ? pl->prog.flops : 0.0; }
+int ss4k_plan_launches(const ss4k_plan* pl) { return pl ? static_cast<int>(pl->prog.steps.size()) : 0; }
+int ss4k_plan_io_bytes(const ss4k_plan* pl, int64_t* in_bytes, int64_t* out_bytes) {
+  if (!pl) return SS4K_E_INVALID;
+  if (in_bytes) *in_bytes = pl->in_bytes;
+  if (out_bytes) *out_bytes = pl->out_bytes;
+  return SS4K_OK;
+}
+
+int ss4k_run(ss4k_plan* pl, const void* in_dev, void* out_dev, void* cuda_stream) {
+  if (!pl || !in_dev || !out_dev) return fail(pl ? pl->ctx : nullptr, SS4K_E_INVALID, "null argument to ss4k_run");
+  ss4k_ctx* ctx = pl->ctx;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(cuda_stream);
+  const int ns = static_cast<int>(pl->prog.steps.size());
+  for (int si = 0; si < ns; ++si) {
+    if (pl->graph && si == pl->graph_first) {
+      CK(ctx, cudaGraphLaunch(pl->graph, st));
+      ctx->launches += pl->graph_last - pl->graph_first + 1;
+      si = pl->graph_last;
+      continue;
+    }
+    int rc = run_step(pl, si, in_dev, out_dev, st);
+    if (rc != SS4K_OK) return rc;
+  }
+  return SS4K_OK;
+}
+
+int ss4k_run_host(ss4k_plan* pl, const void* in_host, void* out_host) {
+  if (!pl || !in_host || !out_host) return fail(pl ? pl->ctx : nullptr, SS4K_E_INVALID, "null argument to ss4k_run_host");
+  ss4k_ctx* ctx = pl->ctx;
+  if (!pl->stage_in) CK(ctx, cudaMalloc(&pl->stage_in, pl->in_bytes + 256));
+  if (!pl->stage_out) CK(ctx, cudaMalloc(&pl->stage_out, pl->out_bytes + 256));
+  CK(ctx, cudaMemcpyAsync(pl->stage_in, in_host, pl->in_bytes, cudaMemcpyHostToDevice, ctx->stream));
+  int rc = ss4k_run(pl, pl->stage_in, pl->stage_out, ctx->stream);
+  if (rc != SS4K_OK) return rc;
+  CK(ctx, cudaMemcpyAsync(out_host, pl->stage_out, pl->out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  return check_kernel_health(ctx, cudaStreamSynchronize(ctx->stream), "ss4k_run_host");
+}
+
+// ------------------------------------------------------------------------------------------------
+// operator-level entry
+int ss4k_conv3x3(ss4k_ctx* ctx, const ss4k_conv_desc* d, const float* x, const float* weight, const float* bias,
+                 const float* slope, const float* residual, float* y, void* cuda_stream) {
+  if (!ctx || !d || !x || !weight || !y) return fail(ctx, SS4K_E_INVALID, "null argument to ss4k_conv3x3");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(cuda_stream);
+  const bool bf16 = d->act_mode == SS4K_ACT_BF16;
+  const bool split = d->act_mode == SS4K_ACT_F16_SPLIT;
+  const int direct_f32 = d->reserved[0];
+  const int in_pitch = round_up(d->cin, 16);
+  const int npad = round_up(d->cout, 16);
+  int oh = d->h, ow = d->w;
+  if (d->mode == kModeUp2) { oh *= 2; ow *= 2; }
+  if (d->mode == kModeS2) { oh /= 2; ow /= 2; }
+  // weights to host
+  HostTensor W, B, S;
+  W.shape = {d->cout, d->cin, 3, 3};
+  W.data.resize(static_cast<size_t>(d->cout) * d->cin * 9);
+  CK(ctx, cudaMemcpyAsync(W.data.data(), weight, W.data.size() * 4, cudaMemcpyDeviceToHost, st));
+  if (bias) { B.shape = {d->cout}; B.data.resize(d->cout); CK(ctx, cudaMemcpyAsync(B.data.data(), bias, d->cout * 4, cudaMemcpyDeviceToHost, st)); }
+  if (slope) { S.shape = {d->cout}; S.data.resize(d->cout); CK(ctx, cudaMemcpyAsync(S.data.data(), slope, d->cout * 4, cudaMemcpyDeviceToHost, st)); }
+  CK(ctx, cudaStreamSynchronize(st));
+  // buffers: 0 in, 1 in_lo, 2 out, 3 res, 4 out_lo
+  void* b[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  const size_t in_elems = static_cast<size_t>(d->n) * d->h * d->w * in_pitch;
+  const int out_ch_pitch = d->pixel_shuffle == 2 ? npad / 4 : npad;
+  const int ooh = d->pixel_shuffle == 2 ? oh * 2 : oh, oow = d->pixel_shuffle == 2 ? ow * 2 : ow;
+  const size_t out_elems = static_cast<size_t>(d->n) * ooh * oow * out_ch_pitch;
+  auto cleanup = [&]() { for (void* q : b) if (q) cudaFree(q); };
+  CK(ctx, cudaMalloc(&b[0], in_elems * 2 + 256));
+  if (split) CK(ctx, cudaMalloc(&b[1], in_elems * 2 + 256));
+  CK(ctx, cudaMalloc(&b[2], out_elems * 2 + 256));
+  if (split) CK(ctx, cudaMalloc(&b[4], out_elems * 2 + 256));
+  CK(ctx, prep_launch(SS4K_FMT_F32_NCHW, x, b[0], b[1], d->n, d->cin, d->h, d->w, in_pitch, 1, -1, 0.f, bf16, st));
+  ctx->launches++;
+  const bool ps_f32 = d->pixel_shuffle > 0 && d->pixel_shuffle != 2;
+  const int res_c = d->pixel_shuffle == 2 ? d->cout / 4 : d->cout;
+  if (residual) {
+    CK(ctx, cudaMalloc(&b[3], out_elems * 2 + 256));
+    CK(ctx, prep_launch(SS4K_FMT_F32_NCHW, residual, b[3], nullptr, d->n, res_c, ooh, oow, out_ch_pitch, 1, -1, 0.f, bf16, st));
+    ctx->launches++;
+  }
+  ConvSpec cs;
+  cs.name = "op"; cs.wname = "w"; cs.mode = d->mode; cs.n = d->n; cs.cin = d->cin; cs.cout = d->cout;
+  cs.in_buf = 0; cs.in_lo_buf = split ? 1 : kBufNone; cs.in_h = d->h; cs.in_w = d->w; cs.in_pitch = in_pitch;
+  cs.act = d->act; cs.alpha = d->alpha; cs.split = split ? 1 : 0;
+  if (residual) { cs.res1_buf = 3; cs.res1_pitch = out_ch_pitch; cs.beta1 = d->beta; }
+  if (ps_f32) {
+    cs.out_mode = kOutPSNCHWF32; cs.out_buf = kBufExternalOut; cs.ps_r = d->pixel_shuffle; cs.out_h = oh; cs.out_w = ow;
+  } else if (d->pixel_shuffle == 2) {
+    cs.out_mode = kOutPS2NHWC; cs.out_buf = 2; cs.out_pitch = out_ch_pitch; cs.out_h = ooh; cs.out_w = oow; cs.wperm = 1;
+    cs.out_lo_buf = split ? 4 : kBufNone;
+  } else if (direct_f32) {
+    cs.out_mode = kOutNCHWF32; cs.out_buf = kBufExternalOut; cs.out_h = oh; cs.out_w = ow;
+  } else {
+    cs.out_mode = kOutNHWC; cs.out_buf = 2; cs.out_pitch = npad; cs.out_h = oh; cs.out_w = ow;
+    cs.out_lo_buf = split ? 4 : kBufNone;
+  }
+  ConvExec ex;
+  auto bufptr = [&](int id) -> void* { return id >= 0 ? b[id] : nullptr; };
+  int rc = materialize_conv(ctx, cs, W, bias ? &B : nullptr, slope ? &S : nullptr, d->act_mode, bufptr, &ex);
+  if (rc != SS4K_OK) { free_conv(ex); cleanup(); return rc; }
+  if (ex.ext_out) ex.p.ep.out = y;
+  cudaError_t ce = conv_tc_launch(ex.p, ex.grid, st);
+  ctx->launches++;
+  if (ce == cudaSuccess && !ex.ext_out) {
+    ce = unprep_launch(b[2], b[4], y, d->n, res_c, ooh, oow, out_ch_pitch, 0, bf16, st);
+    ctx->launches++;
+  }
+  if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
+  rc = check_kernel_health(ctx, ce, "ss4k_conv3x3");
+  free_conv(ex);
+  cleanup();
+  return rc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Host-only debug entry: run the weight packer and return its schedule as JSON + the packed weights
+// as floats.  tests/test_pack_cpu.py emulates the kernel's MMA schedule from this on the CPU.
+int ss4k_debug_pack(const ss4k_conv_desc* d, int in_pitch, int in_coff, int wperm, const float* w_host,
+                    const float* bias_host, const float* slope_host, char** out_json, float** out_packed,
+                    int64_t* out_count) {
+  if (!d || !w_host || !out_json || !out_packed || !out_count) return fail(nullptr, SS4K_E_INVALID, "null argument");
+  ConvSpec cs;
+  cs.name = "dbg"; cs.wname = "w"; cs.mode = d->mode; cs.n = d->n; cs.cin = d->cin; cs.cout = d->cout;
+  cs.in_h = d->h; cs.in_w = d->w; cs.in_pitch = in_pitch; cs.in_coff = in_coff; cs.wperm = wperm;
+  cs.split = d->act_mode == SS4K_ACT_F16_SPLIT ? 1 : 0;
+  HostTensor W, B, S;
+  W.shape = {d->cout, d->cin, 3, 3};
+  W.data.assign(w_host, w_host + static_cast<size_t>(d->cout) * d->cin * 9);
+  if (bias_host) { B.shape = {d->cout}; B.data.assign(bias_host, bias_host + d->cout); }
+  if (slope_host) { S.shape = {d->cout}; S.data.assign(slope_host, slope_host + d->cout); }
+  const bool bf16 = d->act_mode == SS4K_ACT_BF16;
+  PackedWeights pw;
+  std::string e = pack_weights(cs, W, bias_host ? &B : nullptr, slope_host ? &S : nullptr, bf16, &pw);
+  if (!e.empty()) return fail(nullptr, SS4K_E_WEIGHTS, e);
+  int AH = d->h, AW = d->w;
+  if (d->mode == kModeS2) { AH /= 2; AW /= 2; }
+  TileCfg t;
+  const int dm = d->reserved[1];
+  e = configure_tiles(dm, 148, d->n, AH, AW, pw.npad_total, pw.ntaps, pw.nsub, pw.max_dr, pw.nkb, &t);
+  if (!e.empty()) return fail(nullptr, SS4K_E_INVALID, e);
+  std::string js = "{";
+  js += fmt("\"nkb\":%d,\"ntaps\":%d,\"nsub\":%d,\"max_dr\":%d,\"npad\":%d,", pw.nkb, pw.ntaps, pw.nsub, pw.max_dr, pw.npad_total);
+  js += fmt("\"R\":%d,\"n_cta\":%d,\"n_chunks\":%d,\"acc_stride\":%d,\"tiles_x\":%d,\"tiles_y\":%d,\"n_tiles\":%d,", t.R, t.n_cta, t.n_chunks, t.acc_stride, t.tiles_x, t.tiles_y, t.n_tiles);
+  js += fmt("\"a_slots\":%d,\"a_slot_bytes\":%d,\"w_slots\":%d,\"w_slot_bytes\":%d,\"w_resident\":%d,", t.a_slots, t.a_slot_bytes, t.w_slots, t.w_slot_bytes, t.w_resident);
+  js += "\"kb\":[";
+  for (int i = 0; i < pw.nkb; ++i) js += fmt("%s[%d,%d,%d]", i ? "," : "", pw.kb[i].tmap, pw.kb[i].c0, pw.kb[i].p);
+  js += "],\"taps\":[";
+  for (int i = 0; i < pw.ntaps; ++i) js += fmt("%s[%d,%d,%d]", i ? "," : "", pw.taps[i].dr, pw.taps[i].shift, pw.taps[i].sub);
+  js += "],\"mask\":[";
+  for (int i = 0; i < pw.nkb; ++i) {
+    js += i ? ",[" : "[";
+    for (int j = 0; j < pw.ntaps; ++j) js += fmt("%s%d", j ? "," : "", pw.mask[static_cast<size_t>(i) * kMaxTaps + j]);
+    js += "]";
+  }
+  js += "],\"bias\":[";
+  for (size_t i = 0; i < pw.bias.size(); ++i) js += fmt("%s%.9g", i ? "," : "", pw.bias[i]);
+  js += "],\"slope\":[";
+  for (size_t i = 0; i < pw.slope.size(); ++i) js += fmt("%s%.9g", i ? "," : "", pw.slope[i]);
+  js += "]}";
+  *out_json = static_cast<char*>(malloc(js.size() + 1));
+  memcpy(*out_json, js.c_str(), js.size() + 1);
+  *out_count = static_cast<int64_t>(pw.w.size());
+  *out_packed = static_cast<float*>(malloc(pw.w.size() * sizeof(float)));
+  for (size_t i = 0; i < pw.w.size(); ++i) (*out_packed)[i] = h2f(pw.w[i], bf16);
+  return SS4K_OK;
+}
+
+// Start-up self-probe: one small 64->64 conv through the tcgen05 path against the naive direct
+// kernel.  Decides which shared-memory-descriptor addressing mode this GPU/driver honours.
+static int self_probe(ss4k_ctx* ctx) {
+  const int N = 1, H = 5, W = 200, C = 64;
+  std::vector<float> hx(static_cast<size_t>(N) * C * H * W), hw(static_cast<size_t>(C) * C * 9), hb(C);
+  uint32_t s = 12345u;
+  auto rnd = [&]() { s = s * 1664525u + 1013904223u; return ((s >> 8) & 0xFFFF) / 65536.0f - 0.5f; };
+  for (auto& v : hx) v = rnd();
+  for (auto& v : hw) v = h2f(f2h(rnd() * 0.2f, false), false);
+  for (auto& v : hb) v = rnd();
+  float *dx = nullptr, *dw = nullptr, *db = nullptr, *dy = nullptr, *dr = nullptr;
+  void* dx16 = nullptr;
+  const size_t osz = static_cast<size_t>(N) * C * H * W;
+  CK(ctx, cudaMalloc(&dx, hx.size() * 4));
+  CK(ctx, cudaMalloc(&dw, hw.size() * 4));
+  CK(ctx, cudaMalloc(&db, hb.size() * 4));
+  CK(ctx, cudaMalloc(&dy, osz * 4));
+  CK(ctx, cudaMalloc(&dr, osz * 4));
+  CK(ctx, cudaMalloc(&dx16, static_cast<size_t>(N) * H * W * C * 2 + 256));
+  CK(ctx, cudaMemcpy(dx, hx.data(), hx.size() * 4, cudaMemcpyHostToDevice));
+  CK(ctx, cudaMemcpy(dw, hw.data(), hw.size() * 4, cudaMemcpyHostToDevice));
+  CK(ctx, cudaMemcpy(db, hb.data(), hb.size() * 4, cudaMemcpyHostToDevice));
+  ss4k_conv_desc d;
+  memset(&d, 0, sizeof(d));
+  d.struct_size = sizeof(d); d.n = N; d.h = H; d.w = W; d.cin = C; d.cout = C; d.alpha = 1.f;
+  d.reserved[0] = 1;
+  int rc = ss4k_conv3x3(ctx, &d, dx, dw, db, nullptr, nullptr, dy, ctx->stream);
+  if (rc == SS4K_OK) {
+    cudaError_t ce = prep_launch(SS4K_FMT_F32_NCHW, dx, dx16, nullptr, N, C, H, W, C, 1, -1, 0.f, 0, ctx->stream);
+    if (ce == cudaSuccess) ce = ref_conv3x3_launch(dx16, dw, db, dr, N, H, W, C, C, C, 0, ctx->stream);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(ctx->stream);
+    rc = check_kernel_health(ctx, ce, "self-probe reference");
+  }
+  if (rc == SS4K_OK) {
+    std::vector<float> y(osz), r(osz);
+    cudaMemcpy(y.data(), dy, osz * 4, cudaMemcpyDeviceToHost);
+    cudaMemcpy(r.data(), dr, osz * 4, cudaMemcpyDeviceToHost);
+    double maxref = 0, maxerr = 0;
+    for (size_t i = 0; i < osz; ++i) {
+      maxref = std::max(maxref, static_cast<double>(std::fabs(r[i])));
+      const double e = std::fabs(static_cast<double>(y[i]) - r[i]);
+      if (!(e <= maxerr)) maxerr = e;  // also catches NaN
+    }
+    if (!(maxerr <= 2e-3 * maxref + 1e-3))
+      rc = fail(ctx, SS4K_E_SELFTEST, fmt("max|err| %.4g vs max|ref| %.4g", maxerr, maxref));
+  }
+  cudaFree(dx); cudaFree(dw); cudaFree(db); cudaFree(dy); cudaFree(dr); cudaFree(dx16);
+  return rc;
+}
+
+}  // extern "C"

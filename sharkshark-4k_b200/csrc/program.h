@@ -1,0 +1,95 @@
+// Host-side layer programs: a network is lowered to a list of buffers and steps (prep + convs with
+// fused epilogues).  This part is pure host code (no CUDA calls) so the planner can be checked on a
+// CPU-only box: ss4k_plan_dry() dumps a program as JSON and tests/test_program_cpu.py interprets it
+// with torch against the oracle.
+#pragma once
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+namespace ss4k {
+
+constexpr int kBufExternalIn = -2;   // caller's input pointer
+constexpr int kBufExternalOut = -3;  // caller's output pointer
+constexpr int kBufNone = -1;
+
+struct BufSpec {
+  std::string name;
+  int n = 0, h = 0, w = 0, pitch = 0;  // NHWC, 16-bit elements
+  bool zero_init = false;
+  size_t bytes() const { return static_cast<size_t>(n) * h * w * pitch * 2 + 256; }
+};
+
+struct PrepSpec {
+  int in_fmt = 0;       // SS4K_FMT_*
+  int c = 3;            // source channels
+  int h = 0, w = 0;     // source frame size
+  int n = 1;
+  int unshuffle = 1;    // pixel_unshuffle factor
+  int out_buf = kBufNone, out_lo_buf = kBufNone;
+  int fill_ch = -1;     // channel receiving a constant (BSVD noise map), or -1
+  float fill_val = 0.f;
+};
+
+struct ConvSpec {
+  std::string name;
+  std::string wname, bname, sname;  // state-dict keys: weight, bias, PReLU slope ("" = none)
+  float const_slope = 0.f;          // LeakyReLU slope when act == 1 and sname is empty
+  int mode = 0;                     // ConvMode
+  int n = 1;
+  int cin = 0, cout = 0;
+  int in_buf = kBufNone, in_lo_buf = kBufNone;
+  int in_h = 0, in_w = 0, in_pitch = 0, in_coff = 0;
+  int act = 0;                      // ActKind
+  float alpha = 1.f, beta1 = 0.f, beta2 = 0.f;
+  int res1_buf = kBufNone, res1_pitch = 0, res1_coff = 0;
+  int res2_buf = kBufNone, res2_pitch = 0, res2_coff = 0;
+  int out_mode = 0;                 // OutMode
+  int out_buf = kBufNone, out_lo_buf = kBufNone, out2_buf = kBufNone, out3_buf = kBufNone;
+  int out_pitch = 0, out_coff = 0;
+  int out_h = 0, out_w = 0;         // see Epilogue::out_h
+  int ps_r = 0, fold = 0, round_u8 = 0;
+  int base_buf = kBufNone, base_pitch = 0;
+  int wperm = 0;                    // 1: permute output channels (c,a,b) -> (a,b,c) for PixelShuffle(2)
+  int split = 0;                    // 1: fp16 hi/lo split operands (3 MMAs per product)
+  double flops() const;
+};
+
+struct Step {
+  int kind = 0;  // 0 prep, 1 conv
+  PrepSpec prep;
+  ConvSpec conv;
+};
+
+struct Program {
+  std::vector<BufSpec> bufs;
+  std::vector<Step> steps;
+  int out_n = 0, out_c = 0, out_h = 0, out_w = 0;
+  int in_n = 0, in_c = 0, in_h = 0, in_w = 0;
+  int in_fmt = 0, out_fmt = 0;
+  double flops = 0;
+  int add_buf(const std::string& name, int n, int h, int w, int pitch, bool zero = false) {
+    BufSpec b;
+    b.name = name; b.n = n; b.h = h; b.w = w; b.pitch = pitch; b.zero_init = zero;
+    bufs.push_back(b);
+    return static_cast<int>(bufs.size()) - 1;
+  }
+  void add_conv(const ConvSpec& c) {
+    Step s; s.kind = 1; s.conv = c; steps.push_back(s);
+    flops += c.flops();
+  }
+  void add_prep(const PrepSpec& p) {
+    Step s; s.kind = 0; s.prep = p; steps.push_back(s);
+  }
+  std::string to_json() const;
+};
+
+struct PlanCfgLite {
+  int arch, n, h, w, scale, depth, tile, tile_pad, act_mode, in_fmt, out_fmt;
+};
+
+// returns "" on success, else an error message
+std::string build_program(const PlanCfgLite& cfg, Program* out);
+
+}  // namespace ss4k

@@ -1,0 +1,181 @@
+"""Drop-in for the reference's RealESRGAN model factory
+(reference: src/upscale/model/realesrgan/factory.py:85-98 ArgsData, :108-234 build_model, :236-245 JitWrapper).
+
+``build_model(factor, device, input_shape, batch_size, denoise_rate, jit_mode)`` keeps the reference
+signature and returns an ``nn.Module`` whose ``forward(x)`` takes ``[N,3,H,W]`` in [0,1] on ``device`` and
+returns ``[N,3,s*H,s*W]`` (un-clamped), exactly what ``FsrcnnUpscalerService`` calls
+(src/upscale/fsrcnn_upscaler.py:181,294).  The arithmetic runs in libss4k.so (tcgen05 convs with fused
+epilogues); plans are built lazily per input shape, so arbitrary shapes work (image server path,
+src/sharkshark/image_server/image_pipeline.py:54-64).
+"""
+import os
+from dataclasses import dataclass
+
+import torch
+from torch import nn
+
+from . import _lib as L
+from .engine import Engine
+
+
+@dataclass
+class ArgsData:
+    # same defaults as the reference (factory.py:85-98)
+    model_name = 'realesr-general-x4v3'
+    denoise_strength = 0.5
+    outscale = 4
+    model_path = None
+    tile = 0
+    tile_pad = 10
+    pre_pad = 0
+
+
+# model_name -> (arch, scale, depth)   (factory.py:112-138)
+MODEL_ZOO = {
+    'RealESRGAN_x4plus': (L.ARCH_RRDB, 4, 23),
+    'RealESRNet_x4plus': (L.ARCH_RRDB, 4, 23),
+    'RealESRGAN_x4plus_anime_6B': (L.ARCH_RRDB, 4, 6),
+    'RealESRGAN_x2plus': (L.ARCH_RRDB, 2, 23),
+    'realesr-animevideov3': (L.ARCH_SRVGG, 4, 16),
+    'realesr-general-x4v3': (L.ARCH_SRVGG, 4, 32),
+}
+
+
+def dni(net_a, net_b, dni_weight):
+    """RealESRGANer.dni (realesrgan/utils.py @5ca1078): w = dni_weight[0]*w_a + dni_weight[1]*w_b for
+    every key; the reference passes [denoise_strength, 1 - denoise_strength] (factory.py:152-157)."""
+    return {k: dni_weight[0] * v + dni_weight[1] * net_b[k] for k, v in net_a.items()}
+
+
+def load_checkpoint(path):
+    """RealESRGANer weight load: key 'params_ema' if present else 'params'."""
+    ck = torch.load(path, map_location='cpu')
+    if 'params_ema' in ck:
+        return ck['params_ema']
+    if 'params' in ck:
+        return ck['params']
+    return ck
+
+
+class _NativeNet(nn.Module):
+    """nn.Module facade over engine plans (``.eval()``, ``.to()``, ``.half()`` are accepted and ignored:
+    weights live inside the engine in its packed 16-bit layout)."""
+
+    arch = None
+
+    def __init__(self, state_dict, scale, depth, device=0, act_mode=L.ACT_F16, tile=0, tile_pad=10,
+                 out_dtype=torch.float32, use_graph=True):
+        super().__init__()
+        self.engine = Engine.get(device)
+        self.scale, self.depth, self.act_mode = scale, depth, act_mode
+        self.tile, self.tile_pad = tile, tile_pad
+        self.out_dtype = out_dtype
+        self.use_graph = use_graph
+        self.net_id = self.engine.new_net(state_dict)
+        self._plans = {}
+
+    def _plan(self, n, h, w, in_fmt, out_fmt):
+        key = (n, h, w, in_fmt, out_fmt)
+        p = self._plans.get(key)
+        if p is None:
+            p = self.engine.plan(self.net_id, self.arch, n, h, w, scale=self.scale, depth=self.depth,
+                                 tile=0, tile_pad=self.tile_pad, act_mode=self.act_mode, in_fmt=in_fmt,
+                                 out_fmt=out_fmt, use_graph=self.use_graph)
+            self._plans[key] = p
+        return p
+
+    def plan_for(self, x):
+        n, _, h, w = x.shape
+        in_fmt = L.FMT_F16_NCHW if x.dtype == torch.float16 else L.FMT_F32_NCHW
+        out_fmt = L.FMT_F16_NCHW if self.out_dtype == torch.float16 else L.FMT_F32_NCHW
+        return self._plan(n, h, w, in_fmt, out_fmt)
+
+    def forward(self, x):
+        if not x.is_cuda:
+            raise L.Ss4kError("native model called with a CPU tensor: there is no CPU path")
+        if x.dtype not in (torch.float16, torch.float32):
+            x = x.float()
+        x = x.contiguous()
+        if self.tile and self.tile > 0:
+            return self._forward_tiled(x)
+        return self.plan_for(x).run(x)
+
+    def _forward_tiled(self, x):
+        """RealESRGANer.tile_process semantics: tiles_x = ceil(W/tile), padded
+        crop clamped to the image, paste of the un-padded centre, no blending."""
+        import math
+        b, c, h, w = x.shape
+        s, tile, pad = self.scale, self.tile, self.tile_pad
+        out = torch.zeros(b, c, h * s, w * s, device=x.device, dtype=self.out_dtype)
+        for ty in range(math.ceil(h / tile)):
+            for tx in range(math.ceil(w / tile)):
+                sx, sy = tx * tile, ty * tile
+                ex, ey = min(sx + tile, w), min(sy + tile, h)
+                sxp, exp_ = max(sx - pad, 0), min(ex + pad, w)
+                syp, eyp = max(sy - pad, 0), min(ey + pad, h)
+                crop = x[:, :, syp:eyp, sxp:exp_].contiguous()
+                o = self.plan_for(crop).run(crop)
+                ox0, oy0 = (sx - sxp) * s, (sy - syp) * s
+                out[:, :, sy * s:ey * s, sx * s:ex * s] = o[:, :, oy0:oy0 + (ey - sy) * s, ox0:ox0 + (ex - sx) * s]
+        return out
+
+    # weights are not nn.Parameters: these keep callers such as ``model.eval().to(device)`` working
+    def half(self):
+        return self
+
+    def float(self):
+        return self
+
+
+class NativeSRVGG(_NativeNet):
+    """SRVGGNetCompact (factory.py:18-82) on the native engine."""
+    arch = L.ARCH_SRVGG
+
+    def __init__(self, state_dict, num_conv=16, upscale=4, device=0, act_mode=L.ACT_F16, **kw):
+        super().__init__(state_dict, upscale, num_conv, device=device, act_mode=act_mode, **kw)
+
+
+class NativeRRDBNet(_NativeNet):
+    """basicsr RRDBNet (constructors at factory.py:113-125) on the native engine."""
+    arch = L.ARCH_RRDB
+
+    def __init__(self, state_dict, scale=4, num_block=23, device=0, act_mode=L.ACT_F16, **kw):
+        super().__init__(state_dict, scale, num_block, device=device, act_mode=act_mode, **kw)
+
+
+def build_model(factor=4, device=0, input_shape=(720, 1280), batch_size=8, denoise_rate=0.5, jit_mode=None,
+                args=None, state_dict=None, act_mode=L.ACT_F16):
+    """Same signature as the reference's build_model (factory.py:108).  ``jit_mode`` is accepted for
+    compatibility; every mode maps to the native engine ('b200').  ``state_dict`` (or
+    ``args.model_path``) supplies the weights; there is no network here, so nothing is downloaded."""
+    args = args or ArgsData()
+    args.denoise_strength = denoise_rate
+    name = args.model_name.split('.')[0]
+    if name not in MODEL_ZOO:
+        raise ValueError(f"unknown model_name {name}")
+    arch, netscale, depth = MODEL_ZOO[name]
+    if state_dict is None:
+        path = args.model_path or os.path.join('weights', name + '.pth')
+        if isinstance(path, (list, tuple)):
+            sds = [load_checkpoint(p) for p in path]
+            state_dict = dni(sds[0], sds[1], [args.denoise_strength, 1 - args.denoise_strength])
+        else:
+            if not os.path.isfile(path):
+                raise FileNotFoundError(f"{path}: weights are downloaded at run time by the reference "
+                                        "(factory.py:140-150); pass state_dict= or args.model_path")
+            state_dict = load_checkpoint(path)
+            if name == 'realesr-general-x4v3' and args.denoise_strength != 1:
+                wdn = path.replace('realesr-general-x4v3', 'realesr-general-wdn-x4v3')
+                if os.path.isfile(wdn):
+                    state_dict = dni(state_dict, load_checkpoint(wdn),
+                                     [args.denoise_strength, 1 - args.denoise_strength])
+    elif isinstance(state_dict, (list, tuple)):
+        state_dict = dni(state_dict[0], state_dict[1], [args.denoise_strength, 1 - args.denoise_strength])
+    cls = NativeSRVGG if arch == L.ARCH_SRVGG else NativeRRDBNet
+    kw = dict(device=device, act_mode=act_mode, tile=args.tile, tile_pad=args.tile_pad)
+    if arch == L.ARCH_SRVGG:
+        model = cls(state_dict, num_conv=depth, upscale=netscale, **kw)
+    else:
+        model = cls(state_dict, scale=netscale, num_block=depth, **kw)
+    model.netscale = netscale
+    return model.eval()

@@ -1,0 +1,159 @@
+"""CPU emulation helpers for tests (test infrastructure only, never used by the product path).
+
+  emulate_packed_conv : executes the kernel's MMA schedule (K blocks x taps x 16-channel k-steps with
+                        shifted halo rows) from the packed weights returned by ss4k_debug_pack;
+                        checks the weight packer / schedule tables of csrc/engine.cu without a GPU.
+  run_program         : interprets a layer program (ss4k_plan_dry JSON) with torch fp32 ops; checks the
+                        network lowering of csrc/program.cpp (buffers, channel offsets, epilogues).
+"""
+import ctypes
+import json
+
+import torch
+import torch.nn.functional as F
+
+
+def debug_pack(lib, L, w, bias=None, slope=None, mode=0, in_pitch=None, in_coff=0, wperm=0, act_mode=0,
+               n=1, h=8, wd=8, desc_mode=0):
+    cout, cin = w.shape[:2]
+    d = L.ConvDesc()
+    d.struct_size = ctypes.sizeof(L.ConvDesc)
+    d.n, d.h, d.w, d.cin, d.cout, d.mode, d.act_mode = n, h, wd, cin, cout, mode, act_mode
+    d.reserved[1] = desc_mode
+    if in_pitch is None:
+        in_pitch = (cin + 15) // 16 * 16
+    w = w.contiguous().float()
+    js, pk, cnt = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_int64()
+    bp = ctypes.c_void_p(bias.contiguous().float().data_ptr()) if bias is not None else None
+    sp = ctypes.c_void_p(slope.contiguous().float().data_ptr()) if slope is not None else None
+    L.check(lib.ss4k_debug_pack(ctypes.byref(d), in_pitch, in_coff, wperm, ctypes.c_void_p(w.data_ptr()), bp, sp,
+                                ctypes.byref(js), ctypes.byref(pk), ctypes.byref(cnt)))
+    meta = json.loads(ctypes.string_at(js).decode())
+    arr = (ctypes.c_float * cnt.value).from_address(pk.value)
+    packed = torch.tensor(list(arr), dtype=torch.float32).reshape(meta["nkb"], meta["ntaps"], meta["npad"], 64)
+    lib.ss4k_free(js)
+    lib.ss4k_free(pk)
+    return meta, packed
+
+
+def emulate_packed_conv(meta, packed, x_nhwc, mode, x_lo=None):
+    """x_nhwc: [N,H,W,pitch] float.  Returns the accumulators in OUTPUT pixel space [N,OH,OW,npad]
+    (before bias / activation), computed exactly the way the kernel schedules its MMAs."""
+    n, h, w, pitch = x_nhwc.shape
+    srcs = [x_nhwc, x_lo if x_lo is not None else x_nhwc]
+    if mode == 2:   # stride-2 view: (2*pitch merged (pb,c), W/2, pa, H/2)
+        ah, aw = h // 2, w // 2
+        def plane(t, p):
+            v = t.reshape(n, ah, 2, aw, 2, pitch)[:, :, p]          # [n, ah, aw, pb, c]
+            return v.reshape(n, ah, aw, 2 * pitch)
+    else:
+        ah, aw = h, w
+        def plane(t, p):
+            return t
+    nsub, npad = meta["nsub"], meta["npad"]
+    acc = torch.zeros(nsub, n, ah, aw, npad, dtype=torch.float64)
+    for kbi, (tmap, c0, p) in enumerate(meta["kb"]):
+        src = plane(srcs[tmap], p)
+        cdim = src.shape[-1]
+        blk = torch.zeros(n, ah, aw, 64, dtype=torch.float64)
+        hi = min(c0 + 64, cdim)
+        if hi > c0:
+            blk[..., :hi - c0] = src[..., c0:hi]                     # TMA zero-fills beyond the tensor
+        padded = F.pad(blk.permute(0, 3, 1, 2), (2, 2, 2, 2)).permute(0, 2, 3, 1)   # zero halo
+        for t, (dr, shift, sub) in enumerate(meta["taps"]):
+            mask = meta["mask"][kbi][t]
+            if not mask:
+                continue
+            # output (y, x) reads input row y - 1 + dr, pixel x - 1 + shift
+            win = padded[:, 1 + dr:1 + dr + ah, 1 + shift:1 + shift + aw, :]
+            for ks in range(4):
+                if mask >> ks & 1:
+                    a = win[..., ks * 16:(ks + 1) * 16]
+                    b = packed[kbi, t, :, ks * 16:(ks + 1) * 16].double()
+                    acc[sub] += a @ b.t()
+    if mode == 1:   # 4 output phases -> 2x resolution
+        out = torch.zeros(n, 2 * ah, 2 * aw, npad, dtype=torch.float64)
+        for sub in range(4):
+            out[:, (sub >> 1)::2, (sub & 1)::2] = acc[sub]
+        return out
+    return acc[0]
+
+
+# ------------------------------------------------------------------------------------------------
+def _nchw(t):
+    return t.permute(0, 3, 1, 2).contiguous()
+
+
+def _nhwc(t):
+    return t.permute(0, 2, 3, 1).contiguous()
+
+
+def run_program(prog, sd, x, quant=None):
+    """Interpret a layer program with fp32 torch ops.  x: the caller's input (float NCHW here).
+    quant: optional callable emulating 16-bit storage of activations (e.g. lambda t: t.half().float())."""
+    q = quant if quant is not None else (lambda t: t)
+    bufs = [torch.zeros(b["n"], b["h"], b["w"], b["pitch"]) for b in prog["bufs"]]
+    result = None
+    for st in prog["steps"]:
+        if st["kind"] == "prep":
+            assert st["in_fmt"] == 0
+            us = st["unshuffle"]
+            src = x
+            if us > 1:
+                src = F.pixel_unshuffle(x, us)
+            dst = bufs[st["out_buf"]]
+            dst.zero_()
+            dst[..., :src.shape[1]] = q(_nhwc(src))
+            if st["fill_ch"] >= 0:
+                dst[..., st["fill_ch"]] = q(torch.tensor(st["fill_val"]))
+            continue
+        c = st
+        cin, cout = c["cin"], c["cout"]
+        src = _nchw(bufs[c["in_buf"]][..., c["in_coff"]:c["in_coff"] + cin])
+        w, b = sd[c["wname"]], sd[c["bname"]]
+        if c["mode"] == 0:
+            v = F.conv2d(src, w, b, padding=1)
+        elif c["mode"] == 1:
+            v = F.conv2d(F.interpolate(src, scale_factor=2, mode="nearest"), w, b, padding=1)
+        else:
+            v = F.conv2d(src, w, b, stride=2, padding=1)
+        if c["act"] == 1:
+            slope = sd[c["sname"]].view(1, -1, 1, 1) if c["sname"] else torch.full((1, cout, 1, 1), c["const_slope"])
+            v = torch.where(v >= 0, v, v * slope)
+        elif c["act"] == 2:
+            v = torch.clamp(v, 0, 6)
+        v = v * c["alpha"]
+        om = c["out_mode"]
+        if om == 3:      # PixelShuffle(2) into NHWC
+            v = F.pixel_shuffle(v, 2)
+        oc = v.shape[1]
+        for k in (1, 2):
+            rb = c[f"res{k}_buf"]
+            if rb >= 0:
+                r = bufs[rb][..., c[f"res{k}_coff"]:c[f"res{k}_coff"] + oc]
+                v = v + c[f"beta{k}"] * _nchw(r)
+        if om in (0, 3):
+            dst = bufs[c["out_buf"]]
+            assert tuple(dst.shape[1:3]) == (c["out_h"], c["out_w"]) == tuple(v.shape[2:]), (c["name"], dst.shape, v.shape)
+            npad = (oc + 15) // 16 * 16
+            dst[..., c["out_coff"]:c["out_coff"] + npad] = 0
+            dst[..., c["out_coff"]:c["out_coff"] + oc] = q(_nhwc(v))
+        elif om == 4:    # temporal-shift scatter
+            fold = c["fold"]
+            vv = q(_nhwc(v))
+            bufs[c["out2_buf"]][..., c["out_coff"]:c["out_coff"] + fold] = vv[..., :fold]
+            bufs[c["out3_buf"]][..., c["out_coff"] + fold:c["out_coff"] + 2 * fold] = vv[..., fold:2 * fold]
+            bufs[c["out_buf"]][..., c["out_coff"] + 2 * fold:c["out_coff"] + oc] = vv[..., 2 * fold:]
+        elif om in (1, 5):
+            result = v if om == 1 else v.half().float()
+        elif om == 6:
+            f = torch.clamp(v, 0, 1) * 255
+            result = (torch.round(f) if c["round_u8"] else f).to(torch.uint8).permute(0, 2, 3, 1)
+        elif om == 2:    # PixelShuffle(r) + nearest-upsampled base image
+            r = c["ps_r"]
+            v = F.pixel_shuffle(v, r)
+            base = _nchw(bufs[c["base_buf"]][..., :v.shape[1]])
+            result = v + F.interpolate(base, scale_factor=float(r), mode="nearest")
+        else:
+            raise AssertionError(om)
+    return result

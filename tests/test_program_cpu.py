@@ -1,0 +1,69 @@
+"""CPU checks of the network lowering (csrc/program.cpp): the layer program emitted by ss4k_plan_dry is
+interpreted with torch fp32 ops and compared with the oracle on the same seeded weights / inputs."""
+import pytest
+import torch
+
+import ss4k_b200
+from ss4k_b200 import _lib as L
+from oracle import rrdbnet, srvgg
+from tests.emulate import run_program
+
+
+@pytest.mark.parametrize("num_conv,upscale", [(16, 4), (32, 4), (4, 2)])
+def test_srvgg_program(lib, num_conv, upscale):
+    torch.manual_seed(0)
+    net = srvgg.SRVGGNetCompact(3, 3, 64, num_conv, upscale).eval()
+    x = torch.rand(2, 3, 20, 28)
+    prog = ss4k_b200.plan_dry(ss4k_b200.make_cfg(0, L.ARCH_SRVGG, 2, 20, 28, scale=upscale, depth=num_conv))
+    assert len(prog["steps"]) == 1 + num_conv + 2
+    with torch.no_grad():
+        want = net(x)
+        got = run_program(prog, net.state_dict(), x)
+    assert got.shape == want.shape
+    assert (got - want).abs().max().item() < 1e-4
+    # algorithmic FLOPs: 2*9*HW*(3*64 + num_conv*64*64 + 64*3*s*s) per frame
+    flops = 2 * 9 * 20 * 28 * 2 * (3 * 64 + num_conv * 64 * 64 + 64 * 3 * upscale * upscale)
+    assert abs(prog["flops"] - flops) / flops < 1e-9
+
+
+@pytest.mark.parametrize("scale,blocks", [(2, 2), (4, 1)])
+def test_rrdb_program(lib, scale, blocks):
+    torch.manual_seed(0)
+    net = rrdbnet.RRDBNet(3, 3, scale, 64, blocks, 32).eval()
+    # upstream init makes RDB convs tiny; also exercise non-zero biases
+    for p in net.parameters():
+        if p.ndim == 1:
+            torch.nn.init.uniform_(p, -0.1, 0.1)
+    x = torch.rand(1, 3, 16, 24)
+    prog = ss4k_b200.plan_dry(ss4k_b200.make_cfg(0, L.ARCH_RRDB, 1, 16, 24, scale=scale, depth=blocks))
+    with torch.no_grad():
+        want = net(x)
+        got = run_program(prog, net.state_dict(), x)
+    assert got.shape == want.shape == (1, 3, 16 * scale, 24 * scale)
+    assert (got - want).abs().max().item() < 1e-4
+
+
+def test_rrdb_flops_match_baseline(lib):
+    """RRDBNet-23 x2 @ 1280x720 = 8.263 TFLOP, x4 @ 1920x1080 = 74.346 TFLOP."""
+    p2 = ss4k_b200.plan_dry(ss4k_b200.make_cfg(0, L.ARCH_RRDB, 1, 720, 1280, scale=2, depth=23))
+    assert abs(p2["flops"] / 1e12 - 8.263) < 0.005
+    p4 = ss4k_b200.plan_dry(ss4k_b200.make_cfg(0, L.ARCH_RRDB, 1, 1080, 1920, scale=4, depth=23))
+    assert abs(p4["flops"] / 1e12 - 74.346) < 0.02
+    ps = ss4k_b200.plan_dry(ss4k_b200.make_cfg(0, L.ARCH_SRVGG, 1, 180, 320, scale=4, depth=32))
+    assert abs(ps["flops"] / 1e12 - 0.139) < 0.001
+
+
+def test_rrdb_fp16_storage_error_budget(lib):
+    """Emulated fp16 activation storage through the lowered program stays inside the parity gate
+    (PSNR >= 50 dB, max abs <= 2/255) for upstream-init RRDBNet -- SURVEY.md section 7 H2."""
+    torch.manual_seed(0)
+    net = rrdbnet.RRDBNet(3, 3, 2, 64, 23, 32).eval()
+    x = torch.rand(1, 3, 32, 32)
+    prog = ss4k_b200.plan_dry(ss4k_b200.make_cfg(0, L.ARCH_RRDB, 1, 32, 32, scale=2, depth=23))
+    sd = {k: (v.half().float() if v.ndim == 4 else v) for k, v in net.state_dict().items()}
+    with torch.no_grad():
+        want = net(x).clamp(0, 1)
+        got = run_program(prog, sd, x, quant=lambda t: t.half().float()).clamp(0, 1)
+    mse = torch.mean((got - want) ** 2).item()
+    psnr = -10 * torch.log10(torch.tensor(mse)).item()
+    assert psnr >= 50 and (got - want).abs().max().item() * 255 <= 2.0
