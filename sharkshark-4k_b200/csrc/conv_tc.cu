@@ -178,8 +178,9 @@ __device__ __forceinline__ float round16(float a, bool bf16) {
 __device__ __forceinline__ void add_residual16(float (&v)[16], const void* res, size_t elem_off,
                                                float beta, bool bf16) {
   const uint4* p = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(res) + elem_off);
-  const uint4 q0 = __ldg(p);
-  const uint4 q1 = __ldg(p + 1);
+  // plain (coherent) loads: the RRDB tail conv updates its residual buffer in place
+  const uint4 q0 = *p;
+  const uint4 q1 = *(p + 1);
   const uint32_t w[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
