@@ -170,6 +170,12 @@ int ss4k_debug_pack(const ss4k_conv_desc* d, int in_pitch, int in_coff, int wper
                     const float* bias_host, const float* slope_host, char** out_json, float** out_packed,
                     int64_t* out_count);
 
+/* profiling entry: average milliseconds of one launch of the described conv over `iters` launches
+ * (CUDA events on the context's stream).  dbg_flags: 1 skip MMA issue, 2 skip TMA loads, 4 skip epilogue
+ * math/stores (pipeline experiments; results are then meaningless).  out_json (optional): tile config. */
+int ss4k_debug_bench_conv(ss4k_ctx* ctx, const ss4k_conv_desc* d, int slab_pitch, int dbg_flags, int iters,
+                          float* ms_per_launch, char** out_json);
+
 #ifdef __cplusplus
 }
 #endif

@@ -53,6 +53,8 @@ SYMBOLS = {
     "ss4k_bsvd_stream_reset": (_i, [_vp]),
     "ss4k_bsvd_stream_close": (_i, [_vp]),
     "ss4k_conv3x3": (_i, [_vp, ctypes.POINTER(ConvDesc), _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "ss4k_debug_bench_conv": (_i, [_vp, ctypes.POINTER(ConvDesc), _i, _i, _i, ctypes.POINTER(ctypes.c_float),
+                                   ctypes.POINTER(_vp)]),
     "ss4k_debug_pack": (_i, [ctypes.POINTER(ConvDesc), _i, _i, _i, _vp, _vp, _vp, ctypes.POINTER(_vp),
                              ctypes.POINTER(_vp), ctypes.POINTER(_i64)]),
 }

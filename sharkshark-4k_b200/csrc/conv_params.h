@@ -98,6 +98,7 @@ struct ConvParams {
   uint32_t a_row_tx;     // bytes one halo row load delivers (all TMA boxes)
   uint32_t w_tx;         // bytes one weight block load delivers
   int32_t* err;          // device int[4]: watchdog diagnostics (tag, block, ...)
+  int32_t dbg_flags;     // profiling experiments: 1 skip MMA issue, 2 skip TMA loads, 4 epilogue without math/stores
 };
 
 }  // namespace ss4k

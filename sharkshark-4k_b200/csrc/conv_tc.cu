@@ -413,9 +413,13 @@ conv3x3_tcgen05_kernel(const __grid_constant__ ConvParams P) {
         for (int kbi = 0; kbi < P.nkb; ++kbi) {
           if (!(P.w_resident && w_loaded)) {
             mbar_wait(w_empty + 8 * ws, wph ^ 1, P.err, 1);
-            mbar_expect_tx(w_full + 8 * ws, P.w_tx);
-            tma_load_3d(w_base + ws * P.w_slot_bytes, &P.tmW, w_full + 8 * ws, 0, nc * P.n_cta,
-                        kbi * P.ntaps);
+            if (P.dbg_flags & 2) {
+              mbar_arrive(w_full + 8 * ws);
+            } else {
+              mbar_expect_tx(w_full + 8 * ws, P.w_tx);
+              tma_load_3d(w_base + ws * P.w_slot_bytes, &P.tmW, w_full + 8 * ws, 0, nc * P.n_cta,
+                          kbi * P.ntaps);
+            }
             w_loaded = true;
             if (++ws == static_cast<uint32_t>(P.w_slots)) { ws = 0; wph ^= 1; }
           }
@@ -423,6 +427,11 @@ conv3x3_tcgen05_kernel(const __grid_constant__ ConvParams P) {
           const CUtensorMap* tm = &P.tmA[kb.tmap];
           for (int r = 0; r < in_rows; ++r) {
             mbar_wait(a_empty + 8 * as, aph ^ 1, P.err, 2);
+            if (P.dbg_flags & 2) {
+              mbar_arrive(a_full + 8 * as);
+              if (++as == static_cast<uint32_t>(P.a_slots)) { as = 0; aph ^= 1; }
+              continue;
+            }
             mbar_expect_tx(a_full + 8 * as, P.a_row_tx);
             const uint32_t dst = a_base + as * P.a_slot_bytes;
             const int y = y0 - 1 + r;
@@ -465,7 +474,7 @@ conv3x3_tcgen05_kernel(const __grid_constant__ ConvParams P) {
             mbar_wait(a_full + 8 * as, aph, P.err, 5);
             tcgen05_after_sync();
             const uint32_t arow = a_base + as * P.a_slot_bytes;
-            for (int t = 0; t < P.ntaps; ++t) {
+            for (int t = 0; t < P.ntaps && !(P.dbg_flags & 1); ++t) {
               const Tap tap = P.taps[t];
               const int j = r - tap.dr;
               if (j < 0 || j >= P.R) continue;
@@ -528,7 +537,7 @@ conv3x3_tcgen05_kernel(const __grid_constant__ ConvParams P) {
           uint32_t raw[16];
           tmem_ld16(tacc + ai * P.acc_stride + cb, raw);
           tmem_ld_wait();
-          if (valid) {
+          if (valid && !(P.dbg_flags & 4)) {
             float v[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(raw[i]);

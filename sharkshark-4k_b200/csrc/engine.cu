@@ -880,6 +880,73 @@ int ss4k_debug_pack(const ss4k_conv_desc* d, int in_pitch, int in_coff, int wper
   return SS4K_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Debug / profiling entry: time `iters` launches of one conv (buffers hold zeros) with CUDA events.
+// dbg_flags: see ConvParams::dbg_flags.  slab_pitch: channel pitch of the input tensor (>= cin).
+int ss4k_debug_bench_conv(ss4k_ctx* ctx, const ss4k_conv_desc* d, int slab_pitch, int dbg_flags, int iters,
+                          float* ms_per_launch, char** out_json) {
+  if (!ctx || !d || !ms_per_launch) return fail(ctx, SS4K_E_INVALID, "null argument");
+  const bool bf16 = d->act_mode == SS4K_ACT_BF16;
+  const int in_pitch = slab_pitch > 0 ? slab_pitch : round_up(d->cin, 16);
+  const int npad = round_up(d->cout, 16);
+  int oh = d->h, ow = d->w;
+  if (d->mode == kModeUp2) { oh *= 2; ow *= 2; }
+  if (d->mode == kModeS2) { oh /= 2; ow /= 2; }
+  HostTensor W;
+  W.shape = {d->cout, d->cin, 3, 3};
+  W.data.assign(static_cast<size_t>(d->cout) * d->cin * 9, 0.01f);
+  void* b[3] = {nullptr, nullptr, nullptr};
+  const size_t in_bytes = static_cast<size_t>(d->n) * d->h * d->w * in_pitch * 2 + 256;
+  const size_t out_bytes = static_cast<size_t>(d->n) * oh * ow * npad * 2 + 256;
+  CK(ctx, cudaMalloc(&b[0], in_bytes));
+  CK(ctx, cudaMalloc(&b[1], out_bytes));
+  CK(ctx, cudaMalloc(&b[2], out_bytes));
+  CK(ctx, cudaMemset(b[0], 0, in_bytes));
+  CK(ctx, cudaMemset(b[2], 0, out_bytes));
+  ConvSpec cs;
+  cs.name = "bench"; cs.wname = "w"; cs.mode = d->mode; cs.n = d->n; cs.cin = d->cin; cs.cout = d->cout;
+  cs.in_buf = 0; cs.in_h = d->h; cs.in_w = d->w; cs.in_pitch = in_pitch;
+  cs.act = d->act; cs.alpha = d->alpha;
+  cs.out_mode = kOutNHWC; cs.out_buf = 1; cs.out_pitch = npad; cs.out_h = oh; cs.out_w = ow;
+  if (d->beta != 0.f) { cs.res1_buf = 2; cs.res1_pitch = npad; cs.beta1 = d->beta; }
+  ConvExec ex;
+  auto bufptr = [&](int id) -> void* { return id >= 0 ? b[id] : nullptr; };
+  int rc = materialize_conv(ctx, cs, W, nullptr, nullptr, d->act_mode, bufptr, &ex);
+  if (rc == SS4K_OK) {
+    ex.p.dbg_flags = dbg_flags;
+    if (d->reserved[2] > 0) {  // override rows per tile
+      ex.p.R = d->reserved[2];
+      ex.p.tiles_y = (ex.p.H + ex.p.R - 1) / ex.p.R;
+      ex.p.n_tiles = ex.p.n_img * ex.p.tiles_y * ex.p.tiles_x * ex.p.n_chunks;
+      ex.grid = std::min(ex.p.n_tiles, ctx->nsm);
+    }
+    if (d->reserved[3] > 0) ex.p.a_slots = std::min(ex.p.a_slots, d->reserved[3]);
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    cudaError_t ce = cudaSuccess;
+    for (int i = 0; i < 3 && ce == cudaSuccess; ++i) ce = conv_tc_launch(ex.p, ex.grid, ctx->stream);
+    cudaEventRecord(e0, ctx->stream);
+    for (int i = 0; i < iters && ce == cudaSuccess; ++i) ce = conv_tc_launch(ex.p, ex.grid, ctx->stream);
+    cudaEventRecord(e1, ctx->stream);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(ctx->stream);
+    rc = check_kernel_health(ctx, ce, "ss4k_debug_bench_conv");
+    float ms = 0.f;
+    if (rc == SS4K_OK) cudaEventElapsedTime(&ms, e0, e1);
+    *ms_per_launch = ms / std::max(1, iters);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    ctx->launches += iters + 3;
+    if (out_json) {
+      std::string js = fmt("{\"R\":%d,\"n_tiles\":%d,\"grid\":%d,\"a_slots\":%d,\"w_slots\":%d,\"w_resident\":%d,\"nkb\":%d,\"n_cta\":%d,\"n_chunks\":%d}",
+                           ex.p.R, ex.p.n_tiles, ex.grid, ex.p.a_slots, ex.p.w_slots, ex.p.w_resident, ex.p.nkb, ex.p.n_cta, ex.p.n_chunks);
+      *out_json = static_cast<char*>(malloc(js.size() + 1));
+      memcpy(*out_json, js.c_str(), js.size() + 1);
+    }
+  }
+  free_conv(ex);
+  for (void* q : b) if (q) cudaFree(q);
+  return rc;
+}
+
 // Start-up self-probe: one small 64->64 conv through the tcgen05 path against the naive direct
 // kernel.  Decides which shared-memory-descriptor addressing mode this GPU/driver honours.
 static int self_probe(ss4k_ctx* ctx) {
