@@ -74,3 +74,113 @@ def bsvd_forward(sd, inp):
     n, f, c, h, w = inp.shape
     out = bsvd_clip(sd, inp.reshape(n * f, c, h, w))
     return out.reshape(n, f, 3, h, w)
+
+
+# --------------------------------------------------------------------------------------------------
+# Weight construction.  /root/reference does not exist on the GPU box, so the oracle must be able to
+# mint the reference's *random-init* BSVD weights by itself.  The classes below restate ONLY the
+# constructors of the reference modules (same attribute names -> same state-dict keys, same creation
+# order and the same three init passes -> same RNG consumption), so ``build_bsvd32(seed)`` reproduces
+# ``torch.manual_seed(seed); BSVD(chns=[32,64,128], mid_ch=32, interm_ch=30, act='relu6',
+# norm='none', pretrain_ckpt=None)`` bit for bit (checked against the reference in
+# tests/test_oracle_cpu.py and pinned by the checksums in tests/golden/).
+#   constructors: bsvd/model.py:22-41 ShiftConv, :63-91 BiBufferConv, :143-154 MemCvBlock,
+#   :221-240 InputCvBlock, :256-267 DownBlock, :285-292 UpBlock, :314-323 OutputCvBlock,
+#   :362-381 DenBlock (+ reset_params :393-400), :471-481 BSVD (+ reset_params :501-508)
+from torch import nn  # noqa: E402
+
+
+def _conv3(cin, cout, stride=1):
+    return nn.Conv2d(cin, cout, kernel_size=3, padding=1, stride=stride, bias=True)
+
+
+class _ShiftConvParams(nn.Module):
+    def __init__(self, c):
+        super().__init__()
+        self.conv = _conv3(c, c)
+
+
+class _BiBufferParams(nn.Module):
+    def __init__(self, c):
+        super().__init__()
+        self.op = _ShiftConvParams(c)
+
+
+class _MemCvParams(nn.Module):
+    def __init__(self, c):
+        super().__init__()
+        self.c1 = _BiBufferParams(c)
+        self.c2 = _BiBufferParams(c)
+
+
+class _Seq(nn.Module):
+    """Holds convs under the numeric child names nn.Sequential would give them."""
+
+    def __init__(self, convs):
+        super().__init__()
+        for idx, m in convs:
+            self.add_module(str(idx), m)
+
+
+class _InputParams(nn.Module):
+    def __init__(self, in_ch, interm, out_ch):
+        super().__init__()
+        self.convblock = _Seq([(0, _conv3(in_ch, interm)), (3, _conv3(interm, out_ch))])
+
+
+class _DownParams(nn.Module):
+    def __init__(self, cin, cout):
+        super().__init__()
+        self.convblock = _Seq([(0, _conv3(cin, cout, stride=2))])
+        self.memconv = _MemCvParams(cout)
+
+
+class _UpParams(nn.Module):
+    def __init__(self, cin, cout):
+        super().__init__()
+        self.memconv = _MemCvParams(cin)
+        self.convblock = _Seq([(0, _conv3(cin, cout * 4))])
+
+
+class _OutParams(nn.Module):
+    def __init__(self, cin, cout):
+        super().__init__()
+        self.convblock = _Seq([(0, _conv3(cin, cin)), (3, _conv3(cin, cout))])
+
+
+def _kaiming_all(module):
+    for m in module.modules():
+        if isinstance(m, nn.Conv2d):
+            nn.init.kaiming_normal_(m.weight, nonlinearity="relu")
+
+
+class _DenBlockParams(nn.Module):
+    def __init__(self, chns, out_ch, in_ch, interm_ch):
+        super().__init__()
+        c0, c1, c2 = chns
+        self.inc = _InputParams(in_ch, interm_ch, c0)
+        self.downc0 = _DownParams(c0, c1)
+        self.downc1 = _DownParams(c1, c2)
+        self.upc2 = _UpParams(c2, c1)
+        self.upc1 = _UpParams(c1, c0)
+        self.outc = _OutParams(c0, out_ch)
+        _kaiming_all(self)
+
+
+class BSVDParams(nn.Module):
+    def __init__(self, chns=(32, 64, 128), mid_ch=32, in_ch=4, out_ch=3, interm_ch=30):
+        super().__init__()
+        self.temp1 = _DenBlockParams(chns, mid_ch, in_ch, interm_ch)
+        self.temp2 = _DenBlockParams(chns, out_ch, mid_ch, interm_ch)
+        _kaiming_all(self)
+
+
+def build_bsvd32(seed=0, weight_scale=1.0):
+    """State dict of the service's BSVD-32 (bsvd/factory.py:31-35) with the reference constructor's
+    random init.  ``weight_scale`` multiplies conv weights (0.5 gives 'trained-like'
+    magnitudes whose outputs stay near [0,1])."""
+    torch.manual_seed(seed)
+    sd = BSVDParams().state_dict()
+    if weight_scale != 1.0:
+        sd = {k: (v * weight_scale if k.endswith(".weight") else v) for k, v in sd.items()}
+    return sd
