@@ -101,4 +101,29 @@ struct ConvParams {
   int32_t dbg_flags;     // profiling experiments: 1 skip MMA issue, 2 skip TMA loads, 4 epilogue without math/stores
 };
 
+
+// ------------------------------------------------------------------------------------------------
+// Row-streaming kernel (conv_stream.cu): 3x3 stride-1 convolutions with the three vertical taps fused
+// into the MMA N dimension.  See DESIGN.md section 4.
+constexpr int kMaxSKB = 8;          // K blocks (64 input channels each) of one conv
+constexpr int kMaxSASlots = 12;     // activation slab ring (one slab = 130 pixels x 64 channels)
+constexpr int kMaxAccSlots = 16;    // TMEM accumulator ring (one slot = one output row of 128 pixels)
+constexpr int kASlotBytes = 17408;  // 130 * 128 rounded up to the 1024-byte swizzle period
+
+struct StreamParams {
+  CUtensorMap tmA[2];   // 5-D (64, W, channel block, H, N), box (64, 130, 1, 1, 1), swizzle 128B
+  CUtensorMap tmW;      // 2-D (64, rows), box (64, 3*NOUT): rows = [chunk][kb][kx][2-ky][NOUT]
+  Epilogue ep;
+  uint8_t a_kb[kMaxSKB];  // source 64-channel block of K block i
+  uint8_t a_tm[kMaxSKB];  // which activation tensor map
+  uint8_t nks[kMaxSKB];   // 16-channel k-steps to issue (1..4)
+  int32_t nkb;
+  int32_t n_img, H, W, strips, chunks;
+  int32_t total_units;    // chunks * n_img * strips * H output rows of 128 pixels
+  int32_t acc_slots, a_slots;
+  uint32_t idesc[3];      // instruction descriptors for N = NOUT, 2*NOUT, 3*NOUT
+  int32_t* err;
+  int32_t dbg_flags;
+};
+
 }  // namespace ss4k

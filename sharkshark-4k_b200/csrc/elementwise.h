@@ -9,6 +9,10 @@ namespace ss4k {
 cudaError_t conv_tc_prepare();
 cudaError_t conv_tc_launch(const ConvParams& p, int grid, cudaStream_t stream);
 
+// conv_stream.cu
+cudaError_t conv_stream_prepare();
+cudaError_t conv_stream_launch(const StreamParams& p, int nout, int grid, cudaStream_t stream);
+
 // elementwise.cu
 // in_fmt: SS4K_FMT_* ; out: [N, H/us, W/us, pitch] 16-bit NHWC (out_lo: low halves for split mode or null)
 cudaError_t prep_launch(int in_fmt, const void* in, void* out, void* out_lo, int N, int C, int H, int W,

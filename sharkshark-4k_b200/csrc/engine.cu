@@ -105,6 +105,9 @@ int round_up(int a, int b) { return (a + b - 1) / b * b; }
 // A materialised convolution: packed weights on the device + kernel parameter block + grid.
 struct ConvExec {
   ConvParams p;
+  StreamParams sp;      // row-streaming kernel (conv_stream.cu) when `stream` is set
+  bool stream = false;
+  int nout = 0;         // accumulator slot width of the streaming kernel
   int grid = 0;
   void* d_w = nullptr;
   float* d_bias = nullptr;
@@ -252,6 +255,86 @@ std::string pack_weights(const ConvSpec& cs, const HostTensor& W, const HostTens
   return "";
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Row-streaming kernel (conv_stream.cu): weight layout [chunk][K block][kx][2-ky][NOUT][64 channels],
+// i.e. one swizzle-128B tile of 3*NOUT rows per (K block, horizontal tap): the three vertical taps
+// are stacked along the MMA N dimension.
+struct StreamPacked {
+  std::vector<uint16_t> w;
+  std::vector<float> bias, slope;
+  int nout = 0, chunks = 0, nkb = 0, npad_total = 0, a_slots = 0, acc_slots = 0;
+  uint8_t nks[kMaxSKB];
+};
+
+bool stream_config(const ConvSpec& cs, StreamPacked* sp) {
+  if (cs.mode != kModeConv3 || cs.split || cs.in_coff % 8 || cs.in_pitch % 8) return false;
+  if (getenv("SS4K_NO_STREAM")) return false;
+  const int npad = round_up(cs.cout, 16);
+  const int nkb = (cs.cin + 63) / 64;
+  if (nkb > kMaxSKB) return false;
+  int cand[4], nc = 0;
+  if (npad <= 64) cand[nc++] = npad;
+  else if (npad % 64 == 0) cand[nc++] = 64;
+  if (npad % 32 == 0 && npad > 32) cand[nc++] = 32;
+  if (npad > 16) cand[nc++] = 16;
+  for (int i = 0; i < nc; ++i) {
+    const int nout = cand[i];
+    if (npad % nout) continue;
+    const int wbytes = nkb * 9 * nout * 128;
+    const int left = kSmemBytes - 2048 - wbytes;
+    const int slots = std::min(kMaxSASlots, left / kASlotBytes);
+    if (slots < 3) continue;
+    sp->nout = nout; sp->chunks = npad / nout; sp->nkb = nkb; sp->npad_total = npad;
+    sp->a_slots = slots; sp->acc_slots = std::min(kMaxAccSlots, kTmemCols / nout);
+    for (int kb = 0; kb < nkb; ++kb) sp->nks[kb] = static_cast<uint8_t>((std::min(64, cs.cin - 64 * kb) + 15) / 16);
+    return true;
+  }
+  return false;
+}
+
+std::string pack_weights_stream(const ConvSpec& cs, const HostTensor& W, const HostTensor* B, const HostTensor* S,
+                                bool bf16, StreamPacked* out) {
+  if (W.shape.size() != 4 || W.shape[0] != cs.cout || W.shape[1] != cs.cin || W.shape[2] != 3 || W.shape[3] != 3)
+    return fmt("weight %s has the wrong shape, expected [%d,%d,3,3]", cs.wname.c_str(), cs.cout, cs.cin);
+  if (B && (int)B->data.size() != cs.cout) return fmt("bias %s has wrong size", cs.bname.c_str());
+  if (S && (int)S->data.size() != cs.cout) return fmt("slope %s has wrong size", cs.sname.c_str());
+  const int npad = out->npad_total, nout = out->nout, nkb = out->nkb;
+  std::vector<int> orow(npad, -1);
+  for (int n = 0; n < cs.cout; ++n) {
+    if (cs.wperm == 1) {
+      const int cq = cs.cout / 4;
+      orow[(n % 4) * cq + n / 4] = n;
+    } else {
+      orow[n] = n;
+    }
+  }
+  out->w.assign(static_cast<size_t>(out->chunks) * nkb * 9 * nout * 64, 0);
+  for (int ch = 0; ch < out->chunks; ++ch)
+    for (int kb = 0; kb < nkb; ++kb)
+      for (int kx = 0; kx < 3; ++kx)
+        for (int blk = 0; blk < 3; ++blk)
+          for (int co = 0; co < nout; ++co) {
+            const int n = orow[ch * nout + co];
+            if (n < 0) continue;
+            const size_t row = ((((static_cast<size_t>(ch) * nkb + kb) * 3 + kx) * 3 + blk) * nout + co);
+            for (int cc = 0; cc < 64; ++cc) {
+              const int c = kb * 64 + cc;
+              if (c >= cs.cin) break;
+              out->w[row * 64 + cc] = f2h(W.data[((static_cast<size_t>(n) * cs.cin + c) * 3 + (2 - blk)) * 3 + kx], bf16);
+            }
+          }
+  out->bias.assign(npad, 0.f);
+  out->slope.assign(npad, 1.f);
+  for (int row = 0; row < npad; ++row) {
+    const int n = orow[row];
+    if (n < 0) continue;
+    if (B) out->bias[row] = B->data[n];
+    out->slope[row] = S ? S->data[n] : cs.const_slope;
+  }
+  return "";
+}
+
 // ------------------------------------------------------------------------------------------------
 struct TileCfg {
   int R, n_cta, n_chunks, acc_stride, tiles_x, tiles_y, n_tiles;
@@ -343,11 +426,116 @@ void free_conv(ConvExec& c) {
   c.d_w = nullptr; c.d_bias = nullptr; c.d_slope = nullptr;
 }
 
+
+template <class BufPtr>
+void fill_epilogue(const ConvSpec& cs, bool bf16, BufPtr bufptr, float* d_bias, float* d_slope, Epilogue* Ep, bool* ext_out) {
+  Epilogue& E = *Ep;
+  E.bias = d_bias;
+  E.slope = d_slope;
+  E.act = cs.act; E.out_mode = cs.out_mode;
+  E.alpha = cs.alpha; E.beta1 = cs.beta1; E.beta2 = cs.beta2;
+  E.is_bf16 = bf16 ? 1 : 0;
+  E.res1 = cs.res1_buf >= 0 ? bufptr(cs.res1_buf) : nullptr;
+  E.res2 = cs.res2_buf >= 0 ? bufptr(cs.res2_buf) : nullptr;
+  E.res1_pitch = cs.res1_pitch; E.res1_coff = cs.res1_coff;
+  E.res2_pitch = cs.res2_pitch; E.res2_coff = cs.res2_coff;
+  *ext_out = cs.out_buf == kBufExternalOut;
+  E.out = cs.out_buf >= 0 ? bufptr(cs.out_buf) : nullptr;
+  E.out_lo = cs.out_lo_buf >= 0 ? bufptr(cs.out_lo_buf) : nullptr;
+  E.out2 = cs.out2_buf >= 0 ? bufptr(cs.out2_buf) : nullptr;
+  E.out3 = cs.out3_buf >= 0 ? bufptr(cs.out3_buf) : nullptr;
+  E.out_pitch = cs.out_pitch; E.out_coff = cs.out_coff;
+  E.out_h = cs.out_h; E.out_w = cs.out_w;
+  E.cout = cs.cout; E.ps_r = cs.ps_r; E.fold = cs.fold; E.round_u8 = cs.round_u8;
+  E.base = cs.base_buf >= 0 ? bufptr(cs.base_buf) : nullptr;
+  E.base_pitch = cs.base_pitch;
+}
+
+// Row-streaming path: parameter block of conv_stream.cu
+template <class BufPtr>
+int materialize_stream(ss4k_ctx* ctx, const ConvSpec& cs, const HostTensor& W, const HostTensor* B,
+                       const HostTensor* S, bool bf16, StreamPacked& pk, BufPtr bufptr, ConvExec* ex) {
+  std::string e = pack_weights_stream(cs, W, B, S, bf16, &pk);
+  if (!e.empty()) return fail(ctx, SS4K_E_WEIGHTS, e);
+  StreamParams& p = ex->sp;
+  memset(&p, 0, sizeof(p));
+  ex->stream = true;
+  ex->nout = pk.nout;
+  ex->name = cs.name;
+  CK(ctx, cudaMalloc(&ex->d_w, pk.w.size() * 2));
+  CK(ctx, cudaMemcpy(ex->d_w, pk.w.data(), pk.w.size() * 2, cudaMemcpyHostToDevice));
+  CK(ctx, cudaMalloc(&ex->d_bias, pk.bias.size() * 4));
+  CK(ctx, cudaMemcpy(ex->d_bias, pk.bias.data(), pk.bias.size() * 4, cudaMemcpyHostToDevice));
+  CK(ctx, cudaMalloc(&ex->d_slope, pk.slope.size() * 4));
+  CK(ctx, cudaMemcpy(ex->d_slope, pk.slope.data(), pk.slope.size() * 4, cudaMemcpyHostToDevice));
+  const CUtensorMapDataType dt = bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  {  // activations: (64 channels, W, channel block, H, N) starting at channel in_coff
+    const cuuint64_t eb = 2;
+    const int avail = cs.in_pitch - cs.in_coff;
+    cuuint64_t dims[5] = {static_cast<cuuint64_t>(pk.nkb == 1 ? std::min(64, avail) : 64), static_cast<cuuint64_t>(cs.in_w),
+                          static_cast<cuuint64_t>(pk.nkb), static_cast<cuuint64_t>(cs.in_h), static_cast<cuuint64_t>(cs.n)};
+    cuuint64_t strides[4] = {cs.in_pitch * eb, 128, static_cast<cuuint64_t>(cs.in_w) * cs.in_pitch * eb,
+                             static_cast<cuuint64_t>(cs.in_h) * cs.in_w * cs.in_pitch * eb};
+    cuuint32_t box[5] = {64, static_cast<cuuint32_t>(kBoxW), 1, 1, 1};
+    cuuint32_t es[5] = {1, 1, 1, 1, 1};
+    void* base = reinterpret_cast<uint8_t*>(bufptr(cs.in_buf)) + static_cast<size_t>(cs.in_coff) * 2;
+    CUresult r = ctx->encode(&p.tmA[0], dt, 5, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(ctx, SS4K_E_CUDA, fmt("cuTensorMapEncodeTiled(stream activation, %s) failed: %d", cs.name.c_str(), (int)r));
+    p.tmA[1] = p.tmA[0];
+  }
+  {  // weights: rows of 64 channels
+    const cuuint64_t rows = pk.w.size() / 64;
+    cuuint64_t dims[2] = {64, rows};
+    cuuint64_t strides[1] = {128};
+    cuuint32_t box[2] = {64, static_cast<cuuint32_t>(3 * pk.nout)};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = ctx->encode(&p.tmW, dt, 2, ex->d_w, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(ctx, SS4K_E_CUDA, fmt("cuTensorMapEncodeTiled(stream weights) failed: %d", (int)r));
+  }
+  p.nkb = pk.nkb;
+  for (int kb = 0; kb < pk.nkb; ++kb) { p.a_kb[kb] = static_cast<uint8_t>(kb); p.a_tm[kb] = 0; p.nks[kb] = pk.nks[kb]; }
+  p.n_img = cs.n; p.H = cs.in_h; p.W = cs.in_w;
+  p.strips = (cs.in_w + kTileW - 1) / kTileW;
+  p.chunks = pk.chunks;
+  p.total_units = pk.chunks * cs.n * p.strips * cs.in_h;
+  p.acc_slots = pk.acc_slots; p.a_slots = pk.a_slots;
+  const uint32_t f = bf16 ? 1u : 0u;
+  for (int i = 0; i < 3; ++i)
+    p.idesc[i] = (1u << 4) | (f << 7) | (f << 10) | (static_cast<uint32_t>((i + 1) * pk.nout >> 3) << 17) | (static_cast<uint32_t>(128 >> 4) << 24);
+  p.err = ctx->err_dev;
+  fill_epilogue(cs, bf16, bufptr, ex->d_bias, ex->d_slope, &p.ep, &ex->ext_out);
+  ex->grid = std::min(p.total_units, ctx->nsm);
+  return SS4K_OK;
+}
+
+cudaError_t launch_exec(const ConvExec& c, void* ext_out, cudaStream_t st) {
+  if (c.stream) {
+    if (c.ext_out) {
+      StreamParams p = c.sp;
+      p.ep.out = ext_out;
+      return conv_stream_launch(p, c.nout, c.grid, st);
+    }
+    return conv_stream_launch(c.sp, c.nout, c.grid, st);
+  }
+  if (c.ext_out) {
+    ConvParams p = c.p;
+    p.ep.out = ext_out;
+    return conv_tc_launch(p, c.grid, st);
+  }
+  return conv_tc_launch(c.p, c.grid, st);
+}
+
 // Build the kernel parameter block of one conv.  bufptr(id) resolves program buffer ids.
 template <class BufPtr>
 int materialize_conv(ss4k_ctx* ctx, const ConvSpec& cs, const HostTensor& W, const HostTensor* B,
                      const HostTensor* S, int act_mode, BufPtr bufptr, ConvExec* ex) {
   const bool bf16 = act_mode == SS4K_ACT_BF16;
+  {
+    StreamPacked spk;
+    if (stream_config(cs, &spk)) return materialize_stream(ctx, cs, W, B, S, bf16, spk, bufptr, ex);
+  }
   PackedWeights pw;
   std::string e = pack_weights(cs, W, B, S, bf16, &pw);
   if (!e.empty()) return fail(ctx, SS4K_E_WEIGHTS, e);
@@ -472,13 +660,7 @@ int run_step(ss4k_plan* pl, int si, const void* in_dev, void* out_dev, cudaStrea
     ctx->launches++;
   } else {
     ConvExec& c = pl->convs[pl->step_conv[si]];
-    if (c.ext_out) {
-      ConvParams p = c.p;
-      p.ep.out = out_dev;
-      CK(ctx, conv_tc_launch(p, c.grid, st));
-    } else {
-      CK(ctx, conv_tc_launch(c.p, c.grid, st));
-    }
+    CK(ctx, launch_exec(c, out_dev, st));
     ctx->launches++;
   }
   return SS4K_OK;
@@ -531,6 +713,7 @@ int ss4k_create(int device_id, ss4k_ctx** out_ctx) {
   CK(nullptr, cudaHostGetDevicePointer(reinterpret_cast<void**>(&ctx->err_dev), ctx->err_host, 0));
   CK(nullptr, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
   CK(nullptr, conv_tc_prepare());
+  CK(nullptr, conv_stream_prepare());
   const char* force = getenv("SS4K_DESC_MODE");
   if (force && *force) {
     ctx->desc_mode = atoi(force);
@@ -813,8 +996,7 @@ int ss4k_conv3x3(ss4k_ctx* ctx, const ss4k_conv_desc* d, const float* x, const f
   auto bufptr = [&](int id) -> void* { return id >= 0 ? b[id] : nullptr; };
   int rc = materialize_conv(ctx, cs, W, bias ? &B : nullptr, slope ? &S : nullptr, d->act_mode, bufptr, &ex);
   if (rc != SS4K_OK) { free_conv(ex); cleanup(); return rc; }
-  if (ex.ext_out) ex.p.ep.out = y;
-  cudaError_t ce = conv_tc_launch(ex.p, ex.grid, st);
+  cudaError_t ce = launch_exec(ex, y, st);
   ctx->launches++;
   if (ce == cudaSuccess && !ex.ext_out) {
     ce = unprep_launch(b[2], b[4], y, d->n, res_c, ooh, oow, out_ch_pitch, 0, bf16, st);
@@ -844,6 +1026,26 @@ int ss4k_debug_pack(const ss4k_conv_desc* d, int in_pitch, int in_coff, int wper
   if (bias_host) { B.shape = {d->cout}; B.data.assign(bias_host, bias_host + d->cout); }
   if (slope_host) { S.shape = {d->cout}; S.data.assign(slope_host, slope_host + d->cout); }
   const bool bf16 = d->act_mode == SS4K_ACT_BF16;
+  if (d->reserved[6] == 1) {  // row-streaming kernel layout
+    StreamPacked sp;
+    if (!stream_config(cs, &sp)) return fail(nullptr, SS4K_E_INVALID, "conv is not eligible for the row-streaming kernel");
+    std::string es = pack_weights_stream(cs, W, bias_host ? &B : nullptr, slope_host ? &S : nullptr, bf16, &sp);
+    if (!es.empty()) return fail(nullptr, SS4K_E_WEIGHTS, es);
+    std::string js = fmt("{\"kernel\":\"stream\",\"nout\":%d,\"chunks\":%d,\"nkb\":%d,\"npad\":%d,\"a_slots\":%d,\"acc_slots\":%d,\"nks\":[",
+                         sp.nout, sp.chunks, sp.nkb, sp.npad_total, sp.a_slots, sp.acc_slots);
+    for (int i = 0; i < sp.nkb; ++i) js += fmt("%s%d", i ? "," : "", sp.nks[i]);
+    js += "],\"bias\":[";
+    for (size_t i = 0; i < sp.bias.size(); ++i) js += fmt("%s%.9g", i ? "," : "", sp.bias[i]);
+    js += "],\"slope\":[";
+    for (size_t i = 0; i < sp.slope.size(); ++i) js += fmt("%s%.9g", i ? "," : "", sp.slope[i]);
+    js += "]}";
+    *out_json = static_cast<char*>(malloc(js.size() + 1));
+    memcpy(*out_json, js.c_str(), js.size() + 1);
+    *out_count = static_cast<int64_t>(sp.w.size());
+    *out_packed = static_cast<float*>(malloc(sp.w.size() * sizeof(float)));
+    for (size_t i = 0; i < sp.w.size(); ++i) (*out_packed)[i] = h2f(sp.w[i], bf16);
+    return SS4K_OK;
+  }
   PackedWeights pw;
   std::string e = pack_weights(cs, W, bias_host ? &B : nullptr, slope_host ? &S : nullptr, bf16, &pw);
   if (!e.empty()) return fail(nullptr, SS4K_E_WEIGHTS, e);
@@ -913,20 +1115,27 @@ int ss4k_debug_bench_conv(ss4k_ctx* ctx, const ss4k_conv_desc* d, int slab_pitch
   auto bufptr = [&](int id) -> void* { return id >= 0 ? b[id] : nullptr; };
   int rc = materialize_conv(ctx, cs, W, nullptr, nullptr, d->act_mode, bufptr, &ex);
   if (rc == SS4K_OK) {
-    ex.p.dbg_flags = dbg_flags;
-    if (d->reserved[2] > 0) {  // override rows per tile
-      ex.p.R = d->reserved[2];
-      ex.p.tiles_y = (ex.p.H + ex.p.R - 1) / ex.p.R;
-      ex.p.n_tiles = ex.p.n_img * ex.p.tiles_y * ex.p.tiles_x * ex.p.n_chunks;
-      ex.grid = std::min(ex.p.n_tiles, ctx->nsm);
+    if (ex.stream) {
+      ex.sp.dbg_flags = dbg_flags;
+      if (d->reserved[3] > 0) ex.sp.a_slots = std::min(ex.sp.a_slots, d->reserved[3]);
+      if (d->reserved[4] > 0) ex.sp.acc_slots = std::min(ex.sp.acc_slots, d->reserved[4]);
+      if (d->reserved[5] > 0) ex.grid = std::min(ex.grid, d->reserved[5]);
+    } else {
+      ex.p.dbg_flags = dbg_flags;
+      if (d->reserved[2] > 0) {  // override rows per tile
+        ex.p.R = d->reserved[2];
+        ex.p.tiles_y = (ex.p.H + ex.p.R - 1) / ex.p.R;
+        ex.p.n_tiles = ex.p.n_img * ex.p.tiles_y * ex.p.tiles_x * ex.p.n_chunks;
+        ex.grid = std::min(ex.p.n_tiles, ctx->nsm);
+      }
+      if (d->reserved[3] > 0) ex.p.a_slots = std::min(ex.p.a_slots, d->reserved[3]);
     }
-    if (d->reserved[3] > 0) ex.p.a_slots = std::min(ex.p.a_slots, d->reserved[3]);
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0); cudaEventCreate(&e1);
     cudaError_t ce = cudaSuccess;
-    for (int i = 0; i < 3 && ce == cudaSuccess; ++i) ce = conv_tc_launch(ex.p, ex.grid, ctx->stream);
+    for (int i = 0; i < 3 && ce == cudaSuccess; ++i) ce = launch_exec(ex, nullptr, ctx->stream);
     cudaEventRecord(e0, ctx->stream);
-    for (int i = 0; i < iters && ce == cudaSuccess; ++i) ce = conv_tc_launch(ex.p, ex.grid, ctx->stream);
+    for (int i = 0; i < iters && ce == cudaSuccess; ++i) ce = launch_exec(ex, nullptr, ctx->stream);
     cudaEventRecord(e1, ctx->stream);
     if (ce == cudaSuccess) ce = cudaStreamSynchronize(ctx->stream);
     rc = check_kernel_health(ctx, ce, "ss4k_debug_bench_conv");
@@ -936,8 +1145,13 @@ int ss4k_debug_bench_conv(ss4k_ctx* ctx, const ss4k_conv_desc* d, int slab_pitch
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     ctx->launches += iters + 3;
     if (out_json) {
-      std::string js = fmt("{\"R\":%d,\"n_tiles\":%d,\"grid\":%d,\"a_slots\":%d,\"w_slots\":%d,\"w_resident\":%d,\"nkb\":%d,\"n_cta\":%d,\"n_chunks\":%d}",
-                           ex.p.R, ex.p.n_tiles, ex.grid, ex.p.a_slots, ex.p.w_slots, ex.p.w_resident, ex.p.nkb, ex.p.n_cta, ex.p.n_chunks);
+      std::string js;
+      if (ex.stream)
+        js = fmt("{\"kernel\":\"stream\",\"nout\":%d,\"chunks\":%d,\"grid\":%d,\"a_slots\":%d,\"acc_slots\":%d,\"nkb\":%d,\"units\":%d}",
+                 ex.nout, ex.sp.chunks, ex.grid, ex.sp.a_slots, ex.sp.acc_slots, ex.sp.nkb, ex.sp.total_units);
+      else
+        js = fmt("{\"kernel\":\"tile\",\"R\":%d,\"n_tiles\":%d,\"grid\":%d,\"a_slots\":%d,\"w_slots\":%d,\"w_resident\":%d,\"nkb\":%d,\"n_cta\":%d,\"n_chunks\":%d}",
+                 ex.p.R, ex.p.n_tiles, ex.grid, ex.p.a_slots, ex.p.w_slots, ex.p.w_resident, ex.p.nkb, ex.p.n_cta, ex.p.n_chunks);
       *out_json = static_cast<char*>(malloc(js.size() + 1));
       memcpy(*out_json, js.c_str(), js.size() + 1);
     }

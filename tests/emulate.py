@@ -157,3 +157,109 @@ def run_program(prog, sd, x, quant=None):
         else:
             raise AssertionError(om)
     return result
+
+
+# ------------------------------------------------------------------------------------------------
+def debug_pack_stream(lib, L, w, bias=None, slope=None, in_pitch=None, in_coff=0, wperm=0, act_mode=0):
+    """Weight layout + configuration of the row-streaming kernel (csrc/conv_stream.cu)."""
+    cout, cin = w.shape[:2]
+    d = L.ConvDesc()
+    d.struct_size = ctypes.sizeof(L.ConvDesc)
+    d.n, d.h, d.w, d.cin, d.cout, d.mode, d.act_mode = 1, 8, 8, cin, cout, 0, act_mode
+    d.reserved[6] = 1
+    if in_pitch is None:
+        in_pitch = (cin + 15) // 16 * 16
+    w = w.contiguous().float()
+    js, pk, cnt = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_int64()
+    bp = ctypes.c_void_p(bias.contiguous().float().data_ptr()) if bias is not None else None
+    sp = ctypes.c_void_p(slope.contiguous().float().data_ptr()) if slope is not None else None
+    L.check(lib.ss4k_debug_pack(ctypes.byref(d), in_pitch, in_coff, wperm, ctypes.c_void_p(w.data_ptr()), bp, sp,
+                                ctypes.byref(js), ctypes.byref(pk), ctypes.byref(cnt)))
+    meta = json.loads(ctypes.string_at(js).decode())
+    arr = (ctypes.c_float * cnt.value).from_address(pk.value)
+    packed = torch.tensor(list(arr), dtype=torch.float32).reshape(meta["chunks"], meta["nkb"], 3, 3, meta["nout"], 64)
+    lib.ss4k_free(js)
+    lib.ss4k_free(pk)
+    return meta, packed
+
+
+def emulate_stream_conv(meta, packed, x_nhwc, grid, in_coff=0, acc_slots=None):
+    """Mirror of conv3x3_stream_kernel's schedule: per-CTA bands of output rows, accumulator ring with
+    vertically fused taps (one 'MMA' adds input row r into the slots of output rows r-1, r, r+1, split
+    where the ring wraps), zero-initialising first MMA, completion commits, in-order epilogue drain.
+    Returns the accumulators [N, H, W, npad] (before bias / activation)."""
+    n_img, H, W, pitch = x_nhwc.shape
+    nout, chunks, nkb, S = meta["nout"], meta["chunks"], meta["nkb"], acc_slots or meta["acc_slots"]
+    strips = (W + 127) // 128
+    total = chunks * n_img * strips * H
+    out = torch.full((n_img, H, W, chunks * nout), float("nan"), dtype=torch.float64)
+    xpad = torch.zeros(n_img, H, strips * 128 + 2, (in_coff // 64 + nkb) * 64 + 64, dtype=torch.float64)
+    xpad[:, :, 1:W + 1, :pitch] = x_nhwc.double()   # column -1 / >= W read zeros (TMA OOB fill)
+    g = min(grid, total)
+    for cta in range(g):
+        u, u1 = cta * total // g, (cta + 1) * total // g
+        tmem = torch.zeros(S, 128, nout, dtype=torch.float64)
+        state = ["empty"] * S          # empty -> busy (being accumulated) -> full (committed) -> empty (drained)
+        qs = 0
+        while u < u1:
+            t = u
+            y = t % H; t //= H
+            strip = t % strips; t //= strips
+            n = t % n_img; chunk = t // n_img
+            yb, ye = y, min(H, y + (u1 - u))
+            u += ye - yb
+            r0, r1 = max(yb - 1, 0), min(ye, H - 1)
+            for r in range(r0, r1 + 1):
+                y_lo, y_hi = max(r - 1, yb), min(r + 1, ye - 1)
+                b_lo, b_hi = y_lo - (r - 1), y_hi - (r - 1)
+                f_lo = y_lo if r == r0 else r + 1
+                for yy in range(f_lo, y_hi + 1):
+                    s = (qs + yy - yb) % S
+                    assert state[s] == "empty", ("accumulator slot not drained", cta, r, yy, s, state)
+                    state[s] = "busy"
+
+                def emit(b0, b1, acc):
+                    s0 = (qs + (r - 1 + b0 - yb)) % S
+                    nblk = b1 - b0 + 1
+                    if s0 + nblk <= S:
+                        return [(s0, b0, nblk, acc)]
+                    n1 = S - s0
+                    return [(s0, b0, n1, acc), (0, b0 + n1, nblk - n1, acc)]
+                rest = emit(b_lo, b_hi, 1)
+                if r == r0:
+                    first = emit(b_lo, b_hi, 0)
+                elif b_hi == 2:
+                    first = (emit(b_lo, 1, 1) if b_lo <= 1 else []) + emit(2, 2, 0)
+                else:
+                    first = emit(b_lo, b_hi, 1)
+                assert len(first) <= 3 and len(rest) <= 2
+                for kb in range(nkb):
+                    c0 = in_coff + kb * 64
+                    slab = xpad[n, r, strip * 128:strip * 128 + 130, c0:c0 + 64]      # 130-pixel halo row
+                    for kx in range(3):
+                        a_full = slab[kx:kx + 128]                                    # shifted start address
+                        for ks in range(meta["nks"][kb]):
+                            a = a_full[:, ks * 16:(ks + 1) * 16]
+                            ops = first if (kb == 0 and kx == 0 and ks == 0) else [(s, b, nb_, 1) for (s, b, nb_, _) in rest]
+                            for (s0, b0, nblk, acc) in ops:
+                                wt = packed[chunk, kb, kx, b0:b0 + nblk, :, ks * 16:(ks + 1) * 16].double()  # [nblk, nout, 16]
+                                d = torch.einsum("mk,bnk->bmn", a, wt)
+                                for i in range(nblk):
+                                    assert state[s0 + i] == "busy"
+                                    tmem[s0 + i] = d[i] + (tmem[s0 + i] if acc else 0)
+                done = []
+                if r - 1 >= yb:
+                    done.append(r - 1)
+                if r == r1 and r <= ye - 1:
+                    done.append(r)
+                for yy in done:           # commit -> epilogue drains (in order) -> slot free
+                    s = (qs + yy - yb) % S
+                    assert state[s] == "busy"
+                    x0 = strip * 128
+                    wv = min(128, W - x0)
+                    out[n, yy, x0:x0 + wv, chunk * nout:(chunk + 1) * nout] = tmem[s, :wv]
+                    state[s] = "empty"
+            qs = (qs + ye - yb) % S
+        assert all(st == "empty" for st in state)
+    assert not torch.isnan(out).any()
+    return out

@@ -119,3 +119,41 @@ def test_tile_config_budget(lib, desc_mode):
         assert meta["a_slots"] >= 2
         assert meta["R"] * meta["nsub"] * meta["acc_stride"] <= 256
         assert meta["n_cta"] % 16 == 0 and meta["n_cta"] <= 64
+
+
+# ---------------------------------------------------------------- row-streaming kernel (conv_stream.cu)
+from tests.emulate import debug_pack_stream, emulate_stream_conv  # noqa: E402
+
+
+@pytest.mark.parametrize("cin,cout,h,w,n,grid,slots", [
+    (64, 32, 9, 140, 1, 148, None),     # RDB conv1: bands shorter than the image, two strips
+    (96, 32, 21, 130, 2, 5, 4),         # partial second K block, small ring -> many wraps, long bands
+    (192, 64, 7, 64, 1, 3, None),       # conv5: Cout split into two 32-wide chunks (weights must fit smem)
+    (64, 64, 30, 128, 1, 2, 8),
+    (3, 64, 6, 40, 2, 148, None),       # first conv: 16-channel source tensor
+    (64, 48, 5, 50, 1, 7, None),        # SRVGG tail (N = 144)
+    (64, 3, 12, 300, 1, 16, None),      # conv_last: Cout padded to 16
+    (128, 256, 4, 70, 3, 11, None),     # BSVD upc2: four 64-wide chunks, weights reloaded per chunk
+    (30, 32, 40, 20, 1, 4, 3),          # minimal ring of three slots
+])
+def test_stream_schedule(lib, cin, cout, h, w, n, grid, slots):
+    wt = _exact_weights(cout, cin, 11)
+    x = torch.randint(-8, 9, (n, cin, h, w), generator=torch.Generator().manual_seed(12)).float() / 8
+    pitch = (cin + 15) // 16 * 16
+    meta, packed = debug_pack_stream(lib, L, wt)
+    got = emulate_stream_conv(meta, packed, _nhwc(x, pitch), grid, acc_slots=slots)
+    want = F.conv2d(x.double(), wt.double(), padding=1).permute(0, 2, 3, 1)
+    assert torch.equal(got[..., :cout], want)
+    assert torch.count_nonzero(got[..., cout:]) == 0
+    assert meta["nkb"] == (cin + 63) // 64
+
+
+def test_stream_channel_offset_and_permutation(lib):
+    """Input at a channel offset of a wider slab (tensor-map base shift) and the PixelShuffle(2) row order."""
+    wt = _exact_weights(64, 64, 13)
+    slab = torch.randint(-8, 9, (1, 6, 33, 192), generator=torch.Generator().manual_seed(14)).float() / 8
+    meta, packed = debug_pack_stream(lib, L, wt, in_pitch=192, in_coff=64, wperm=1)
+    got = emulate_stream_conv(meta, packed, slab, 9, in_coff=64)
+    want = F.conv2d(slab[..., 64:128].permute(0, 3, 1, 2).double(), wt.double(), padding=1).permute(0, 2, 3, 1)
+    perm = [(r % 16) * 4 + r // 16 for r in range(64)]   # packed row (a*2+b)*16 + c  <-  channel c*4 + a*2 + b
+    assert torch.equal(got, want[..., perm])
