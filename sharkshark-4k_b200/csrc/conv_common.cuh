@@ -64,6 +64,30 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int32_t
     if (globaltimer_ns() - t0 > 4000000000ull) mbar_timeout(err, tag, parity);
   }
 }
+
+// Wait with the retry loop INSIDE the asm block: the surrounding C++ control flow stays warp-uniform for
+// ptxas, so descriptors / addresses of the MMA and TMA issue loops live in uniform registers.
+// Bounded: after ~4 s without progress the kernel traps (a pipeline bug must not hang the GPU).
+__device__ __forceinline__ void mbar_wait_u(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1, P2;\n\t"
+      ".reg .u64 t0, t1;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra LAB_DONE;\n\t"
+      "mov.u64 t0, %%globaltimer;\n\t"
+      "LAB_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra LAB_DONE;\n\t"
+      "mov.u64 t1, %%globaltimer;\n\t"
+      "sub.u64 t1, t1, t0;\n\t"
+      "setp.lt.u64 P2, t1, 4000000000;\n\t"
+      "@P2 bra LAB_WAIT;\n\t"
+      "trap;\n\t"
+      "LAB_DONE:\n\t"
+      "}" ::"r"(bar), "r"(parity)
+      : "memory");
+}
 __device__ __forceinline__ void fence_barrier_init() {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
@@ -230,16 +254,22 @@ __device__ __forceinline__ void epilogue_chunk(const Epilogue& E, int mode, int 
   const bool bf16 = E.is_bf16 != 0;
   // ---- bias + activation
   {
-    const float4* bp = reinterpret_cast<const float4*>(E.bias + ch0);
+    if (E.bias != nullptr) {  // null: the bias was already added by the accumulator-init MMA (conv_stream.cu)
+      const float4* bp = reinterpret_cast<const float4*>(E.bias + ch0);
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const float4 b = __ldg(bp + q);
-      v[4 * q + 0] += b.x;
-      v[4 * q + 1] += b.y;
-      v[4 * q + 2] += b.z;
-      v[4 * q + 3] += b.w;
+      for (int q = 0; q < 4; ++q) {
+        const float4 b = __ldg(bp + q);
+        v[4 * q + 0] += b.x;
+        v[4 * q + 1] += b.y;
+        v[4 * q + 2] += b.z;
+        v[4 * q + 3] += b.w;
+      }
     }
-    if (E.act == kActPRelu) {
+    if (E.act == kActPRelu && E.slope == nullptr) {
+      const float sl = E.slope_const;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] = v[i] >= 0.f ? v[i] : v[i] * sl;
+    } else if (E.act == kActPRelu) {
       const float4* sp = reinterpret_cast<const float4*>(E.slope + ch0);
 #pragma unroll
       for (int q = 0; q < 4; ++q) {

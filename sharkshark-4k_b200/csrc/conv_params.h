@@ -74,6 +74,7 @@ struct Epilogue {
   const void* base;      // kOutPSNCHWF32: NHWC 16-bit base image (input of the net), pitch base_pitch
   int32_t base_pitch;
   int32_t res_sub;       // 1: residuals are indexed at output pixel, 0 same (kept for clarity)
+  float slope_const;     // negative-side slope used when `slope` is null (LeakyReLU)
 };
 
 struct ConvParams {
@@ -110,10 +111,17 @@ constexpr int kMaxSASlots = 12;     // activation slab ring (one slab = 130 pixe
 constexpr int kMaxAccSlots = 16;    // TMEM accumulator ring (one slot = one output row of 128 pixels)
 constexpr int kASlotBytes = 17408;  // 130 * 128 rounded up to the 1024-byte swizzle period
 
+constexpr int kStreamEpiWarps = 8;  // two per TMEM lane quarter, alternating output rows
+constexpr int kStreamThreads = 32 * (2 + kStreamEpiWarps);
+
 struct StreamParams {
   CUtensorMap tmA[2];   // 5-D (64, W, channel block, H, N), box (64, 130, 1, 1, 1), swizzle 128B
-  CUtensorMap tmW;      // 2-D (64, rows), box (64, 3*NOUT): rows = [chunk][kb][kx][2-ky][NOUT]
+  CUtensorMap tmW;      // 2-D (64, rows), box (64, 3*NOUT): rows = [chunk][kb][kx][2-ky][NOUT], then bias tiles
+  CUtensorMap tmB;      // same tensor, box (64, NOUT): the per-chunk bias tile (bias hi/lo in K columns 0/1)
+  CUtensorMap tmO;      // NHWC output, 4-D (C, W, H, N), box (NOUT, 32, 1, 1), swizzled: TMA store of the fast path
   Epilogue ep;
+  int32_t fast_store;   // 1: plain NHWC output -> registers -> swizzled smem tile -> TMA store
+  int32_t bias_row0;    // first row of the bias tiles inside the weight tensor
   uint8_t a_kb[kMaxSKB];  // source 64-channel block of K block i
   uint8_t a_tm[kMaxSKB];  // which activation tensor map
   uint8_t nks[kMaxSKB];   // 16-channel k-steps to issue (1..4)

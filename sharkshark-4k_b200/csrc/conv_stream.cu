@@ -17,8 +17,13 @@
 //     stream never drains between rows, and the epilogue warps retire output row y as soon as input
 //     row y+1 has been accumulated.  Rows are split evenly over the persistent grid (one CTA per SM).
 //   * all weights of the conv (every K block and tap) stay resident in shared memory.
-//   * warp 0 = TMA producer, warp 1 = MMA issuer, warps 2..5 = epilogue (TMEM -> registers ->
-//     bias / PReLU / ReLU6 / scaled residual adds -> NHWC / PixelShuffle / NCHW / uint8 stores).
+//   * the bias is added by the tensor core: the MMA that zero-initialises a fresh accumulator slot is
+//     ones[128 x 16] x bias_tile[NOUT x 16] (bias hi/lo halves in K columns 0/1), so every real MMA
+//     accumulates and the epilogue has no per-channel bias loads.
+//   * warp 0 = TMA producer, warp 1 = MMA issuer, warps 2..9 = epilogue, two warps per TMEM lane
+//     quarter taking alternate output rows: TMEM -> registers -> activation / scaled residual adds ->
+//     16-bit pack -> swizzled shared-memory tile -> TMA store (plain NHWC outputs), or the generic
+//     path (PixelShuffle / NCHW / uint8 / temporal-shift scatter stores).
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -55,6 +60,19 @@ __device__ __forceinline__ uint64_t sdesc(uint32_t saddr) {
   return kSdescHi | static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4);
 }
 
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* tm, uint32_t src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               :
+               : "l"(reinterpret_cast<uint64_t>(tm)), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
 struct Band {
   int chunk, n, strip, yb, ye;
 };
@@ -75,24 +93,23 @@ __device__ __forceinline__ bool next_band(const StreamParams& P, int& u, int u1,
   return true;
 }
 
-struct MmaOp {
-  uint32_t col;    // TMEM column of the first accumulator slot written
-  uint32_t boff;   // byte offset of the first weight row block inside a (kb, kx) tile
-  uint32_t idesc;
-  uint32_t acc;    // accumulate flag of the row's very first MMA
-};
-
 }  // namespace
 
 template <int NOUT>
-__global__ void __launch_bounds__(kConvThreads, 1)
+__global__ void __launch_bounds__(kStreamThreads, 1)
 conv3x3_stream_kernel(const __grid_constant__ StreamParams P) {
   extern __shared__ uint8_t smem_raw[];
-  constexpr uint32_t kWTile = 3u * NOUT * 128u;  // one (K block, horizontal tap) weight tile
+  constexpr uint32_t kWTile = 3u * NOUT * 128u;      // one (K block, horizontal tap) weight tile
+  constexpr uint32_t kBiasTile = NOUT * 128u;
+  constexpr uint32_t kOnesTile = 128u * 128u;
+  constexpr uint32_t kStageWarp = 32u * NOUT * 2u;   // one epilogue warp's 32-pixel output tile
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t w_base = smem_base;
-  const uint32_t a_base = w_base + static_cast<uint32_t>(P.nkb) * 3u * kWTile;
-  const uint32_t bar_base = a_base + static_cast<uint32_t>(P.a_slots) * kASlotBytes;
+  const uint32_t bias_base = w_base + static_cast<uint32_t>(P.nkb) * 3u * kWTile;
+  const uint32_t ones_base = bias_base + kBiasTile;
+  const uint32_t a_base = ones_base + kOnesTile;
+  const uint32_t stage_base = a_base + static_cast<uint32_t>(P.a_slots) * kASlotBytes;
+  const uint32_t bar_base = stage_base + kStreamEpiWarps * ((kStageWarp + 1023u) & ~1023u);
   const uint32_t a_full = bar_base;
   const uint32_t a_empty = a_full + 8 * kMaxSASlots;
   const uint32_t acc_full = a_empty + 8 * kMaxSASlots;
@@ -103,19 +120,21 @@ conv3x3_stream_kernel(const __grid_constant__ StreamParams P) {
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);  // warp-uniform for ptxas
   const int lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&P.tmA[0]);
     prefetch_tmap(&P.tmW);
+    prefetch_tmap(&P.tmB);
+    if (P.fast_store) prefetch_tmap(&P.tmO);
     for (int i = 0; i < kMaxSASlots; ++i) {
       mbar_init(a_full + 8 * i, 1);
       mbar_init(a_empty + 8 * i, 1);
     }
     for (int i = 0; i < kMaxAccSlots; ++i) {
       mbar_init(acc_full + 8 * i, 1);
-      mbar_init(acc_empty + 8 * i, 4);  // one arrive per epilogue warp
+      mbar_init(acc_empty + 8 * i, 4);  // one arrive per epilogue warp of the row's parity group
     }
     mbar_init(w_full, 1);
     mbar_init(w_empty, 1);
@@ -127,10 +146,23 @@ conv3x3_stream_kernel(const __grid_constant__ StreamParams P) {
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  {
+    // "ones" operand of the accumulator-init MMA: 128 rows x 64 channels, swizzle-128B K-major, value 1 in
+    // K columns 0 and 1 (they meet the hi / lo halves of the bias), 0 elsewhere
+    const uint32_t one2 = P.ep.is_bf16 ? 0x3F803F80u : 0x3C003C00u;
+    for (uint32_t ci = threadIdx.x; ci < 1024u; ci += kStreamThreads) {
+      const uint32_t r = ci >> 3, pc = ci & 7u;
+      sts128(ones_base + ci * 16u, pc == (r & 7u) ? one2 : 0u, 0u, 0u, 0u);
+    }
+    fence_proxy_async();
+  }
   tcgen05_before_sync();
   __syncthreads();
   tcgen05_after_sync();
-  const uint32_t tmem_base = *tmem_slot_ptr;
+  // this CTA owns all 512 TMEM columns (one CTA per SM), so the allocation starts at column 0 / lane 0;
+  // using the constant keeps TMEM addresses in uniform registers
+  if (*tmem_slot_ptr != 0u) __trap();
+  constexpr uint32_t tmem_base = 0u;
 
   const int u0 = static_cast<int>(static_cast<int64_t>(blockIdx.x) * P.total_units / gridDim.x);
   const int u1 = static_cast<int>(static_cast<int64_t>(blockIdx.x + 1) * P.total_units / gridDim.x);
@@ -144,12 +176,13 @@ conv3x3_stream_kernel(const __grid_constant__ StreamParams P) {
     Band b;
     while (next_band(P, u, u1, b)) {
       if (b.chunk != loaded_chunk) {
-        mbar_wait(w_empty, wph ^ 1, P.err, 1);
+        mbar_wait_u(w_empty, wph ^ 1);
         if (elect_one()) {
           const int ntile = P.nkb * 3;
-          mbar_expect_tx(w_full, static_cast<uint32_t>(ntile) * kWTile);
+          mbar_expect_tx(w_full, static_cast<uint32_t>(ntile) * kWTile + kBiasTile);
           for (int t = 0; t < ntile; ++t)
             tma_load_2d(w_base + t * kWTile, &P.tmW, w_full, 0, (b.chunk * ntile + t) * 3 * NOUT);
+          tma_load_2d(bias_base, &P.tmB, w_full, 0, P.bias_row0 + b.chunk * NOUT);
         }
         __syncwarp();
         wph ^= 1;
@@ -160,7 +193,7 @@ conv3x3_stream_kernel(const __grid_constant__ StreamParams P) {
       const int x0 = b.strip * kTileW - 1;
       for (int r = r0; r <= r1; ++r) {
         for (int kb = 0; kb < P.nkb; ++kb) {
-          mbar_wait(a_empty + 8 * as, aph ^ 1, P.err, 2);
+          mbar_wait_u(a_empty + 8 * as, aph ^ 1);
           if (elect_one()) {
             if (P.dbg_flags & 2) {
               mbar_arrive(a_full + 8 * as);
@@ -176,16 +209,19 @@ conv3x3_stream_kernel(const __grid_constant__ StreamParams P) {
     }
   } else if (warp == 1) {
     // ======================================================= MMA issuer
+    // The whole warp runs this loop convergently (waits are asm-internal loops) so that ptxas keeps
+    // every descriptor in uniform registers; one elected lane issues the tcgen05 instructions.
     uint32_t as = 0, aph = 0, wph = 0;
     int cur_chunk = -1;
     int qs = 0, qk = 0;  // accumulator ring position of the band's first output row: slot, wrap count
     int u = u0;
     Band b, nb;
     bool has = next_band(P, u, u1, b);
+    const uint64_t d_ones = sdesc(ones_base), d_bias = sdesc(bias_base);
     while (has) {
       const bool has_next = next_band(P, u, u1, nb);
       if (b.chunk != cur_chunk) {
-        mbar_wait(w_full, wph, P.err, 4);
+        mbar_wait_u(w_full, wph);
         tcgen05_after_sync();
         wph ^= 1;
         cur_chunk = b.chunk;
@@ -196,43 +232,30 @@ conv3x3_stream_kernel(const __grid_constant__ StreamParams P) {
         const int y_lo = r - 1 > b.yb ? r - 1 : b.yb;
         const int y_hi = r + 1 < b.ye - 1 ? r + 1 : b.ye - 1;
         const int b_lo = y_lo - (r - 1), b_hi = y_hi - (r - 1);  // weight row blocks (block = 2 - ky)
-        // ---- accumulator slots touched for the first time by this input row must be drained
+        // ---- accumulator slots touched for the first time by this input row: wait until the epilogue has
+        //      drained their previous row, then initialise them with the bias (ones x bias, accumulate = 0)
         {
           const int f_lo = (r == r0) ? y_lo : r + 1;
           for (int y = f_lo; y <= y_hi; ++y) {
             int s = qs + (y - b.yb), k = qk;
             while (s >= S) { s -= S; ++k; }
-            mbar_wait(acc_empty + 8 * s, (k & 1) ^ 1, P.err, 3);
+            mbar_wait_u(acc_empty + 8 * s, (k & 1) ^ 1);
+            tcgen05_after_sync();
+            if (!(P.dbg_flags & 1)) umma_f16_elect(tmem_base + static_cast<uint32_t>(s * NOUT), d_ones, d_bias, P.idesc[0], 0u);
           }
-          tcgen05_after_sync();
         }
-        // ---- MMA op lists: `first` for the row's first MMA (zero-initialises fresh slots), `rest` after
-        MmaOp first[3], rest[2];
-        int nfirst = 0, nrest = 0;
-        auto emit = [&](MmaOp* list, int& cnt, int b0, int b1, uint32_t acc) {
-          int s0 = qs + (r - 1 + b0 - b.yb);
-          while (s0 >= S) s0 -= S;
-          const int nblk = b1 - b0 + 1;
-          if (s0 + nblk <= S) {
-            list[cnt++] = MmaOp{static_cast<uint32_t>(s0 * NOUT), static_cast<uint32_t>(b0 * NOUT * 128), P.idesc[nblk - 1], acc};
-          } else {
-            const int n1 = S - s0;
-            list[cnt++] = MmaOp{static_cast<uint32_t>(s0 * NOUT), static_cast<uint32_t>(b0 * NOUT * 128), P.idesc[n1 - 1], acc};
-            list[cnt++] = MmaOp{0u, static_cast<uint32_t>((b0 + n1) * NOUT * 128), P.idesc[nblk - n1 - 1], acc};
-          }
-        };
-        emit(rest, nrest, b_lo, b_hi, 1u);
-        if (r == r0) {
-          emit(first, nfirst, b_lo, b_hi, 0u);
-        } else if (b_hi == 2) {
-          if (b_lo <= 1) emit(first, nfirst, b_lo, 1, 1u);
-          emit(first, nfirst, 2, 2, 0u);
-        } else {
-          emit(first, nfirst, b_lo, b_hi, 1u);
-        }
-        // ---- K loop: K blocks x horizontal taps x 16-channel steps
+        // ---- the row's MMAs cover accumulator slots [s0, s0 + nblk) (ring order), split where the ring wraps:
+        //      op A = blocks [b_lo, b_lo + nA) at slot s0, op B = the remaining nB blocks at slot 0
+        int s0 = qs + (y_lo - b.yb);
+        while (s0 >= S) s0 -= S;
+        const int nblk = b_hi - b_lo + 1;
+        const int nA = s0 + nblk <= S ? nblk : S - s0;
+        const int nB = nblk - nA;
+        const uint32_t colA = tmem_base + static_cast<uint32_t>(s0 * NOUT);
+        const uint32_t boffA = static_cast<uint32_t>(b_lo * NOUT * 128), boffB = static_cast<uint32_t>((b_lo + nA) * NOUT * 128);
+        const uint32_t idA = P.idesc[nA - 1], idB = P.idesc[nB > 0 ? nB - 1 : 0];
         for (int kb = 0; kb < P.nkb; ++kb) {
-          mbar_wait(a_full + 8 * as, aph, P.err, 5);
+          mbar_wait_u(a_full + 8 * as, aph);
           tcgen05_after_sync();
           const uint32_t arow = a_base + as * kASlotBytes;
           const int nks = P.nks[kb];
@@ -245,15 +268,8 @@ conv3x3_stream_kernel(const __grid_constant__ StreamParams P) {
                 if (ks < nks) {
                   const uint64_t da = sdesc(arow + kx * kRowBytes + ks * 32);
                   const uint32_t wb = wt + ks * 32;
-                  if (kb == 0 && kx == 0 && ks == 0) {
-#pragma unroll
-                    for (int i = 0; i < 3; ++i)
-                      if (i < nfirst) umma_f16_elect(tmem_base + first[i].col, da, sdesc(wb + first[i].boff), first[i].idesc, first[i].acc);
-                  } else {
-#pragma unroll
-                    for (int i = 0; i < 2; ++i)
-                      if (i < nrest) umma_f16_elect(tmem_base + rest[i].col, da, sdesc(wb + rest[i].boff), rest[i].idesc, 1u);
-                  }
+                  umma_f16_elect(colA, da, sdesc(wb + boffA), idA, 1u);
+                  if (nB > 0) umma_f16_elect(tmem_base, da, sdesc(wb + boffB), idB, 1u);
                 }
               }
             }
@@ -280,38 +296,125 @@ conv3x3_stream_kernel(const __grid_constant__ StreamParams P) {
       has = has_next;
     }
   } else {
-    // ======================================================= epilogue (warps 2..5)
+    // ======================================================= epilogue (warps 2..9)
+    const Epilogue& E = P.ep;
+    const int ew = warp - 2;
     const int qd = warp & 3;       // TMEM lane quarter this warp may access
+    const int par = ew >> 2;       // this warp takes the CTA's output rows with (row counter & 1) == par
     const int m = qd * 32 + lane;  // accumulator row == pixel inside the strip
-    int s = 0, k = 0;
+    const uint32_t stage = stage_base + static_cast<uint32_t>(ew) * ((kStageWarp + 1023u) & ~1023u);
+    const bool bf16 = E.is_bf16 != 0;
+    const bool fast = P.fast_store != 0;
+    int s = 0, k = 0, q = 0;
     int u = u0;
     Band b;
     while (next_band(P, u, u1, b)) {
       const int ax = b.strip * kTileW + m;
       const bool valid = ax < P.W;
-      for (int y = b.yb; y < b.ye; ++y) {
-        mbar_wait(acc_full + 8 * s, k & 1, P.err, 6);
-        tcgen05_after_sync();
-        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(qd * 32) << 16) + static_cast<uint32_t>(s * NOUT);
-        uint32_t raw[NOUT];
+      for (int y = b.yb; y < b.ye; ++y, ++q) {
+        if ((q & 1) == par) {
+          // residual prefetch (fast path): issued before the accumulator wait so the latency is hidden
+          uint4 r1v[NOUT / 8], r2v[NOUT / 8];
+          const size_t pix = (static_cast<size_t>(b.n) * E.out_h + y) * E.out_w + ax;
+          const bool has_r1 = fast && E.res1 != nullptr, has_r2 = fast && E.res2 != nullptr;
+          if (has_r1 && valid) {
+            const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(E.res1) + pix * E.res1_pitch + E.res1_coff + b.chunk * NOUT);
 #pragma unroll
-        for (int c = 0; c < NOUT; c += 16) tmem_ld16p(taddr + c, &raw[c]);
-        tmem_ld_wait();
-        tcgen05_before_sync();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(acc_empty + 8 * s);  // slot free: the MMA stream may reuse it
-        if (valid && !(P.dbg_flags & 4)) {
+            for (int j = 0; j < NOUT / 8; ++j) r1v[j] = rp[j];
+          }
+          if (has_r2 && valid) {
+            const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(E.res2) + pix * E.res2_pitch + E.res2_coff + b.chunk * NOUT);
 #pragma unroll
-          for (int c = 0; c < NOUT; c += 16) {
-            float v[16];
+            for (int j = 0; j < NOUT / 8; ++j) r2v[j] = rp[j];
+          }
+          mbar_wait_u(acc_full + 8 * s, k & 1);
+          tcgen05_after_sync();
+          const uint32_t taddr = tmem_base + (static_cast<uint32_t>(qd * 32) << 16) + static_cast<uint32_t>(s * NOUT);
+          uint32_t raw[NOUT];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(raw[c + i]);
-            epilogue_chunk(P.ep, kModeConv3, b.n, y, ax, 0, b.chunk * NOUT + c, v);
+          for (int c = 0; c < NOUT; c += 16) tmem_ld16p(taddr + c, &raw[c]);
+          tmem_ld_wait();
+          tcgen05_before_sync();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(acc_empty + 8 * s);  // slot free: the MMA stream may reuse it
+          if (!(P.dbg_flags & 4)) {
+            if (fast) {
+              // ---- activation, residuals, 16-bit pack into the warp's swizzled staging tile, TMA store
+              if (lane == 0) bulk_wait_read0();  // this warp's previous store has finished reading the tile
+              __syncwarp();
+#pragma unroll
+              for (int j = 0; j < NOUT / 8; ++j) {
+                float v[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(raw[8 * j + i]);
+                if (E.act == kActPRelu) {
+                  if (E.slope == nullptr) {
+                    const float sl = E.slope_const;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) v[i] = v[i] >= 0.f ? v[i] : v[i] * sl;
+                  } else {
+                    const float4* sp = reinterpret_cast<const float4*>(E.slope + b.chunk * NOUT + 8 * j);
+                    const float4 sa = __ldg(sp), sb = __ldg(sp + 1);
+                    const float sl[8] = {sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w};
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) v[i] = v[i] >= 0.f ? v[i] : v[i] * sl[i];
+                  }
+                } else if (E.act == kActRelu6) {
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) v[i] = fminf(fmaxf(v[i], 0.f), 6.f);
+                }
+                if (E.alpha != 1.0f) {
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) v[i] *= E.alpha;
+                }
+                if (has_r1) {
+                  const uint32_t w4[4] = {r1v[j].x, r1v[j].y, r1v[j].z, r1v[j].w};
+#pragma unroll
+                  for (int i = 0; i < 4; ++i) {
+                    const float2 f = unpack2(w4[i], bf16);
+                    v[2 * i] = fmaf(E.beta1, f.x, v[2 * i]);
+                    v[2 * i + 1] = fmaf(E.beta1, f.y, v[2 * i + 1]);
+                  }
+                }
+                if (has_r2) {
+                  const uint32_t w4[4] = {r2v[j].x, r2v[j].y, r2v[j].z, r2v[j].w};
+#pragma unroll
+                  for (int i = 0; i < 4; ++i) {
+                    const float2 f = unpack2(w4[i], bf16);
+                    v[2 * i] = fmaf(E.beta2, f.x, v[2 * i]);
+                    v[2 * i + 1] = fmaf(E.beta2, f.y, v[2 * i + 1]);
+                  }
+                }
+                // swizzled 16-byte chunk position inside the [32 pixels][NOUT] tile (matches tmO's swizzle mode)
+                uint32_t pj;
+                if (NOUT == 64) pj = static_cast<uint32_t>(j) ^ (lane & 7u);
+                else if (NOUT == 32) pj = static_cast<uint32_t>(j) ^ ((lane >> 1) & 3u);
+                else if (NOUT == 16) pj = static_cast<uint32_t>(j) ^ ((lane >> 2) & 1u);
+                else pj = static_cast<uint32_t>(j);
+                sts128(stage + lane * (NOUT * 2u) + pj * 16u, pack2(v[0], v[1], bf16), pack2(v[2], v[3], bf16),
+                       pack2(v[4], v[5], bf16), pack2(v[6], v[7], bf16));
+              }
+              fence_proxy_async();
+              __syncwarp();
+              if (lane == 0) {
+                tma_store_4d(&P.tmO, stage, b.chunk * NOUT, b.strip * kTileW + qd * 32, y, b.n);
+                bulk_commit();
+              }
+            } else if (valid) {
+#pragma unroll
+              for (int c = 0; c < NOUT; c += 16) {
+                float v[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(raw[c + i]);
+                epilogue_chunk(E, kModeConv3, b.n, y, ax, 0, b.chunk * NOUT + c, v);
+              }
+            }
           }
         }
         if (++s == S) { s = 0; ++k; }
       }
     }
+    if (fast && lane == 0) bulk_wait0();  // all output tiles written before the CTA releases its shared memory
   }
 
   // ---------------------------------------------------------------- teardown
@@ -336,10 +439,10 @@ cudaError_t conv_stream_prepare() {
 
 cudaError_t conv_stream_launch(const StreamParams& p, int nout, int grid, cudaStream_t stream) {
   switch (nout) {
-    case 16: conv3x3_stream_kernel<16><<<grid, kConvThreads, kSmemBytes, stream>>>(p); break;
-    case 32: conv3x3_stream_kernel<32><<<grid, kConvThreads, kSmemBytes, stream>>>(p); break;
-    case 48: conv3x3_stream_kernel<48><<<grid, kConvThreads, kSmemBytes, stream>>>(p); break;
-    case 64: conv3x3_stream_kernel<64><<<grid, kConvThreads, kSmemBytes, stream>>>(p); break;
+    case 16: conv3x3_stream_kernel<16><<<grid, kStreamThreads, kSmemBytes, stream>>>(p); break;
+    case 32: conv3x3_stream_kernel<32><<<grid, kStreamThreads, kSmemBytes, stream>>>(p); break;
+    case 48: conv3x3_stream_kernel<48><<<grid, kStreamThreads, kSmemBytes, stream>>>(p); break;
+    case 64: conv3x3_stream_kernel<64><<<grid, kStreamThreads, kSmemBytes, stream>>>(p); break;
     default: return cudaErrorInvalidValue;
   }
   return cudaGetLastError();

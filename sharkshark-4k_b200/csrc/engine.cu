@@ -264,6 +264,8 @@ struct StreamPacked {
   std::vector<uint16_t> w;
   std::vector<float> bias, slope;
   int nout = 0, chunks = 0, nkb = 0, npad_total = 0, a_slots = 0, acc_slots = 0;
+  int bias_row0 = 0;     // first row of the per-chunk bias tiles (appended after the weight tiles)
+  float alpha_out = 1.f; // epilogue scale left after folding alpha into weights and bias
   uint8_t nks[kMaxSKB];
 };
 
@@ -281,8 +283,9 @@ bool stream_config(const ConvSpec& cs, StreamPacked* sp) {
   for (int i = 0; i < nc; ++i) {
     const int nout = cand[i];
     if (npad % nout) continue;
-    const int wbytes = nkb * 9 * nout * 128;
-    const int left = kSmemBytes - 2048 - wbytes;
+    const int wbytes = nkb * 9 * nout * 128 + nout * 128 /* bias tile */ + 128 * 128 /* ones tile */;
+    const int stage = kStreamEpiWarps * round_up(32 * nout * 2, 1024);
+    const int left = kSmemBytes - 2048 - wbytes - stage;
     const int slots = std::min(kMaxSASlots, left / kASlotBytes);
     if (slots < 3) continue;
     sp->nout = nout; sp->chunks = npad / nout; sp->nkb = nkb; sp->npad_total = npad;
@@ -309,7 +312,12 @@ std::string pack_weights_stream(const ConvSpec& cs, const HostTensor& W, const H
       orow[n] = n;
     }
   }
-  out->w.assign(static_cast<size_t>(out->chunks) * nkb * 9 * nout * 64, 0);
+  // alpha * act(conv + bias) == act(alpha*conv + alpha*bias) for the positively homogeneous activations
+  // (none, PReLU / LeakyReLU): fold alpha into weights and bias so the epilogue does not multiply
+  const float fold = (cs.act != kActRelu6) ? cs.alpha : 1.f;
+  out->alpha_out = (cs.act != kActRelu6) ? 1.f : cs.alpha;
+  out->bias_row0 = out->chunks * nkb * 9 * nout;
+  out->w.assign((static_cast<size_t>(out->bias_row0) + npad) * 64, 0);
   for (int ch = 0; ch < out->chunks; ++ch)
     for (int kb = 0; kb < nkb; ++kb)
       for (int kx = 0; kx < 3; ++kx)
@@ -321,9 +329,18 @@ std::string pack_weights_stream(const ConvSpec& cs, const HostTensor& W, const H
             for (int cc = 0; cc < 64; ++cc) {
               const int c = kb * 64 + cc;
               if (c >= cs.cin) break;
-              out->w[row * 64 + cc] = f2h(W.data[((static_cast<size_t>(n) * cs.cin + c) * 3 + (2 - blk)) * 3 + kx], bf16);
+              out->w[row * 64 + cc] = f2h(fold * W.data[((static_cast<size_t>(n) * cs.cin + c) * 3 + (2 - blk)) * 3 + kx], bf16);
             }
           }
+  // bias tiles: row = output channel, K column 0 = high half, column 1 = low half (the "ones" operand has 1 there)
+  for (int row = 0; row < npad; ++row) {
+    const int n = orow[row];
+    if (n < 0 || !B) continue;
+    const float bv = fold * B->data[n];
+    const uint16_t hi = f2h(bv, bf16);
+    out->w[(static_cast<size_t>(out->bias_row0) + row) * 64 + 0] = hi;
+    out->w[(static_cast<size_t>(out->bias_row0) + row) * 64 + 1] = f2h(bv - h2f(hi, bf16), bf16);
+  }
   out->bias.assign(npad, 0.f);
   out->slope.assign(npad, 1.f);
   for (int row = 0; row < npad; ++row) {
@@ -449,6 +466,7 @@ void fill_epilogue(const ConvSpec& cs, bool bf16, BufPtr bufptr, float* d_bias, 
   E.cout = cs.cout; E.ps_r = cs.ps_r; E.fold = cs.fold; E.round_u8 = cs.round_u8;
   E.base = cs.base_buf >= 0 ? bufptr(cs.base_buf) : nullptr;
   E.base_pitch = cs.base_pitch;
+  E.slope_const = cs.const_slope;
 }
 
 // Row-streaming path: parameter block of conv_stream.cu
@@ -494,6 +512,36 @@ int materialize_stream(ss4k_ctx* ctx, const ConvSpec& cs, const HostTensor& W, c
                              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(ctx, SS4K_E_CUDA, fmt("cuTensorMapEncodeTiled(stream weights) failed: %d", (int)r));
   }
+  {  // bias tiles: same tensor, NOUT-row box
+    const cuuint64_t rows = pk.w.size() / 64;
+    cuuint64_t dims[2] = {64, rows};
+    cuuint64_t strides[1] = {128};
+    cuuint32_t box[2] = {64, static_cast<cuuint32_t>(pk.nout)};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = ctx->encode(&p.tmB, dt, 2, ex->d_w, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(ctx, SS4K_E_CUDA, fmt("cuTensorMapEncodeTiled(stream bias) failed: %d", (int)r));
+  }
+  p.bias_row0 = pk.bias_row0;
+  // fast epilogue: plain NHWC 16-bit output -> swizzled shared-memory tile -> TMA store
+  p.fast_store = 0;
+  if (cs.out_mode == kOutNHWC && cs.out_buf >= 0 && cs.out_lo_buf < 0 && cs.out_coff % 8 == 0 && cs.out_pitch % 8 == 0 &&
+      (pk.nout == 16 || pk.nout == 32 || pk.nout == 64) && getenv("SS4K_NO_FAST_STORE") == nullptr) {
+    const cuuint64_t eb = 2;
+    const int cavail = std::min(cs.out_pitch - cs.out_coff, pk.npad_total);
+    cuuint64_t dims[4] = {static_cast<cuuint64_t>(cavail), static_cast<cuuint64_t>(cs.out_w), static_cast<cuuint64_t>(cs.out_h),
+                          static_cast<cuuint64_t>(cs.n)};
+    cuuint64_t strides[3] = {cs.out_pitch * eb, static_cast<cuuint64_t>(cs.out_w) * cs.out_pitch * eb,
+                             static_cast<cuuint64_t>(cs.out_h) * cs.out_w * cs.out_pitch * eb};
+    cuuint32_t box[4] = {static_cast<cuuint32_t>(pk.nout), 32, 1, 1};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    const CUtensorMapSwizzle sw = pk.nout == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (pk.nout == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+    void* base = reinterpret_cast<uint8_t*>(bufptr(cs.out_buf)) + static_cast<size_t>(cs.out_coff) * 2;
+    CUresult r = ctx->encode(&p.tmO, dt, 4, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                             CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(ctx, SS4K_E_CUDA, fmt("cuTensorMapEncodeTiled(stream output, %s) failed: %d", cs.name.c_str(), (int)r));
+    p.fast_store = 1;
+  }
   p.nkb = pk.nkb;
   for (int kb = 0; kb < pk.nkb; ++kb) { p.a_kb[kb] = static_cast<uint8_t>(kb); p.a_tm[kb] = 0; p.nks[kb] = pk.nks[kb]; }
   p.n_img = cs.n; p.H = cs.in_h; p.W = cs.in_w;
@@ -506,6 +554,10 @@ int materialize_stream(ss4k_ctx* ctx, const ConvSpec& cs, const HostTensor& W, c
     p.idesc[i] = (1u << 4) | (f << 7) | (f << 10) | (static_cast<uint32_t>((i + 1) * pk.nout >> 3) << 17) | (static_cast<uint32_t>(128 >> 4) << 24);
   p.err = ctx->err_dev;
   fill_epilogue(cs, bf16, bufptr, ex->d_bias, ex->d_slope, &p.ep, &ex->ext_out);
+  p.ep.bias = nullptr;                  // added by the accumulator-init MMA
+  p.ep.slope = S ? ex->d_slope : nullptr;
+  p.ep.slope_const = cs.const_slope;
+  p.ep.alpha = pk.alpha_out;            // folded into weights / bias when the activation allows
   ex->grid = std::min(p.total_units, ctx->nsm);
   return SS4K_OK;
 }
@@ -1028,11 +1080,12 @@ int ss4k_debug_pack(const ss4k_conv_desc* d, int in_pitch, int in_coff, int wper
   const bool bf16 = d->act_mode == SS4K_ACT_BF16;
   if (d->reserved[6] == 1) {  // row-streaming kernel layout
     StreamPacked sp;
+    cs.act = d->act; cs.alpha = d->alpha != 0.f ? d->alpha : 1.f;
     if (!stream_config(cs, &sp)) return fail(nullptr, SS4K_E_INVALID, "conv is not eligible for the row-streaming kernel");
     std::string es = pack_weights_stream(cs, W, bias_host ? &B : nullptr, slope_host ? &S : nullptr, bf16, &sp);
     if (!es.empty()) return fail(nullptr, SS4K_E_WEIGHTS, es);
-    std::string js = fmt("{\"kernel\":\"stream\",\"nout\":%d,\"chunks\":%d,\"nkb\":%d,\"npad\":%d,\"a_slots\":%d,\"acc_slots\":%d,\"nks\":[",
-                         sp.nout, sp.chunks, sp.nkb, sp.npad_total, sp.a_slots, sp.acc_slots);
+    std::string js = fmt("{\"kernel\":\"stream\",\"nout\":%d,\"chunks\":%d,\"nkb\":%d,\"npad\":%d,\"a_slots\":%d,\"acc_slots\":%d,\"bias_row0\":%d,\"nks\":[",
+                         sp.nout, sp.chunks, sp.nkb, sp.npad_total, sp.a_slots, sp.acc_slots, sp.chunks * sp.nkb * 9 * sp.nout);
     for (int i = 0; i < sp.nkb; ++i) js += fmt("%s%d", i ? "," : "", sp.nks[i]);
     js += "],\"bias\":[";
     for (size_t i = 0; i < sp.bias.size(); ++i) js += fmt("%s%.9g", i ? "," : "", sp.bias[i]);

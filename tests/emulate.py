@@ -160,12 +160,13 @@ def run_program(prog, sd, x, quant=None):
 
 
 # ------------------------------------------------------------------------------------------------
-def debug_pack_stream(lib, L, w, bias=None, slope=None, in_pitch=None, in_coff=0, wperm=0, act_mode=0):
+def debug_pack_stream(lib, L, w, bias=None, slope=None, in_pitch=None, in_coff=0, wperm=0, act_mode=0, act=0, alpha=1.0):
     """Weight layout + configuration of the row-streaming kernel (csrc/conv_stream.cu)."""
     cout, cin = w.shape[:2]
     d = L.ConvDesc()
     d.struct_size = ctypes.sizeof(L.ConvDesc)
     d.n, d.h, d.w, d.cin, d.cout, d.mode, d.act_mode = 1, 8, 8, cin, cout, 0, act_mode
+    d.act, d.alpha = act, alpha
     d.reserved[6] = 1
     if in_pitch is None:
         in_pitch = (cin + 15) // 16 * 16
@@ -177,7 +178,10 @@ def debug_pack_stream(lib, L, w, bias=None, slope=None, in_pitch=None, in_coff=0
                                 ctypes.byref(js), ctypes.byref(pk), ctypes.byref(cnt)))
     meta = json.loads(ctypes.string_at(js).decode())
     arr = (ctypes.c_float * cnt.value).from_address(pk.value)
-    packed = torch.tensor(list(arr), dtype=torch.float32).reshape(meta["chunks"], meta["nkb"], 3, 3, meta["nout"], 64)
+    flat = torch.tensor(list(arr), dtype=torch.float32).reshape(-1, 64)
+    packed = flat[:meta["bias_row0"]].reshape(meta["chunks"], meta["nkb"], 3, 3, meta["nout"], 64)
+    # bias tiles [chunks][nout][64]: K column 0 = high half, column 1 = low half, the rest zero
+    meta["bias_tiles"] = flat[meta["bias_row0"]:].reshape(meta["chunks"], meta["nout"], 64)
     lib.ss4k_free(js)
     lib.ss4k_free(pk)
     return meta, packed
@@ -187,7 +191,8 @@ def emulate_stream_conv(meta, packed, x_nhwc, grid, in_coff=0, acc_slots=None):
     """Mirror of conv3x3_stream_kernel's schedule: per-CTA bands of output rows, accumulator ring with
     vertically fused taps (one 'MMA' adds input row r into the slots of output rows r-1, r, r+1, split
     where the ring wraps), zero-initialising first MMA, completion commits, in-order epilogue drain.
-    Returns the accumulators [N, H, W, npad] (before bias / activation)."""
+    Fresh slots are initialised by the ones x bias-tile MMA.  Returns the accumulators [N, H, W, npad]
+    (alpha-folded conv + bias, before the activation)."""
     n_img, H, W, pitch = x_nhwc.shape
     nout, chunks, nkb, S = meta["nout"], meta["chunks"], meta["nkb"], acc_slots or meta["acc_slots"]
     strips = (W + 127) // 128
@@ -213,26 +218,18 @@ def emulate_stream_conv(meta, packed, x_nhwc, grid, in_coff=0, acc_slots=None):
                 y_lo, y_hi = max(r - 1, yb), min(r + 1, ye - 1)
                 b_lo, b_hi = y_lo - (r - 1), y_hi - (r - 1)
                 f_lo = y_lo if r == r0 else r + 1
+                ones = torch.zeros(128, 16, dtype=torch.float64)
+                ones[:, :2] = 1.0
                 for yy in range(f_lo, y_hi + 1):
                     s = (qs + yy - yb) % S
                     assert state[s] == "empty", ("accumulator slot not drained", cta, r, yy, s, state)
                     state[s] = "busy"
+                    tmem[s] = ones @ meta["bias_tiles"][chunk, :, :16].double().t()      # accumulate = 0
 
-                def emit(b0, b1, acc):
-                    s0 = (qs + (r - 1 + b0 - yb)) % S
-                    nblk = b1 - b0 + 1
-                    if s0 + nblk <= S:
-                        return [(s0, b0, nblk, acc)]
-                    n1 = S - s0
-                    return [(s0, b0, n1, acc), (0, b0 + n1, nblk - n1, acc)]
-                rest = emit(b_lo, b_hi, 1)
-                if r == r0:
-                    first = emit(b_lo, b_hi, 0)
-                elif b_hi == 2:
-                    first = (emit(b_lo, 1, 1) if b_lo <= 1 else []) + emit(2, 2, 0)
-                else:
-                    first = emit(b_lo, b_hi, 1)
-                assert len(first) <= 3 and len(rest) <= 2
+                s0 = (qs + (y_lo - yb)) % S
+                nblk = b_hi - b_lo + 1
+                nA = nblk if s0 + nblk <= S else S - s0
+                ops = [(s0, b_lo, nA)] + ([(0, b_lo + nA, nblk - nA)] if nblk > nA else [])
                 for kb in range(nkb):
                     c0 = in_coff + kb * 64
                     slab = xpad[n, r, strip * 128:strip * 128 + 130, c0:c0 + 64]      # 130-pixel halo row
@@ -240,13 +237,12 @@ def emulate_stream_conv(meta, packed, x_nhwc, grid, in_coff=0, acc_slots=None):
                         a_full = slab[kx:kx + 128]                                    # shifted start address
                         for ks in range(meta["nks"][kb]):
                             a = a_full[:, ks * 16:(ks + 1) * 16]
-                            ops = first if (kb == 0 and kx == 0 and ks == 0) else [(s, b, nb_, 1) for (s, b, nb_, _) in rest]
-                            for (s0, b0, nblk, acc) in ops:
-                                wt = packed[chunk, kb, kx, b0:b0 + nblk, :, ks * 16:(ks + 1) * 16].double()  # [nblk, nout, 16]
+                            for (sa, b0, nb_) in ops:
+                                wt = packed[chunk, kb, kx, b0:b0 + nb_, :, ks * 16:(ks + 1) * 16].double()  # [nb_, nout, 16]
                                 d = torch.einsum("mk,bnk->bmn", a, wt)
-                                for i in range(nblk):
-                                    assert state[s0 + i] == "busy"
-                                    tmem[s0 + i] = d[i] + (tmem[s0 + i] if acc else 0)
+                                for i in range(nb_):
+                                    assert state[sa + i] == "busy"
+                                    tmem[sa + i] += d[i]
                 done = []
                 if r - 1 >= yb:
                     done.append(r - 1)

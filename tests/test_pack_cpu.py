@@ -140,9 +140,10 @@ def test_stream_schedule(lib, cin, cout, h, w, n, grid, slots):
     wt = _exact_weights(cout, cin, 11)
     x = torch.randint(-8, 9, (n, cin, h, w), generator=torch.Generator().manual_seed(12)).float() / 8
     pitch = (cin + 15) // 16 * 16
-    meta, packed = debug_pack_stream(lib, L, wt)
+    bias = torch.randint(-64, 65, (cout,), generator=torch.Generator().manual_seed(15)).float() / 32   # exact in fp16
+    meta, packed = debug_pack_stream(lib, L, wt, bias=bias)
     got = emulate_stream_conv(meta, packed, _nhwc(x, pitch), grid, acc_slots=slots)
-    want = F.conv2d(x.double(), wt.double(), padding=1).permute(0, 2, 3, 1)
+    want = F.conv2d(x.double(), wt.double(), bias.double(), padding=1).permute(0, 2, 3, 1)
     assert torch.equal(got[..., :cout], want)
     assert torch.count_nonzero(got[..., cout:]) == 0
     assert meta["nkb"] == (cin + 63) // 64
@@ -157,3 +158,17 @@ def test_stream_channel_offset_and_permutation(lib):
     want = F.conv2d(slab[..., 64:128].permute(0, 3, 1, 2).double(), wt.double(), padding=1).permute(0, 2, 3, 1)
     perm = [(r % 16) * 4 + r // 16 for r in range(64)]   # packed row (a*2+b)*16 + c  <-  channel c*4 + a*2 + b
     assert torch.equal(got, want[..., perm])
+
+
+def test_stream_alpha_fold_and_bias_split(lib):
+    """alpha is folded into weights and bias for none / PReLU activations (not for ReLU6); a bias that is not
+    representable in fp16 is carried as hi + lo halves in K columns 0 / 1 of the bias tile."""
+    wt = _exact_weights(32, 64, 21)
+    bias = torch.full((32,), 0.1234567)
+    meta, packed = debug_pack_stream(lib, L, wt, bias=bias, alpha=0.25, act=1)
+    assert torch.equal(packed[0, 0, 1, 1, :, :], (0.25 * wt[:, :, 1, 1]))
+    bt = meta["bias_tiles"][0]
+    assert abs((bt[:, 0] + bt[:, 1]).double() - 0.25 * 0.1234567).max().item() < 2e-8
+    assert torch.count_nonzero(bt[:, 2:]) == 0
+    meta6, packed6 = debug_pack_stream(lib, L, wt, bias=bias, alpha=0.25, act=2)
+    assert torch.equal(packed6[0, 0, 1, 1, :, :], wt[:, :, 1, 1])
