@@ -131,6 +131,12 @@ int ss4k_run(ss4k_plan* plan, const void* in_dev, void* out_dev, void* cuda_stre
  * internal stream; returns after the result is in out_host. */
 int ss4k_run_host(ss4k_plan* plan, const void* in_host, void* out_host);
 int ss4k_plan_io_bytes(const ss4k_plan* plan, int64_t* in_bytes, int64_t* out_bytes);
+/* measurement entry (bench.py roofline): one run of the plan without its CUDA graph, a CUDA event between
+ * every step on `cuda_stream`.  ms[i] = device time of step i, flops[i] = its algorithmic FLOPs,
+ * kind[i] = 0 layout/colour kernel, 1 row-streaming conv kernel, 2 tile conv kernel.  Returns the step
+ * count (<= cap) or a negative error. */
+int ss4k_plan_profile(ss4k_plan* plan, const void* in_dev, void* out_dev, void* cuda_stream, float* ms,
+                      double* flops, int32_t* kind, int cap);
 
 /* BSVD streaming (persistent per-stream ring buffers) ----------------------------------- */
 /* open: plan must be an SS4K_ARCH_BSVD plan (its n is ignored; frames are pushed one at a time) */

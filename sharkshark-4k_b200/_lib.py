@@ -47,6 +47,8 @@ SYMBOLS = {
     "ss4k_run": (_i, [_vp, _vp, _vp, _vp]),
     "ss4k_run_host": (_i, [_vp, _vp, _vp]),
     "ss4k_plan_io_bytes": (_i, [_vp, ctypes.POINTER(_i64), ctypes.POINTER(_i64)]),
+    "ss4k_plan_profile": (_i, [_vp, _vp, _vp, _vp, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_double),
+                               ctypes.POINTER(ctypes.c_int32), _i]),
     "ss4k_bsvd_stream_open": (_i, [_vp, ctypes.POINTER(_vp)]),
     "ss4k_bsvd_stream_push": (_i, [_vp, _vp, _vp, ctypes.POINTER(_i), _vp]),
     "ss4k_bsvd_stream_flush": (_i, [_vp, _vp, ctypes.POINTER(_i), _vp]),

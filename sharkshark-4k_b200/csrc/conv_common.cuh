@@ -303,20 +303,54 @@ __device__ __forceinline__ void epilogue_chunk(const Epilogue& E, int mode, int 
   }
   const size_t pix = (static_cast<size_t>(n) * E.out_h + oy) * E.out_w + ox;
   // ---- residuals (indexed at the output pixel, NHWC)
-  if (E.res1 != nullptr)
-    add_residual16(v, E.res1, pix * E.res1_pitch + E.res1_coff + oc, E.beta1, bf16);
-  if (E.res2 != nullptr)
+  if (E.res1 != nullptr) {
+    if (E.res1_nch > 0) {
+      if (oc < E.res1_nch) {
+        float r[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) r[i] = 0.f;
+        add_residual16(r, E.res1, pix * E.res1_pitch + E.res1_coff + oc, E.beta1, bf16);
+        if (E.res1_lo_off != 0) add_residual16(r, E.res1, pix * E.res1_pitch + E.res1_coff + oc + E.res1_lo_off, E.beta1, bf16);
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          if (oc + i < E.res1_nch) v[i] += r[i];
+      }
+    } else {
+      add_residual16(v, E.res1, pix * E.res1_pitch + E.res1_coff + oc, E.beta1, bf16);
+      if (E.res1_lo_off != 0) add_residual16(v, E.res1, pix * E.res1_pitch + E.res1_coff + oc + E.res1_lo_off, E.beta1, bf16);
+    }
+  }
+  if (E.res2 != nullptr) {
     add_residual16(v, E.res2, pix * E.res2_pitch + E.res2_coff + oc, E.beta2, bf16);
+    if (E.res2_lo_off != 0) add_residual16(v, E.res2, pix * E.res2_pitch + E.res2_coff + oc + E.res2_lo_off, E.beta2, bf16);
+  }
   // ---- store
   switch (E.out_mode) {
     case kOutNHWC:
     case kOutPS2NHWC: {
       const size_t off = pix * E.out_pitch + E.out_coff + oc;
-      store8(E.out, off, v, bf16);
-      store8(E.out, off + 8, v + 8, bf16);
-      if (E.out_lo != nullptr) {
-        store8_lo(E.out_lo, off, v, bf16);
-        store8_lo(E.out_lo, off + 8, v + 8, bf16);
+      if (E.fold > 0) {  // temporal-shift scatter
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int c = oc + 8 * h;
+          const int t = E.t0 + n;
+          int64_t delta = 0;
+          bool ok = true;
+          if (c < E.fold) { delta = E.off_prev; ok = t > 0; }
+          else if (c < 2 * E.fold) { delta = E.off_next; ok = t < E.t_count - 1; }
+          if (ok) {
+            const size_t o2 = static_cast<size_t>(static_cast<int64_t>(off) + 8 * h + delta);
+            store8(E.out, o2, v + 8 * h, bf16);
+            if (E.out_lo != nullptr) store8_lo(E.out_lo, o2, v + 8 * h, bf16);
+          }
+        }
+      } else {
+        store8(E.out, off, v, bf16);
+        store8(E.out, off + 8, v + 8, bf16);
+        if (E.out_lo != nullptr) {
+          store8_lo(E.out_lo, off, v, bf16);
+          store8_lo(E.out_lo, off + 8, v + 8, bf16);
+        }
       }
     } break;
     case kOutScatterNHWC: {

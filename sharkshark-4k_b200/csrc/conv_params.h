@@ -75,6 +75,13 @@ struct Epilogue {
   int32_t base_pitch;
   int32_t res_sub;       // 1: residuals are indexed at output pixel, 0 same (kept for clarity)
   float slope_const;     // negative-side slope used when `slope` is null (LeakyReLU)
+  int32_t res1_nch;      // > 0: only the first res1_nch channels of res1 are added (BSVD none_minus, model.py:436-442)
+  // BSVD temporal shift (model.py:43-52) as channel-sliced STORES: when fold > 0 and out_mode is NHWC / PS2-NHWC,
+  // output channels [0, fold) of frame t go to the tensor of frame t-1 (its "X_{t+1}[:fold]" input slice), channels
+  // [fold, 2 fold) to frame t+1, the rest to frame t; slices that fall outside the clip are dropped (zero features).
+  int64_t off_prev, off_next;  // element offsets from frame t's tensor to frame t-1's / t+1's
+  int32_t t0, t_count;         // frame index of image n = 0 of this launch, clip length
+  int64_t res1_lo_off, res2_lo_off;  // split mode: element offset of the residual's low halves (0: none)
 };
 
 struct ConvParams {

@@ -986,6 +986,35 @@ int ss4k_run_host(ss4k_plan* pl, const void* in_host, void* out_host) {
   return check_kernel_health(ctx, cudaStreamSynchronize(ctx->stream), "ss4k_run_host");
 }
 
+
+// Per-step timing of one plan run (no CUDA graph): a CUDA event between every step on `cuda_stream`.
+// kind[i]: 0 prep / layout kernel, 1 row-streaming conv kernel, 2 tile conv kernel.  Returns the number of steps.
+int ss4k_plan_profile(ss4k_plan* pl, const void* in_dev, void* out_dev, void* cuda_stream, float* ms, double* flops,
+                      int32_t* kind, int cap) {
+  if (!pl || !in_dev || !out_dev || !ms || !flops || !kind) return fail(pl ? pl->ctx : nullptr, SS4K_E_INVALID, "null argument to ss4k_plan_profile");
+  ss4k_ctx* ctx = pl->ctx;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(cuda_stream);
+  const int ns = static_cast<int>(pl->prog.steps.size());
+  if (cap < ns) return fail(ctx, SS4K_E_INVALID, "ss4k_plan_profile: arrays too small");
+  std::vector<cudaEvent_t> ev(ns + 1);
+  for (auto& e : ev) cudaEventCreate(&e);
+  int rc = SS4K_OK;
+  cudaEventRecord(ev[0], st);
+  for (int si = 0; si < ns && rc == SS4K_OK; ++si) {
+    rc = run_step(pl, si, in_dev, out_dev, st);
+    cudaEventRecord(ev[si + 1], st);
+  }
+  if (rc == SS4K_OK) rc = check_kernel_health(ctx, cudaStreamSynchronize(st), "ss4k_plan_profile");
+  for (int si = 0; si < ns && rc == SS4K_OK; ++si) {
+    cudaEventElapsedTime(&ms[si], ev[si], ev[si + 1]);
+    const Step& s = pl->prog.steps[si];
+    flops[si] = s.kind == 1 ? s.conv.flops() : 0.0;
+    kind[si] = s.kind == 0 ? 0 : (pl->convs[pl->step_conv[si]].stream ? 1 : 2);
+  }
+  for (auto& e : ev) cudaEventDestroy(e);
+  return rc == SS4K_OK ? ns : rc;
+}
+
 // ------------------------------------------------------------------------------------------------
 // operator-level entry
 int ss4k_conv3x3(ss4k_ctx* ctx, const ss4k_conv_desc* d, const float* x, const float* weight, const float* bias,

@@ -238,6 +238,7 @@ std::string Program::to_json() const {
       js_kv(o, "out_coff", c.out_coff); js_kv(o, "out_h", c.out_h); js_kv(o, "out_w", c.out_w);
       js_kv(o, "ps_r", c.ps_r); js_kv(o, "fold", c.fold); js_kv(o, "round_u8", c.round_u8);
       js_kv(o, "base_buf", c.base_buf); js_kv(o, "base_pitch", c.base_pitch); js_kv(o, "wperm", c.wperm);
+      js_kv(o, "neg_first", c.neg_first); js_kv(o, "res1_nch", c.res1_nch); js_kv(o, "tshift", c.tshift);
       js_kv(o, "split", c.split, true);
     }
     o << "}" << (i + 1 < steps.size() ? "," : "");

@@ -53,6 +53,9 @@ struct ConvSpec {
   int base_buf = kBufNone, base_pitch = 0;
   int wperm = 0;                    // 1: permute output channels (c,a,b) -> (a,b,c) for PixelShuffle(2)
   int split = 0;                    // 1: fp16 hi/lo split operands (3 MMAs per product)
+  int neg_first = 0;                // negate weights and bias of the first k output channels (BSVD none_minus)
+  int res1_nch = 0;                 // > 0: add only the first k channels of res1
+  int tshift = 0;                   // 1: temporal-shift scatter store with fold = `fold` (time == batch index)
   double flops() const;
 };
 

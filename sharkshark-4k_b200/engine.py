@@ -150,6 +150,20 @@ class Plan:
                 self.engine.h)
         return out
 
+    def profile(self, x, out=None):
+        """One un-graphed run with a CUDA event between every step: list of (ms, flops, kind) per step
+        (kind 0 layout/colour kernel, 1 row-streaming conv kernel, 2 tile conv kernel)."""
+        if out is None:
+            out = self.new_output()
+        cap = self.launches + 8
+        ms, fl, kd = (ctypes.c_float * cap)(), (ctypes.c_double * cap)(), (ctypes.c_int32 * cap)()
+        st = ctypes.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)
+        n = self.lib.ss4k_plan_profile(self.h, ctypes.c_void_p(x.data_ptr()), ctypes.c_void_p(out.data_ptr()), st,
+                                       ms, fl, kd, cap)
+        if n < 0:
+            L.check(n, self.engine.h)
+        return [(ms[i], fl[i], kd[i]) for i in range(n)]
+
     def run_host(self, x_host, out_host):
         """Host (pinned) tensors in / out: H2D + run + D2H inside the call (bench.py e2e)."""
         assert not x_host.is_cuda and not out_host.is_cuda
