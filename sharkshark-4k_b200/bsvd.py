@@ -1,0 +1,106 @@
+"""Drop-in for the reference's BSVD denoiser factory
+(reference: src/upscale/model/bsvd/factory.py:21-83 build_model; src/upscale/model/bsvd/model.py:467-588 BSVD).
+
+``build_model(device, input_shape, jit_mode)`` keeps the reference signature and returns an ``nn.Module`` whose
+``forward(x)`` takes ``[N, F, 4, H, W]`` (noisy RGB + noise map, as fsrcnn_upscaler.py:262-277 builds it) and returns
+``[N, F, 3, H, W]``.  Like the reference (model.py:519-520) the N*F frames are ONE stream; each call is a
+self-contained clip (pipeline filled, drained and reset, model.py:555-580).  All arithmetic runs in libss4k.so.
+"""
+import os
+
+import torch
+from torch import nn
+
+from . import _lib as L
+from .engine import Engine
+
+
+def load_checkpoint(path):
+    """BSVD.load (model.py:487-499): ckpt['params'], prefix [module.]base_model.nets_list.{0,1}. -> temp1. / temp2.;
+    DownBlock / UpBlock / MemCvBlock key renames of model.py:167-169,276-279,304-306."""
+    ck = torch.load(path, map_location="cpu")["params"]
+    base = "module.base_model." if "module" in next(iter(ck)) else "base_model."
+    out = {}
+    for k, v in ck.items():
+        for i, t in ((0, "temp1."), (1, "temp2.")):
+            pre = f"{base}nets_list.{i}."
+            if not k.startswith(pre):
+                continue
+            r = k[len(pre):]
+            blk, rest = r.split(".", 1)
+            if blk in ("downc0", "downc1"):
+                if rest.startswith("convblock.0."):
+                    rest = rest
+                elif rest.startswith("convblock.3."):
+                    rest = "memconv." + rest[len("convblock.3."):].replace("net.", "op.conv.")
+                else:
+                    continue
+            elif blk in ("upc2", "upc1"):
+                if rest.startswith("convblock.1."):
+                    rest = "convblock.0." + rest[len("convblock.1."):]
+                elif rest.startswith("convblock.0."):
+                    rest = "memconv." + rest[len("convblock.0."):].replace("net.", "op.conv.")
+                else:
+                    continue
+            out[t + blk + "." + rest] = v
+    return out
+
+
+class NativeBSVD(nn.Module):
+    """BSVD(chns=[32,64,128], mid_ch=32, interm_ch=30, act='relu6', norm='none') on the native engine."""
+
+    shift_num = 16  # BSVD.count_shift (model.py:582-588): 16 BiBufferConvs -> +-16 frame receptive field
+
+    def __init__(self, state_dict, device=0, act_mode=L.ACT_F16, out_dtype=torch.float32, use_graph=True):
+        super().__init__()
+        self.engine = Engine.get(device)
+        self.act_mode, self.out_dtype, self.use_graph = act_mode, out_dtype, use_graph
+        self.net_id = self.engine.new_net(state_dict)
+        self._plans = {}
+
+    def _plan(self, t, h, w, in_fmt, out_fmt):
+        key = (t, h, w, in_fmt, out_fmt)
+        p = self._plans.get(key)
+        if p is None:
+            p = self.engine.plan(self.net_id, L.ARCH_BSVD, t, h, w, act_mode=self.act_mode, in_fmt=in_fmt,
+                                 out_fmt=out_fmt, use_graph=self.use_graph)
+            self._plans[key] = p
+        return p
+
+    def forward(self, x, noise_map=None):
+        if noise_map is not None:
+            x = torch.cat([x, noise_map], dim=2)
+        if not x.is_cuda:
+            raise L.Ss4kError("native BSVD called with a CPU tensor: there is no CPU path")
+        n, f, c, h, w = x.shape
+        if c != 4:
+            raise ValueError("BSVD input is [N, F, 4, H, W] (RGB + noise map)")
+        if x.dtype not in (torch.float16, torch.float32):
+            x = x.float()
+        x = x.reshape(n * f, c, h, w).contiguous()
+        in_fmt = L.FMT_F16_NCHW if x.dtype == torch.float16 else L.FMT_F32_NCHW
+        out_fmt = L.FMT_F16_NCHW if self.out_dtype == torch.float16 else L.FMT_F32_NCHW
+        out = self._plan(n * f, h, w, in_fmt, out_fmt).run(x)
+        return out.reshape(n, f, 3, h, w)
+
+    def reset(self):
+        """Every forward() is a complete clip, so there is no state to reset (model.py:482-484,579)."""
+
+    def half(self):
+        return self
+
+    def float(self):
+        return self
+
+
+def build_model(device=0, input_shape=(360, 640), jit_mode='ds', state_dict=None, pretrain_ckpt=None,
+                act_mode=L.ACT_F16):
+    """Same signature as the reference (bsvd/factory.py:21); ``jit_mode`` is accepted and ignored (every mode
+    maps to the native engine).  Weights: ``state_dict`` (reference key names) or a ``bsvd-32.pth`` checkpoint."""
+    if state_dict is None:
+        path = pretrain_ckpt or './upscale/model/bsvd/bsvd-32.pth'
+        if not os.path.isfile(path):
+            raise FileNotFoundError(f"{path}: bsvd-32.pth is not shipped with the reference (.MISSING_LARGE_BLOBS); "
+                                    "pass state_dict=")
+        state_dict = load_checkpoint(path)
+    return NativeBSVD(state_dict, device=device, act_mode=act_mode).eval()

@@ -143,7 +143,8 @@ std::string pack_weights(const ConvSpec& cs, const HostTensor& W, const HostTens
   const int npad = round_up(cs.cout, 16);
   out->npad_total = npad;
   auto w_at = [&](int n, int c, int ky, int kx) -> float {
-    return W.data[((static_cast<size_t>(n) * cs.cin + c) * 3 + ky) * 3 + kx];
+    const float v = W.data[((static_cast<size_t>(n) * cs.cin + c) * 3 + ky) * 3 + kx];
+    return n < cs.neg_first ? -v : v;
   };
   // output-channel permutation (PixelShuffle(2) fused store): packed row (a*2+b)*Cq + c  <-  c*4 + a*2 + b
   std::vector<int> orow(npad, -1);
@@ -249,7 +250,7 @@ std::string pack_weights(const ConvSpec& cs, const HostTensor& W, const HostTens
   for (int row = 0; row < npad; ++row) {
     const int n = orow[row];
     if (n < 0) continue;
-    if (B) out->bias[row] = B->data[n];
+    if (B) out->bias[row] = n < cs.neg_first ? -B->data[n] : B->data[n];
     out->slope[row] = S ? S->data[n] : cs.const_slope;
   }
   return "";
@@ -329,14 +330,14 @@ std::string pack_weights_stream(const ConvSpec& cs, const HostTensor& W, const H
             for (int cc = 0; cc < 64; ++cc) {
               const int c = kb * 64 + cc;
               if (c >= cs.cin) break;
-              out->w[row * 64 + cc] = f2h(fold * W.data[((static_cast<size_t>(n) * cs.cin + c) * 3 + (2 - blk)) * 3 + kx], bf16);
+              out->w[row * 64 + cc] = f2h((n < cs.neg_first ? -fold : fold) * W.data[((static_cast<size_t>(n) * cs.cin + c) * 3 + (2 - blk)) * 3 + kx], bf16);
             }
           }
   // bias tiles: row = output channel, K column 0 = high half, column 1 = low half (the "ones" operand has 1 there)
   for (int row = 0; row < npad; ++row) {
     const int n = orow[row];
     if (n < 0 || !B) continue;
-    const float bv = fold * B->data[n];
+    const float bv = (n < cs.neg_first ? -fold : fold) * B->data[n];
     const uint16_t hi = f2h(bv, bf16);
     out->w[(static_cast<size_t>(out->bias_row0) + row) * 64 + 0] = hi;
     out->w[(static_cast<size_t>(out->bias_row0) + row) * 64 + 1] = f2h(bv - h2f(hi, bf16), bf16);
@@ -346,7 +347,7 @@ std::string pack_weights_stream(const ConvSpec& cs, const HostTensor& W, const H
   for (int row = 0; row < npad; ++row) {
     const int n = orow[row];
     if (n < 0) continue;
-    if (B) out->bias[row] = B->data[n];
+    if (B) out->bias[row] = n < cs.neg_first ? -B->data[n] : B->data[n];
     out->slope[row] = S ? S->data[n] : cs.const_slope;
   }
   return "";
@@ -467,6 +468,16 @@ void fill_epilogue(const ConvSpec& cs, bool bf16, BufPtr bufptr, float* d_bias, 
   E.base = cs.base_buf >= 0 ? bufptr(cs.base_buf) : nullptr;
   E.base_pitch = cs.base_pitch;
   E.slope_const = cs.const_slope;
+  E.res1_nch = cs.res1_nch;
+  E.t0 = 0; E.t_count = cs.n;
+  E.off_prev = E.off_next = 0;
+  E.res1_lo_off = E.res2_lo_off = 0;
+  if (cs.tshift) {  // clip mode: time == batch index, neighbouring frames are one image stride away
+    const int64_t frame = static_cast<int64_t>(cs.out_h) * cs.out_w * cs.out_pitch;
+    E.off_prev = -frame; E.off_next = frame;
+  } else {
+    E.fold = 0;
+  }
 }
 
 // Row-streaming path: parameter block of conv_stream.cu
@@ -526,6 +537,7 @@ int materialize_stream(ss4k_ctx* ctx, const ConvSpec& cs, const HostTensor& W, c
   // fast epilogue: plain NHWC 16-bit output -> swizzled shared-memory tile -> TMA store
   p.fast_store = 0;
   if (cs.out_mode == kOutNHWC && cs.out_buf >= 0 && cs.out_lo_buf < 0 && cs.out_coff % 8 == 0 && cs.out_pitch % 8 == 0 &&
+      !cs.tshift && cs.res1_nch == 0 &&
       (pk.nout == 16 || pk.nout == 32 || pk.nout == 64) && getenv("SS4K_NO_FAST_STORE") == nullptr) {
     const cuuint64_t eb = 2;
     const int cavail = std::min(cs.out_pitch - cs.out_coff, pk.npad_total);
@@ -637,27 +649,7 @@ int materialize_conv(ss4k_ctx* ctx, const ConvSpec& cs, const HostTensor& W, con
   p.a_row_tx = ctx->desc_mode == 2 ? 3u * kTileW * kRowBytes : static_cast<uint32_t>(kBoxW) * kRowBytes;
   p.w_tx = static_cast<uint32_t>(t.w_slot_bytes);
   p.err = ctx->err_dev;
-  // epilogue
-  Epilogue& E = p.ep;
-  E.bias = ex->d_bias;
-  E.slope = ex->d_slope;
-  E.act = cs.act; E.out_mode = cs.out_mode;
-  E.alpha = cs.alpha; E.beta1 = cs.beta1; E.beta2 = cs.beta2;
-  E.is_bf16 = bf16 ? 1 : 0;
-  E.res1 = cs.res1_buf >= 0 ? bufptr(cs.res1_buf) : nullptr;
-  E.res2 = cs.res2_buf >= 0 ? bufptr(cs.res2_buf) : nullptr;
-  E.res1_pitch = cs.res1_pitch; E.res1_coff = cs.res1_coff;
-  E.res2_pitch = cs.res2_pitch; E.res2_coff = cs.res2_coff;
-  ex->ext_out = cs.out_buf == kBufExternalOut;
-  E.out = cs.out_buf >= 0 ? bufptr(cs.out_buf) : nullptr;
-  E.out_lo = cs.out_lo_buf >= 0 ? bufptr(cs.out_lo_buf) : nullptr;
-  E.out2 = cs.out2_buf >= 0 ? bufptr(cs.out2_buf) : nullptr;
-  E.out3 = cs.out3_buf >= 0 ? bufptr(cs.out3_buf) : nullptr;
-  E.out_pitch = cs.out_pitch; E.out_coff = cs.out_coff;
-  E.out_h = cs.out_h; E.out_w = cs.out_w;
-  E.cout = cs.cout; E.ps_r = cs.ps_r; E.fold = cs.fold; E.round_u8 = cs.round_u8;
-  E.base = cs.base_buf >= 0 ? bufptr(cs.base_buf) : nullptr;
-  E.base_pitch = cs.base_pitch;
+  fill_epilogue(cs, bf16, bufptr, ex->d_bias, ex->d_slope, &p.ep, &ex->ext_out);
   ex->grid = std::min(t.n_tiles, ctx->nsm);
   return SS4K_OK;
 }

@@ -99,6 +99,8 @@ def run_program(prog, sd, x, quant=None):
             assert st["in_fmt"] == 0
             us = st["unshuffle"]
             src = x
+            if x.ndim == 5:   # BSVD: [N, F, C, H, W] is one stream of N*F frames (model.py:519-520)
+                src = x.reshape(-1, *x.shape[2:])
             if us > 1:
                 src = F.pixel_unshuffle(x, us)
             dst = bufs[st["out_buf"]]
@@ -111,6 +113,10 @@ def run_program(prog, sd, x, quant=None):
         cin, cout = c["cin"], c["cout"]
         src = _nchw(bufs[c["in_buf"]][..., c["in_coff"]:c["in_coff"] + cin])
         w, b = sd[c["wname"]], sd[c["bname"]]
+        if c.get("neg_first", 0):
+            w, b = w.clone(), b.clone()
+            w[:c["neg_first"]] *= -1
+            b[:c["neg_first"]] *= -1
         if c["mode"] == 0:
             v = F.conv2d(src, w, b, padding=1)
         elif c["mode"] == 1:
@@ -130,14 +136,26 @@ def run_program(prog, sd, x, quant=None):
         for k in (1, 2):
             rb = c[f"res{k}_buf"]
             if rb >= 0:
-                r = bufs[rb][..., c[f"res{k}_coff"]:c[f"res{k}_coff"] + oc]
-                v = v + c[f"beta{k}"] * _nchw(r)
+                if k == 1 and c.get("res1_nch", 0):
+                    nch = c["res1_nch"]
+                    r = torch.zeros_like(v)
+                    r[:, :nch] = _nchw(bufs[rb][..., c["res1_coff"]:c["res1_coff"] + nch])
+                else:
+                    r = _nchw(bufs[rb][..., c[f"res{k}_coff"]:c[f"res{k}_coff"] + oc])
+                v = v + c[f"beta{k}"] * r
         if om in (0, 3):
             dst = bufs[c["out_buf"]]
             assert tuple(dst.shape[1:3]) == (c["out_h"], c["out_w"]) == tuple(v.shape[2:]), (c["name"], dst.shape, v.shape)
             npad = (oc + 15) // 16 * 16
-            dst[..., c["out_coff"]:c["out_coff"] + npad] = 0
-            dst[..., c["out_coff"]:c["out_coff"] + oc] = q(_nhwc(v))
+            vv = q(_nhwc(v))
+            if c.get("tshift", 0):   # temporal-shift scatter: time == batch index, out-of-clip slices dropped
+                fold, o = c["fold"], c["out_coff"]
+                dst[:-1, ..., o:o + fold] = vv[1:, ..., :fold]
+                dst[1:, ..., o + fold:o + 2 * fold] = vv[:-1, ..., fold:2 * fold]
+                dst[..., o + 2 * fold:o + oc] = vv[..., 2 * fold:]
+            else:
+                dst[..., c["out_coff"]:c["out_coff"] + npad] = 0
+                dst[..., c["out_coff"]:c["out_coff"] + oc] = vv
         elif om == 4:    # temporal-shift scatter
             fold = c["fold"]
             vv = q(_nhwc(v))

@@ -67,3 +67,22 @@ def test_rrdb_fp16_storage_error_budget(lib):
     mse = torch.mean((got - want) ** 2).item()
     psnr = -10 * torch.log10(torch.tensor(mse)).item()
     assert psnr >= 50 and (got - want).abs().max().item() * 255 <= 2.0
+
+
+@pytest.mark.parametrize("frames", [1, 5])
+def test_bsvd_program(lib, frames):
+    """BSVD clip lowering (temporal-shift scatter stores, PixelShuffle + skip adds, none_minus as negated
+    weights + masked residual) against the oracle clip function, i.e. the reference BSVD.forward."""
+    from oracle import bsvd
+    sd = bsvd.build_bsvd32(0)
+    x = torch.rand(1, frames, 4, 16, 24, generator=torch.Generator().manual_seed(1234))
+    x[:, :, 3] = 0.075
+    prog = ss4k_b200.plan_dry(ss4k_b200.make_cfg(0, L.ARCH_BSVD, frames, 16, 24))
+    assert sum(1 for s in prog["steps"] if s["kind"] == "conv") == 32
+    want = bsvd.bsvd_forward(sd, x)[0]
+    got = run_program(prog, sd, x)
+    assert got.shape == want.shape == (frames, 3, 16, 24)
+    assert (got - want).abs().max().item() < 2e-4 * max(1.0, want.abs().max().item())
+    # algorithmic FLOPs (BASELINE.md section 2): 272.0 GMAC per 1280x720 frame
+    p720 = ss4k_b200.plan_dry(ss4k_b200.make_cfg(0, L.ARCH_BSVD, 1, 720, 1280))
+    assert abs(p720["flops"] / 2e9 - 271.99) < 0.05
