@@ -145,10 +145,38 @@ int ss4k_bsvd_stream_open(ss4k_plan* plan, ss4k_bsvd_stream** out_stream);
  * *got_output = 1 when the denoised frame t-16 was written to out_dev (3 channels). */
 int ss4k_bsvd_stream_push(ss4k_bsvd_stream* s, const void* in_dev, void* out_dev,
                           int* got_output, void* cuda_stream);
-/* flush: feed one "None" (end-of-clip) step; call until *got_output == 0 */
+/* flush: feed "None" (end-of-clip) steps until the next denoised frame falls out of the pipeline;
+ * call until *got_output == 0 (all frames of the clip delivered) */
 int ss4k_bsvd_stream_flush(ss4k_bsvd_stream* s, void* out_dev, int* got_output, void* cuda_stream);
 int ss4k_bsvd_stream_reset(ss4k_bsvd_stream* s);
+/* frames of latency between a push and its output (BSVD.count_shift, model.py:582-588: 16) */
+int ss4k_bsvd_stream_latency(const ss4k_bsvd_stream* s);
 int ss4k_bsvd_stream_close(ss4k_bsvd_stream* s);
+
+/* service glue (fsrcnn_upscaler.py:168-326): HBM-bound statistics / pooling / stencil / finalising kernels -------- */
+/* image formats: 0 float NCHW, 1 half NCHW, 2 uint8 NHWC (read as value/255).  All pointers are DEVICE pointers. */
+/* per-(n,c) sum and sum of squares (double[n*c][2]); replaces .mean()/.std() of fsrcnn_upscaler.py:191-196,305-310 */
+int ss4k_glue_chan_stats(const void* img, int fmt, int n, int c, int h, int w, double* sums_dev, void* cuda_stream);
+/* F.interpolate(mode='area') -> float NCHW [n,c,oh,ow]  (fsrcnn_upscaler.py:174-176,204-209,239-241) */
+int ss4k_glue_area_pool(const void* img, int fmt, int n, int c, int h, int w, float* out_dev, int oh, int ow,
+                        void* cuda_stream);
+/* low-res colour difference blur_k(a*hb + b - lb), reflect padding (fsrcnn_upscaler.py:211-213); a, b = the
+ * distribution-match affine map derived from the sums (NULL sums: a=1, b=0) */
+int ss4k_glue_blur_diff(const float* hb, const float* lb, float* diff, const float* kern_dev, int ksize, int n, int c,
+                        int h, int w, const double* hr_sums, const double* lr_sums, double cnt_hr, double cnt_lr,
+                        void* cuda_stream);
+/* clamp(a*hr + b - bilinear_up(diff), 0, 1) -> uint8 NHWC (truncating unless round_u8) or float NCHW
+ * (fsrcnn_upscaler.py:197-198,214-220,232-233); diff may be NULL */
+int ss4k_glue_finalize(const void* hr, int fmt, int n, int c, int h, int w, const float* diff, int dh, int dw,
+                       const double* hr_sums, const double* lr_sums, double cnt_hr, double cnt_lr, uint8_t* out_u8,
+                       float* out_f32, int round_u8, void* cuda_stream);
+/* F.interpolate(mode='bicubic') of a float NCHW image, clamp, uint8 NHWC (fsrcnn_upscaler.py:222-233) */
+int ss4k_glue_bicubic_u8(const float* in, int n, int c, int h, int w, uint8_t* out, int oh, int ow, int round_u8,
+                         void* cuda_stream);
+/* opacity * clamp(sharpen_ker(strength)(x), 0, 1) + (1-opacity) * other -> float NCHW; other may be NULL
+ * (fsrcnn_upscaler.py:54-84,278-281,298-299) */
+int ss4k_glue_sharpen_blend(const void* x, int fmt, int n, int c, int h, int w, float strength, float opacity,
+                            const void* other, int other_fmt, float* out, void* cuda_stream);
 
 /* operator-level entry (kernel parity tests) -------------------------------------------- */
 typedef struct ss4k_conv_desc {

@@ -91,3 +91,29 @@ def denoise_frame(frame_chw, denoise_model, denoise_rate, first_frame):
     den = denoise_model(x)[:, -1][0]
     den = torch.clamp(depthwise_reflect(den.view(3, 1, h, w), sharpen_weight(0.00002)).view(3, h, w), 0, 1)
     return den * 0.8 + 0.2 * frame_chw                              # :281
+
+
+def upscale_single(frame_u8, model, lr_shape, output_shape=None, denoise_model=None, denoise_rate=1.0,
+                   first_frame=True):
+    """frame_u8 [H,W,3] uint8 -> uint8 [H',W',3]  (fsrcnn_upscaler.py:235-326, realesrgan branch).
+    denoise_model: callable [1,1,4,H,W] -> [1,1,3,H,W] or None (denoising=False)."""
+    with torch.no_grad():
+        img = frame_u8.permute(2, 0, 1).unsqueeze(0) / 255.0
+        lr_before = F.interpolate(img, size=lr_shape, mode="area").squeeze(0)            # :237-241
+        lr = lr_before
+        if denoise_model is not None:
+            lr = denoise_frame(lr_before, denoise_model, denoise_rate, first_frame)      # :245-284
+        hr = model(lr.unsqueeze(0).float())[0]                                           # :293-295
+        c, h, w = hr.shape
+        if denoise_model is not None:
+            hr = torch.clamp(depthwise_reflect(hr.view(c, 1, h, w), sharpen_weight(0.00007)).view(c, h, w), 0, 1)  # :298-299
+        hm = hr.reshape(c, -1).mean(dim=-1).view(c, 1, 1)                                 # :302-313
+        hs = hr.reshape(c, -1).std(dim=-1).view(c, 1, 1)
+        lm = lr_before.reshape(c, -1).mean(dim=-1).view(c, 1, 1)
+        ls = lr_before.reshape(c, -1).std(dim=-1).view(c, 1, 1)
+        hr = (hr - hm) / (hs + 1e-8) * ls + lm
+        out = torch.clamp(hr, 0, 1).unsqueeze(0)
+        if output_shape is not None:
+            out = F.interpolate(out, size=output_shape, mode="bicubic")                  # :316-325 (bicubic in practice)
+        out = torch.clamp(out, 0, 1)
+        return (out * 255)[0].permute(1, 2, 0).to(torch.uint8)

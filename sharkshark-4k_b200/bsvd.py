@@ -83,6 +83,20 @@ class NativeBSVD(nn.Module):
         out = self._plan(n * f, h, w, in_fmt, out_fmt).run(x)
         return out.reshape(n, f, 3, h, w)
 
+    def stream(self, h, w):
+        return BSVDStream(self, h, w)
+
+    def streaming_forward(self, input_seq):
+        """BSVD.streaming_forward (model.py:526-580) through the ring-buffer engine: feed, drain, reset."""
+        if isinstance(input_seq, torch.Tensor):
+            input_seq = [input_seq[i:i + 1] for i in range(input_seq.shape[0])]
+        _, _, h, w = input_seq[0].shape
+        s = self.stream(h, w)
+        outs = [o for o in (s.push(x) for x in input_seq) if o is not None]
+        outs += list(s.flush())
+        s.close()
+        return torch.cat(outs, dim=0)
+
     def reset(self):
         """Every forward() is a complete clip, so there is no state to reset (model.py:482-484,579)."""
 
@@ -91,6 +105,61 @@ class NativeBSVD(nn.Module):
 
     def float(self):
         return self
+
+
+class BSVDStream:
+    """Frame-at-a-time denoising with persistent ring buffers in HBM (BSVD.feedin_one_element, model.py:510-513):
+    ``push(frame)`` returns the denoised frame t-16 once the 16-stage pipeline is full, else None; ``flush()``
+    yields the remaining frames (the reference feeds ``None``, model.py:555-569); ``reset()`` starts a new clip."""
+
+    def __init__(self, model, h, w):
+        import ctypes
+        self.model, self.h, self.w = model, h, w
+        self.lib = model.engine.lib
+        self.plan = model._plan(1, h, w, L.FMT_F32_NCHW, L.FMT_F32_NCHW)
+        hdl = ctypes.c_void_p()
+        L.check(self.lib.ss4k_bsvd_stream_open(self.plan.h, ctypes.byref(hdl)), model.engine.h)
+        self.hdl = hdl
+        self.latency = self.lib.ss4k_bsvd_stream_latency(hdl)
+
+    def _st(self, dev):
+        import ctypes
+        return ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+    def push(self, frame):
+        import ctypes
+        x = frame.reshape(4, self.h, self.w).float().contiguous()
+        out = torch.empty(1, 3, self.h, self.w, device=x.device, dtype=torch.float32)
+        got = ctypes.c_int(0)
+        L.check(self.lib.ss4k_bsvd_stream_push(self.hdl, ctypes.c_void_p(x.data_ptr()), ctypes.c_void_p(out.data_ptr()),
+                                               ctypes.byref(got), self._st(x.device)), self.model.engine.h)
+        return out if got.value else None
+
+    def flush(self):
+        import ctypes
+        dev = self.model.engine.device
+        while True:
+            out = torch.empty(1, 3, self.h, self.w, device=dev, dtype=torch.float32)
+            got = ctypes.c_int(0)
+            L.check(self.lib.ss4k_bsvd_stream_flush(self.hdl, ctypes.c_void_p(out.data_ptr()), ctypes.byref(got), self._st(dev)),
+                    self.model.engine.h)
+            if not got.value:
+                return
+            yield out
+
+    def reset(self):
+        self.lib.ss4k_bsvd_stream_reset(self.hdl)
+
+    def close(self):
+        if self.hdl:
+            self.lib.ss4k_bsvd_stream_close(self.hdl)
+            self.hdl = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def build_model(device=0, input_shape=(360, 640), jit_mode='ds', state_dict=None, pretrain_ckpt=None,

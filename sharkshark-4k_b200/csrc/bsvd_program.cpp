@@ -45,6 +45,16 @@ std::string build_bsvd_clip(const PlanCfgLite& c, Program* P) {
   const int p1 = P->add_buf("p1", T, H, W, c0);
   const int o0 = P->add_buf("o0", T, H, W, c0);
   const int t1out = P->add_buf("t1out", T, H, W, mid);
+  // streaming: both DenBlocks are in flight at once (temp2 runs 8 frames behind temp1) -> own buffers
+  int alt[16];
+  const int firsts[16] = {x0a, x0, d0, m0a, x1, d1, m1a, m1b, u2a, u2b, p2, u1a, u1b, p1, o0, -1};
+  for (int i = 0; i < 15; ++i) {
+    alt[i] = firsts[i];
+    if (c.bsvd_stream) {
+      const BufSpec bs = P->bufs[firsts[i]];
+      alt[i] = P->add_buf(bs.name + "_2", bs.n, bs.h, bs.w, bs.pitch, bs.zero_init);
+    }
+  }
 
   PrepSpec pp;
   pp.in_fmt = c.in_fmt; pp.c = 4; pp.h = H; pp.w = W; pp.n = T; pp.out_buf = in16;
@@ -67,6 +77,10 @@ std::string build_bsvd_clip(const PlanCfgLite& c, Program* P) {
   auto plain = [&](ConvSpec& v, int out_buf, int pitch) { v.out_buf = out_buf; v.out_pitch = pitch; };
 
   auto den_block = [&](const std::string& p, int in_buf, int in_pitch, int in_c, int out_c, bool last) {
+    // (temp2 of the streaming layout uses the second buffer set)
+    const int* B = last ? alt : firsts;
+    const int x0a = B[0], x0 = B[1], d0 = B[2], m0a = B[3], x1 = B[4], d1 = B[5], m1a = B[6], m1b = B[7], u2a = B[8],
+              u2b = B[9], p2 = B[10], u1a = B[11], u1b = B[12], p1 = B[13], o0 = B[14];
     { ConvSpec v = conv(p + "inc.convblock.0", kModeConv3, in_buf, H, W, in_pitch, in_c, interm, kActRelu6); plain(v, x0a, 32); P->add_conv(v); }
     { ConvSpec v = conv(p + "inc.convblock.3", kModeConv3, x0a, H, W, 32, interm, c0, kActRelu6); plain(v, x0, c0); P->add_conv(v); }
     { ConvSpec v = conv(p + "downc0.convblock.0", kModeS2, x0, H, W, c0, c0, c1, kActRelu6); shifted(v, d0, c1); P->add_conv(v); }

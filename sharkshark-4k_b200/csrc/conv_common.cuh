@@ -393,6 +393,7 @@ __device__ __forceinline__ void epilogue_chunk(const Epilogue& E, int mode, int 
         }
       }
     } break;
+    case kOutPSNCHWF16:
     case kOutPSNCHWF32: {
       // conv channel ch = c*r*r + a*r + b  ->  out[n, c, oy*r + a, ox*r + b]  (+ base[n, oy, ox, c])
       float* o = reinterpret_cast<float*>(E.out);
@@ -414,7 +415,9 @@ __device__ __forceinline__ void epilogue_chunk(const Epilogue& E, int mode, int 
             val += bf16 ? __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(&raw))
                         : __half2float(*reinterpret_cast<const __half*>(&raw));
           }
-          o[((static_cast<size_t>(n) * oc_total + c) * OH + (static_cast<size_t>(oy) * r + a)) * OW + static_cast<size_t>(ox) * r + b] = val;
+          const size_t oi = ((static_cast<size_t>(n) * oc_total + c) * OH + (static_cast<size_t>(oy) * r + a)) * OW + static_cast<size_t>(ox) * r + b;
+          if (E.out_mode == kOutPSNCHWF16) reinterpret_cast<__half*>(E.out)[oi] = __float2half_rn(val);
+          else o[oi] = val;
         }
       }
     } break;

@@ -31,7 +31,8 @@ enum OutMode : int {
   kOutPS2NHWC = 3,    // PixelShuffle(2) into NHWC (weights' output channels pre-permuted to (a,b,c))
   kOutScatterNHWC = 4,// BSVD temporal shift: channel slices go to the t-1 / t+1 / t ring slots
   kOutNCHWF16 = 5,
-  kOutU8NHWC = 6      // clamp [0,1], *255, truncate or round, uint8 NHWC (3 channels)
+  kOutU8NHWC = 6,     // clamp [0,1], *255, truncate or round, uint8 NHWC (3 channels)
+  kOutPSNCHWF16 = 7   // like kOutPSNCHWF32 with a half-precision destination
 };
 
 enum ActKind : int { kActNone = 0, kActPRelu = 1, kActRelu6 = 2 };
@@ -107,6 +108,7 @@ struct ConvParams {
   uint32_t w_tx;         // bytes one weight block load delivers
   int32_t* err;          // device int[4]: watchdog diagnostics (tag, block, ...)
   int32_t dbg_flags;     // profiling experiments: 1 skip MMA issue, 2 skip TMA loads, 4 epilogue without math/stores
+  int32_t n_in0;         // added to the image coordinate of activation loads (BSVD streaming: ring slot of the frame)
 };
 
 
@@ -139,6 +141,7 @@ struct StreamParams {
   uint32_t idesc[3];      // instruction descriptors for N = NOUT, 2*NOUT, 3*NOUT
   int32_t* err;
   int32_t dbg_flags;
+  int32_t n_in0, n_out0;  // added to the image coordinate of TMA loads / stores (BSVD streaming: ring slots)
 };
 
 }  // namespace ss4k

@@ -199,7 +199,7 @@ conv3x3_stream_kernel(const __grid_constant__ StreamParams P) {
               mbar_arrive(a_full + 8 * as);
             } else {
               mbar_expect_tx(a_full + 8 * as, kBoxW * kRowBytes);
-              tma_load_5d(a_base + as * kASlotBytes, &P.tmA[P.a_tm[kb]], a_full + 8 * as, 0, x0, P.a_kb[kb], r, b.n);
+              tma_load_5d(a_base + as * kASlotBytes, &P.tmA[P.a_tm[kb]], a_full + 8 * as, 0, x0, P.a_kb[kb], r, b.n + P.n_in0);
             }
           }
           __syncwarp();
@@ -397,7 +397,7 @@ conv3x3_stream_kernel(const __grid_constant__ StreamParams P) {
               fence_proxy_async();
               __syncwarp();
               if (lane == 0) {
-                tma_store_4d(&P.tmO, stage, b.chunk * NOUT, b.strip * kTileW + qd * 32, y, b.n);
+                tma_store_4d(&P.tmO, stage, b.chunk * NOUT, b.strip * kTileW + qd * 32, y, b.n + P.n_out0);
                 bulk_commit();
               }
             } else if (valid) {

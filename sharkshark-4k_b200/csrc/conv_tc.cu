@@ -122,9 +122,9 @@ conv3x3_tcgen05_kernel(const __grid_constant__ ConvParams P) {
             if (P.desc_mode == 2) {
 #pragma unroll
               for (int s = 0; s < 3; ++s)
-                tma_load_5d(dst + s * P.a_sub_bytes, tm, a_full + 8 * as, kb.c0, x0 - 1 + s, kb.p, y, n);
+                tma_load_5d(dst + s * P.a_sub_bytes, tm, a_full + 8 * as, kb.c0, x0 - 1 + s, kb.p, y, n + P.n_in0);
             } else {
-              tma_load_5d(dst, tm, a_full + 8 * as, kb.c0, x0 - 1, kb.p, y, n);
+              tma_load_5d(dst, tm, a_full + 8 * as, kb.c0, x0 - 1, kb.p, y, n + P.n_in0);
             }
             if (++as == static_cast<uint32_t>(P.a_slots)) { as = 0; aph ^= 1; }
           }

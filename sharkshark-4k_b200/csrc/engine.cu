@@ -502,7 +502,8 @@ int materialize_stream(ss4k_ctx* ctx, const ConvSpec& cs, const HostTensor& W, c
     const cuuint64_t eb = 2;
     const int avail = cs.in_pitch - cs.in_coff;
     cuuint64_t dims[5] = {static_cast<cuuint64_t>(pk.nkb == 1 ? std::min(64, avail) : 64), static_cast<cuuint64_t>(cs.in_w),
-                          static_cast<cuuint64_t>(pk.nkb), static_cast<cuuint64_t>(cs.in_h), static_cast<cuuint64_t>(cs.n)};
+                          static_cast<cuuint64_t>(pk.nkb), static_cast<cuuint64_t>(cs.in_h),
+                          static_cast<cuuint64_t>(cs.in_ring ? cs.in_ring : cs.n)};
     cuuint64_t strides[4] = {cs.in_pitch * eb, 128, static_cast<cuuint64_t>(cs.in_w) * cs.in_pitch * eb,
                              static_cast<cuuint64_t>(cs.in_h) * cs.in_w * cs.in_pitch * eb};
     cuuint32_t box[5] = {64, static_cast<cuuint32_t>(kBoxW), 1, 1, 1};
@@ -542,7 +543,7 @@ int materialize_stream(ss4k_ctx* ctx, const ConvSpec& cs, const HostTensor& W, c
     const cuuint64_t eb = 2;
     const int cavail = std::min(cs.out_pitch - cs.out_coff, pk.npad_total);
     cuuint64_t dims[4] = {static_cast<cuuint64_t>(cavail), static_cast<cuuint64_t>(cs.out_w), static_cast<cuuint64_t>(cs.out_h),
-                          static_cast<cuuint64_t>(cs.n)};
+                          static_cast<cuuint64_t>(cs.out_ring ? cs.out_ring : cs.n)};
     cuuint64_t strides[3] = {cs.out_pitch * eb, static_cast<cuuint64_t>(cs.out_w) * cs.out_pitch * eb,
                              static_cast<cuuint64_t>(cs.out_h) * cs.out_w * cs.out_pitch * eb};
     cuuint32_t box[4] = {static_cast<cuuint32_t>(pk.nout), 32, 1, 1};
@@ -621,10 +622,11 @@ int materialize_conv(ss4k_ctx* ctx, const ConvSpec& cs, const HostTensor& W, con
   CK(ctx, cudaMemcpy(ex->d_slope, pw.slope.data(), pw.slope.size() * 4, cudaMemcpyHostToDevice));
   // tensor maps
   const int box_w = ctx->desc_mode == 2 ? kTileW : kBoxW;
-  e = encode_act_map(ctx, &p.tmA[0], bufptr(cs.in_buf), cs.n, cs.in_h, cs.in_w, cs.in_pitch, cs.mode, bf16, box_w);
+  const int in_imgs = cs.in_ring ? cs.in_ring : cs.n;
+  e = encode_act_map(ctx, &p.tmA[0], bufptr(cs.in_buf), in_imgs, cs.in_h, cs.in_w, cs.in_pitch, cs.mode, bf16, box_w);
   if (!e.empty()) return fail(ctx, SS4K_E_CUDA, e);
   if (cs.split) {
-    e = encode_act_map(ctx, &p.tmA[1], bufptr(cs.in_lo_buf), cs.n, cs.in_h, cs.in_w, cs.in_pitch, cs.mode, bf16, box_w);
+    e = encode_act_map(ctx, &p.tmA[1], bufptr(cs.in_lo_buf), in_imgs, cs.in_h, cs.in_w, cs.in_pitch, cs.mode, bf16, box_w);
     if (!e.empty()) return fail(ctx, SS4K_E_CUDA, e);
   } else {
     p.tmA[1] = p.tmA[0];
@@ -1286,3 +1288,5 @@ static int self_probe(ss4k_ctx* ctx) {
 }
 
 }  // extern "C"
+
+#include "bsvd_stream.inc"

@@ -1,0 +1,304 @@
+// Service glue of the upscaler (HBM-bound elementwise / stencil / reduction kernels around the convnets).
+//
+// Reference: src/upscale/fsrcnn_upscaler.py
+//   upscale_multi  :168-233  /255 + NHWC->NCHW (+ area downscale), model, per-(N,C) mean / unbiased-std match
+//                            to the LR frame (:188-199), local colour match (area /8, 17x17 sigma-8 reflect
+//                            gaussian, bilinear up, subtract :201-218), clamp, bicubic resize (:222-231),
+//                            *255 -> uint8 truncating, ->NHWC (:232-233)
+//   upscale_single :235-326  denoise blend: 3x3 reflect sharpen + clamp, 0.8*den + 0.2*orig (:273-281),
+//                            HR sharpen (:298-299), mean/std match (:302-313)
+//   blur_ker / sharpen_ker :20-84
+// The reference runs ~10 separate ATen passes over the HR frame; here: one statistics pass, one pooling pass,
+// a tiny low-resolution blur and ONE finalising pass that applies the affine match, subtracts the bilinearly
+// upsampled colour difference, clamps and writes uint8 NHWC.
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/ss4k.h"
+
+namespace ss4k {
+namespace {
+
+// image access: fmt 0 float NCHW, 1 half NCHW, 2 uint8 NHWC (value / 255)
+struct Img {
+  const void* p;
+  int fmt, N, C, H, W;
+  __device__ __forceinline__ float at(int n, int c, int y, int x) const {
+    if (fmt == 0) return reinterpret_cast<const float*>(p)[((static_cast<size_t>(n) * C + c) * H + y) * W + x];
+    if (fmt == 1) return __half2float(reinterpret_cast<const __half*>(p)[((static_cast<size_t>(n) * C + c) * H + y) * W + x]);
+    return static_cast<float>(reinterpret_cast<const uint8_t*>(p)[((static_cast<size_t>(n) * H + y) * W + x) * C + c]) / 255.0f;
+  }
+};
+
+// ---- per (n, c) sum and sum of squares (double) ----------------------------------------------------
+__global__ void chan_stats_kernel(Img im, double* __restrict__ sums /* [N*C][2] */) {
+  const int nc = blockIdx.y;
+  const int n = nc / im.C, c = nc - n * im.C;
+  const size_t total = static_cast<size_t>(im.H) * im.W;
+  double s = 0.0, q = 0.0;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int y = static_cast<int>(i / im.W), x = static_cast<int>(i - static_cast<size_t>(y) * im.W);
+    const float v = im.at(n, c, y, x);
+    s += v;
+    q += static_cast<double>(v) * v;
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    q += __shfl_xor_sync(0xffffffffu, q, o);
+  }
+  __shared__ double sh[2][32];
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) { sh[0][w] = s; sh[1][w] = q; }
+  __syncthreads();
+  if (w == 0) {
+    const int nw = blockDim.x >> 5;
+    s = l < nw ? sh[0][l] : 0.0;
+    q = l < nw ? sh[1][l] : 0.0;
+    for (int o = 16; o > 0; o >>= 1) {
+      s += __shfl_xor_sync(0xffffffffu, s, o);
+      q += __shfl_xor_sync(0xffffffffu, q, o);
+    }
+    if (l == 0) {
+      atomicAdd(&sums[2 * nc], s);
+      atomicAdd(&sums[2 * nc + 1], q);
+    }
+  }
+}
+
+// affine map of the distribution match: hr' = a*hr + b with a = std_lr / (std_hr + 1e-8), b = mean_lr - a*mean_hr
+// (unbiased std like torch.Tensor.std)
+__device__ __forceinline__ void match_coeffs(const double* hr_sums, const double* lr_sums, int nc, double cnt_hr,
+                                             double cnt_lr, float* a, float* b) {
+  if (hr_sums == nullptr) { *a = 1.f; *b = 0.f; return; }
+  const double mh = hr_sums[2 * nc] / cnt_hr, ml = lr_sums[2 * nc] / cnt_lr;
+  double vh = (hr_sums[2 * nc + 1] - cnt_hr * mh * mh) / (cnt_hr - 1.0);
+  double vl = (lr_sums[2 * nc + 1] - cnt_lr * ml * ml) / (cnt_lr - 1.0);
+  vh = vh > 0.0 ? vh : 0.0;
+  vl = vl > 0.0 ? vl : 0.0;
+  const double aa = sqrt(vl) / (sqrt(vh) + 1e-8);
+  *a = static_cast<float>(aa);
+  *b = static_cast<float>(ml - aa * mh);
+}
+
+// ---- F.interpolate(mode='area') == adaptive average pooling -> float NCHW ---------------------------
+__global__ void area_pool_kernel(Img im, float* __restrict__ out, int oh, int ow) {
+  const size_t total = static_cast<size_t>(im.N) * im.C * oh * ow;
+  const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int ox = static_cast<int>(idx % ow);
+  const int oy = static_cast<int>((idx / ow) % oh);
+  const int c = static_cast<int>((idx / (static_cast<size_t>(ow) * oh)) % im.C);
+  const int n = static_cast<int>(idx / (static_cast<size_t>(ow) * oh * im.C));
+  const int y0 = static_cast<int>((static_cast<int64_t>(oy) * im.H) / oh);
+  const int y1 = static_cast<int>((static_cast<int64_t>(oy + 1) * im.H + oh - 1) / oh);
+  const int x0 = static_cast<int>((static_cast<int64_t>(ox) * im.W) / ow);
+  const int x1 = static_cast<int>((static_cast<int64_t>(ox + 1) * im.W + ow - 1) / ow);
+  float s = 0.f;
+  for (int y = y0; y < y1; ++y)
+    for (int x = x0; x < x1; ++x) s += im.at(n, c, y, x);
+  out[idx] = s / static_cast<float>((y1 - y0) * (x1 - x0));
+}
+
+__device__ __forceinline__ int reflect(int i, int n) {  // padding_mode='reflect' (no edge repeat)
+  if (i < 0) i = -i;
+  if (i >= n) i = 2 * (n - 1) - i;
+  return i;
+}
+
+// ---- low-resolution colour difference: blur_k(a*hb + b - lb), k x k normalised gaussian, reflect padding ----
+__global__ void blur_diff_kernel(const float* __restrict__ hb, const float* __restrict__ lb, float* __restrict__ diff,
+                                 const float* __restrict__ kern, int ksize, int N, int C, int h, int w,
+                                 const double* hr_sums, const double* lr_sums, double cnt_hr, double cnt_lr) {
+  const size_t total = static_cast<size_t>(N) * C * h * w;
+  const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int x = static_cast<int>(idx % w);
+  const int y = static_cast<int>((idx / w) % h);
+  const int nc = static_cast<int>(idx / (static_cast<size_t>(w) * h));
+  float a, b;
+  match_coeffs(hr_sums, lr_sums, nc, cnt_hr, cnt_lr, &a, &b);
+  const float* hp = hb + static_cast<size_t>(nc) * h * w;
+  const float* lp = lb + static_cast<size_t>(nc) * h * w;
+  const int r = ksize / 2;
+  float acc = 0.f;
+  for (int dy = 0; dy < ksize; ++dy) {
+    const int yy = reflect(y + dy - r, h);
+    for (int dx = 0; dx < ksize; ++dx) {
+      const int xx = reflect(x + dx - r, w);
+      acc += kern[dy * ksize + dx] * (a * hp[yy * w + xx] + b - lp[yy * w + xx]);
+    }
+  }
+  diff[idx] = acc;
+}
+
+// ---- finalise: clamp(a*hr + b - bilinear_up(diff), 0, 1) -> uint8 NHWC (truncating) or float NCHW ----------
+__global__ void finalize_kernel(Img hr, const float* __restrict__ diff, int dh, int dw, const double* hr_sums,
+                                const double* lr_sums, double cnt_hr, double cnt_lr, uint8_t* __restrict__ out_u8,
+                                float* __restrict__ out_f32, int round_u8) {
+  const size_t total = static_cast<size_t>(hr.N) * hr.H * hr.W;
+  const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int x = static_cast<int>(idx % hr.W);
+  const int y = static_cast<int>((idx / hr.W) % hr.H);
+  const int n = static_cast<int>(idx / (static_cast<size_t>(hr.W) * hr.H));
+  // bilinear, align_corners=False (area_pixel_compute_source_index): src = (dst + 0.5) * in/out - 0.5, clamped at 0
+  int y0 = 0, y1 = 0, x0 = 0, x1 = 0;
+  float ly = 0.f, lx = 0.f;
+  if (diff != nullptr) {
+    float sy = (y + 0.5f) * (static_cast<float>(dh) / hr.H) - 0.5f;
+    float sx = (x + 0.5f) * (static_cast<float>(dw) / hr.W) - 0.5f;
+    sy = sy < 0.f ? 0.f : sy;
+    sx = sx < 0.f ? 0.f : sx;
+    y0 = static_cast<int>(sy); x0 = static_cast<int>(sx);
+    y1 = y0 < dh - 1 ? y0 + 1 : y0;
+    x1 = x0 < dw - 1 ? x0 + 1 : x0;
+    ly = sy - y0; lx = sx - x0;
+  }
+  for (int c = 0; c < hr.C; ++c) {
+    const int nc = n * hr.C + c;
+    float a, b;
+    match_coeffs(hr_sums, lr_sums, nc, cnt_hr, cnt_lr, &a, &b);
+    float v = a * hr.at(n, c, y, x) + b;
+    if (diff != nullptr) {
+      const float* d = diff + static_cast<size_t>(nc) * dh * dw;
+      const float top = d[y0 * dw + x0] * (1.f - lx) + d[y0 * dw + x1] * lx;
+      const float bot = d[y1 * dw + x0] * (1.f - lx) + d[y1 * dw + x1] * lx;
+      v -= top * (1.f - ly) + bot * ly;
+    }
+    v = fminf(fmaxf(v, 0.f), 1.f);
+    if (out_u8 != nullptr) {
+      float f = v * 255.f;
+      if (round_u8) f = rintf(f);
+      out_u8[idx * hr.C + c] = static_cast<uint8_t>(f);
+    } else {
+      out_f32[((static_cast<size_t>(n) * hr.C + c) * hr.H + y) * hr.W + x] = v;
+    }
+  }
+}
+
+// ---- bicubic resize (A = -0.75, align_corners=False, clamped taps) of a float NCHW image -> clamp -> uint8 NHWC ----
+__device__ __forceinline__ float cubic1(float x, float A) { return ((A + 2.f) * x - (A + 3.f)) * x * x + 1.f; }
+__device__ __forceinline__ float cubic2(float x, float A) { return ((A * x - 5.f * A) * x + 8.f * A) * x - 4.f * A; }
+__global__ void bicubic_u8_kernel(const float* __restrict__ in, int N, int C, int H, int W, uint8_t* __restrict__ out,
+                                  int OH, int OW, int round_u8) {
+  const size_t total = static_cast<size_t>(N) * OH * OW;
+  const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int x = static_cast<int>(idx % OW);
+  const int y = static_cast<int>((idx / OW) % OH);
+  const int n = static_cast<int>(idx / (static_cast<size_t>(OW) * OH));
+  const float A = -0.75f;
+  const float sy = (y + 0.5f) * (static_cast<float>(H) / OH) - 0.5f;
+  const float sx = (x + 0.5f) * (static_cast<float>(W) / OW) - 0.5f;
+  const int iy = static_cast<int>(floorf(sy)), ix = static_cast<int>(floorf(sx));
+  const float ty = sy - iy, tx = sx - ix;
+  const float wy[4] = {cubic2(ty + 1.f, A), cubic1(ty, A), cubic1(1.f - ty, A), cubic2(2.f - ty, A)};
+  const float wx[4] = {cubic2(tx + 1.f, A), cubic1(tx, A), cubic1(1.f - tx, A), cubic2(2.f - tx, A)};
+  for (int c = 0; c < C; ++c) {
+    const float* p = in + (static_cast<size_t>(n) * C + c) * H * W;
+    float acc = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int yy = min(max(iy - 1 + j, 0), H - 1);
+      float row = 0.f;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int xx = min(max(ix - 1 + i, 0), W - 1);
+        row += wx[i] * p[static_cast<size_t>(yy) * W + xx];
+      }
+      acc += wy[j] * row;
+    }
+    float f = fminf(fmaxf(acc, 0.f), 1.f) * 255.f;
+    if (round_u8) f = rintf(f);
+    out[idx * C + c] = static_cast<uint8_t>(f);
+  }
+}
+
+// ---- 3x3 depthwise reflect "sharpen" + clamp, optional blend with another image (float NCHW in/out) ----------
+//   out = opacity * clamp(sum k[dy][dx] * x[reflect], 0, 1) + (1 - opacity) * other
+__global__ void sharpen_blend_kernel(Img x, float k_center, float k_side, float opacity, Img other, float* __restrict__ out) {
+  const size_t total = static_cast<size_t>(x.N) * x.C * x.H * x.W;
+  const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int px = static_cast<int>(idx % x.W);
+  const int py = static_cast<int>((idx / x.W) % x.H);
+  const int c = static_cast<int>((idx / (static_cast<size_t>(x.W) * x.H)) % x.C);
+  const int n = static_cast<int>(idx / (static_cast<size_t>(x.W) * x.H * x.C));
+  float acc = 0.f;
+#pragma unroll
+  for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+    for (int dx = -1; dx <= 1; ++dx)
+      acc += ((dy == 0 && dx == 0) ? k_center : k_side) * x.at(n, c, reflect(py + dy, x.H), reflect(px + dx, x.W));
+  float v = fminf(fmaxf(acc, 0.f), 1.f);
+  if (other.p != nullptr) v = opacity * v + (1.f - opacity) * other.at(n, c, py, px);
+  out[idx] = v;
+}
+
+inline unsigned blocks_for(size_t total, int threads) { return static_cast<unsigned>((total + threads - 1) / threads); }
+
+}  // namespace
+}  // namespace ss4k
+
+using namespace ss4k;
+
+extern "C" {
+
+int ss4k_glue_chan_stats(const void* img, int fmt, int n, int c, int h, int w, double* sums_dev, void* stream) {
+  if (!img || !sums_dev || fmt < 0 || fmt > 2) return SS4K_E_INVALID;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (cudaMemsetAsync(sums_dev, 0, sizeof(double) * 2 * n * c, st) != cudaSuccess) return SS4K_E_CUDA;
+  const size_t total = static_cast<size_t>(h) * w;
+  dim3 grid(static_cast<unsigned>(std::min<size_t>((total + 1023) / 1024, 296)), static_cast<unsigned>(n * c));
+  chan_stats_kernel<<<grid, 256, 0, st>>>(Img{img, fmt, n, c, h, w}, sums_dev);
+  return cudaGetLastError() == cudaSuccess ? SS4K_OK : SS4K_E_CUDA;
+}
+
+int ss4k_glue_area_pool(const void* img, int fmt, int n, int c, int h, int w, float* out_dev, int oh, int ow, void* stream) {
+  if (!img || !out_dev || fmt < 0 || fmt > 2 || oh < 1 || ow < 1) return SS4K_E_INVALID;
+  const size_t total = static_cast<size_t>(n) * c * oh * ow;
+  area_pool_kernel<<<blocks_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(Img{img, fmt, n, c, h, w}, out_dev, oh, ow);
+  return cudaGetLastError() == cudaSuccess ? SS4K_OK : SS4K_E_CUDA;
+}
+
+int ss4k_glue_blur_diff(const float* hb, const float* lb, float* diff, const float* kern_dev, int ksize, int n, int c, int h,
+                        int w, const double* hr_sums, const double* lr_sums, double cnt_hr, double cnt_lr, void* stream) {
+  if (!hb || !lb || !diff || !kern_dev) return SS4K_E_INVALID;
+  const size_t total = static_cast<size_t>(n) * c * h * w;
+  blur_diff_kernel<<<blocks_for(total, 128), 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(hb, lb, diff, kern_dev, ksize, n, c, h, w,
+                                                                                           hr_sums, lr_sums, cnt_hr, cnt_lr);
+  return cudaGetLastError() == cudaSuccess ? SS4K_OK : SS4K_E_CUDA;
+}
+
+int ss4k_glue_finalize(const void* hr, int fmt, int n, int c, int h, int w, const float* diff, int dh, int dw,
+                       const double* hr_sums, const double* lr_sums, double cnt_hr, double cnt_lr, uint8_t* out_u8,
+                       float* out_f32, int round_u8, void* stream) {
+  if (!hr || (!out_u8 && !out_f32) || fmt < 0 || fmt > 1) return SS4K_E_INVALID;
+  const size_t total = static_cast<size_t>(n) * h * w;
+  finalize_kernel<<<blocks_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(Img{hr, fmt, n, c, h, w}, diff, dh, dw, hr_sums,
+                                                                                          lr_sums, cnt_hr, cnt_lr, out_u8, out_f32, round_u8);
+  return cudaGetLastError() == cudaSuccess ? SS4K_OK : SS4K_E_CUDA;
+}
+
+int ss4k_glue_bicubic_u8(const float* in, int n, int c, int h, int w, uint8_t* out, int oh, int ow, int round_u8, void* stream) {
+  if (!in || !out) return SS4K_E_INVALID;
+  const size_t total = static_cast<size_t>(n) * oh * ow;
+  bicubic_u8_kernel<<<blocks_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(in, n, c, h, w, out, oh, ow, round_u8);
+  return cudaGetLastError() == cudaSuccess ? SS4K_OK : SS4K_E_CUDA;
+}
+
+int ss4k_glue_sharpen_blend(const void* x, int fmt, int n, int c, int h, int w, float strength, float opacity, const void* other,
+                            int other_fmt, float* out, void* stream) {
+  if (!x || !out || fmt < 0 || fmt > 2) return SS4K_E_INVALID;
+  // sharpen_ker (fsrcnn_upscaler.py:54-84): (sharp*s + identity*(1-s)) / sum, sharp = [-1..9..-1]
+  const float center = 9.f * strength + (1.f - strength), side = -strength;
+  const float sum = center + 8.f * side;
+  const size_t total = static_cast<size_t>(n) * c * h * w;
+  sharpen_blend_kernel<<<blocks_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      Img{x, fmt, n, c, h, w}, center / sum, side / sum, opacity, Img{other, other_fmt, n, c, h, w}, out);
+  return cudaGetLastError() == cudaSuccess ? SS4K_OK : SS4K_E_CUDA;
+}
+
+}  // extern "C"

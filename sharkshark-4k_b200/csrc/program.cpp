@@ -38,7 +38,7 @@ int final_out_mode(int out_fmt) {
 std::string build_srvgg(const PlanCfgLite& c, Program* P) {
   const int s = c.scale;
   if (s != 2 && s != 4 && s != 1 && s != 3) return "SRVGG: unsupported upscale";
-  if (c.out_fmt != 0) return "SRVGG: only float NCHW output is implemented";
+  if (c.out_fmt != 0 && c.out_fmt != 1) return "SRVGG: output is float / half NCHW";
   const int nf = 64, nconv = c.depth > 0 ? c.depth : 16;
   const int cl = 3 * s * s;
   P->in_n = c.n; P->in_c = 3; P->in_h = c.h; P->in_w = c.w;
@@ -73,7 +73,7 @@ std::string build_srvgg(const PlanCfgLite& c, Program* P) {
   L.mode = kModeConv3; L.n = c.n; L.cin = nf; L.cout = cl;
   L.in_buf = cur; L.in_h = c.h; L.in_w = c.w; L.in_pitch = nf;
   L.act = kActNone;
-  L.out_mode = kOutPSNCHWF32; L.out_buf = kBufExternalOut; L.out_h = c.h; L.out_w = c.w; L.ps_r = s;
+  L.out_mode = c.out_fmt == 1 ? kOutPSNCHWF16 : kOutPSNCHWF32; L.out_buf = kBufExternalOut; L.out_h = c.h; L.out_w = c.w; L.ps_r = s;
   L.base_buf = in16; L.base_pitch = 16;
   P->add_conv(L);
   return "";

@@ -56,6 +56,7 @@ struct ConvSpec {
   int neg_first = 0;                // negate weights and bias of the first k output channels (BSVD none_minus)
   int res1_nch = 0;                 // > 0: add only the first k channels of res1
   int tshift = 0;                   // 1: temporal-shift scatter store with fold = `fold` (time == batch index)
+  int in_ring = 0, out_ring = 0;    // BSVD streaming: images (ring slots) of the input / output tensors (0: n)
   double flops() const;
 };
 
@@ -90,6 +91,7 @@ struct Program {
 
 struct PlanCfgLite {
   int arch, n, h, w, scale, depth, tile, tile_pad, act_mode, in_fmt, out_fmt;
+  int bsvd_stream = 0;  // 1: BSVD program for the streaming engine (separate buffers for temp1 / temp2)
 };
 
 // returns "" on success, else an error message

@@ -171,6 +171,13 @@ def build_model(factor=4, device=0, input_shape=(720, 1280), batch_size=8, denoi
                                      [args.denoise_strength, 1 - args.denoise_strength])
     elif isinstance(state_dict, (list, tuple)):
         state_dict = dni(state_dict[0], state_dict[1], [args.denoise_strength, 1 - args.denoise_strength])
+    # depth follows the weights actually supplied (the zoo entry is the published architecture)
+    if arch == L.ARCH_RRDB:
+        blocks = {int(k.split('.')[1]) for k in state_dict if k.startswith('body.') and '.rdb1.conv1.weight' in k}
+        depth = max(blocks) + 1 if blocks else depth
+    else:
+        convs = [k for k, v in state_dict.items() if k.startswith('body.') and k.endswith('.weight') and v.ndim == 4]
+        depth = len(convs) - 2 if len(convs) >= 2 else depth
     cls = NativeSRVGG if arch == L.ARCH_SRVGG else NativeRRDBNet
     kw = dict(device=device, act_mode=act_mode, tile=args.tile, tile_pad=args.tile_pad)
     if arch == L.ARCH_SRVGG:

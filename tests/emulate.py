@@ -167,7 +167,7 @@ def run_program(prog, sd, x, quant=None):
         elif om == 6:
             f = torch.clamp(v, 0, 1) * 255
             result = (torch.round(f) if c["round_u8"] else f).to(torch.uint8).permute(0, 2, 3, 1)
-        elif om == 2:    # PixelShuffle(r) + nearest-upsampled base image
+        elif om in (2, 7):    # PixelShuffle(r) + nearest-upsampled base image
             r = c["ps_r"]
             v = F.pixel_shuffle(v, r)
             base = _nchw(bufs[c["base_buf"]][..., :v.shape[1]])

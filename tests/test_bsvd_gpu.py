@@ -65,3 +65,29 @@ def test_bsvd_constructor_init_report(engine):
     rel = (got.float().cpu() - want).abs().max().item() / want.abs().max().item()
     print(f"BSVD-32 (constructor init) fp16: PSNR {psnr:.1f} dB, max|err| {maxabs:.2f}/255, rel {rel:.2e}")
     assert psnr >= 45 and rel < 5e-3
+
+
+def test_bsvd_streaming_equals_clip(engine):
+    """Ring-buffer streaming (one frame per push, 16 frames of latency, flush at the end) must reproduce the clip
+    result; a second clip after reset() must not see state of the first (model.py:579)."""
+    sd = bsvd.build_bsvd32(0, weight_scale=0.5)
+    model = native_bsvd.NativeBSVD(sd, device=0)
+    x = _clip(21, 32, 136, seed=11).cuda()
+    clip = model(x)[0]
+    s = model.stream(32, 136)
+    assert s.latency == 16
+    outs = []
+    for i in range(21):
+        o = s.push(x[0, i])
+        assert (o is None) == (i < 16)
+        if o is not None:
+            outs.append(o)
+    outs += list(s.flush())
+    got = torch.cat(outs, dim=0)
+    assert tuple(got.shape) == (21, 3, 32, 136)
+    assert (got - clip).abs().max().item() <= 1e-3
+    s.reset()
+    x2 = _clip(3, 32, 136, seed=12).cuda()
+    got2 = torch.cat([o for o in (s.push(x2[0, i]) for i in range(3)) if o is not None] + list(s.flush()), dim=0)
+    assert (got2 - model(x2)[0]).abs().max().item() <= 1e-3
+    assert (model.streaming_forward(x2[0]) - got2).abs().max().item() == 0.0

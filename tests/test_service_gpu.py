@@ -1,0 +1,85 @@
+"""GPU parity of the drop-in upscaler service (uint8 frames in -> uint8 frames out) against the oracle glue
+(oracle/glue.py, a line-by-line fp32 restatement of fsrcnn_upscaler.py:168-326) on the same seeded weights."""
+import pytest
+import torch
+
+from ss4k_b200 import service
+from oracle import bsvd, glue, rrdbnet, srvgg
+
+pytestmark = pytest.mark.gpu
+
+
+def _cmp(got, want, max_lsb=3, mean_lsb=0.6):
+    assert got.dtype == torch.uint8 and got.shape == want.shape, (got.shape, want.shape)
+    d = (got.cpu().int() - want.int()).abs()
+    print(f"uint8 diff: mean {d.float().mean().item():.3f}, max {d.max().item()}, >1 LSB {100.0 * (d > 1).float().mean().item():.3f}%")
+    assert d.max().item() <= max_lsb and d.float().mean().item() <= mean_lsb
+
+
+def _frames(n, h, w, seed):
+    g = torch.Generator().manual_seed(seed)
+    base = torch.rand(n, h // 8 + 1, w // 8 + 1, 3, generator=g)
+    up = torch.nn.functional.interpolate(base.permute(0, 3, 1, 2), size=(h, w), mode="bilinear").permute(0, 2, 3, 1)
+    return (up * 255 + torch.randn(n, h, w, 3, generator=g) * 6).clamp(0, 255).to(torch.uint8)
+
+
+def test_upscale_multi_rrdb_x2(engine):
+    """Default wiring (upscale_multi): RRDBNet x2, colour-distribution + local colour match, uint8 out."""
+    torch.manual_seed(0)
+    net = rrdbnet.RRDBNet(3, 3, 2, 64, 2, 32).eval()
+    frames = _frames(2, 96, 160, 1)
+    want = glue.upscale_multi(frames, net, lr_shape=(720, 1280), output_shape=(192, 320))
+    svc = service.FsrcnnUpscalerService(lr_level=3, device=0, denoising=False, model_name='RealESRGAN_x2plus',
+                                        state_dict=net.state_dict(), batch_size=2)
+    svc.proc_init()
+    svc.output_shape = (192, 320)
+    got = svc.upscale(frames.cuda())
+    torch.cuda.synchronize()
+    _cmp(got, want)
+
+
+def test_upscale_multi_srvgg_x4_bicubic_down(engine):
+    """The reference's live default: SRVGG x4 then bicubic resize to output_shape (fsrcnn_upscaler.py:222-231),
+    with the LR area-downscale branch (:173-176) because the input is larger than lr_shape."""
+    torch.manual_seed(0)
+    net = srvgg.SRVGGNetCompact(3, 3, 64, 16, 4).eval()
+    frames = _frames(1, 2 * 360, 2 * 640, 2)
+    want = glue.upscale_multi(frames, net, lr_shape=(360, 640), output_shape=(720, 1280))
+    svc = service.FsrcnnUpscalerService(lr_level=0, device=0, denoising=False, model_name='realesr-animevideov3',
+                                        state_dict=net.state_dict())
+    svc.proc_init()
+    svc.output_shape = (720, 1280)
+    got = svc.upscale(frames.cuda())
+    _cmp(got, want)
+
+
+def test_upscale_single_denoise_then_rrdb(engine):
+    """The composition the north star names (dead by default in the reference): BSVD denoise
+    (F = 1 clip, noise map 0.05 on the first frame) -> sharpen/blend -> RRDBNet x2 -> HR sharpen -> match."""
+    torch.manual_seed(0)
+    net = rrdbnet.RRDBNet(3, 3, 2, 64, 2, 32).eval()
+    sd = bsvd.build_bsvd32(0, weight_scale=0.5)
+    frames = _frames(2, 360, 640, 3)
+    den = lambda x: bsvd.bsvd_forward(sd, x)  # noqa: E731
+    want0 = glue.upscale_single(frames[0], net, (360, 640), (720, 1280), den, 0.75, True)
+    want1 = glue.upscale_single(frames[1], net, (360, 640), (720, 1280), den, 0.75, False)
+    svc = service.FsrcnnUpscalerService(lr_level=0, device=0, denoising=True, denoise_rate=0.75,
+                                        model_name='RealESRGAN_x2plus', state_dict=net.state_dict(),
+                                        denoise_state_dict=sd)
+    svc.single_mode = True
+    svc.proc_init()
+    svc.output_shape = (720, 1280)
+    got = svc.upscale(frames.cuda())
+    _cmp(got[0], want0)
+    _cmp(got[1], want1)
+
+
+def test_proc_job_recieved_roundtrip(engine):
+    torch.manual_seed(0)
+    net = srvgg.SRVGGNetCompact(3, 3, 64, 16, 4).eval()
+    svc = service.FsrcnnUpscalerService(lr_level=0, device=0, denoising=False, model_name='realesr-animevideov3',
+                                        state_dict=net.state_dict())
+    svc.proc_init()
+    job = service.UpscalerQueueEntry(frames=_frames(1, 40, 72, 4).cuda(), step=7)
+    out = svc.proc_job_recieved(job)
+    assert out.step == 7 and tuple(out.frames.shape) == (1, 160, 288, 3) and out.frames.dtype == torch.uint8
