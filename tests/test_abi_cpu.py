@@ -1,0 +1,49 @@
+"""The C-ABI library loads and exports every symbol include/ss4k.h declares; the ctypes table covers them all;
+without a GPU the engine refuses to start (no CPU fallback) instead of crashing."""
+import ctypes
+import os
+import re
+
+import ss4k_b200
+from ss4k_b200 import _lib as L
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    src = open(os.path.join(ROOT, "include", "ss4k.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(ss4k_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_every_declared_symbol_is_exported_and_bound(lib):
+    names = _declared()
+    assert len(names) >= 30
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in ss4k.h but not exported by libss4k.so"
+        assert n in L.SYMBOLS, f"{n} has no ctypes signature in _lib.SYMBOLS"
+    assert lib.ss4k_abi_version() == 1
+
+
+def test_no_cpu_fallback(lib):
+    import torch
+    if torch.cuda.is_available():
+        return
+    h = ctypes.c_void_p()
+    rc = lib.ss4k_create(0, ctypes.byref(h))
+    assert rc == -2 and not h.value                       # SS4K_E_NODEVICE
+    assert b"no CPU path" in lib.ss4k_last_error(None)
+    try:
+        ss4k_b200.Engine(0)
+        raise AssertionError("Engine() must fail without a GPU")
+    except L.Ss4kError:
+        pass
+
+
+def test_product_package_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "sharkshark-4k_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cpp", ".h", ".cuh", ".inc")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), f
