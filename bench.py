@@ -224,7 +224,8 @@ def run_native(args, rank, world, local_rank):
                        "weights": "random init (upstream basicsr init, seed 0)",
                        "l2": "no flush: one step streams > 1 GB of activation slabs (>> 126 MB L2); 3 input buffers rotated",
                        "desc_mode": eng.desc_mode, "parallelism": f"frame-sharded x{world}",
-                       "launch": "one CUDA graph per step (prep + %d conv kernels)" % (plan.launches - 1)},
+                       "launch": "%d of %d kernels per step replay from one CUDA graph; programmatic dependent launch %s"
+                                 % (plan.graph_steps, plan.launches, "off" if os.environ.get("SS4K_NO_PDL") else "on")},
             "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": plan.in_bytes, "d2h_bytes_per_step": plan.out_bytes},
             "gpu_launches": int(launches),
             "clocks": clk.summary(),

@@ -120,6 +120,8 @@ int ss4k_plan_out_shape(const ss4k_plan* plan, int32_t out_nchw[4]);
 double ss4k_plan_flops(const ss4k_plan* plan);
 /* number of kernel launches (graph nodes included) one ss4k_run issues */
 int ss4k_plan_launches(const ss4k_plan* plan);
+/* how many of those steps replay from the plan's CUDA graph (0: graph capture unavailable / disabled) */
+int ss4k_plan_graph_steps(const ss4k_plan* plan);
 /* JSON description of the layer program (buffers, convs, epilogues); malloc'd, free with ss4k_free.
  * Works without a GPU when the plan was built with ss4k_plan_dry (host-side planner only). */
 int ss4k_plan_dry(const ss4k_plan_cfg* cfg, char** out_json);

@@ -1,0 +1,13 @@
+"""clock64 phase stamps of the streaming conv kernel (CTA 0, middle, last), cycles since kernel entry:
+[0 entry, 1 setup done, 2 weights landed (MMA warp), 3 first slab landed, 4 last MMA issued, 5 first accumulator
+complete (epilogue warp 2), 6 last row stored, 7 stores drained, 8 TMEM freed]"""
+import json, os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "scripts"))
+import ss4k_b200
+from bench_conv import bench
+eng = ss4k_b200.Engine.get(0)
+for cin, cout, n in [(64, 32, 1), (160, 32, 1), (192, 64, 1), (64, 64, 1), (64, 32, 4)]:
+    for flags in (0, 7):
+        print(json.dumps(bench(eng, cin, cout, 360, 640, n=n, pitch=192 if cout == 32 or cin == 192 else 0, flags=flags, trace=1)))

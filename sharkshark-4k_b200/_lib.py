@@ -42,6 +42,7 @@ SYMBOLS = {
     "ss4k_plan_out_shape": (_i, [_vp, ctypes.POINTER(ctypes.c_int32 * 4)]),
     "ss4k_plan_flops": (ctypes.c_double, [_vp]),
     "ss4k_plan_launches": (_i, [_vp]),
+    "ss4k_plan_graph_steps": (_i, [_vp]),
     "ss4k_plan_dry": (_i, [ctypes.POINTER(PlanCfg), ctypes.POINTER(_vp)]),
     "ss4k_free": (None, [_vp]),
     "ss4k_run": (_i, [_vp, _vp, _vp, _vp]),

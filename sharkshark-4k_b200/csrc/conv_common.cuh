@@ -164,6 +164,25 @@ __device__ __forceinline__ void umma_f16_elect(uint32_t tmem_d, uint64_t desc_a,
       : "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+
+// Same, with the 64-bit shared-memory descriptors given as their low words (start address >> 4); the high word
+// (SBO = 1024 B, version 1, swizzle 128B) is a constant.  Keeps the per-MMA issue cost at a couple of uniform adds.
+__device__ __forceinline__ void umma_f16_lo(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, e;\n\t"
+      ".reg .b64 da, db;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "mov.b64 da, {%1, %5};\n\t"
+      "mov.b64 db, {%2, %5};\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t"
+      "}"
+      :
+      : "r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(0x40004040u)
+      : "memory");
+}
 __device__ __forceinline__ void umma_commit_elect(uint32_t bar) {
   asm volatile(
       "{\n\t"
@@ -343,6 +362,14 @@ __device__ __forceinline__ void epilogue_chunk(const Epilogue& E, int mode, int 
             store8(E.out, o2, v + 8 * h, bf16);
             if (E.out_lo != nullptr) store8_lo(E.out_lo, o2, v + 8 * h, bf16);
           }
+        }
+      } else if (E.up2_store) {  // nearest-x2 upsample fused into the store (RRDBNet upsample stages)
+#pragma unroll
+        for (int ab = 0; ab < 4; ++ab) {
+          const size_t p2 = (static_cast<size_t>(n) * 2 * E.out_h + 2 * oy + (ab >> 1)) * (2 * E.out_w) + 2 * ox + (ab & 1);
+          const size_t o2 = p2 * E.out_pitch + E.out_coff + oc;
+          store8(E.out, o2, v, bf16);
+          store8(E.out, o2 + 8, v + 8, bf16);
         }
       } else {
         store8(E.out, off, v, bf16);

@@ -83,6 +83,8 @@ struct Epilogue {
   int64_t off_prev, off_next;  // element offsets from frame t's tensor to frame t-1's / t+1's
   int32_t t0, t_count;         // frame index of image n = 0 of this launch, clip length
   int64_t res1_lo_off, res2_lo_off;  // split mode: element offset of the residual's low halves (0: none)
+  int32_t up2_store;     // 1: NHWC output is the nearest-x2 upsampled image: every pixel is stored at (2y+a, 2x+b), a, b in {0,1}
+                         //    (out_h / out_w stay the conv's own grid; the destination tensor is 2*out_h x 2*out_w)
 };
 
 struct ConvParams {
@@ -129,7 +131,8 @@ struct StreamParams {
   CUtensorMap tmB;      // same tensor, box (64, NOUT): the per-chunk bias tile (bias hi/lo in K columns 0/1)
   CUtensorMap tmO;      // NHWC output, 4-D (C, W, H, N), box (NOUT, 32, 1, 1), swizzled: TMA store of the fast path
   Epilogue ep;
-  int32_t fast_store;   // 1: plain NHWC output -> registers -> swizzled smem tile -> TMA store
+  int32_t fast_store;   // 1: plain NHWC output -> registers -> swizzled smem tile -> TMA store;
+                        // 2: the same tile stored four times through a 5-D (C, b, W, a, N*H) map: nearest-x2 upsample
   int32_t bias_row0;    // first row of the bias tiles inside the weight tensor
   uint8_t a_kb[kMaxSKB];  // source 64-channel block of K block i
   uint8_t a_tm[kMaxSKB];  // which activation tensor map
@@ -142,6 +145,7 @@ struct StreamParams {
   int32_t* err;
   int32_t dbg_flags;
   int32_t n_in0, n_out0;  // added to the image coordinate of TMA loads / stores (BSVD streaming: ring slots)
+  long long* trace;       // debug: per-CTA clock64 stamps [grid][16] (null in production)
 };
 
 }  // namespace ss4k

@@ -66,6 +66,16 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* tm, uint32_t src
                : "l"(reinterpret_cast<uint64_t>(tm)), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
                : "memory");
 }
+__device__ __forceinline__ void tma_store_5d(const CUtensorMap* tm, uint32_t src, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];"
+               :
+               : "l"(reinterpret_cast<uint64_t>(tm)), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+               : "memory");
+}
+// programmatic dependent launch: let the next kernel of the stream start its prologue early / wait for the
+// previous kernel's results before touching them
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
@@ -122,7 +132,11 @@ conv3x3_stream_kernel(const __grid_constant__ StreamParams P) {
 
   const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);  // warp-uniform for ptxas
   const int lane = threadIdx.x & 31;
+  long long* const trace = P.trace != nullptr ? P.trace + blockIdx.x * 16 : nullptr;
+#define SS4K_TRACE(i) do { if (trace != nullptr && lane == 0) trace[i] = clock64(); } while (0)
+  if (warp == 0) SS4K_TRACE(0);
 
+  pdl_launch_dependents();
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&P.tmA[0]);
     prefetch_tmap(&P.tmW);
@@ -163,6 +177,7 @@ conv3x3_stream_kernel(const __grid_constant__ StreamParams P) {
   // using the constant keeps TMEM addresses in uniform registers
   if (*tmem_slot_ptr != 0u) __trap();
   constexpr uint32_t tmem_base = 0u;
+  if (warp == 0) SS4K_TRACE(1);
 
   const int u0 = static_cast<int>(static_cast<int64_t>(blockIdx.x) * P.total_units / gridDim.x);
   const int u1 = static_cast<int>(static_cast<int64_t>(blockIdx.x + 1) * P.total_units / gridDim.x);
@@ -174,6 +189,7 @@ conv3x3_stream_kernel(const __grid_constant__ StreamParams P) {
     int loaded_chunk = -1;
     int u = u0;
     Band b;
+    bool dep_ready = false;
     while (next_band(P, u, u1, b)) {
       if (b.chunk != loaded_chunk) {
         mbar_wait_u(w_empty, wph ^ 1);
@@ -187,6 +203,10 @@ conv3x3_stream_kernel(const __grid_constant__ StreamParams P) {
         __syncwarp();
         wph ^= 1;
         loaded_chunk = b.chunk;
+      }
+      if (!dep_ready) {  // weights are constants; the activations belong to the previous kernel of the stream
+        pdl_wait();
+        dep_ready = true;
       }
       const int r0 = b.yb > 0 ? b.yb - 1 : 0;
       const int r1 = b.ye < P.H ? b.ye : P.H - 1;
@@ -223,6 +243,7 @@ conv3x3_stream_kernel(const __grid_constant__ StreamParams P) {
       if (b.chunk != cur_chunk) {
         mbar_wait_u(w_full, wph);
         tcgen05_after_sync();
+        if (cur_chunk < 0) SS4K_TRACE(2);
         wph ^= 1;
         cur_chunk = b.chunk;
       }
@@ -239,8 +260,10 @@ conv3x3_stream_kernel(const __grid_constant__ StreamParams P) {
           for (int y = f_lo; y <= y_hi; ++y) {
             int s = qs + (y - b.yb), k = qk;
             while (s >= S) { s -= S; ++k; }
-            mbar_wait_u(acc_empty + 8 * s, (k & 1) ^ 1);
-            tcgen05_after_sync();
+            if (k > 0) {  // the slot's first use needs no drain
+              mbar_wait_u(acc_empty + 8 * s, (k & 1) ^ 1);
+              tcgen05_after_sync();
+            }
             if (!(P.dbg_flags & 1)) umma_f16_elect(tmem_base + static_cast<uint32_t>(s * NOUT), d_ones, d_bias, P.idesc[0], 0u);
           }
         }
@@ -257,19 +280,29 @@ conv3x3_stream_kernel(const __grid_constant__ StreamParams P) {
         for (int kb = 0; kb < P.nkb; ++kb) {
           mbar_wait_u(a_full + 8 * as, aph);
           tcgen05_after_sync();
-          const uint32_t arow = a_base + as * kASlotBytes;
+          if (trace != nullptr && lane == 0 && trace[3] == 0) trace[3] = clock64();
+          // descriptor low words (address >> 4): per-MMA offsets are compile-time constants
+          const uint32_t a_lo = (a_base + as * kASlotBytes) >> 4;
+          const uint32_t wA_lo = (w_base + static_cast<uint32_t>(kb * 3) * kWTile + boffA) >> 4;
+          const uint32_t wB_lo = (w_base + static_cast<uint32_t>(kb * 3) * kWTile + boffB) >> 4;
           const int nks = P.nks[kb];
           if (!(P.dbg_flags & 1)) {
+            if (nB == 0) {
 #pragma unroll
-            for (int kx = 0; kx < 3; ++kx) {
-              const uint32_t wt = w_base + static_cast<uint32_t>(kb * 3 + kx) * kWTile;
+              for (int kx = 0; kx < 3; ++kx) {
 #pragma unroll
-              for (int ks = 0; ks < 4; ++ks) {
-                if (ks < nks) {
-                  const uint64_t da = sdesc(arow + kx * kRowBytes + ks * 32);
-                  const uint32_t wb = wt + ks * 32;
-                  umma_f16_elect(colA, da, sdesc(wb + boffA), idA, 1u);
-                  if (nB > 0) umma_f16_elect(tmem_base, da, sdesc(wb + boffB), idB, 1u);
+                for (int ks = 0; ks < 4; ++ks)
+                  if (ks < nks) umma_f16_lo(colA, a_lo + (kx * kRowBytes + ks * 32) / 16, wA_lo + (kx * kWTile + ks * 32) / 16, idA, 1u);
+              }
+            } else {  // the accumulator ring wraps inside this row's slot range: two MMAs per step
+#pragma unroll
+              for (int kx = 0; kx < 3; ++kx) {
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) {
+                  if (ks < nks) {
+                    umma_f16_lo(colA, a_lo + (kx * kRowBytes + ks * 32) / 16, wA_lo + (kx * kWTile + ks * 32) / 16, idA, 1u);
+                    umma_f16_lo(tmem_base, a_lo + (kx * kRowBytes + ks * 32) / 16, wB_lo + (kx * kWTile + ks * 32) / 16, idB, 1u);
+                  }
                 }
               }
             }
@@ -295,6 +328,7 @@ conv3x3_stream_kernel(const __grid_constant__ StreamParams P) {
       b = nb;
       has = has_next;
     }
+    SS4K_TRACE(4);
   } else {
     // ======================================================= epilogue (warps 2..9)
     const Epilogue& E = P.ep;
@@ -308,6 +342,7 @@ conv3x3_stream_kernel(const __grid_constant__ StreamParams P) {
     int s = 0, k = 0, q = 0;
     int u = u0;
     Band b;
+    pdl_wait();  // residual loads and output stores touch tensors of the previous kernel
     while (next_band(P, u, u1, b)) {
       const int ax = b.strip * kTileW + m;
       const bool valid = ax < P.W;
@@ -329,6 +364,7 @@ conv3x3_stream_kernel(const __grid_constant__ StreamParams P) {
           }
           mbar_wait_u(acc_full + 8 * s, k & 1);
           tcgen05_after_sync();
+          if (warp == 2 && trace != nullptr && lane == 0 && trace[5] == 0) trace[5] = clock64();
           const uint32_t taddr = tmem_base + (static_cast<uint32_t>(qd * 32) << 16) + static_cast<uint32_t>(s * NOUT);
           uint32_t raw[NOUT];
 #pragma unroll
@@ -397,7 +433,13 @@ conv3x3_stream_kernel(const __grid_constant__ StreamParams P) {
               fence_proxy_async();
               __syncwarp();
               if (lane == 0) {
-                tma_store_4d(&P.tmO, stage, b.chunk * NOUT, b.strip * kTileW + qd * 32, y, b.n + P.n_out0);
+                if (P.fast_store == 2) {
+#pragma unroll
+                  for (int ab = 0; ab < 4; ++ab)
+                    tma_store_5d(&P.tmO, stage, b.chunk * NOUT, ab & 1, b.strip * kTileW + qd * 32, ab >> 1, (b.n + P.n_out0) * P.H + y);
+                } else {
+                  tma_store_4d(&P.tmO, stage, b.chunk * NOUT, b.strip * kTileW + qd * 32, y, b.n + P.n_out0);
+                }
                 bulk_commit();
               }
             } else if (valid) {
@@ -414,7 +456,9 @@ conv3x3_stream_kernel(const __grid_constant__ StreamParams P) {
         if (++s == S) { s = 0; ++k; }
       }
     }
+    if (warp == 2) SS4K_TRACE(6);
     if (fast && lane == 0) bulk_wait0();  // all output tiles written before the CTA releases its shared memory
+    if (warp == 2) SS4K_TRACE(7);
   }
 
   // ---------------------------------------------------------------- teardown
@@ -425,7 +469,9 @@ conv3x3_stream_kernel(const __grid_constant__ StreamParams P) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
                  "r"(static_cast<uint32_t>(kTmemCols))
                  : "memory");
+    SS4K_TRACE(8);
   }
+#undef SS4K_TRACE
 }
 
 // ---------------------------------------------------------------- host launcher
@@ -437,15 +483,32 @@ cudaError_t conv_stream_prepare() {
   return e;
 }
 
-cudaError_t conv_stream_launch(const StreamParams& p, int nout, int grid, cudaStream_t stream) {
+template <int NOUT>
+static cudaError_t launch_one(const StreamParams& p, int grid, cudaStream_t stream, bool pdl) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kStreamThreads);
+  cfg.dynamicSmemBytes = kSmemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, conv3x3_stream_kernel<NOUT>, p);
+}
+
+// pdl: programmatic dependent launch -- this kernel may start its prologue (barrier init, TMEM allocation,
+// weight loads) while the previous kernel of the stream drains; it waits (griddepcontrol.wait) before it
+// touches activations.
+cudaError_t conv_stream_launch(const StreamParams& p, int nout, int grid, cudaStream_t stream, bool pdl) {
   switch (nout) {
-    case 16: conv3x3_stream_kernel<16><<<grid, kStreamThreads, kSmemBytes, stream>>>(p); break;
-    case 32: conv3x3_stream_kernel<32><<<grid, kStreamThreads, kSmemBytes, stream>>>(p); break;
-    case 48: conv3x3_stream_kernel<48><<<grid, kStreamThreads, kSmemBytes, stream>>>(p); break;
-    case 64: conv3x3_stream_kernel<64><<<grid, kStreamThreads, kSmemBytes, stream>>>(p); break;
+    case 16: return launch_one<16>(p, grid, stream, pdl);
+    case 32: return launch_one<32>(p, grid, stream, pdl);
+    case 48: return launch_one<48>(p, grid, stream, pdl);
+    case 64: return launch_one<64>(p, grid, stream, pdl);
     default: return cudaErrorInvalidValue;
   }
-  return cudaGetLastError();
 }
 
 }  // namespace ss4k

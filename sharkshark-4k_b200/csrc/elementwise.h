@@ -11,7 +11,7 @@ cudaError_t conv_tc_launch(const ConvParams& p, int grid, cudaStream_t stream);
 
 // conv_stream.cu
 cudaError_t conv_stream_prepare();
-cudaError_t conv_stream_launch(const StreamParams& p, int nout, int grid, cudaStream_t stream);
+cudaError_t conv_stream_launch(const StreamParams& p, int nout, int grid, cudaStream_t stream, bool pdl);
 
 // elementwise.cu
 // in_fmt: SS4K_FMT_* ; out: [N, H/us, W/us, pitch] 16-bit NHWC (out_lo: low halves for split mode or null)

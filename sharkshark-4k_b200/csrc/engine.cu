@@ -469,6 +469,7 @@ void fill_epilogue(const ConvSpec& cs, bool bf16, BufPtr bufptr, float* d_bias, 
   E.base_pitch = cs.base_pitch;
   E.slope_const = cs.const_slope;
   E.res1_nch = cs.res1_nch;
+  E.up2_store = cs.up2_store;
   E.t0 = 0; E.t_count = cs.n;
   E.off_prev = E.off_next = 0;
   E.res1_lo_off = E.res2_lo_off = 0;
@@ -547,13 +548,25 @@ int materialize_stream(ss4k_ctx* ctx, const ConvSpec& cs, const HostTensor& W, c
     cuuint64_t strides[3] = {cs.out_pitch * eb, static_cast<cuuint64_t>(cs.out_w) * cs.out_pitch * eb,
                              static_cast<cuuint64_t>(cs.out_h) * cs.out_w * cs.out_pitch * eb};
     cuuint32_t box[4] = {static_cast<cuuint32_t>(pk.nout), 32, 1, 1};
-    cuuint32_t es[4] = {1, 1, 1, 1};
+    cuuint32_t es[5] = {1, 1, 1, 1, 1};
     const CUtensorMapSwizzle sw = pk.nout == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (pk.nout == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
     void* base = reinterpret_cast<uint8_t*>(bufptr(cs.out_buf)) + static_cast<size_t>(cs.out_coff) * 2;
-    CUresult r = ctx->encode(&p.tmO, dt, 4, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
-                             CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r;
+    if (cs.up2_store) {
+      // nearest-x2 upsample in the store: destination viewed as (C, b, W, a, N*H): pixel (2y+a, 2x+b) of the 2H x 2W image
+      const cuuint64_t pb = cs.out_pitch * eb;
+      cuuint64_t d5[5] = {static_cast<cuuint64_t>(cavail), 2, static_cast<cuuint64_t>(cs.out_w), 2,
+                          static_cast<cuuint64_t>(cs.out_h) * (cs.out_ring ? cs.out_ring : cs.n)};
+      cuuint64_t s5[4] = {pb, 2 * pb, 2 * static_cast<cuuint64_t>(cs.out_w) * pb, 4 * static_cast<cuuint64_t>(cs.out_w) * pb};
+      cuuint32_t b5[5] = {static_cast<cuuint32_t>(pk.nout), 1, 32, 1, 1};
+      r = ctx->encode(&p.tmO, dt, 5, base, d5, s5, b5, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    } else {
+      r = ctx->encode(&p.tmO, dt, 4, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                      CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    }
     if (r != CUDA_SUCCESS) return fail(ctx, SS4K_E_CUDA, fmt("cuTensorMapEncodeTiled(stream output, %s) failed: %d", cs.name.c_str(), (int)r));
-    p.fast_store = 1;
+    p.fast_store = cs.up2_store ? 2 : 1;
   }
   p.nkb = pk.nkb;
   for (int kb = 0; kb < pk.nkb; ++kb) { p.a_kb[kb] = static_cast<uint8_t>(kb); p.a_tm[kb] = 0; p.nks[kb] = pk.nks[kb]; }
@@ -575,14 +588,16 @@ int materialize_stream(ss4k_ctx* ctx, const ConvSpec& cs, const HostTensor& W, c
   return SS4K_OK;
 }
 
+const bool g_use_pdl = getenv("SS4K_NO_PDL") == nullptr;
+
 cudaError_t launch_exec(const ConvExec& c, void* ext_out, cudaStream_t st) {
   if (c.stream) {
     if (c.ext_out) {
       StreamParams p = c.sp;
       p.ep.out = ext_out;
-      return conv_stream_launch(p, c.nout, c.grid, st);
+      return conv_stream_launch(p, c.nout, c.grid, st, g_use_pdl);
     }
-    return conv_stream_launch(c.sp, c.nout, c.grid, st);
+    return conv_stream_launch(c.sp, c.nout, c.grid, st, g_use_pdl);
   }
   if (c.ext_out) {
     ConvParams p = c.p;
@@ -943,6 +958,7 @@ int ss4k_plan_out_shape(const ss4k_plan* pl, int32_t out_nchw[4]) {
 }
 double ss4k_plan_flops(const ss4k_plan* pl) { return pl ? pl->prog.flops : 0.0; }
 int ss4k_plan_launches(const ss4k_plan* pl) { return pl ? static_cast<int>(pl->prog.steps.size()) : 0; }
+int ss4k_plan_graph_steps(const ss4k_plan* pl) { return (pl && pl->graph) ? pl->graph_last - pl->graph_first + 1 : 0; }
 int ss4k_plan_io_bytes(const ss4k_plan* pl, int64_t* in_bytes, int64_t* out_bytes) {
   if (!pl) return SS4K_E_INVALID;
   if (in_bytes) *in_bytes = pl->in_bytes;
@@ -1191,6 +1207,11 @@ int ss4k_debug_bench_conv(ss4k_ctx* ctx, const ss4k_conv_desc* d, int slab_pitch
   auto bufptr = [&](int id) -> void* { return id >= 0 ? b[id] : nullptr; };
   int rc = materialize_conv(ctx, cs, W, nullptr, nullptr, d->act_mode, bufptr, &ex);
   if (rc == SS4K_OK) {
+    long long* d_trace = nullptr;
+    if (ex.stream && d->reserved[7] == 1) {
+      cudaMalloc(&d_trace, sizeof(long long) * 16 * 148);
+      cudaMemset(d_trace, 0, sizeof(long long) * 16 * 148);
+    }
     if (ex.stream) {
       ex.sp.dbg_flags = dbg_flags;
       if (d->reserved[3] > 0) ex.sp.a_slots = std::min(ex.sp.a_slots, d->reserved[3]);
@@ -1220,6 +1241,24 @@ int ss4k_debug_bench_conv(ss4k_ctx* ctx, const ss4k_conv_desc* d, int slab_pitch
     *ms_per_launch = ms / std::max(1, iters);
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     ctx->launches += iters + 3;
+    std::string trace_js;
+    if (d_trace != nullptr) {  // one extra traced launch: clock64 stamps of CTA 0 and the last CTA, relative to entry
+      cudaMemset(d_trace, 0, sizeof(long long) * 16 * 148);
+      ex.sp.trace = d_trace;
+      launch_exec(ex, nullptr, ctx->stream);
+      cudaStreamSynchronize(ctx->stream);
+      ex.sp.trace = nullptr;
+      std::vector<long long> h(16 * 148);
+      cudaMemcpy(h.data(), d_trace, sizeof(long long) * 16 * 148, cudaMemcpyDeviceToHost);
+      cudaFree(d_trace);
+      trace_js = ",\"trace\":[";
+      for (int b : {0, ex.grid / 2, ex.grid - 1}) {
+        trace_js += (b == 0 ? "[" : ",[");
+        for (int i = 0; i < 9; ++i) trace_js += fmt("%s%lld", i ? "," : "", h[b * 16 + i] ? h[b * 16 + i] - h[b * 16] : -1LL);
+        trace_js += "]";
+      }
+      trace_js += "]";
+    }
     if (out_json) {
       std::string js;
       if (ex.stream)
@@ -1228,6 +1267,7 @@ int ss4k_debug_bench_conv(ss4k_ctx* ctx, const ss4k_conv_desc* d, int slab_pitch
       else
         js = fmt("{\"kernel\":\"tile\",\"R\":%d,\"n_tiles\":%d,\"grid\":%d,\"a_slots\":%d,\"w_slots\":%d,\"w_resident\":%d,\"nkb\":%d,\"n_cta\":%d,\"n_chunks\":%d}",
                  ex.p.R, ex.p.n_tiles, ex.grid, ex.p.a_slots, ex.p.w_slots, ex.p.w_resident, ex.p.nkb, ex.p.n_cta, ex.p.n_chunks);
+      if (!trace_js.empty()) js.insert(js.size() - 1, trace_js);
       *out_json = static_cast<char*>(malloc(js.size() + 1));
       memcpy(*out_json, js.c_str(), js.size() + 1);
     }

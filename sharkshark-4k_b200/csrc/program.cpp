@@ -100,6 +100,7 @@ std::string build_rrdb(const PlanCfgLite& c, Program* P) {
   const int up1 = P->add_buf("up1", c.n, th * 2, tw * 2, nf);
   const int up2 = P->add_buf("up2", c.n, th * 4, tw * 4, nf);
   const int hr = P->add_buf("hr", c.n, th * 4, tw * 4, nf);
+  const int hr2 = P->add_buf("hr2", c.n, th * 4, tw * 4, nf);
 
   PrepSpec pp;
   pp.in_fmt = c.in_fmt; pp.c = 3; pp.h = c.h; pp.w = c.w; pp.n = c.n; pp.unshuffle = us; pp.out_buf = in16;
@@ -145,28 +146,31 @@ std::string build_rrdb(const PlanCfgLite& c, Program* P) {
       P->add_conv(v);
     }
   }
-  {  // feat = feat + conv_body(body(feat))   (in place over the skip buffer)
+  // F.interpolate(nearest, x2) is fused into the STORE of the conv in front of each upsample stage: the epilogue
+  // writes every pixel 2x2 times (four TMA stores of the same tile), so conv_up1 / conv_up2 are plain 3x3 convs on
+  // the upsampled grid through the row-streaming kernel.
+  {  // feat + conv_body(body(feat)), stored nearest-x2 upsampled
     ConvSpec v = base_conv("conv_body", S[0], th, tw, slab, nf, nf);
-    v.out_buf = feat; v.out_pitch = nf;
+    v.out_buf = up1; v.out_pitch = nf; v.up2_store = 1;
     v.res1_buf = feat; v.res1_pitch = nf; v.beta1 = 1.f;
     P->add_conv(v);
   }
-  {  // lrelu(conv_up1(nearest x2)) and lrelu(conv_up2(nearest x2)): upsample fused as 4-phase 2x2 convs
-    ConvSpec v = base_conv("conv_up1", feat, th, tw, nf, nf, nf);
-    v.mode = kModeUp2; v.act = kActPRelu; v.const_slope = 0.2f;
-    v.out_buf = up1; v.out_pitch = nf; v.out_h = th * 2; v.out_w = tw * 2;
+  {
+    ConvSpec v = base_conv("conv_up1", up1, th * 2, tw * 2, nf, nf, nf);
+    v.act = kActPRelu; v.const_slope = 0.2f;
+    v.out_buf = up2; v.out_pitch = nf; v.up2_store = 1;
     P->add_conv(v);
-    ConvSpec u = base_conv("conv_up2", up1, th * 2, tw * 2, nf, nf, nf);
-    u.mode = kModeUp2; u.act = kActPRelu; u.const_slope = 0.2f;
-    u.out_buf = up2; u.out_pitch = nf; u.out_h = th * 4; u.out_w = tw * 4;
+    ConvSpec u = base_conv("conv_up2", up2, th * 4, tw * 4, nf, nf, nf);
+    u.act = kActPRelu; u.const_slope = 0.2f;
+    u.out_buf = hr; u.out_pitch = nf;
     P->add_conv(u);
   }
   {
-    ConvSpec v = base_conv("conv_hr", up2, th * 4, tw * 4, nf, nf, nf);
+    ConvSpec v = base_conv("conv_hr", hr, th * 4, tw * 4, nf, nf, nf);
     v.act = kActPRelu; v.const_slope = 0.2f;
-    v.out_buf = hr; v.out_pitch = nf;
+    v.out_buf = hr2; v.out_pitch = nf;
     P->add_conv(v);
-    ConvSpec l = base_conv("conv_last", hr, th * 4, tw * 4, nf, nf, 3);
+    ConvSpec l = base_conv("conv_last", hr2, th * 4, tw * 4, nf, nf, 3);
     l.out_mode = om; l.out_buf = kBufExternalOut;
     P->add_conv(l);
   }
@@ -239,6 +243,7 @@ std::string Program::to_json() const {
       js_kv(o, "ps_r", c.ps_r); js_kv(o, "fold", c.fold); js_kv(o, "round_u8", c.round_u8);
       js_kv(o, "base_buf", c.base_buf); js_kv(o, "base_pitch", c.base_pitch); js_kv(o, "wperm", c.wperm);
       js_kv(o, "neg_first", c.neg_first); js_kv(o, "res1_nch", c.res1_nch); js_kv(o, "tshift", c.tshift);
+      js_kv(o, "up2_store", c.up2_store);
       js_kv(o, "split", c.split, true);
     }
     o << "}" << (i + 1 < steps.size() ? "," : "");

@@ -57,6 +57,7 @@ struct ConvSpec {
   int res1_nch = 0;                 // > 0: add only the first k channels of res1
   int tshift = 0;                   // 1: temporal-shift scatter store with fold = `fold` (time == batch index)
   int in_ring = 0, out_ring = 0;    // BSVD streaming: images (ring slots) of the input / output tensors (0: n)
+  int up2_store = 0;                // 1: store every output pixel 2x2 times: the destination is the nearest-x2 upsampled image
   double flops() const;
 };
 

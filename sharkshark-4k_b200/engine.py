@@ -128,6 +128,7 @@ class Plan:
         self.out_nchw = tuple(shp)
         self.flops = self.lib.ss4k_plan_flops(h)
         self.launches = self.lib.ss4k_plan_launches(h)
+        self.graph_steps = self.lib.ss4k_plan_graph_steps(h)
         ib, ob = ctypes.c_int64(), ctypes.c_int64()
         self.lib.ss4k_plan_io_bytes(h, ctypes.byref(ib), ctypes.byref(ob))
         self.in_bytes, self.out_bytes = ib.value, ob.value

@@ -145,7 +145,12 @@ def run_program(prog, sd, x, quant=None):
                 v = v + c[f"beta{k}"] * r
         if om in (0, 3):
             dst = bufs[c["out_buf"]]
-            assert tuple(dst.shape[1:3]) == (c["out_h"], c["out_w"]) == tuple(v.shape[2:]), (c["name"], dst.shape, v.shape)
+            if c.get("up2_store", 0):   # nearest-x2 upsample fused into the store
+                assert (c["out_h"], c["out_w"]) == tuple(v.shape[2:])
+                v = F.interpolate(v, scale_factor=2, mode="nearest")
+                assert tuple(dst.shape[1:3]) == tuple(v.shape[2:])
+            else:
+                assert tuple(dst.shape[1:3]) == (c["out_h"], c["out_w"]) == tuple(v.shape[2:]), (c["name"], dst.shape, v.shape)
             npad = (oc + 15) // 16 * 16
             vv = q(_nhwc(v))
             if c.get("tshift", 0):   # temporal-shift scatter: time == batch index, out-of-clip slices dropped
