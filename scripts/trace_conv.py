@@ -9,5 +9,12 @@ import ss4k_b200
 from bench_conv import bench
 eng = ss4k_b200.Engine.get(0)
 for cin, cout, n in [(64, 32, 1), (160, 32, 1), (192, 64, 1), (64, 64, 1), (64, 32, 4)]:
-    for flags in (0, 7):
-        print(json.dumps(bench(eng, cin, cout, 360, 640, n=n, pitch=192 if cout == 32 or cin == 192 else 0, flags=flags, trace=1)))
+    for flags in (0, 6, 7):
+        d = bench(eng, cin, cout, 360, 640, n=n, pitch=192 if cout == 32 or cin == 192 else 0, flags=flags, trace=1)
+        tr = d.pop("trace")
+        print(json.dumps(d))
+        for t in tr[:2]:
+            print("   phases", t[:9])
+            for i in range(8):
+                q = t[16 + 6 * i: 22 + 6 * i]
+                print("   row", i + 3, "start", q[0], " +init", q[1] - q[0], " +afull", q[2] - q[1], " +issue", q[3] - q[2], " +commitA", q[4] - q[3], " +commitAcc", q[5] - q[4])

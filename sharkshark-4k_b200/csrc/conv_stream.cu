@@ -132,7 +132,7 @@ conv3x3_stream_kernel(const __grid_constant__ StreamParams P) {
 
   const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);  // warp-uniform for ptxas
   const int lane = threadIdx.x & 31;
-  long long* const trace = P.trace != nullptr ? P.trace + blockIdx.x * 16 : nullptr;
+  long long* const trace = P.trace != nullptr ? P.trace + blockIdx.x * 64 : nullptr;
 #define SS4K_TRACE(i) do { if (trace != nullptr && lane == 0) trace[i] = clock64(); } while (0)
   if (warp == 0) SS4K_TRACE(0);
 
@@ -250,6 +250,9 @@ conv3x3_stream_kernel(const __grid_constant__ StreamParams P) {
       const int r0 = b.yb > 0 ? b.yb - 1 : 0;
       const int r1 = b.ye < P.H ? b.ye : P.H - 1;
       for (int r = r0; r <= r1; ++r) {
+        const int tri = r - r0 - 3;  // traced rows: 3..10 of the CTA's first band
+        const bool trow = trace != nullptr && lane == 0 && tri >= 0 && tri < 8 && trace[16 + 6 * tri] == 0;
+        if (trow) trace[16 + 6 * tri] = clock64();
         const int y_lo = r - 1 > b.yb ? r - 1 : b.yb;
         const int y_hi = r + 1 < b.ye - 1 ? r + 1 : b.ye - 1;
         const int b_lo = y_lo - (r - 1), b_hi = y_hi - (r - 1);  // weight row blocks (block = 2 - ky)
@@ -267,6 +270,7 @@ conv3x3_stream_kernel(const __grid_constant__ StreamParams P) {
             if (!(P.dbg_flags & 1)) umma_f16_elect(tmem_base + static_cast<uint32_t>(s * NOUT), d_ones, d_bias, P.idesc[0], 0u);
           }
         }
+        if (trow) trace[16 + 6 * tri + 1] = clock64();
         // ---- the row's MMAs cover accumulator slots [s0, s0 + nblk) (ring order), split where the ring wraps:
         //      op A = blocks [b_lo, b_lo + nA) at slot s0, op B = the remaining nB blocks at slot 0
         int s0 = qs + (y_lo - b.yb);
@@ -281,6 +285,7 @@ conv3x3_stream_kernel(const __grid_constant__ StreamParams P) {
           mbar_wait_u(a_full + 8 * as, aph);
           tcgen05_after_sync();
           if (trace != nullptr && lane == 0 && trace[3] == 0) trace[3] = clock64();
+          if (trow && kb == 0) trace[16 + 6 * tri + 2] = clock64();
           // descriptor low words (address >> 4): per-MMA offsets are compile-time constants
           const uint32_t a_lo = (a_base + as * kASlotBytes) >> 4;
           const uint32_t wA_lo = (w_base + static_cast<uint32_t>(kb * 3) * kWTile + boffA) >> 4;
@@ -307,9 +312,11 @@ conv3x3_stream_kernel(const __grid_constant__ StreamParams P) {
               }
             }
           }
+          if (trow && kb == P.nkb - 1) trace[16 + 6 * tri + 3] = clock64();
           umma_commit_elect(a_empty + 8 * as);  // slab reusable once these MMAs have read it
           if (++as == static_cast<uint32_t>(P.a_slots)) { as = 0; aph ^= 1; }
         }
+        if (trow) trace[16 + 6 * tri + 4] = clock64();
         // ---- output rows completed by this input row
         if (r - 1 >= b.yb) {
           int s = qs + (r - 1 - b.yb);
@@ -321,6 +328,7 @@ conv3x3_stream_kernel(const __grid_constant__ StreamParams P) {
           while (s >= S) s -= S;
           umma_commit_elect(acc_full + 8 * s);
         }
+        if (trow) trace[16 + 6 * tri + 5] = clock64();
       }
       qs += b.ye - b.yb;
       while (qs >= S) { qs -= S; ++qk; }

@@ -1189,6 +1189,10 @@ int ss4k_debug_bench_conv(ss4k_ctx* ctx, const ss4k_conv_desc* d, int slab_pitch
   HostTensor W;
   W.shape = {d->cout, d->cin, 3, 3};
   W.data.assign(static_cast<size_t>(d->cout) * d->cin * 9, 0.01f);
+  if (d->reserved[6] == 1) {  // random weights (power measurements: MMA energy depends on the operand values)
+    uint32_t s = 2463534242u;
+    for (auto& v : W.data) { s = s * 1664525u + 1013904223u; v = (((s >> 8) & 0xFFFF) / 65536.0f - 0.5f) * 0.1f; }
+  }
   void* b[3] = {nullptr, nullptr, nullptr};
   const size_t in_bytes = static_cast<size_t>(d->n) * d->h * d->w * in_pitch * 2 + 256;
   const size_t out_bytes = static_cast<size_t>(d->n) * oh * ow * npad * 2 + 256;
@@ -1197,6 +1201,12 @@ int ss4k_debug_bench_conv(ss4k_ctx* ctx, const ss4k_conv_desc* d, int slab_pitch
   CK(ctx, cudaMalloc(&b[2], out_bytes));
   CK(ctx, cudaMemset(b[0], 0, in_bytes));
   CK(ctx, cudaMemset(b[2], 0, out_bytes));
+  if (d->reserved[6] == 1) {  // random activations in (-1, 1)
+    std::vector<uint16_t> hx(in_bytes / 2);
+    uint32_t s = 88172645u;
+    for (auto& v : hx) { s = s * 1664525u + 1013904223u; v = f2h((((s >> 8) & 0xFFFF) / 32768.0f - 1.0f), bf16); }
+    CK(ctx, cudaMemcpy(b[0], hx.data(), hx.size() * 2, cudaMemcpyHostToDevice));
+  }
   ConvSpec cs;
   cs.name = "bench"; cs.wname = "w"; cs.mode = d->mode; cs.n = d->n; cs.cin = d->cin; cs.cout = d->cout;
   cs.in_buf = 0; cs.in_h = d->h; cs.in_w = d->w; cs.in_pitch = in_pitch;
@@ -1209,8 +1219,8 @@ int ss4k_debug_bench_conv(ss4k_ctx* ctx, const ss4k_conv_desc* d, int slab_pitch
   if (rc == SS4K_OK) {
     long long* d_trace = nullptr;
     if (ex.stream && d->reserved[7] == 1) {
-      cudaMalloc(&d_trace, sizeof(long long) * 16 * 148);
-      cudaMemset(d_trace, 0, sizeof(long long) * 16 * 148);
+      cudaMalloc(&d_trace, sizeof(long long) * 64 * 148);
+      cudaMemset(d_trace, 0, sizeof(long long) * 64 * 148);
     }
     if (ex.stream) {
       ex.sp.dbg_flags = dbg_flags;
@@ -1243,18 +1253,18 @@ int ss4k_debug_bench_conv(ss4k_ctx* ctx, const ss4k_conv_desc* d, int slab_pitch
     ctx->launches += iters + 3;
     std::string trace_js;
     if (d_trace != nullptr) {  // one extra traced launch: clock64 stamps of CTA 0 and the last CTA, relative to entry
-      cudaMemset(d_trace, 0, sizeof(long long) * 16 * 148);
+      cudaMemset(d_trace, 0, sizeof(long long) * 64 * 148);
       ex.sp.trace = d_trace;
       launch_exec(ex, nullptr, ctx->stream);
       cudaStreamSynchronize(ctx->stream);
       ex.sp.trace = nullptr;
-      std::vector<long long> h(16 * 148);
-      cudaMemcpy(h.data(), d_trace, sizeof(long long) * 16 * 148, cudaMemcpyDeviceToHost);
+      std::vector<long long> h(64 * 148);
+      cudaMemcpy(h.data(), d_trace, sizeof(long long) * 64 * 148, cudaMemcpyDeviceToHost);
       cudaFree(d_trace);
       trace_js = ",\"trace\":[";
       for (int b : {0, ex.grid / 2, ex.grid - 1}) {
         trace_js += (b == 0 ? "[" : ",[");
-        for (int i = 0; i < 9; ++i) trace_js += fmt("%s%lld", i ? "," : "", h[b * 16 + i] ? h[b * 16 + i] - h[b * 16] : -1LL);
+        for (int i = 0; i < 64; ++i) trace_js += fmt("%s%lld", i ? "," : "", h[b * 64 + i] ? h[b * 64 + i] - h[b * 64] : -1LL);
         trace_js += "]";
       }
       trace_js += "]";
