@@ -39,7 +39,7 @@ if __name__ == "__main__":
     for cin, cout in [(64, 32), (160, 32)]:
         for slots in (3, 4, 6, 12):
             print(json.dumps(bench(eng, cin, cout, H, W, pitch=192, slots=slots)))
-        for acc in (3, 4, 8, 16):
+        for acc in (4, 8, 16):
             print(json.dumps(bench(eng, cin, cout, H, W, pitch=192, acc=acc)))
     print("# batch 4 (bands of ~49 rows)")
     for cin, cout in [(64, 32), (96, 32), (128, 32), (160, 32), (192, 64), (64, 64)]:

@@ -17,4 +17,4 @@ for cin, cout, n in [(64, 32, 1), (160, 32, 1), (192, 64, 1), (64, 64, 1), (64, 
             print("   phases", t[:9])
             for i in range(8):
                 q = t[16 + 6 * i: 22 + 6 * i]
-                print("   row", i + 3, "start", q[0], " +init", q[1] - q[0], " +afull", q[2] - q[1], " +issue", q[3] - q[2], " +commitA", q[4] - q[3], " +commitAcc", q[5] - q[4])
+                print("   row", i, "start", q[0], " +issue8", q[1] - q[0], " +fetch", q[2] - q[1], " +prepare", q[3] - q[2], " +issue4", q[4] - q[3], " +commits", q[5] - q[4])

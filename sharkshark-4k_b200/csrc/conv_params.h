@@ -145,7 +145,9 @@ struct StreamParams {
   int32_t* err;
   int32_t dbg_flags;
   int32_t n_in0, n_out0;  // added to the image coordinate of TMA loads / stores (BSVD streaming: ring slots)
-  long long* trace;       // debug: per-CTA clock64 stamps [grid][16] (null in production)
+  long long* trace;       // debug: per-CTA clock64 stamps [grid][64] (null in production)
+  const void* next_w;     // packed weights of the next kernel of the plan (L2 prefetch), or null
+  uint32_t next_w_bytes;
 };
 
 }  // namespace ss4k

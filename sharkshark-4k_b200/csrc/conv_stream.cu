@@ -83,6 +83,10 @@ __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, ui
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
+// row record flags (word 5; bits 0..1 = accumulator blocks after the ring wrap)
+constexpr uint32_t kRecLast = 4u, kRecNewChunk = 8u, kRecFreeW = 16u;
+constexpr uint32_t kRecWords = 8u;
+
 struct Band {
   int chunk, n, strip, yb, ye;
 };
@@ -127,6 +131,7 @@ conv3x3_stream_kernel(const __grid_constant__ StreamParams P) {
   const uint32_t w_full = acc_empty + 8 * kMaxAccSlots;
   const uint32_t w_empty = w_full + 8;
   const uint32_t tmem_slot = w_empty + 8;
+  const uint32_t rec_base = tmem_slot + 32;  // row records, one per activation slab slot (kRecWords x 4 bytes each)
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
 
@@ -137,22 +142,44 @@ conv3x3_stream_kernel(const __grid_constant__ StreamParams P) {
   if (warp == 0) SS4K_TRACE(0);
 
   pdl_launch_dependents();
-  if (warp == 0 && lane == 0) {
-    prefetch_tmap(&P.tmA[0]);
-    prefetch_tmap(&P.tmW);
-    prefetch_tmap(&P.tmB);
-    if (P.fast_store) prefetch_tmap(&P.tmO);
-    for (int i = 0; i < kMaxSASlots; ++i) {
-      mbar_init(a_full + 8 * i, 1);
-      mbar_init(a_empty + 8 * i, 1);
+  const int u0 = static_cast<int>(static_cast<int64_t>(blockIdx.x) * P.total_units / gridDim.x);
+  const int u1 = static_cast<int>(static_cast<int64_t>(blockIdx.x + 1) * P.total_units / gridDim.x);
+  int early_chunk = -1;  // weights requested in the prologue (producer warp)
+  if (warp == 0) {
+    if (lane == 0) {
+      prefetch_tmap(&P.tmA[0]);
+      prefetch_tmap(&P.tmW);
+      prefetch_tmap(&P.tmB);
+      if (P.fast_store) prefetch_tmap(&P.tmO);
+      for (int i = 0; i < kMaxSASlots; ++i) {
+        mbar_init(a_full + 8 * i, 1);
+        mbar_init(a_empty + 8 * i, 1);
+      }
+      for (int i = 0; i < kMaxAccSlots; ++i) {
+        mbar_init(acc_full + 8 * i, 1);
+        mbar_init(acc_empty + 8 * i, 4);  // one arrive per epilogue warp of the row's parity group
+      }
+      mbar_init(w_full, 1);
+      mbar_init(w_empty, 1);
+      fence_barrier_init();
     }
-    for (int i = 0; i < kMaxAccSlots; ++i) {
-      mbar_init(acc_full + 8 * i, 1);
-      mbar_init(acc_empty + 8 * i, 4);  // one arrive per epilogue warp of the row's parity group
+    __syncwarp();
+    // the first chunk's weights are constants of the launch: request them before the rest of the set-up
+    // (TMEM allocation, ones tile, block barrier) so that their latency overlaps it
+    if (u0 < u1) {
+      int uu = u0;
+      Band fb;
+      next_band(P, uu, u1, fb);
+      early_chunk = fb.chunk;
+      if (elect_one()) {
+        const int ntile = P.nkb * 3;
+        mbar_expect_tx(w_full, static_cast<uint32_t>(ntile) * kWTile + kBiasTile);
+        for (int t = 0; t < ntile; ++t)
+          tma_load_2d(w_base + t * kWTile, &P.tmW, w_full, 0, (fb.chunk * ntile + t) * 3 * NOUT);
+        tma_load_2d(bias_base, &P.tmB, w_full, 0, P.bias_row0 + fb.chunk * NOUT);
+      }
+      __syncwarp();
     }
-    mbar_init(w_full, 1);
-    mbar_init(w_empty, 1);
-    fence_barrier_init();
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
@@ -179,21 +206,29 @@ conv3x3_stream_kernel(const __grid_constant__ StreamParams P) {
   constexpr uint32_t tmem_base = 0u;
   if (warp == 0) SS4K_TRACE(1);
 
-  const int u0 = static_cast<int>(static_cast<int64_t>(blockIdx.x) * P.total_units / gridDim.x);
-  const int u1 = static_cast<int>(static_cast<int64_t>(blockIdx.x + 1) * P.total_units / gridDim.x);
   const int S = P.acc_slots;
 
   if (warp == 0) {
-    // ======================================================= TMA producer
+    // ======================================================= TMA producer + row planner
+    // Besides the loads, this warp does the per-row bookkeeping of the MMA stream (accumulator ring positions,
+    // which slots an input row touches first / completes, where the ring wraps) and hands it to the MMA
+    // warp as a small record that travels with the row's first activation slab: the issuing warp is the
+    // critical resource of the kernel (one thread feeds the tensor pipe), this one has time to spare.
     uint32_t as = 0, aph = 0, wph = 0;
     int loaded_chunk = -1;
     int u = u0;
-    Band b;
+    Band b, nb;
     bool dep_ready = false;
-    while (next_band(P, u, u1, b)) {
-      if (b.chunk != loaded_chunk) {
+    int sL = 0, kL = 0;  // accumulator ring position (slot, wrap count) of output row y_lo
+    bool has = next_band(P, u, u1, b);
+    while (has) {
+      const bool has_next = next_band(P, u, u1, nb);
+      const bool new_chunk = b.chunk != loaded_chunk;
+      if (new_chunk) {
         mbar_wait_u(w_empty, wph ^ 1);
-        if (elect_one()) {
+        if (b.chunk == early_chunk) {
+          early_chunk = -1;  // already requested in the prologue
+        } else if (elect_one()) {
           const int ntile = P.nkb * 3;
           mbar_expect_tx(w_full, static_cast<uint32_t>(ntile) * kWTile + kBiasTile);
           for (int t = 0; t < ntile; ++t)
@@ -211,10 +246,50 @@ conv3x3_stream_kernel(const __grid_constant__ StreamParams P) {
       const int r0 = b.yb > 0 ? b.yb - 1 : 0;
       const int r1 = b.ye < P.H ? b.ye : P.H - 1;
       const int x0 = b.strip * kTileW - 1;
+      int y_lo = b.yb;
       for (int r = r0; r <= r1; ++r) {
+        // ---- the row's record
+        {
+          const int y = r - 1 > b.yb ? r - 1 : b.yb;
+          if (y != y_lo) {
+            y_lo = y;
+            if (++sL == S) { sL = 0; ++kL; }
+          }
+        }
+        const int y_hi = r + 1 < b.ye - 1 ? r + 1 : b.ye - 1;
+        const int b_lo = y_lo - (r - 1);  // weight row block (block = 2 - ky) of output row y_lo
+        const int nblk = y_hi - y_lo + 1;
+        const int nA = sL + nblk <= S ? nblk : S - sL;  // the MMAs split where the ring wraps
+        const int nB = nblk - nA;
+        uint32_t fresh = 0;  // up to 3 x {bit 7 valid, bit 6 parity, bit 5 wait, bits 0..4 slot}
+        {
+          const int f_lo = (r == r0) ? y_lo : r + 1;
+          int sh = 0;
+          for (int y = f_lo; y <= y_hi; ++y, sh += 8) {
+            int s2 = sL + (y - y_lo), k2 = kL;
+            if (s2 >= S) { s2 -= S; ++k2; }
+            fresh |= (0x80u | (k2 > 0 ? 0x20u : 0u) | (((k2 & 1) ^ 1) ? 0x40u : 0u) | static_cast<uint32_t>(s2)) << sh;
+          }
+        }
+        uint32_t c0 = 0xFFu, c1 = 0xFFu;  // accumulator slots completed by this input row
+        if (r - 1 >= b.yb) c0 = static_cast<uint32_t>(sL);
+        if (r == r1 && r <= b.ye - 1) {  // image bottom: row H-1 has no row below it
+          int s2 = sL + (r - y_lo);
+          if (s2 >= S) s2 -= S;
+          c1 = static_cast<uint32_t>(s2);
+        }
+        const uint32_t flags = static_cast<uint32_t>(nB) | ((r == r1 && !has_next) ? kRecLast : 0u) |
+                               ((r == r0 && new_chunk) ? kRecNewChunk : 0u) |
+                               ((r == r1 && has_next && nb.chunk != b.chunk) ? kRecFreeW : 0u);
         for (int kb = 0; kb < P.nkb; ++kb) {
           mbar_wait_u(a_empty + 8 * as, aph ^ 1);
           if (elect_one()) {
+            if (kb == 0) {
+              const uint32_t ra = rec_base + as * (kRecWords * 4u);
+              sts128(ra, static_cast<uint32_t>(sL * NOUT), P.idesc[nA - 1], P.idesc[nB > 0 ? nB - 1 : 0],
+                     static_cast<uint32_t>(b_lo * NOUT * 128) >> 4);
+              sts128(ra + 16, static_cast<uint32_t>((b_lo + nA) * NOUT * 128) >> 4, flags, c0 | (c1 << 8), fresh);
+            }
             if (P.dbg_flags & 2) {
               mbar_arrive(a_full + 8 * as);
             } else {
@@ -226,115 +301,150 @@ conv3x3_stream_kernel(const __grid_constant__ StreamParams P) {
           if (++as == static_cast<uint32_t>(P.a_slots)) { as = 0; aph ^= 1; }
         }
       }
+      // ring position of the next band's first output row
+      sL += b.ye - y_lo;
+      if (sL >= S) { sL -= S; ++kL; }
+      b = nb;
+      has = has_next;
+    }
+    // all loads of this CTA are in flight: pull this CTA's share of the NEXT kernel's weights into L2 (they were
+    // evicted by a frame's worth of activations since their last use; an HBM miss would sit on its prologue)
+    if (P.next_w != nullptr && lane == 0) {
+      const uint32_t per = ((P.next_w_bytes + gridDim.x - 1) / gridDim.x + 15u) & ~15u;
+      const uint32_t off = blockIdx.x * per;
+      if (off < P.next_w_bytes) {
+        const uint32_t sz = P.next_w_bytes - off < per ? ((P.next_w_bytes - off) & ~15u) : per;
+        if (sz > 0)
+          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<const uint8_t*>(P.next_w) + off), "r"(sz) : "memory");
+      }
     }
   } else if (warp == 1) {
     // ======================================================= MMA issuer
-    // The whole warp runs this loop convergently (waits are asm-internal loops) so that ptxas keeps
-    // every descriptor in uniform registers; one elected lane issues the tcgen05 instructions.
+    // The whole warp runs this loop convergently (waits are asm-internal loops, record words are broadcast
+    // with shuffles) so that ptxas keeps every descriptor in uniform registers; one elected lane issues the
+    // tcgen05 instructions.  One thread feeds the tensor pipe and the pipe queues almost nothing, so every
+    // instruction this warp executes between two MMAs is dead time for the pipe: the row bookkeeping comes
+    // precomputed from the producer warp (row records), and the next row's record, its fresh accumulator slots
+    // (wait for the epilogue's drain, bias-init MMA) are handled in the middle of the current row's last burst.
     uint32_t as = 0, aph = 0, wph = 0;
-    int cur_chunk = -1;
-    int qs = 0, qk = 0;  // accumulator ring position of the band's first output row: slot, wrap count
-    int u = u0;
-    Band b, nb;
-    bool has = next_band(P, u, u1, b);
+    const int nkb = P.nkb;
+    const bool do_mma = !(P.dbg_flags & 1);
+    const uint32_t idesc0 = P.idesc[0];
     const uint64_t d_ones = sdesc(ones_base), d_bias = sdesc(bias_base);
-    while (has) {
-      const bool has_next = next_band(P, u, u1, nb);
-      if (b.chunk != cur_chunk) {
+    const uint32_t n_aslots = static_cast<uint32_t>(P.a_slots);
+
+    uint32_t rc[kRecWords];
+    // waits for the first slab of a row, reads its record and prepares its fresh accumulator slots
+    auto fetch = [&](uint32_t slot, uint32_t ph) {
+      mbar_wait_u(a_full + 8 * slot, ph);
+      uint32_t v0, v1, v2, v3, v4, v5, v6, v7;
+      const uint32_t ra = rec_base + slot * (kRecWords * 4u);
+      asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v0), "=r"(v1), "=r"(v2), "=r"(v3) : "r"(ra) : "memory");
+      asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v4), "=r"(v5), "=r"(v6), "=r"(v7) : "r"(ra + 16) : "memory");
+      rc[0] = __shfl_sync(0xffffffffu, v0, 0); rc[1] = __shfl_sync(0xffffffffu, v1, 0);
+      rc[2] = __shfl_sync(0xffffffffu, v2, 0); rc[3] = __shfl_sync(0xffffffffu, v3, 0);
+      rc[4] = __shfl_sync(0xffffffffu, v4, 0); rc[5] = __shfl_sync(0xffffffffu, v5, 0);
+      rc[6] = __shfl_sync(0xffffffffu, v6, 0); rc[7] = __shfl_sync(0xffffffffu, v7, 0);
+    };
+    auto prepare = [&]() {  // rc = record of the row about to be issued
+      if (rc[5] & kRecNewChunk) {
         mbar_wait_u(w_full, wph);
-        tcgen05_after_sync();
-        if (cur_chunk < 0) SS4K_TRACE(2);
         wph ^= 1;
-        cur_chunk = b.chunk;
+        if (trace != nullptr && lane == 0 && trace[2] == 0) trace[2] = clock64();
       }
-      const int r0 = b.yb > 0 ? b.yb - 1 : 0;
-      const int r1 = b.ye < P.H ? b.ye : P.H - 1;
-      for (int r = r0; r <= r1; ++r) {
-        const int tri = r - r0 - 3;  // traced rows: 3..10 of the CTA's first band
-        const bool trow = trace != nullptr && lane == 0 && tri >= 0 && tri < 8 && trace[16 + 6 * tri] == 0;
-        if (trow) trace[16 + 6 * tri] = clock64();
-        const int y_lo = r - 1 > b.yb ? r - 1 : b.yb;
-        const int y_hi = r + 1 < b.ye - 1 ? r + 1 : b.ye - 1;
-        const int b_lo = y_lo - (r - 1), b_hi = y_hi - (r - 1);  // weight row blocks (block = 2 - ky)
-        // ---- accumulator slots touched for the first time by this input row: wait until the epilogue has
-        //      drained their previous row, then initialise them with the bias (ones x bias, accumulate = 0)
-        {
-          const int f_lo = (r == r0) ? y_lo : r + 1;
-          for (int y = f_lo; y <= y_hi; ++y) {
-            int s = qs + (y - b.yb), k = qk;
-            while (s >= S) { s -= S; ++k; }
-            if (k > 0) {  // the slot's first use needs no drain
-              mbar_wait_u(acc_empty + 8 * s, (k & 1) ^ 1);
-              tcgen05_after_sync();
-            }
-            if (!(P.dbg_flags & 1)) umma_f16_elect(tmem_base + static_cast<uint32_t>(s * NOUT), d_ones, d_bias, P.idesc[0], 0u);
+      tcgen05_after_sync();
+      uint32_t f = rc[7];
+#pragma unroll
+      for (int j = 0; j < 3; ++j, f >>= 8) {
+        if (f & 0x80u) {
+          const uint32_t s2 = f & 0x1Fu;
+          if (f & 0x20u) {  // the slot's first use needs no drain
+            mbar_wait_u(acc_empty + 8 * s2, (f >> 6) & 1u);
+            tcgen05_after_sync();
           }
+          if (do_mma) umma_f16_elect(tmem_base + s2 * NOUT, d_ones, d_bias, idesc0, 0u);
         }
-        if (trow) trace[16 + 6 * tri + 1] = clock64();
-        // ---- the row's MMAs cover accumulator slots [s0, s0 + nblk) (ring order), split where the ring wraps:
-        //      op A = blocks [b_lo, b_lo + nA) at slot s0, op B = the remaining nB blocks at slot 0
-        int s0 = qs + (y_lo - b.yb);
-        while (s0 >= S) s0 -= S;
-        const int nblk = b_hi - b_lo + 1;
-        const int nA = s0 + nblk <= S ? nblk : S - s0;
-        const int nB = nblk - nA;
-        const uint32_t colA = tmem_base + static_cast<uint32_t>(s0 * NOUT);
-        const uint32_t boffA = static_cast<uint32_t>(b_lo * NOUT * 128), boffB = static_cast<uint32_t>((b_lo + nA) * NOUT * 128);
-        const uint32_t idA = P.idesc[nA - 1], idB = P.idesc[nB > 0 ? nB - 1 : 0];
-        for (int kb = 0; kb < P.nkb; ++kb) {
-          mbar_wait_u(a_full + 8 * as, aph);
-          tcgen05_after_sync();
-          if (trace != nullptr && lane == 0 && trace[3] == 0) trace[3] = clock64();
-          if (trow && kb == 0) trace[16 + 6 * tri + 2] = clock64();
+      }
+    };
+
+    if (u0 < u1) {
+      fetch(0, 0);
+      prepare();
+      SS4K_TRACE(3);
+      bool last = false;
+      int rowcnt = 0;
+      while (!last) {
+        // this row's plan in uniform registers
+        const uint32_t colA = tmem_base + rc[0], idA = rc[1], idB = rc[2], woffA = rc[3], woffB = rc[4];
+        const uint32_t flags = rc[5], cc = rc[6];
+        const bool wrap = (flags & 3u) != 0;
+        last = (flags & kRecLast) != 0;
+        // (a row that frees the weights cannot look ahead: the next row's weights load after its last MMA)
+        const bool overlap = !last && !(flags & kRecFreeW);
+        const bool trow = trace != nullptr && lane == 0 && rowcnt < 8;
+        long long* const trw = trace + 16 + 6 * rowcnt;
+        if (trow) trw[0] = clock64();
+        for (int kb = 0; kb < nkb; ++kb) {
+          if (kb > 0) {
+            mbar_wait_u(a_full + 8 * as, aph);
+            tcgen05_after_sync();
+          }
           // descriptor low words (address >> 4): per-MMA offsets are compile-time constants
           const uint32_t a_lo = (a_base + as * kASlotBytes) >> 4;
-          const uint32_t wA_lo = (w_base + static_cast<uint32_t>(kb * 3) * kWTile + boffA) >> 4;
-          const uint32_t wB_lo = (w_base + static_cast<uint32_t>(kb * 3) * kWTile + boffB) >> 4;
+          const uint32_t w_lo = (w_base + static_cast<uint32_t>(kb * 3) * kWTile) >> 4;
+          const uint32_t wA_lo = w_lo + woffA, wB_lo = w_lo + woffB;
           const int nks = P.nks[kb];
-          if (!(P.dbg_flags & 1)) {
-            if (nB == 0) {
+          const uint32_t as_cur = as;
+          if (++as == n_aslots) { as = 0; aph ^= 1; }
+#define SS4K_MMA(KX, KS)                                                                                                   \
+          {                                                                                                                \
+            umma_f16_lo(colA, a_lo + ((KX) * kRowBytes + (KS) * 32) / 16, wA_lo + ((KX) * kWTile + (KS) * 32) / 16, idA, 1u); \
+            if (wrap) umma_f16_lo(tmem_base, a_lo + ((KX) * kRowBytes + (KS) * 32) / 16, wB_lo + ((KX) * kWTile + (KS) * 32) / 16, idB, 1u); \
+          }
+          if (do_mma) {
+            if (nks == 4) {
+              SS4K_MMA(0, 0) SS4K_MMA(0, 1) SS4K_MMA(0, 2) SS4K_MMA(0, 3)
+              SS4K_MMA(1, 0) SS4K_MMA(1, 1) SS4K_MMA(1, 2) SS4K_MMA(1, 3)
+            } else {
 #pragma unroll
-              for (int kx = 0; kx < 3; ++kx) {
+              for (int kx = 0; kx < 2; ++kx) {
 #pragma unroll
-                for (int ks = 0; ks < 4; ++ks)
-                  if (ks < nks) umma_f16_lo(colA, a_lo + (kx * kRowBytes + ks * 32) / 16, wA_lo + (kx * kWTile + ks * 32) / 16, idA, 1u);
-              }
-            } else {  // the accumulator ring wraps inside this row's slot range: two MMAs per step
-#pragma unroll
-              for (int kx = 0; kx < 3; ++kx) {
-#pragma unroll
-                for (int ks = 0; ks < 4; ++ks) {
-                  if (ks < nks) {
-                    umma_f16_lo(colA, a_lo + (kx * kRowBytes + ks * 32) / 16, wA_lo + (kx * kWTile + ks * 32) / 16, idA, 1u);
-                    umma_f16_lo(tmem_base, a_lo + (kx * kRowBytes + ks * 32) / 16, wB_lo + (kx * kWTile + ks * 32) / 16, idB, 1u);
-                  }
-                }
+                for (int ks = 0; ks < 3; ++ks)
+                  if (ks < nks) SS4K_MMA(kx, ks)
               }
             }
           }
-          if (trow && kb == P.nkb - 1) trace[16 + 6 * tri + 3] = clock64();
-          umma_commit_elect(a_empty + 8 * as);  // slab reusable once these MMAs have read it
-          if (++as == static_cast<uint32_t>(P.a_slots)) { as = 0; aph ^= 1; }
+          if (trow && kb == nkb - 1) trw[1] = clock64();
+          if (kb == nkb - 1 && overlap) {  // next row: first slab, record, fresh accumulator slots
+            fetch(as, aph);
+            if (trow) trw[2] = clock64();
+            prepare();
+          }
+          if (trow && kb == nkb - 1) trw[3] = clock64();
+          if (do_mma) {
+            if (nks == 4) {
+              SS4K_MMA(2, 0) SS4K_MMA(2, 1) SS4K_MMA(2, 2) SS4K_MMA(2, 3)
+            } else {
+#pragma unroll
+              for (int ks = 0; ks < 3; ++ks)
+                if (ks < nks) SS4K_MMA(2, ks)
+            }
+          }
+#undef SS4K_MMA
+          umma_commit_elect(a_empty + 8 * as_cur);  // slab reusable once these MMAs have read it
         }
-        if (trow) trace[16 + 6 * tri + 4] = clock64();
+        if (trow) trw[4] = clock64();
         // ---- output rows completed by this input row
-        if (r - 1 >= b.yb) {
-          int s = qs + (r - 1 - b.yb);
-          while (s >= S) s -= S;
-          umma_commit_elect(acc_full + 8 * s);
+        if ((cc & 0xFFu) != 0xFFu) umma_commit_elect(acc_full + 8 * (cc & 0xFFu));
+        if (((cc >> 8) & 0xFFu) != 0xFFu) umma_commit_elect(acc_full + 8 * ((cc >> 8) & 0xFFu));
+        if (flags & kRecFreeW) umma_commit_elect(w_empty);  // weights may be replaced
+        if (!last && !overlap) {
+          fetch(as, aph);
+          prepare();
         }
-        if (r == r1 && r <= b.ye - 1) {  // image bottom: row H-1 has no row below it
-          int s = qs + (r - b.yb);
-          while (s >= S) s -= S;
-          umma_commit_elect(acc_full + 8 * s);
-        }
-        if (trow) trace[16 + 6 * tri + 5] = clock64();
+        if (trow) trw[5] = clock64();
+        ++rowcnt;
       }
-      qs += b.ye - b.yb;
-      while (qs >= S) { qs -= S; ++qk; }
-      if (has_next && nb.chunk != b.chunk) umma_commit_elect(w_empty);  // weights may be replaced
-      b = nb;
-      has = has_next;
     }
     SS4K_TRACE(4);
   } else {
@@ -372,7 +482,7 @@ conv3x3_stream_kernel(const __grid_constant__ StreamParams P) {
           }
           mbar_wait_u(acc_full + 8 * s, k & 1);
           tcgen05_after_sync();
-          if (warp == 2 && trace != nullptr && lane == 0 && trace[5] == 0) trace[5] = clock64();
+          if (warp == 2 && q == 0) SS4K_TRACE(5);
           const uint32_t taddr = tmem_base + (static_cast<uint32_t>(qd * 32) << 16) + static_cast<uint32_t>(s * NOUT);
           uint32_t raw[NOUT];
 #pragma unroll

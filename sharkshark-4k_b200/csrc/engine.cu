@@ -110,6 +110,7 @@ struct ConvExec {
   int nout = 0;         // accumulator slot width of the streaming kernel
   int grid = 0;
   void* d_w = nullptr;
+  size_t w_bytes = 0;
   float* d_bias = nullptr;
   float* d_slope = nullptr;
   bool ext_out = false;  // ep.out is the caller's output pointer (patched per run)
@@ -493,6 +494,7 @@ int materialize_stream(ss4k_ctx* ctx, const ConvSpec& cs, const HostTensor& W, c
   ex->nout = pk.nout;
   ex->name = cs.name;
   CK(ctx, cudaMalloc(&ex->d_w, pk.w.size() * 2));
+  ex->w_bytes = pk.w.size() * 2;
   CK(ctx, cudaMemcpy(ex->d_w, pk.w.data(), pk.w.size() * 2, cudaMemcpyHostToDevice));
   CK(ctx, cudaMalloc(&ex->d_bias, pk.bias.size() * 4));
   CK(ctx, cudaMemcpy(ex->d_bias, pk.bias.data(), pk.bias.size() * 4, cudaMemcpyHostToDevice));
@@ -918,6 +920,18 @@ int ss4k_plan_create(ss4k_ctx* ctx, const ss4k_plan_cfg* cfg, ss4k_plan** out_pl
     int rc = materialize_conv(ctx, cs, w->second, B, S, cfg->act_mode, bufptr, &pl->convs.back());
     if (rc != SS4K_OK) { ss4k_plan_destroy(pl.release()); return rc; }
   }
+  // each streaming conv prefetches the next conv's packed weights into L2 (the last one: the first conv's, for the next frame)
+  if (getenv("SS4K_NO_W_PREFETCH") == nullptr) {
+    const int nc = static_cast<int>(pl->convs.size());
+    for (int i = 0; i < nc; ++i) {
+      ConvExec& c = pl->convs[i];
+      const ConvExec& nx = pl->convs[(i + 1) % nc];
+      if (c.stream && nx.stream && nx.d_w != nullptr && nc > 1) {
+        c.sp.next_w = nx.d_w;
+        c.sp.next_w_bytes = static_cast<uint32_t>(nx.w_bytes);
+      }
+    }
+  }
   pl->in_bytes = fmt_bytes(P.in_fmt, P.in_n, P.in_c, P.in_h, P.in_w);
   pl->out_bytes = fmt_bytes(P.out_fmt, P.out_n, P.out_c, P.out_h, P.out_w);
   // CUDA graph over the internal (non-external) middle of the program
@@ -1225,7 +1239,7 @@ int ss4k_debug_bench_conv(ss4k_ctx* ctx, const ss4k_conv_desc* d, int slab_pitch
     if (ex.stream) {
       ex.sp.dbg_flags = dbg_flags;
       if (d->reserved[3] > 0) ex.sp.a_slots = std::min(ex.sp.a_slots, d->reserved[3]);
-      if (d->reserved[4] > 0) ex.sp.acc_slots = std::min(ex.sp.acc_slots, d->reserved[4]);
+      if (d->reserved[4] > 0) ex.sp.acc_slots = std::max(4, std::min(ex.sp.acc_slots, d->reserved[4]));
       if (d->reserved[5] > 0) ex.grid = std::min(ex.grid, d->reserved[5]);
     } else {
       ex.p.dbg_flags = dbg_flags;
