@@ -46,6 +46,22 @@ def load_checkpoint(path):
     return out
 
 
+def pick_act_mode(state_dict):
+    """fp16 single-MMA operands pass the parity gate for trained-like weight magnitudes; weights with the gain of
+    the reference constructor's ``kaiming_normal_`` init (model.py:393-400,501-508: fan_in * var(W) == 2, outputs
+    span +-14 in fp32) need the hi/lo split mode.  Decision: median over the 3x3 convs of
+    fan_in * var(W) above 1.2 -> split."""
+    gains = []
+    for k, v in state_dict.items():
+        if k.endswith(".weight") and v.dim() == 4:
+            fan_in = v.shape[1] * v.shape[2] * v.shape[3]
+            gains.append(float(v.float().var().item()) * fan_in)
+    if not gains:
+        return L.ACT_F16
+    gains.sort()
+    return L.ACT_F16_SPLIT if gains[len(gains) // 2] > 1.2 else L.ACT_F16
+
+
 class NativeBSVD(nn.Module):
     """BSVD(chns=[32,64,128], mid_ch=32, interm_ch=30, act='relu6', norm='none') on the native engine."""
 
@@ -54,6 +70,8 @@ class NativeBSVD(nn.Module):
     def __init__(self, state_dict, device=0, act_mode=L.ACT_F16, out_dtype=torch.float32, use_graph=True):
         super().__init__()
         self.engine = Engine.get(device)
+        if act_mode == "auto":
+            act_mode = pick_act_mode(state_dict)
         self.act_mode, self.out_dtype, self.use_graph = act_mode, out_dtype, use_graph
         self.net_id = self.engine.new_net(state_dict)
         self._plans = {}
@@ -84,6 +102,9 @@ class NativeBSVD(nn.Module):
         return out.reshape(n, f, 3, h, w)
 
     def stream(self, h, w):
+        if self.act_mode == L.ACT_F16_SPLIT:
+            raise L.Ss4kError("the ring-buffer streaming engine runs single-MMA fp16/bf16 only; "
+                              "use forward() (clip mode) with the split precision mode")
         return BSVDStream(self, h, w)
 
     def streaming_forward(self, input_seq):
@@ -163,7 +184,7 @@ class BSVDStream:
 
 
 def build_model(device=0, input_shape=(360, 640), jit_mode='ds', state_dict=None, pretrain_ckpt=None,
-                act_mode=L.ACT_F16):
+                act_mode="auto"):
     """Same signature as the reference (bsvd/factory.py:21); ``jit_mode`` is accepted and ignored (every mode
     maps to the native engine).  Weights: ``state_dict`` (reference key names) or a ``bsvd-32.pth`` checkpoint."""
     if state_dict is None:

@@ -13,6 +13,8 @@
 // [fold, 2 fold) into frame t+1's, so the consumer's TMA loader reads one contiguous pixel row.
 #include "program.h"
 
+#include <vector>
+
 #include "conv_params.h"
 
 namespace ss4k {
@@ -26,6 +28,11 @@ std::string build_bsvd_clip(const PlanCfgLite& c, Program* P) {
   if (H % 4 || W % 4) return "BSVD: H and W must be multiples of 4 (two stride-2 stages)";
   if (c.out_fmt != 0 && c.out_fmt != 1) return "BSVD: output is float / half NCHW";
   const int c0 = 32, c1 = 64, c2 = 128, mid = 32, interm = 30;
+  // fp16 hi/lo split precision (SS4K_ACT_F16_SPLIT): every activation tensor has a low-half twin, every product is
+  // three MMAs (hi*hi + hi*lo + lo*hi).  Needed for parity with ill-conditioned weights such as the reference
+  // constructor's kaiming init (fp32 outputs span +-14); clip mode only.
+  const bool split = c.act_mode == 2;
+  if (split && c.bsvd_stream) return "BSVD: the split precision mode is available in clip mode only";
   P->in_n = T; P->in_c = 4; P->in_h = H; P->in_w = W;
   P->out_n = T; P->out_c = 3; P->out_h = H; P->out_w = W;
   const int in16 = P->add_buf("in16", T, H, W, 16);
@@ -56,8 +63,19 @@ std::string build_bsvd_clip(const PlanCfgLite& c, Program* P) {
     }
   }
 
+  std::vector<int> lo_of;  // buffer id -> id of its low-half twin
+  if (split) {
+    const int nb = static_cast<int>(P->bufs.size());
+    lo_of.assign(nb, kBufNone);
+    for (int i = 0; i < nb; ++i) {
+      const BufSpec bs = P->bufs[i];
+      lo_of[i] = P->add_buf(bs.name + "_lo", bs.n, bs.h, bs.w, bs.pitch, bs.zero_init);
+    }
+  }
+  auto lo = [&](int id) { return split && id >= 0 && id < static_cast<int>(lo_of.size()) ? lo_of[id] : kBufNone; };
+
   PrepSpec pp;
-  pp.in_fmt = c.in_fmt; pp.c = 4; pp.h = H; pp.w = W; pp.n = T; pp.out_buf = in16;
+  pp.in_fmt = c.in_fmt; pp.c = 4; pp.h = H; pp.w = W; pp.n = T; pp.out_buf = in16; pp.out_lo_buf = lo(in16);
   P->add_prep(pp);
 
   auto conv = [&](const std::string& nm, int mode, int in_buf, int ih, int iw, int ipitch, int cin, int cout, int act) {
@@ -65,6 +83,7 @@ std::string build_bsvd_clip(const PlanCfgLite& c, Program* P) {
     v.name = nm; v.wname = nm + ".weight"; v.bname = nm + ".bias";
     v.mode = mode; v.n = T; v.cin = cin; v.cout = cout;
     v.in_buf = in_buf; v.in_h = ih; v.in_w = iw; v.in_pitch = ipitch;
+    v.in_lo_buf = lo(in_buf); v.split = split ? 1 : 0;
     v.act = act;
     v.out_mode = kOutNHWC;
     v.out_h = mode == kModeS2 ? ih / 2 : ih;
@@ -72,9 +91,9 @@ std::string build_bsvd_clip(const PlanCfgLite& c, Program* P) {
     return v;
   };
   auto shifted = [&](ConvSpec& v, int out_buf, int C) {  // the consumer is a shift conv
-    v.out_buf = out_buf; v.out_pitch = C; v.tshift = 1; v.fold = C / 8;
+    v.out_buf = out_buf; v.out_lo_buf = lo(out_buf); v.out_pitch = C; v.tshift = 1; v.fold = C / 8;
   };
-  auto plain = [&](ConvSpec& v, int out_buf, int pitch) { v.out_buf = out_buf; v.out_pitch = pitch; };
+  auto plain = [&](ConvSpec& v, int out_buf, int pitch) { v.out_buf = out_buf; v.out_lo_buf = lo(out_buf); v.out_pitch = pitch; };
 
   auto den_block = [&](const std::string& p, int in_buf, int in_pitch, int in_c, int out_c, bool last) {
     // (temp2 of the streaming layout uses the second buffer set)
@@ -94,7 +113,7 @@ std::string build_bsvd_clip(const PlanCfgLite& c, Program* P) {
     {  // conv + PixelShuffle(2) + skip3, feeding upc1's first shift conv
       ConvSpec v = conv(p + "upc2.convblock.0", kModeConv3, u2b, H / 4, W / 4, c2, c2, c1 * 4, kActNone);
       v.out_mode = kOutPS2NHWC; v.wperm = 1; v.out_h = H / 2; v.out_w = W / 2;
-      v.res1_buf = x1; v.res1_pitch = c1; v.beta1 = 1.f;
+      v.res1_buf = x1; v.res1_lo_buf = lo(x1); v.res1_pitch = c1; v.beta1 = 1.f;
       shifted(v, p2, c1);
       P->add_conv(v);
     }
@@ -103,7 +122,7 @@ std::string build_bsvd_clip(const PlanCfgLite& c, Program* P) {
     {  // conv + PixelShuffle(2) + skip2
       ConvSpec v = conv(p + "upc1.convblock.0", kModeConv3, u1b, H / 2, W / 2, c1, c1, c0 * 4, kActNone);
       v.out_mode = kOutPS2NHWC; v.wperm = 1; v.out_h = H; v.out_w = W;
-      v.res1_buf = x0; v.res1_pitch = c0; v.beta1 = 1.f;
+      v.res1_buf = x0; v.res1_lo_buf = lo(x0); v.res1_pitch = c0; v.beta1 = 1.f;
       plain(v, p1, c0);
       P->add_conv(v);
     }
@@ -111,7 +130,7 @@ std::string build_bsvd_clip(const PlanCfgLite& c, Program* P) {
     {  // out[:, :3] = in[:, :3] - out[:, :3]: first three output channels negated in the weights, + masked input residual
       ConvSpec v = conv(p + "outc.convblock.3", kModeConv3, o0, H, W, c0, c0, out_c, kActNone);
       v.neg_first = 3;
-      v.res1_buf = in_buf; v.res1_pitch = in_pitch; v.res1_nch = 3; v.beta1 = 1.f;
+      v.res1_buf = in_buf; v.res1_lo_buf = lo(in_buf); v.res1_pitch = in_pitch; v.res1_nch = 3; v.beta1 = 1.f;
       if (last) {
         v.out_mode = c.out_fmt == 1 ? kOutNCHWF16 : kOutNCHWF32; v.out_buf = kBufExternalOut;
       } else {

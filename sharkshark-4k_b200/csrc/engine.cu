@@ -474,6 +474,10 @@ void fill_epilogue(const ConvSpec& cs, bool bf16, BufPtr bufptr, float* d_bias, 
   E.t0 = 0; E.t_count = cs.n;
   E.off_prev = E.off_next = 0;
   E.res1_lo_off = E.res2_lo_off = 0;
+  if (cs.res1_buf >= 0 && cs.res1_lo_buf >= 0)
+    E.res1_lo_off = reinterpret_cast<const uint16_t*>(bufptr(cs.res1_lo_buf)) - reinterpret_cast<const uint16_t*>(bufptr(cs.res1_buf));
+  if (cs.res2_buf >= 0 && cs.res2_lo_buf >= 0)
+    E.res2_lo_off = reinterpret_cast<const uint16_t*>(bufptr(cs.res2_lo_buf)) - reinterpret_cast<const uint16_t*>(bufptr(cs.res2_buf));
   if (cs.tshift) {  // clip mode: time == batch index, neighbouring frames are one image stride away
     const int64_t frame = static_cast<int64_t>(cs.out_h) * cs.out_w * cs.out_pitch;
     E.off_prev = -frame; E.off_next = frame;

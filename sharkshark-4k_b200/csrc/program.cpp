@@ -234,7 +234,7 @@ std::string Program::to_json() const {
       js_kv(o, "in_buf", c.in_buf); js_kv(o, "in_lo_buf", c.in_lo_buf); js_kv(o, "in_h", c.in_h);
       js_kv(o, "in_w", c.in_w); js_kv(o, "in_pitch", c.in_pitch); js_kv(o, "in_coff", c.in_coff);
       js_kv(o, "act", c.act); js_kv(o, "alpha", c.alpha); js_kv(o, "beta1", c.beta1);
-      js_kv(o, "beta2", c.beta2); js_kv(o, "res1_buf", c.res1_buf); js_kv(o, "res1_pitch", c.res1_pitch);
+      js_kv(o, "beta2", c.beta2); js_kv(o, "res1_buf", c.res1_buf); js_kv(o, "res1_lo_buf", c.res1_lo_buf); js_kv(o, "res2_lo_buf", c.res2_lo_buf); js_kv(o, "res1_pitch", c.res1_pitch);
       js_kv(o, "res1_coff", c.res1_coff); js_kv(o, "res2_buf", c.res2_buf);
       js_kv(o, "res2_pitch", c.res2_pitch); js_kv(o, "res2_coff", c.res2_coff);
       js_kv(o, "out_mode", c.out_mode); js_kv(o, "out_buf", c.out_buf); js_kv(o, "out_lo_buf", c.out_lo_buf);

@@ -45,6 +45,7 @@ struct ConvSpec {
   float alpha = 1.f, beta1 = 0.f, beta2 = 0.f;
   int res1_buf = kBufNone, res1_pitch = 0, res1_coff = 0;
   int res2_buf = kBufNone, res2_pitch = 0, res2_coff = 0;
+  int res1_lo_buf = kBufNone, res2_lo_buf = kBufNone;  // split mode: low halves of the residual tensors
   int out_mode = 0;                 // OutMode
   int out_buf = kBufNone, out_lo_buf = kBufNone, out2_buf = kBufNone, out3_buf = kBufNone;
   int out_pitch = 0, out_coff = 0;

@@ -67,6 +67,29 @@ def test_bsvd_constructor_init_report(engine):
     assert psnr >= 45 and rel < 5e-3
 
 
+@pytest.mark.parametrize("frames,h,w", [(3, 48, 128), (1, 72, 128), (5, 64, 136)])
+def test_bsvd_constructor_init_split_precision(engine, frames, h, w):
+    """Reference constructor init (kaiming_normal_, model.py:393-400,501-508; fp32 outputs span +-14) through the
+    fp16 hi/lo split mode (3 MMAs per product, every activation tensor stored as hi + lo): full north-star gate."""
+    sd = bsvd.build_bsvd32(0)
+    x = _clip(frames, h, w)
+    want = bsvd.bsvd_forward(sd, x)
+    model = native_bsvd.NativeBSVD(sd, device=0, act_mode=L.ACT_F16_SPLIT)
+    got = model(x.cuda())
+    torch.cuda.synchronize()
+    psnr, maxabs = gate(got, want)
+    rel = (got.float().cpu() - want).abs().max().item() / want.abs().max().item()
+    print(f"BSVD-32 (constructor init) fp16 split F={frames} {h}x{w}: PSNR {psnr:.1f} dB, max|err| {maxabs:.3f}/255, rel {rel:.2e}")
+    assert psnr >= 50 and maxabs <= 2.0
+
+
+def test_bsvd_auto_precision(engine):
+    """act_mode='auto' (the build_model default) picks the split mode for kaiming-magnitude weights and the
+    single-MMA mode for trained-like magnitudes."""
+    assert native_bsvd.NativeBSVD(bsvd.build_bsvd32(0), device=0, act_mode="auto").act_mode == L.ACT_F16_SPLIT
+    assert native_bsvd.NativeBSVD(bsvd.build_bsvd32(0, weight_scale=0.5), device=0, act_mode="auto").act_mode == L.ACT_F16
+
+
 def test_bsvd_streaming_equals_clip(engine):
     """Ring-buffer streaming (one frame per push, 16 frames of latency, flush at the end) must reproduce the clip
     result; a second clip after reset() must not see state of the first (model.py:579)."""
