@@ -140,6 +140,12 @@ int ss4k_plan_io_bytes(const ss4k_plan* plan, int64_t* in_bytes, int64_t* out_by
 int ss4k_plan_profile(ss4k_plan* plan, const void* in_dev, void* out_dev, void* cuda_stream, float* ms,
                       double* flops, int32_t* kind, int cap);
 
+/* colour stage on the encoder side (north star part 4; the reference hands rgb24 to an ffmpeg pipe,
+ * src/stream/twitch_stream/output_stream.py:115-175, and lets swscale convert): uint8 NHWC RGB frames
+ * [n,h,w,3] -> NV12 (Y plane u8[h,w] + interleaved UV u8[h/2,w] per frame), BT.709 limited range, 15-bit fixed
+ * point, chroma = mean of the 2x2 block.  h % 2 == 0, w % 4 == 0.  Device pointers. */
+int ss4k_rgb_to_nv12(ss4k_ctx* ctx, const void* rgb_dev, void* nv12_dev, int n, int h, int w, void* cuda_stream);
+
 /* BSVD streaming (persistent per-stream ring buffers) ----------------------------------- */
 /* open: plan must be an SS4K_ARCH_BSVD plan (its n is ignored; frames are pushed one at a time) */
 int ss4k_bsvd_stream_open(ss4k_plan* plan, ss4k_bsvd_stream** out_stream);

@@ -56,6 +56,7 @@ SYMBOLS = {
     "ss4k_bsvd_stream_reset": (_i, [_vp]),
     "ss4k_bsvd_stream_latency": (_i, [_vp]),
     "ss4k_bsvd_stream_close": (_i, [_vp]),
+    "ss4k_rgb_to_nv12": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
     "ss4k_glue_chan_stats": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "ss4k_glue_area_pool": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _i, _i, _vp]),
     "ss4k_glue_blur_diff": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, ctypes.c_double, ctypes.c_double, _vp]),

@@ -156,6 +156,48 @@ __global__ void ref_conv3x3_kernel(const uint16_t* __restrict__ in, const float*
   out[idx] = acc;
 }
 
+// uint8 NHWC RGB -> NV12 (encoder side of the north star's colour stage; no reference implementation: the
+// reference hands rgb24 to ffmpeg, output_stream.py:127).  BT.709 limited range in 15-bit fixed point, chroma =
+// mean of the 2x2 block; integer arithmetic so that the oracle (oracle/colour.py) matches bit for bit.
+// One thread per 2x2 block pair (2 rows x 4 pixels): 24 bytes in, 8 Y + 4 UV bytes out.
+__global__ void rgb_to_nv12_kernel(const uint8_t* __restrict__ rgb, uint8_t* __restrict__ nv12, int N, int H, int W) {
+  const int W4 = W >> 2, H2 = H >> 1;
+  const size_t total = static_cast<size_t>(N) * H2 * W4;
+  const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int bx = static_cast<int>(idx % W4);
+  const int by = static_cast<int>((idx / W4) % H2);
+  const int n = static_cast<int>(idx / (static_cast<size_t>(W4) * H2));
+  const uint8_t* src = rgb + (static_cast<size_t>(n) * H + 2 * by) * W * 3 + static_cast<size_t>(bx) * 12;
+  uint8_t* frame = nv12 + static_cast<size_t>(n) * (static_cast<size_t>(H) * W * 3 / 2);
+  int sr[2] = {0, 0}, sg[2] = {0, 0}, sb[2] = {0, 0};
+#pragma unroll
+  for (int dy = 0; dy < 2; ++dy) {
+    const uint32_t* p = reinterpret_cast<const uint32_t*>(src + static_cast<size_t>(dy) * W * 3);  // 12-byte aligned: W % 4 == 0
+    const uint32_t w0 = __ldg(p), w1 = __ldg(p + 1), w2 = __ldg(p + 2);
+    const uint8_t px[12] = {static_cast<uint8_t>(w0), static_cast<uint8_t>(w0 >> 8), static_cast<uint8_t>(w0 >> 16), static_cast<uint8_t>(w0 >> 24),
+                            static_cast<uint8_t>(w1), static_cast<uint8_t>(w1 >> 8), static_cast<uint8_t>(w1 >> 16), static_cast<uint8_t>(w1 >> 24),
+                            static_cast<uint8_t>(w2), static_cast<uint8_t>(w2 >> 8), static_cast<uint8_t>(w2 >> 16), static_cast<uint8_t>(w2 >> 24)};
+    uint32_t ypack = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = px[3 * i], g = px[3 * i + 1], b = px[3 * i + 2];
+      const int y = 16 + ((5983 * r + 20127 * g + 2032 * b + 16384) >> 15);
+      ypack |= static_cast<uint32_t>(y) << (8 * i);
+      sr[i >> 1] += r; sg[i >> 1] += g; sb[i >> 1] += b;
+    }
+    *reinterpret_cast<uint32_t*>(frame + (static_cast<size_t>(2 * by + dy)) * W + 4 * bx) = ypack;
+  }
+  uint32_t uvpack = 0;
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const int u = 128 + ((-3298 * sr[j] - 11094 * sg[j] + 14392 * sb[j] + 65536) >> 17);
+    const int v = 128 + ((14392 * sr[j] - 13073 * sg[j] - 1319 * sb[j] + 65536) >> 17);
+    uvpack |= (static_cast<uint32_t>(u) | (static_cast<uint32_t>(v) << 8)) << (16 * j);
+  }
+  *reinterpret_cast<uint32_t*>(frame + static_cast<size_t>(H) * W + static_cast<size_t>(by) * W + 4 * bx) = uvpack;
+}
+
 template <class Src>
 cudaError_t launch_prep(Src src, void* out, void* out_lo, int N, int pitch, int us, int fill_ch,
                         float fill_val, int bf16, cudaStream_t s) {
@@ -185,6 +227,15 @@ cudaError_t prep_launch(int in_fmt, const void* in, void* out, void* out_lo, int
     default:
       return cudaErrorInvalidValue;
   }
+}
+
+cudaError_t rgb_to_nv12_launch(const void* rgb, void* nv12, int N, int H, int W, cudaStream_t s) {
+  if (H % 2 || W % 4) return cudaErrorInvalidValue;
+  const size_t total = static_cast<size_t>(N) * (H / 2) * (W / 4);
+  const int threads = 256;
+  const unsigned blocks = static_cast<unsigned>((total + threads - 1) / threads);
+  rgb_to_nv12_kernel<<<blocks, threads, 0, s>>>(reinterpret_cast<const uint8_t*>(rgb), reinterpret_cast<uint8_t*>(nv12), N, H, W);
+  return cudaGetLastError();
 }
 
 cudaError_t unprep_launch(const void* in, const void* in_lo, float* out, int N, int C, int H, int W,

@@ -17,6 +17,8 @@ cudaError_t conv_stream_launch(const StreamParams& p, int nout, int grid, cudaSt
 // in_fmt: SS4K_FMT_* ; out: [N, H/us, W/us, pitch] 16-bit NHWC (out_lo: low halves for split mode or null)
 cudaError_t prep_launch(int in_fmt, const void* in, void* out, void* out_lo, int N, int C, int H, int W,
                         int pitch, int unshuffle, int fill_ch, float fill_val, int bf16, cudaStream_t s);
+// uint8 NHWC RGB [N,H,W,3] -> NV12 (Y plane + interleaved UV per frame), BT.709 limited range, H % 2 == 0, W % 4 == 0
+cudaError_t rgb_to_nv12_launch(const void* rgb, void* nv12, int N, int H, int W, cudaStream_t s);
 cudaError_t unprep_launch(const void* in, const void* in_lo, float* out, int N, int C, int H, int W,
                           int pitch, int coff, int bf16, cudaStream_t s);
 cudaError_t ref_conv3x3_launch(const void* in, const float* w, const float* bias, float* out, int N, int H,

@@ -969,6 +969,14 @@ int ss4k_plan_create(ss4k_ctx* ctx, const ss4k_plan_cfg* cfg, ss4k_plan** out_pl
   return SS4K_OK;
 }
 
+int ss4k_rgb_to_nv12(ss4k_ctx* ctx, const void* rgb_dev, void* nv12_dev, int n, int h, int w, void* cuda_stream) {
+  if (!ctx || !rgb_dev || !nv12_dev || n <= 0 || h <= 0 || w <= 0) return fail(ctx, SS4K_E_INVALID, "bad argument to ss4k_rgb_to_nv12");
+  if (h % 2 || w % 4) return fail(ctx, SS4K_E_INVALID, "ss4k_rgb_to_nv12 needs h % 2 == 0 and w % 4 == 0");
+  CK(ctx, rgb_to_nv12_launch(rgb_dev, nv12_dev, n, h, w, static_cast<cudaStream_t>(cuda_stream)));
+  ctx->launches += 1;
+  return SS4K_OK;
+}
+
 int ss4k_plan_out_shape(const ss4k_plan* pl, int32_t out_nchw[4]) {
   if (!pl || !out_nchw) return SS4K_E_INVALID;
   out_nchw[0] = pl->prog.out_n; out_nchw[1] = pl->prog.out_c; out_nchw[2] = pl->prog.out_h; out_nchw[3] = pl->prog.out_w;

@@ -63,6 +63,17 @@ class Engine:
         return Plan(self, make_cfg(net_id, arch, n, h, w, scale, depth, tile, tile_pad, act_mode, in_fmt,
                                    out_fmt, use_graph))
 
+    def rgb_to_nv12(self, frames):
+        """uint8 NHWC RGB CUDA frames [N,H,W,3] -> uint8 [N, H*W*3/2] NV12 (Y plane + interleaved UV), BT.709 limited
+        range (encoder side of the colour stage; ss4k_rgb_to_nv12)."""
+        assert frames.is_cuda and frames.dtype == torch.uint8 and frames.is_contiguous() and frames.shape[-1] == 3
+        n, h, w, _ = frames.shape
+        out = torch.empty(n, h * w * 3 // 2, device=frames.device, dtype=torch.uint8)
+        st = ctypes.c_void_p(torch.cuda.current_stream(frames.device).cuda_stream)
+        L.check(self.lib.ss4k_rgb_to_nv12(self.h, ctypes.c_void_p(frames.data_ptr()), ctypes.c_void_p(out.data_ptr()),
+                                          n, h, w, st), self.h)
+        return out
+
     def conv3x3(self, x, weight, bias=None, slope=None, residual=None, mode=L.MODE_CONV3, act=0,
                 act_mode=L.ACT_F16, pixel_shuffle=0, alpha=1.0, beta=1.0, direct_f32=False):
         """Operator-level entry (kernel parity tests): float NCHW CUDA tensors in / out."""

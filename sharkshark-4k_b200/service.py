@@ -67,7 +67,8 @@ class FsrcnnUpscalerService:
 
     def __init__(self, lr_level=3, device=0, on_queue=None, denoising=True, denoise_rate=1.0,
                  upscaler_model='realesrgan', batch_size=1, jit_mode=None, lr_hr_resize=True,
-                 model_name=None, state_dict=None, denoise_state_dict=None, act_mode=L.ACT_F16):
+                 model_name=None, state_dict=None, denoise_state_dict=None, act_mode=L.ACT_F16,
+                 denoise_act_mode="auto"):
         self.lr_shape = self.LR_SHAPES[lr_level]
         self.scale = 4
         self.denoise_rate = denoise_rate
@@ -87,6 +88,7 @@ class FsrcnnUpscalerService:
         self.state_dict = state_dict
         self.denoise_state_dict = denoise_state_dict
         self.act_mode = act_mode
+        self.denoise_act_mode = denoise_act_mode   # 'auto': fp16, or fp16 hi/lo split for kaiming-magnitude weights
         self.model = None
 
     # ------------------------------------------------------------------ life cycle (fsrcnn_upscaler.py:118-142)
@@ -107,7 +109,7 @@ class FsrcnnUpscalerService:
         self.lib = self.engine.lib
         if self.denoising:
             self.denoise_model = native_bsvd.build_model(device=self.device.index or 0, input_shape=self.lr_shape,
-                                                         state_dict=self.denoise_state_dict, act_mode=self.act_mode)
+                                                         state_dict=self.denoise_state_dict, act_mode=self.denoise_act_mode)
         self.match_blur = gaussian_kernel(8 * 2 + 1, 8.0).to(self.device)     # :138
         self._sums = {}
 

@@ -1,0 +1,58 @@
+"""Colour stage at the frame boundary (north star part 4): NV12 in (fused into the layout kernel that feeds the
+first conv) and RGB -> NV12 out.  The reference has no implementation of either (frames are rgb24 on its pipes), so
+the oracle is this repository's own definition (oracle/colour.py): unpinned by construction."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from ss4k_b200 import _lib as L
+from ss4k_b200 import realesrgan
+from oracle import colour, rrdbnet
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("n,h,w", [(1, 2, 4), (2, 36, 68), (1, 720, 1280), (1, 1440, 2560)])
+def test_rgb_to_nv12_bit_exact(engine, n, h, w):
+    g = torch.Generator().manual_seed(5)
+    frames = torch.randint(0, 256, (n, h, w, 3), dtype=torch.uint8, generator=g)
+    frames[0, 0, :4] = torch.tensor([[0, 0, 0], [255, 255, 255], [255, 0, 0], [0, 0, 255]], dtype=torch.uint8)
+    want = colour.rgb_to_nv12(frames.numpy())
+    got = engine.rgb_to_nv12(frames.cuda()).cpu().numpy()
+    assert got.shape == want.shape
+    assert np.array_equal(got, want)
+
+
+def test_nv12_roundtrip_property(engine):
+    """Full-size property: NV12 -> (layout kernel) -> identity is not available, but RGB -> NV12 -> RGB through the
+    oracle's decoder must stay within the 4:2:0 quantisation error for a smooth image."""
+    h, w = 720, 1280
+    yy, xx = torch.meshgrid(torch.arange(h), torch.arange(w), indexing="ij")
+    img = torch.stack([(xx * 255 // w), (yy * 255 // h), ((xx + yy) * 255 // (w + h))], dim=-1).to(torch.uint8)[None]
+    nv = engine.rgb_to_nv12(img.cuda()).cpu().numpy()
+    back = colour.nv12_to_rgb(nv, h, w)[0].transpose(1, 2, 0) * 255.0
+    assert np.abs(back - img[0].numpy()).max() <= 3.0
+
+
+def test_nv12_input_path_matches_oracle(engine):
+    """NV12 frames in -> RRDBNet x2 -> uint8 RGB out; the oracle decodes NV12 with oracle/colour.py and runs the
+    fp32 net."""
+    torch.manual_seed(0)
+    net = rrdbnet.RRDBNet(3, 3, 2, 64, 2, 32).eval()
+    h, w = 40, 64
+    g = torch.Generator().manual_seed(9)
+    rgb = torch.randint(0, 256, (2, h, w, 3), dtype=torch.uint8, generator=g)
+    nv = colour.rgb_to_nv12(rgb.numpy())
+    x = torch.from_numpy(colour.nv12_to_rgb(nv, h, w))
+    with torch.no_grad():
+        want = net(x).clamp(0, 1)
+    model = realesrgan.NativeRRDBNet(net.state_dict(), scale=2, num_block=2, device=0)
+    plan = model._plan(2, h, w, L.FMT_NV12, L.FMT_F32_NCHW)
+    got = plan.run(torch.from_numpy(nv).cuda()).cpu().clamp(0, 1)
+    mse = torch.mean((got - want) ** 2).item()
+    psnr = 99.0 if mse == 0 else -10 * math.log10(mse)
+    maxabs = (got - want).abs().max().item() * 255
+    print(f"NV12 -> RRDBNet-2 x2: PSNR {psnr:.1f} dB, max|err| {maxabs:.3f}/255")
+    assert psnr >= 50 and maxabs <= 2.0

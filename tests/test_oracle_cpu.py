@@ -151,3 +151,18 @@ def test_bsvd_matches_live_reference():
         assert torch.equal(sd[k], v), k
     got = bsvd.bsvd_forward(sd, x)
     assert (got - want).abs().max().item() <= 2e-5 * want.abs().max().item()
+
+
+def test_colour_oracle_known_answers():
+    """oracle/colour.py (BT.709 limited range): black / white / primaries land on the standard code values and the
+    decode of the encode returns the colour within 4:2:0 rounding."""
+    import numpy as np
+    from oracle import colour
+    cases = {(0, 0, 0): (16, 128, 128), (255, 255, 255): (235, 128, 128), (255, 0, 0): (63, 102, 240),
+             (0, 255, 0): (173, 42, 26), (0, 0, 255): (32, 240, 118)}
+    for rgb, yuv in cases.items():
+        a = np.array(rgb, dtype=np.uint8).reshape(1, 1, 1, 3).repeat(2, 1).repeat(4, 2)
+        q = colour.rgb_to_nv12(a)
+        assert (int(q[0, 0]), int(q[0, 8]), int(q[0, 9])) == yuv, (rgb, q[0, 0], q[0, 8], q[0, 9])
+        back = colour.nv12_to_rgb(q, 2, 4)[0, :, 0, 0] * 255
+        assert np.abs(back - np.array(rgb)).max() <= 1.5
