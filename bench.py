@@ -227,6 +227,11 @@ def run_native(args, rank, world, local_rank):
         nbytes = hr.numel() * 1.5
         hbm_kernels.append({"kernel": "rgb_to_nv12_kernel", "bytes_per_launch": nbytes, "us": 1000 * t, "GB/s": nbytes / t / 1e6,
                             "what": "uint8 RGB 2560x1440 -> NV12: 3 B/px read + 1.5 B/px written"})
+        big = torch.randint(0, 256, (8, 2 * FRAME_H, 2 * FRAME_W, 3), dtype=torch.uint8, device=dev)
+        t8 = timed(lambda: eng.rgb_to_nv12(big))
+        hbm_kernels.append({"kernel": "rgb_to_nv12_kernel", "bytes_per_launch": big.numel() * 1.5, "us": 1000 * t8,
+                            "GB/s": big.numel() * 1.5 / t8 / 1e6, "what": "the same on 8 frames per launch (133 MB: above launch latency and L2)"})
+        del big
         layout = [(ms_, kd) for (ms_, fl, kd) in prof[0] if kd == 0]
         if layout:
             # prep_kernel: uint8 NHWC 1280x720 -> fp16 NHWC, pixel-unshuffle(2), 16-channel pitch: 3 B/px in, 32 B per trunk px out

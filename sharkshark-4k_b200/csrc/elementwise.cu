@@ -113,6 +113,43 @@ __global__ void prep_kernel(Src src, uint16_t* __restrict__ out, uint16_t* __res
   }
 }
 
+// Hot case of the service boundary (fsrcnn_upscaler.py:170-172 + RRDBNet x2's pixel_unshuffle(2)): uint8 NHWC RGB frame
+// -> /255 -> pixel_unshuffle(2) -> 16-channel-pitch 16-bit NHWC.  One thread per TWO trunk pixels: 2 rows x 12 source
+// bytes (three aligned 32-bit loads per row), 64 bytes out (four 16-byte stores).  W % 4 == 0.
+__global__ void prep_u8_unshuffle2_kernel(const uint8_t* __restrict__ in, uint16_t* __restrict__ out, int N, int H, int W, int bf16) {
+  const int OH = H >> 1, OW2 = W >> 2;
+  const size_t total = static_cast<size_t>(N) * OH * OW2;
+  const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int px = static_cast<int>(idx % OW2);
+  const int oy = static_cast<int>((idx / OW2) % OH);
+  const int n = static_cast<int>(idx / (static_cast<size_t>(OW2) * OH));
+  uint8_t b[2][12];
+#pragma unroll
+  for (int dy = 0; dy < 2; ++dy) {
+    const uint32_t* p = reinterpret_cast<const uint32_t*>(in + (static_cast<size_t>(n) * H + 2 * oy + dy) * W * 3 + static_cast<size_t>(px) * 12);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      const uint32_t w = __ldg(p + i);
+      b[dy][4 * i] = static_cast<uint8_t>(w); b[dy][4 * i + 1] = static_cast<uint8_t>(w >> 8);
+      b[dy][4 * i + 2] = static_cast<uint8_t>(w >> 16); b[dy][4 * i + 3] = static_cast<uint8_t>(w >> 24);
+    }
+  }
+  uint16_t* o = out + ((static_cast<size_t>(n) * OH + oy) * (W >> 1) + 2 * px) * 16;
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {  // trunk pixel 2*px + q: source pixels (2*oy + i, 4*px + 2*q + j)
+    uint16_t v[16];
+#pragma unroll
+    for (int ch = 0; ch < 12; ++ch) {  // torch pixel_unshuffle: ch = c*4 + i*2 + j
+      const int c = ch >> 2, i = (ch >> 1) & 1, j = ch & 1;
+      v[ch] = to16(static_cast<float>(b[i][(2 * q + j) * 3 + c]) / 255.0f, bf16 != 0);
+    }
+    v[12] = v[13] = v[14] = v[15] = 0;
+    *reinterpret_cast<uint4*>(o + 16 * q) = *reinterpret_cast<uint4*>(v);
+    *reinterpret_cast<uint4*>(o + 16 * q + 8) = *reinterpret_cast<uint4*>(v + 8);
+  }
+}
+
 __global__ void unprep_kernel(const uint16_t* __restrict__ in, const uint16_t* __restrict__ in_lo,
                               float* __restrict__ out, int N, int C, int H, int W, int pitch, int coff,
                               int bf16) {
@@ -198,6 +235,44 @@ __global__ void rgb_to_nv12_kernel(const uint8_t* __restrict__ rgb, uint8_t* __r
   *reinterpret_cast<uint32_t*>(frame + static_cast<size_t>(H) * W + static_cast<size_t>(by) * W + 4 * bx) = uvpack;
 }
 
+// Same conversion, 2 rows x 16 pixels per thread with 16-byte loads / stores (W % 16 == 0).
+__global__ void rgb_to_nv12_wide_kernel(const uint8_t* __restrict__ rgb, uint8_t* __restrict__ nv12, int N, int H, int W) {
+  const int W16 = W >> 4, H2 = H >> 1;
+  const size_t total = static_cast<size_t>(N) * H2 * W16;
+  const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int bx = static_cast<int>(idx % W16);
+  const int by = static_cast<int>((idx / W16) % H2);
+  const int n = static_cast<int>(idx / (static_cast<size_t>(W16) * H2));
+  uint8_t* frame = nv12 + static_cast<size_t>(n) * (static_cast<size_t>(H) * W * 3 / 2);
+  int sr[8], sg[8], sb[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) sr[j] = sg[j] = sb[j] = 0;
+#pragma unroll
+  for (int dy = 0; dy < 2; ++dy) {
+    const uint4* p = reinterpret_cast<const uint4*>(rgb + (static_cast<size_t>(n) * H + 2 * by + dy) * W * 3 + static_cast<size_t>(bx) * 48);
+    uint4 q[3] = {__ldg(p), __ldg(p + 1), __ldg(p + 2)};
+    const uint8_t* px = reinterpret_cast<const uint8_t*>(q);
+    uint32_t yw[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const int r = px[3 * i], g = px[3 * i + 1], b = px[3 * i + 2];
+      const int y = 16 + ((5983 * r + 20127 * g + 2032 * b + 16384) >> 15);
+      yw[i >> 2] |= static_cast<uint32_t>(y) << (8 * (i & 3));
+      sr[i >> 1] += r; sg[i >> 1] += g; sb[i >> 1] += b;
+    }
+    *reinterpret_cast<uint4*>(frame + static_cast<size_t>(2 * by + dy) * W + 16 * bx) = make_uint4(yw[0], yw[1], yw[2], yw[3]);
+  }
+  uint32_t uvw[4] = {0, 0, 0, 0};
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int u = 128 + ((-3298 * sr[j] - 11094 * sg[j] + 14392 * sb[j] + 65536) >> 17);
+    const int v = 128 + ((14392 * sr[j] - 13073 * sg[j] - 1319 * sb[j] + 65536) >> 17);
+    uvw[j >> 1] |= (static_cast<uint32_t>(u) | (static_cast<uint32_t>(v) << 8)) << (16 * (j & 1));
+  }
+  *reinterpret_cast<uint4*>(frame + static_cast<size_t>(H) * W + static_cast<size_t>(by) * W + 16 * bx) = make_uint4(uvw[0], uvw[1], uvw[2], uvw[3]);
+}
+
 template <class Src>
 cudaError_t launch_prep(Src src, void* out, void* out_lo, int N, int pitch, int us, int fill_ch,
                         float fill_val, int bf16, cudaStream_t s) {
@@ -221,6 +296,12 @@ cudaError_t prep_launch(int in_fmt, const void* in, void* out, void* out_lo, int
     case 1:
       return launch_prep(SrcF16NCHW{reinterpret_cast<const __half*>(in), C, H, W}, out, out_lo, N, pitch, us, fill_ch, fill_val, bf16, s);
     case 2:
+      if (us == 2 && C == 3 && pitch == 16 && out_lo == nullptr && fill_ch < 0 && W % 4 == 0 && H % 2 == 0) {
+        const size_t total = static_cast<size_t>(N) * (H / 2) * (W / 4);
+        prep_u8_unshuffle2_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(
+            reinterpret_cast<const uint8_t*>(in), reinterpret_cast<uint16_t*>(out), N, H, W, bf16);
+        return cudaGetLastError();
+      }
       return launch_prep(SrcU8NHWC{reinterpret_cast<const uint8_t*>(in), C, H, W}, out, out_lo, N, pitch, us, fill_ch, fill_val, bf16, s);
     case 3:
       return launch_prep(SrcNV12{reinterpret_cast<const uint8_t*>(in), 3, H, W}, out, out_lo, N, pitch, us, fill_ch, fill_val, bf16, s);
@@ -231,6 +312,12 @@ cudaError_t prep_launch(int in_fmt, const void* in, void* out, void* out_lo, int
 
 cudaError_t rgb_to_nv12_launch(const void* rgb, void* nv12, int N, int H, int W, cudaStream_t s) {
   if (H % 2 || W % 4) return cudaErrorInvalidValue;
+  if (W % 16 == 0 && (reinterpret_cast<uintptr_t>(rgb) & 15) == 0 && (reinterpret_cast<uintptr_t>(nv12) & 15) == 0) {
+    const size_t tw = static_cast<size_t>(N) * (H / 2) * (W / 16);
+    rgb_to_nv12_wide_kernel<<<static_cast<unsigned>((tw + 127) / 128), 128, 0, s>>>(reinterpret_cast<const uint8_t*>(rgb),
+                                                                                   reinterpret_cast<uint8_t*>(nv12), N, H, W);
+    return cudaGetLastError();
+  }
   const size_t total = static_cast<size_t>(N) * (H / 2) * (W / 4);
   const int threads = 256;
   const unsigned blocks = static_cast<unsigned>((total + threads - 1) / threads);

@@ -269,13 +269,20 @@ struct StreamPacked {
   int bias_row0 = 0;     // first row of the per-chunk bias tiles (appended after the weight tiles)
   float alpha_out = 1.f; // epilogue scale left after folding alpha into weights and bias
   uint8_t nks[kMaxSKB];
+  uint8_t src_kb[kMaxSKB];  // 64-channel block of the source tensor read by K block i
+  uint8_t src_tm[kMaxSKB];  // 0: the tensor itself (high halves in split mode), 1: its low-half twin
+  uint8_t whalf[kMaxSKB];   // 0: weights (high halves), 1: low halves of the weights
 };
 
 bool stream_config(const ConvSpec& cs, StreamPacked* sp) {
-  if (cs.mode != kModeConv3 || cs.split || cs.in_coff % 8 || cs.in_pitch % 8) return false;
+  if (cs.mode != kModeConv3 || cs.in_coff % 8 || cs.in_pitch % 8) return false;
   if (getenv("SS4K_NO_STREAM")) return false;
+  if (cs.split && getenv("SS4K_NO_STREAM_SPLIT")) return false;
   const int npad = round_up(cs.cout, 16);
-  const int nkb = (cs.cin + 63) / 64;
+  // fp16 hi/lo split operands: three K blocks per 64 source channels: A_hi*W_hi, A_hi*W_lo, A_lo*W_hi
+  const int nsplit = cs.split ? 3 : 1;
+  const int nkb0 = (cs.cin + 63) / 64;
+  const int nkb = nkb0 * nsplit;
   if (nkb > kMaxSKB) return false;
   int cand[4], nc = 0;
   if (npad <= 64) cand[nc++] = npad;
@@ -292,7 +299,13 @@ bool stream_config(const ConvSpec& cs, StreamPacked* sp) {
     if (slots < 3) continue;
     sp->nout = nout; sp->chunks = npad / nout; sp->nkb = nkb; sp->npad_total = npad;
     sp->a_slots = slots; sp->acc_slots = std::min(kMaxAccSlots, kTmemCols / nout);
-    for (int kb = 0; kb < nkb; ++kb) sp->nks[kb] = static_cast<uint8_t>((std::min(64, cs.cin - 64 * kb) + 15) / 16);
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int b0 = kb / nsplit, part = kb % nsplit;
+      sp->nks[kb] = static_cast<uint8_t>((std::min(64, cs.cin - 64 * b0) + 15) / 16);
+      sp->src_kb[kb] = static_cast<uint8_t>(b0);
+      sp->src_tm[kb] = part == 2 ? 1 : 0;
+      sp->whalf[kb] = part == 1 ? 1 : 0;
+    }
     return true;
   }
   return false;
@@ -329,9 +342,11 @@ std::string pack_weights_stream(const ConvSpec& cs, const HostTensor& W, const H
             if (n < 0) continue;
             const size_t row = ((((static_cast<size_t>(ch) * nkb + kb) * 3 + kx) * 3 + blk) * nout + co);
             for (int cc = 0; cc < 64; ++cc) {
-              const int c = kb * 64 + cc;
+              const int c = out->src_kb[kb] * 64 + cc;
               if (c >= cs.cin) break;
-              out->w[row * 64 + cc] = f2h((n < cs.neg_first ? -fold : fold) * W.data[((static_cast<size_t>(n) * cs.cin + c) * 3 + (2 - blk)) * 3 + kx], bf16);
+              const float wv = (n < cs.neg_first ? -fold : fold) * W.data[((static_cast<size_t>(n) * cs.cin + c) * 3 + (2 - blk)) * 3 + kx];
+              const uint16_t hi = f2h(wv, bf16);
+              out->w[row * 64 + cc] = out->whalf[kb] ? f2h(wv - h2f(hi, bf16), bf16) : hi;
             }
           }
   // bias tiles: row = output channel, K column 0 = high half, column 1 = low half (the "ones" operand has 1 there)
@@ -508,8 +523,9 @@ int materialize_stream(ss4k_ctx* ctx, const ConvSpec& cs, const HostTensor& W, c
   {  // activations: (64 channels, W, channel block, H, N) starting at channel in_coff
     const cuuint64_t eb = 2;
     const int avail = cs.in_pitch - cs.in_coff;
-    cuuint64_t dims[5] = {static_cast<cuuint64_t>(pk.nkb == 1 ? std::min(64, avail) : 64), static_cast<cuuint64_t>(cs.in_w),
-                          static_cast<cuuint64_t>(pk.nkb), static_cast<cuuint64_t>(cs.in_h),
+    const int nkb0 = (cs.cin + 63) / 64;  // 64-channel blocks of the source tensor (split mode: 3 K blocks each)
+    cuuint64_t dims[5] = {static_cast<cuuint64_t>(nkb0 == 1 ? std::min(64, avail) : 64), static_cast<cuuint64_t>(cs.in_w),
+                          static_cast<cuuint64_t>(nkb0), static_cast<cuuint64_t>(cs.in_h),
                           static_cast<cuuint64_t>(cs.in_ring ? cs.in_ring : cs.n)};
     cuuint64_t strides[4] = {cs.in_pitch * eb, 128, static_cast<cuuint64_t>(cs.in_w) * cs.in_pitch * eb,
                              static_cast<cuuint64_t>(cs.in_h) * cs.in_w * cs.in_pitch * eb};
@@ -520,6 +536,12 @@ int materialize_stream(ss4k_ctx* ctx, const ConvSpec& cs, const HostTensor& W, c
                              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(ctx, SS4K_E_CUDA, fmt("cuTensorMapEncodeTiled(stream activation, %s) failed: %d", cs.name.c_str(), (int)r));
     p.tmA[1] = p.tmA[0];
+    if (cs.split) {
+      void* base_lo = reinterpret_cast<uint8_t*>(bufptr(cs.in_lo_buf)) + static_cast<size_t>(cs.in_coff) * 2;
+      r = ctx->encode(&p.tmA[1], dt, 5, base_lo, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) return fail(ctx, SS4K_E_CUDA, fmt("cuTensorMapEncodeTiled(stream activation lo, %s) failed: %d", cs.name.c_str(), (int)r));
+    }
   }
   {  // weights: rows of 64 channels
     const cuuint64_t rows = pk.w.size() / 64;
@@ -575,7 +597,7 @@ int materialize_stream(ss4k_ctx* ctx, const ConvSpec& cs, const HostTensor& W, c
     p.fast_store = cs.up2_store ? 2 : 1;
   }
   p.nkb = pk.nkb;
-  for (int kb = 0; kb < pk.nkb; ++kb) { p.a_kb[kb] = static_cast<uint8_t>(kb); p.a_tm[kb] = 0; p.nks[kb] = pk.nks[kb]; }
+  for (int kb = 0; kb < pk.nkb; ++kb) { p.a_kb[kb] = pk.src_kb[kb]; p.a_tm[kb] = pk.src_tm[kb]; p.nks[kb] = pk.nks[kb]; }
   p.n_img = cs.n; p.H = cs.in_h; p.W = cs.in_w;
   p.strips = (cs.in_w + kTileW - 1) / kTileW;
   p.chunks = pk.chunks;
