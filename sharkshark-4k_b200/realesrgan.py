@@ -69,6 +69,7 @@ class _NativeNet(nn.Module):
         self.engine = Engine.get(device)
         self.scale, self.depth, self.act_mode = scale, depth, act_mode
         self.tile, self.tile_pad = tile, tile_pad
+        self.tile_batch = 16   # crops of one shape per engine run (memory bound: 16 x 1024^2 x4 crops fit 180 GB easily)
         self.out_dtype = out_dtype
         self.use_graph = use_graph
         self.net_id = self.engine.new_net(state_dict)
@@ -102,21 +103,32 @@ class _NativeNet(nn.Module):
 
     def _forward_tiled(self, x):
         """RealESRGANer.tile_process semantics: tiles_x = ceil(W/tile), padded
-        crop clamped to the image, paste of the un-padded centre, no blending."""
+        crop clamped to the image, paste of the un-padded centre, no blending.
+
+        Tiles are independent images, so all padded crops of one shape (interior tiles, and each border class) go
+        through the engine as ONE batch: at tile 256..512 a single crop is only a few rows of work per SM and the
+        per-kernel prologue / tail would dominate."""
         import math
         b, c, h, w = x.shape
         s, tile, pad = self.scale, self.tile, self.tile_pad
         out = torch.zeros(b, c, h * s, w * s, device=x.device, dtype=self.out_dtype)
+        groups = {}  # padded crop shape -> list of tile boxes
         for ty in range(math.ceil(h / tile)):
             for tx in range(math.ceil(w / tile)):
                 sx, sy = tx * tile, ty * tile
                 ex, ey = min(sx + tile, w), min(sy + tile, h)
                 sxp, exp_ = max(sx - pad, 0), min(ex + pad, w)
                 syp, eyp = max(sy - pad, 0), min(ey + pad, h)
-                crop = x[:, :, syp:eyp, sxp:exp_].contiguous()
-                o = self.plan_for(crop).run(crop)
-                ox0, oy0 = (sx - sxp) * s, (sy - syp) * s
-                out[:, :, sy * s:ey * s, sx * s:ex * s] = o[:, :, oy0:oy0 + (ey - sy) * s, ox0:ox0 + (ex - sx) * s]
+                groups.setdefault((eyp - syp, exp_ - sxp), []).append((sx, sy, ex, ey, sxp, syp, exp_, eyp))
+        max_batch = max(1, self.tile_batch // b)
+        for boxes in groups.values():
+            for g0 in range(0, len(boxes), max_batch):
+                part = boxes[g0:g0 + max_batch]
+                crops = torch.cat([x[:, :, syp:eyp, sxp:exp_] for (_, _, _, _, sxp, syp, exp_, eyp) in part], dim=0).contiguous()
+                o = self.plan_for(crops).run(crops)
+                for i, (sx, sy, ex, ey, sxp, syp, _, _) in enumerate(part):
+                    ox0, oy0 = (sx - sxp) * s, (sy - syp) * s
+                    out[:, :, sy * s:ey * s, sx * s:ex * s] = o[i * b:(i + 1) * b, :, oy0:oy0 + (ey - sy) * s, ox0:ox0 + (ex - sx) * s]
         return out
 
     # weights are not nn.Parameters: these keep callers such as ``model.eval().to(device)`` working

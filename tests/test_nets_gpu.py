@@ -85,6 +85,43 @@ def test_rrdbnet_tiled_matches_oracle_tiles(engine):
     assert psnr >= 50 and maxabs <= 2.0
 
 
+def test_rrdbnet_tiled_batched_groups(engine):
+    """Many tiles per shape class and a batch of two frames: same-shape crops run as one engine batch."""
+    torch.manual_seed(1)
+    net = rrdbnet.RRDBNet(3, 3, 4, 64, 2, 32).eval()
+    x = torch.rand(2, 3, 100, 150)
+    with torch.no_grad():
+        want = rrdbnet.tile_process(net, x, 4, 32, 6)
+    model = realesrgan.NativeRRDBNet(net.state_dict(), scale=4, num_block=2, device=0, tile=32, tile_pad=6)
+    model.tile_batch = 8
+    got = model(x.cuda())
+    assert tuple(got.shape) == (2, 3, 400, 600)
+    psnr, maxabs = gate(got, want)
+    assert psnr >= 50 and maxabs <= 2.0
+
+
+def test_error_behaviour(engine):
+    """Errors come back as Ss4kError (a RuntimeError, so BaseService.proc_main's except path fires,
+    base_service.py:64-70), never as a crash: CPU tensors, BSVD sizes that are not multiples of 4, missing weights."""
+    torch.manual_seed(0)
+    net = rrdbnet.RRDBNet(3, 3, 2, 64, 1, 32).eval()
+    model = realesrgan.NativeRRDBNet(net.state_dict(), scale=2, num_block=1, device=0)
+    with pytest.raises(L.Ss4kError):
+        model(torch.rand(1, 3, 16, 16))                       # CPU tensor: no CPU path
+    sd = {k: v for k, v in net.state_dict().items() if k != "conv_last.weight"}
+    with pytest.raises(RuntimeError):
+        realesrgan.NativeRRDBNet(sd, scale=2, num_block=1, device=0)(torch.rand(1, 3, 16, 16).cuda())
+    from ss4k_b200 import bsvd as nb
+    from oracle import bsvd as ob
+    den = nb.NativeBSVD(ob.build_bsvd32(0, weight_scale=0.5), device=0)
+    with pytest.raises(RuntimeError):
+        den(torch.rand(1, 1, 4, 18, 32).cuda())               # H % 4 != 0 (two stride-2 stages)
+    with pytest.raises(ValueError):
+        den(torch.rand(1, 1, 3, 16, 32).cuda())               # needs RGB + noise map
+    # the engine is still usable afterwards
+    assert tuple(model(torch.rand(1, 3, 16, 32).cuda()).shape) == (1, 3, 32, 64)
+
+
 def test_u8_boundary_and_host_path(engine):
     """upscale(frames) boundary: uint8 NHWC in -> uint8 NHWC out, and the host-buffer entry."""
     torch.manual_seed(0)
