@@ -76,6 +76,10 @@ std::string build_bsvd_clip(const PlanCfgLite& c, Program* P) {
 
   PrepSpec pp;
   pp.in_fmt = c.in_fmt; pp.c = 4; pp.h = H; pp.w = W; pp.n = T; pp.out_buf = in16; pp.out_lo_buf = lo(in16);
+  if (c.in_fmt == 2 || c.in_fmt == 3) {  // uint8 NHWC RGB / NV12 frames: the noise map (fsrcnn_upscaler.py:262) is filled in
+    pp.c = 3; pp.fill_ch = 3; pp.fill_val = c.bsvd_noise;
+    P->in_c = 3;
+  }
   P->add_prep(pp);
 
   auto conv = [&](const std::string& nm, int mode, int in_buf, int ih, int iw, int ipitch, int cin, int cout, int act) {

@@ -871,6 +871,7 @@ static PlanCfgLite lite(const ss4k_plan_cfg* c) {
   PlanCfgLite l;
   l.arch = c->arch; l.n = c->n; l.h = c->h; l.w = c->w; l.scale = c->scale; l.depth = c->depth;
   l.tile = c->tile; l.tile_pad = c->tile_pad; l.act_mode = c->act_mode; l.in_fmt = c->in_fmt; l.out_fmt = c->out_fmt;
+  memcpy(&l.bsvd_noise, &c->reserved[0], 4);
   return l;
 }
 

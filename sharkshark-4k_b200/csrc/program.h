@@ -93,7 +93,8 @@ struct Program {
 
 struct PlanCfgLite {
   int arch, n, h, w, scale, depth, tile, tile_pad, act_mode, in_fmt, out_fmt;
-  int bsvd_stream = 0;  // 1: BSVD program for the streaming engine (separate buffers for temp1 / temp2)
+  int bsvd_stream = 0;
+  float bsvd_noise = 0.f;  // noise-map value for 3-channel frame inputs (uint8 NHWC / NV12)  // 1: BSVD program for the streaming engine (separate buffers for temp1 / temp2)
 };
 
 // returns "" on success, else an error message

@@ -3,6 +3,7 @@
 PyTorch is used only for device buffers and streams; all arithmetic runs in libss4k.so.
 """
 import ctypes
+import struct
 import json
 
 import torch
@@ -59,9 +60,10 @@ class Engine:
         return net_id
 
     def plan(self, net_id, arch, n, h, w, scale=4, depth=0, tile=0, tile_pad=10, act_mode=L.ACT_F16,
-             in_fmt=L.FMT_F32_NCHW, out_fmt=L.FMT_F32_NCHW, use_graph=True):
-        return Plan(self, make_cfg(net_id, arch, n, h, w, scale, depth, tile, tile_pad, act_mode, in_fmt,
-                                   out_fmt, use_graph))
+             in_fmt=L.FMT_F32_NCHW, out_fmt=L.FMT_F32_NCHW, use_graph=True, bsvd_noise=0.0):
+        cfg = make_cfg(net_id, arch, n, h, w, scale, depth, tile, tile_pad, act_mode, in_fmt, out_fmt, use_graph)
+        cfg.reserved[0] = struct.unpack("<i", struct.pack("<f", float(bsvd_noise)))[0]
+        return Plan(self, cfg)
 
     def rgb_to_nv12(self, frames):
         """uint8 NHWC RGB CUDA frames [N,H,W,3] -> uint8 [N, H*W*3/2] NV12 (Y plane + interleaved UV), BT.709 limited

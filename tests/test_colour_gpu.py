@@ -56,3 +56,26 @@ def test_nv12_input_path_matches_oracle(engine):
     maxabs = (got - want).abs().max().item() * 255
     print(f"NV12 -> RRDBNet-2 x2: PSNR {psnr:.1f} dB, max|err| {maxabs:.3f}/255")
     assert psnr >= 50 and maxabs <= 2.0
+
+
+def test_bsvd_takes_nv12_and_u8_frames(engine):
+    """BSVD plans with a frame format: the layout kernel decodes NV12 (or /255 for uint8 RGB) and fills the constant
+    noise-map channel (0.1 * denoise_rate, fsrcnn_upscaler.py:262); oracle = oracle/colour.py decode + oracle BSVD."""
+    from ss4k_b200 import bsvd as nb
+    from oracle import bsvd as ob
+    sd = ob.build_bsvd32(0, weight_scale=0.5)
+    t, h, w = 3, 32, 136
+    g = torch.Generator().manual_seed(4)
+    rgb = torch.randint(0, 256, (t, h, w, 3), dtype=torch.uint8, generator=g)
+    nv = colour.rgb_to_nv12(rgb.numpy())
+    den = nb.NativeBSVD(sd, device=0)
+    for name, frames, x3 in (("nv12", torch.from_numpy(nv), torch.from_numpy(colour.nv12_to_rgb(nv, h, w))),
+                             ("u8", rgb, rgb.permute(0, 3, 1, 2).float() / 255.0)):
+        x = torch.cat([x3, torch.full((t, 1, h, w), 0.075)], dim=1)[None]
+        want = ob.bsvd_forward(sd, x)[0].clamp(0, 1)
+        got = den.denoise_frames(frames.cuda(), h, w, 0.075, nv12=(name == "nv12")).float().cpu().clamp(0, 1)
+        mse = torch.mean((got - want) ** 2).item()
+        psnr = 99.0 if mse == 0 else -10 * math.log10(mse)
+        maxabs = (got - want).abs().max().item() * 255
+        print(f"BSVD from {name} frames: PSNR {psnr:.1f} dB, max|err| {maxabs:.3f}/255")
+        assert psnr >= 50 and maxabs <= 2.0
