@@ -20,10 +20,20 @@
 //   * the bias is added by the tensor core: the MMA that zero-initialises a fresh accumulator slot is
 //     ones[128 x 16] x bias_tile[NOUT x 16] (bias hi/lo halves in K columns 0/1), so every real MMA
 //     accumulates and the epilogue has no per-channel bias loads.
-//   * warp 0 = TMA producer, warp 1 = MMA issuer, warps 2..9 = epilogue, two warps per TMEM lane
+//   * warp 0 = TMA producer and row planner, warp 1 = MMA issuer, warps 2..9 = epilogue, two warps per TMEM lane
 //     quarter taking alternate output rows: TMEM -> registers -> activation / scaled residual adds ->
 //     16-bit pack -> swizzled shared-memory tile -> TMA store (plain NHWC outputs), or the generic
-//     path (PixelShuffle / NCHW / uint8 / temporal-shift scatter stores).
+//     path (PixelShuffle / NCHW / uint8 / temporal-shift scatter / hi+lo split stores).
+//   * row records: the accumulator-ring bookkeeping of every input row (which slots it touches first / completes,
+//     where the ring wraps, descriptors, chunk switches) is computed by the producer warp and travels with the
+//     row's first activation slab as a 32-byte record; the issuing warp reads the NEXT row's record, waits for
+//     its fresh accumulator slot and issues its bias-init MMA in the middle of the current row's last burst, so
+//     the tensor pipe's queue (about 6 instructions, scripts/mma_issue_probe.cu) never drains at a row boundary.
+//   * fp16 hi/lo split operands (BSVD precision mode): three K blocks per 64 source channels
+//     (A_hi*W_hi, A_hi*W_lo, A_lo*W_hi), the low halves through a second activation tensor map.
+//   * measured bound: an M=128, N=96, K=16 MMA costs 56 clk of shared-memory port time for
+//     48 clk of math; with the slab written by TMA and the epilogue's staging tile the port carries 121.6 KB per
+//     row of a 64->32 conv = 950 clk, which is the row period the kernel runs at.
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
