@@ -181,6 +181,11 @@ int ss4k_glue_finalize(const void* hr, int fmt, int n, int c, int h, int w, cons
                        const double* hr_sums, const double* lr_sums, double cnt_hr, double cnt_lr, uint8_t* out_u8,
                        float* out_f32, int round_u8, void* cuda_stream);
 /* F.interpolate(mode='bicubic') of a float NCHW image, clamp, uint8 NHWC (fsrcnn_upscaler.py:222-233) */
+/* finalize + bicubic resize + uint8 in one pass (no full-resolution fp32 intermediate): the tail of upscale_multi /
+ * upscale_single when output_shape differs from the net's output (fsrcnn_upscaler.py:214-233,315-326) */
+int ss4k_glue_finalize_bicubic_u8(const void* hr, int fmt, int n, int c, int h, int w, const float* diff, int dh, int dw,
+                                  const double* hr_sums, const double* lr_sums, double cnt_hr, double cnt_lr,
+                                  uint8_t* out_u8, int oh, int ow, int round_u8, void* cuda_stream);
 int ss4k_glue_bicubic_u8(const float* in, int n, int c, int h, int w, uint8_t* out, int oh, int ow, int round_u8,
                          void* cuda_stream);
 /* opacity * clamp(sharpen_ker(strength)(x), 0, 1) + (1-opacity) * other -> float NCHW; other may be NULL

@@ -48,6 +48,25 @@ def main():
                 print(json.dumps({"config": name, "frame": [h, w], "tile": tile, "bsvd_mode": mode, "frames_per_clip": F,
                                   "bsvd_ms_per_frame": t_den / F, "total_ms_per_frame": t_all / F, "frames/s": 1000 * F / t_all}), flush=True)
                 del den
+    if "live" in which:
+        # The one figure the reference publishes (README.md:20): live 720p -> 1440p with the default wiring =
+        # FsrcnnUpscalerService.upscale_multi, SRVGGNetCompact-32 x4 (realesr-general-x4v3), batch 4, colour match,
+        # bicubic down to 1440p, uint8 in / out: 24 fps on an RTX 4090 (TensorRT fp16).
+        from ss4k_b200 import service
+        from oracle import srvgg
+        net = srvgg.SRVGGNetCompact(3, 3, 64, 32, 4).eval()
+        svc = service.FsrcnnUpscalerService(lr_level=3, device=0, denoising=False, model_name='realesr-general-x4v3',
+                                            state_dict=net.state_dict(), batch_size=4, denoise_rate=1.0)
+        svc.proc_init()
+        svc.output_shape = (1440, 2560)
+        frames = torch.randint(0, 256, (4, 720, 1280, 3), dtype=torch.uint8, device="cuda")
+        t = ev_time(lambda: svc.upscale(frames), 5)
+        m = realesrgan.NativeSRVGG(net.state_dict(), num_conv=32, upscale=4, device=0)
+        plan = m._plan(4, 720, 1280, L.FMT_U8_NHWC, L.FMT_F16_NCHW)
+        tm = ev_time(lambda: plan.run(frames), 5)
+        print(json.dumps({"config": "live default (README.md:20: 24 fps on RTX 4090)", "what": "FsrcnnUpscalerService.upscale, SRVGG-32 x4 720p -> 2880p -> colour match -> bicubic 1440p, batch 4, uint8 in/out",
+                          "ms_per_batch": t, "frames/s": 4000 / t, "model_only_ms_per_batch": tm, "model_only_frames/s": 4000 / tm,
+                          "model_TFLOP/s": 4 * 2.228 / tm}), flush=True)
     if "cfg5" in which:
         net4 = rrdbnet.RRDBNet(3, 3, 4, 64, 23, 32).eval()
         h, w = 1080, 1920

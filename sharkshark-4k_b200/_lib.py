@@ -62,6 +62,8 @@ SYMBOLS = {
     "ss4k_glue_blur_diff": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, ctypes.c_double, ctypes.c_double, _vp]),
     "ss4k_glue_finalize": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _i, _i, _vp, _vp, ctypes.c_double, ctypes.c_double, _vp, _vp,
                                 _i, _vp]),
+    "ss4k_glue_finalize_bicubic_u8": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _i, _i, _vp, _vp, ctypes.c_double, ctypes.c_double, _vp,
+                                           _i, _i, _i, _vp]),
     "ss4k_glue_bicubic_u8": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _i, _i, _vp]),
     "ss4k_glue_sharpen_blend": (_i, [_vp, _i, _i, _i, _i, _i, ctypes.c_float, ctypes.c_float, _vp, _i, _vp, _vp]),
     "ss4k_conv3x3": (_i, [_vp, ctypes.POINTER(ConvDesc), _vp, _vp, _vp, _vp, _vp, _vp, _vp]),

@@ -216,6 +216,81 @@ __global__ void bicubic_u8_kernel(const float* __restrict__ in, int N, int C, in
   }
 }
 
+// ---- finalise + bicubic resize in ONE pass: every bicubic tap is clamp(a*hr + b - bilinear_up(diff), 0, 1), so the
+//      full-resolution fp32 intermediate of the two-kernel form (708 MB written + read per 4-frame batch at 2880p)
+//      never exists.  A block owns a 32 x 8 tile of OUTPUT pixels: it finalises the source patch its taps touch once
+//      into shared memory (about 5 evaluations per output pixel at a 2x downscale), then every thread runs its 4x4
+//      bicubic from there.  Same arithmetic as finalize_kernel followed by bicubic_u8_kernel
+//      (fsrcnn_upscaler.py:214-233).  Source patch limit kFbMaxH x kFbMaxW (downscale factors up to 2).
+constexpr int kFbTw = 32, kFbTh = 8, kFbMaxW = 72, kFbMaxH = 24;
+__global__ void __launch_bounds__(kFbTw * kFbTh)
+finalize_bicubic_u8_kernel(Img hr, const float* __restrict__ diff, int dh, int dw, const double* hr_sums,
+                           const double* lr_sums, double cnt_hr, double cnt_lr, uint8_t* __restrict__ out,
+                           int OH, int OW, int round_u8) {
+  __shared__ float patch[3][kFbMaxH][kFbMaxW];
+  const int n = blockIdx.z;
+  const int ox0 = blockIdx.x * kFbTw, oy0 = blockIdx.y * kFbTh;
+  const int H = hr.H, W = hr.W;
+  const float fy = static_cast<float>(H) / OH, fx = static_cast<float>(W) / OW;
+  // source patch: rows / columns touched by the taps of the tile's first and last output pixel (before clamping)
+  const int oy1 = min(oy0 + kFbTh, OH) - 1, ox1 = min(ox0 + kFbTw, OW) - 1;
+  const int py0 = static_cast<int>(floorf((oy0 + 0.5f) * fy - 0.5f)) - 1;
+  const int py1 = static_cast<int>(floorf((oy1 + 0.5f) * fy - 0.5f)) + 2;
+  const int px0 = static_cast<int>(floorf((ox0 + 0.5f) * fx - 0.5f)) - 1;
+  const int px1 = static_cast<int>(floorf((ox1 + 0.5f) * fx - 0.5f)) + 2;
+  const int ph = py1 - py0 + 1, pw = px1 - px0 + 1;  // host guarantees ph <= kFbMaxH, pw <= kFbMaxW
+  float ma[3], mb[3];
+  for (int c = 0; c < 3; ++c) match_coeffs(hr_sums, lr_sums, n * hr.C + c, cnt_hr, cnt_lr, &ma[c], &mb[c]);
+  for (int i = threadIdx.x; i < ph * pw; i += kFbTw * kFbTh) {
+    const int ry = i / pw, rx = i - ry * pw;
+    const int y = min(max(py0 + ry, 0), H - 1), x = min(max(px0 + rx, 0), W - 1);  // clamped taps (border replicate)
+    float sub[3] = {0.f, 0.f, 0.f};
+    if (diff != nullptr) {
+      float sy = (y + 0.5f) * (static_cast<float>(dh) / H) - 0.5f;
+      float sx = (x + 0.5f) * (static_cast<float>(dw) / W) - 0.5f;
+      sy = sy < 0.f ? 0.f : sy;
+      sx = sx < 0.f ? 0.f : sx;
+      const int y0 = static_cast<int>(sy), x0 = static_cast<int>(sx);
+      const int y1 = y0 < dh - 1 ? y0 + 1 : y0, x1 = x0 < dw - 1 ? x0 + 1 : x0;
+      const float ly = sy - y0, lx = sx - x0;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float* d = diff + static_cast<size_t>(n * hr.C + c) * dh * dw;
+        const float top = d[y0 * dw + x0] * (1.f - lx) + d[y0 * dw + x1] * lx;
+        const float bot = d[y1 * dw + x0] * (1.f - lx) + d[y1 * dw + x1] * lx;
+        sub[c] = top * (1.f - ly) + bot * ly;
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) patch[c][ry][rx] = fminf(fmaxf(ma[c] * hr.at(n, c, y, x) + mb[c] - sub[c], 0.f), 1.f);
+  }
+  __syncthreads();
+  const int x = ox0 + (threadIdx.x % kFbTw), y = oy0 + (threadIdx.x / kFbTw);
+  if (x >= OW || y >= OH) return;
+  const float A = -0.75f;
+  const float sy = (y + 0.5f) * fy - 0.5f, sx = (x + 0.5f) * fx - 0.5f;
+  const int iy = static_cast<int>(floorf(sy)), ix = static_cast<int>(floorf(sx));
+  const float ty = sy - iy, tx = sx - ix;
+  const float wy[4] = {cubic2(ty + 1.f, A), cubic1(ty, A), cubic1(1.f - ty, A), cubic2(2.f - ty, A)};
+  const float wx[4] = {cubic2(tx + 1.f, A), cubic1(tx, A), cubic1(1.f - tx, A), cubic2(2.f - tx, A)};
+  const size_t oidx = (static_cast<size_t>(n) * OH + y) * OW + x;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    float acc = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int ry = iy - 1 + j - py0;  // the patch already holds the border-replicated value at out-of-image taps
+      float row = 0.f;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) row += wx[i] * patch[c][ry][ix - 1 + i - px0];
+      acc += wy[j] * row;
+    }
+    float f = fminf(fmaxf(acc, 0.f), 1.f) * 255.f;
+    if (round_u8) f = rintf(f);
+    out[oidx * 3 + c] = static_cast<uint8_t>(f);
+  }
+}
+
 // ---- 3x3 depthwise reflect "sharpen" + clamp, optional blend with another image (float NCHW in/out) ----------
 //   out = opacity * clamp(sum k[dy][dx] * x[reflect], 0, 1) + (1 - opacity) * other
 __global__ void sharpen_blend_kernel(Img x, float k_center, float k_side, float opacity, Img other, float* __restrict__ out) {
@@ -279,6 +354,19 @@ int ss4k_glue_finalize(const void* hr, int fmt, int n, int c, int h, int w, cons
   const size_t total = static_cast<size_t>(n) * h * w;
   finalize_kernel<<<blocks_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(Img{hr, fmt, n, c, h, w}, diff, dh, dw, hr_sums,
                                                                                           lr_sums, cnt_hr, cnt_lr, out_u8, out_f32, round_u8);
+  return cudaGetLastError() == cudaSuccess ? SS4K_OK : SS4K_E_CUDA;
+}
+
+int ss4k_glue_finalize_bicubic_u8(const void* hr, int fmt, int n, int c, int h, int w, const float* diff, int dh, int dw,
+                                  const double* hr_sums, const double* lr_sums, double cnt_hr, double cnt_lr, uint8_t* out_u8,
+                                  int oh, int ow, int round_u8, void* stream) {
+  if (!hr || !out_u8 || fmt < 0 || fmt > 1 || c != 3 || oh <= 0 || ow <= 0) return SS4K_E_INVALID;
+  // the tile kernel's shared-memory patch covers downscale factors up to 2 (plus the 3-pixel tap margin)
+  const double fy = static_cast<double>(h) / oh, fx = static_cast<double>(w) / ow;
+  if (fy * (kFbTh - 1) + 5.0 > kFbMaxH || fx * (kFbTw - 1) + 5.0 > kFbMaxW) return SS4K_E_INVALID;
+  dim3 grid((ow + kFbTw - 1) / kFbTw, (oh + kFbTh - 1) / kFbTh, n);
+  finalize_bicubic_u8_kernel<<<grid, kFbTw * kFbTh, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      Img{hr, fmt, n, c, h, w}, diff, dh, dw, hr_sums, lr_sums, cnt_hr, cnt_lr, out_u8, oh, ow, round_u8);
   return cudaGetLastError() == cudaSuccess ? SS4K_OK : SS4K_E_CUDA;
 }
 

@@ -150,11 +150,16 @@ class FsrcnnUpscalerService:
         dh, dw = (diff.shape[-2], diff.shape[-1]) if diff is not None else (0, 0)
         st = self._stream()
         if want_resize:
-            tmp = torch.empty(n, 3, h, w, dtype=torch.float32, device=self.device)
-            L.check(self.lib.ss4k_glue_finalize(_ptr(hr), _fmt(hr), n, 3, h, w, _ptr(diff), dh, dw, _ptr(hs), _ptr(ls),
-                                                cnt_hr, cnt_lr, None, _ptr(tmp), 0, st))
             oh, ow = self.output_shape
             out = torch.empty(n, oh, ow, 3, dtype=torch.uint8, device=self.device)
+            if h <= 2 * oh and w <= 2 * ow:
+                # clamp(match - colour diff) and the bicubic resize (:214-231) in one pass over the net's output
+                L.check(self.lib.ss4k_glue_finalize_bicubic_u8(_ptr(hr), _fmt(hr), n, 3, h, w, _ptr(diff), dh, dw, _ptr(hs),
+                                                               _ptr(ls), cnt_hr, cnt_lr, _ptr(out), oh, ow, 0, st))
+                return out
+            tmp = torch.empty(n, 3, h, w, dtype=torch.float32, device=self.device)   # downscale > 2: two passes
+            L.check(self.lib.ss4k_glue_finalize(_ptr(hr), _fmt(hr), n, 3, h, w, _ptr(diff), dh, dw, _ptr(hs), _ptr(ls),
+                                                cnt_hr, cnt_lr, None, _ptr(tmp), 0, st))
             L.check(self.lib.ss4k_glue_bicubic_u8(_ptr(tmp), n, 3, h, w, _ptr(out), oh, ow, 0, st))
             return out
         out = torch.empty(n, h, w, 3, dtype=torch.uint8, device=self.device)

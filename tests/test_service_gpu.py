@@ -53,6 +53,23 @@ def test_upscale_multi_srvgg_x4_bicubic_down(engine):
     _cmp(got, want)
 
 
+@pytest.mark.parametrize("out_shape", [(225, 400), (300, 530), (400, 700), (180, 320), (100, 200)])
+def test_upscale_multi_resize_factors(engine, out_shape):
+    """Bicubic resize to output_shape (fsrcnn_upscaler.py:222-231) at non-integer factors, up- and down-scaling: the
+    fused finalise + bicubic tile kernel (factors <= 2) and the two-pass path (factor > 2) against the oracle."""
+    torch.manual_seed(0)
+    net = srvgg.SRVGGNetCompact(3, 3, 64, 16, 4).eval()
+    frames = _frames(2, 90, 160, 5)
+    want = glue.upscale_multi(frames, net, lr_shape=(720, 1280), output_shape=out_shape)
+    svc = service.FsrcnnUpscalerService(lr_level=3, device=0, denoising=False, model_name='realesr-animevideov3',
+                                        state_dict=net.state_dict(), batch_size=2)
+    svc.proc_init()
+    svc.output_shape = out_shape
+    got = svc.upscale(frames.cuda())
+    assert tuple(got.shape) == (2,) + tuple(out_shape) + (3,)
+    _cmp(got, want)
+
+
 def test_upscale_single_denoise_then_rrdb(engine):
     """The composition the north star names (dead by default in the reference): BSVD denoise
     (F = 1 clip, noise map 0.05 on the first frame) -> sharpen/blend -> RRDBNet x2 -> HR sharpen -> match."""
