@@ -122,18 +122,19 @@ constexpr int kMaxSASlots = 12;     // activation slab ring (one slab = 130 pixe
 constexpr int kMaxAccSlots = 16;    // TMEM accumulator ring (one slot = one output row of 128 pixels)
 constexpr int kASlotBytes = 17408;  // 130 * 128 rounded up to the 1024-byte swizzle period
 
+constexpr int kStreamBiasBytes = 1024;  // fp32 bias of every output channel (<= 256 padded channels per conv)
+
 constexpr int kStreamEpiWarps = 8;  // two per TMEM lane quarter, alternating output rows
 constexpr int kStreamThreads = 32 * (2 + kStreamEpiWarps);
 
 struct StreamParams {
   CUtensorMap tmA[2];   // 5-D (64, W, channel block, H, N), box (64, 130, 1, 1, 1), swizzle 128B
-  CUtensorMap tmW;      // 2-D (64, rows), box (64, 3*NOUT): rows = [chunk][kb][kx][2-ky][NOUT], then bias tiles
-  CUtensorMap tmB;      // same tensor, box (64, NOUT): the per-chunk bias tile (bias hi/lo in K columns 0/1)
+  CUtensorMap tmW;      // 2-D (64, rows), box (64, 3*NOUT): rows = [chunk][kb][kx][2-ky][NOUT]
   CUtensorMap tmO;      // NHWC output, 4-D (C, W, H, N), box (NOUT, 32, 1, 1), swizzled: TMA store of the fast path
   Epilogue ep;
   int32_t fast_store;   // 1: plain NHWC output -> registers -> swizzled smem tile -> TMA store;
                         // 2: the same tile stored four times through a 5-D (C, b, W, a, N*H) map: nearest-x2 upsample
-  int32_t bias_row0;    // first row of the bias tiles inside the weight tensor
+  const float* bias_f;  // [chunks * NOUT] fp32 bias with alpha folded in: the accumulators' initial value
   uint8_t a_kb[kMaxSKB];  // source 64-channel block of K block i
   uint8_t a_tm[kMaxSKB];  // which activation tensor map
   uint8_t nks[kMaxSKB];   // 16-channel k-steps to issue (1..4)

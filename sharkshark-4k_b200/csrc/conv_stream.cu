@@ -17,23 +17,23 @@
 //     stream never drains between rows, and the epilogue warps retire output row y as soon as input
 //     row y+1 has been accumulated.  Rows are split evenly over the persistent grid (one CTA per SM).
 //   * all weights of the conv (every K block and tap) stay resident in shared memory.
-//   * the bias is added by the tensor core: the MMA that zero-initialises a fresh accumulator slot is
-//     ones[128 x 16] x bias_tile[NOUT x 16] (bias hi/lo halves in K columns 0/1), so every real MMA
-//     accumulates and the epilogue has no per-channel bias loads.
+//   * accumulator slots are (re-)initialised WITH THE BIAS by the epilogue warps (tcgen05.st of the fp32 bias row
+//     right after they drained the slot with tcgen05.ld), so every MMA accumulates, the issuing warp spends no
+//     instruction on zero-initialisation and the bias costs no shared-memory operand traffic.
 //   * warp 0 = TMA producer and row planner, warp 1 = MMA issuer, warps 2..9 = epilogue, two warps per TMEM lane
 //     quarter taking alternate output rows: TMEM -> registers -> activation / scaled residual adds ->
 //     16-bit pack -> swizzled shared-memory tile -> TMA store (plain NHWC outputs), or the generic
 //     path (PixelShuffle / NCHW / uint8 / temporal-shift scatter / hi+lo split stores).
 //   * row records: the accumulator-ring bookkeeping of every input row (which slots it touches first / completes,
 //     where the ring wraps, descriptors, chunk switches) is computed by the producer warp and travels with the
-//     row's first activation slab as a 32-byte record; the issuing warp reads the NEXT row's record, waits for
-//     its fresh accumulator slot and issues its bias-init MMA in the middle of the current row's last burst, so
-//     the tensor pipe's queue (about 6 instructions, scripts/mma_issue_probe.cu) never drains at a row boundary.
+//     row's first activation slab as a 32-byte record; the issuing warp reads the NEXT row's record and waits for
+//     its fresh (bias-initialised) accumulator slot in the middle of the current row's last burst, so the tensor
+//     pipe's queue (about 6 instructions, scripts/mma_issue_probe.cu) never drains at a row boundary.
 //   * fp16 hi/lo split operands (BSVD precision mode): three K blocks per 64 source channels
 //     (A_hi*W_hi, A_hi*W_lo, A_lo*W_hi), the low halves through a second activation tensor map.
 //   * measured bound: an M=128, N=96, K=16 MMA costs 56 clk of shared-memory port time for
-//     48 clk of math; with the slab written by TMA and the epilogue's staging tile the port carries 121.6 KB per
-//     row of a 64->32 conv = 950 clk, which is the row period the kernel runs at.
+//     48 clk of math; with the slab written by TMA and the epilogue's staging tile the port carries about 117 KB
+//     per row of a 64->32 conv, which sets the row period the kernel runs at.
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -124,14 +124,11 @@ __global__ void __launch_bounds__(kStreamThreads, 1)
 conv3x3_stream_kernel(const __grid_constant__ StreamParams P) {
   extern __shared__ uint8_t smem_raw[];
   constexpr uint32_t kWTile = 3u * NOUT * 128u;      // one (K block, horizontal tap) weight tile
-  constexpr uint32_t kBiasTile = NOUT * 128u;
-  constexpr uint32_t kOnesTile = 128u * 128u;
   constexpr uint32_t kStageWarp = 32u * NOUT * 2u;   // one epilogue warp's 32-pixel output tile
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t w_base = smem_base;
-  const uint32_t bias_base = w_base + static_cast<uint32_t>(P.nkb) * 3u * kWTile;
-  const uint32_t ones_base = bias_base + kBiasTile;
-  const uint32_t a_base = ones_base + kOnesTile;
+  const uint32_t bias_base = w_base + static_cast<uint32_t>(P.nkb) * 3u * kWTile;  // fp32 bias of every chunk
+  const uint32_t a_base = bias_base + kStreamBiasBytes;
   const uint32_t stage_base = a_base + static_cast<uint32_t>(P.a_slots) * kASlotBytes;
   const uint32_t bar_base = stage_base + kStreamEpiWarps * ((kStageWarp + 1023u) & ~1023u);
   const uint32_t a_full = bar_base;
@@ -159,7 +156,6 @@ conv3x3_stream_kernel(const __grid_constant__ StreamParams P) {
     if (lane == 0) {
       prefetch_tmap(&P.tmA[0]);
       prefetch_tmap(&P.tmW);
-      prefetch_tmap(&P.tmB);
       if (P.fast_store) prefetch_tmap(&P.tmO);
       for (int i = 0; i < kMaxSASlots; ++i) {
         mbar_init(a_full + 8 * i, 1);
@@ -175,7 +171,7 @@ conv3x3_stream_kernel(const __grid_constant__ StreamParams P) {
     }
     __syncwarp();
     // the first chunk's weights are constants of the launch: request them before the rest of the set-up
-    // (TMEM allocation, ones tile, block barrier) so that their latency overlaps it
+    // (TMEM allocation, bias copy, block barrier) so that their latency overlaps it
     if (u0 < u1) {
       int uu = u0;
       Band fb;
@@ -183,10 +179,9 @@ conv3x3_stream_kernel(const __grid_constant__ StreamParams P) {
       early_chunk = fb.chunk;
       if (elect_one()) {
         const int ntile = P.nkb * 3;
-        mbar_expect_tx(w_full, static_cast<uint32_t>(ntile) * kWTile + kBiasTile);
+        mbar_expect_tx(w_full, static_cast<uint32_t>(ntile) * kWTile);
         for (int t = 0; t < ntile; ++t)
           tma_load_2d(w_base + t * kWTile, &P.tmW, w_full, 0, (fb.chunk * ntile + t) * 3 * NOUT);
-        tma_load_2d(bias_base, &P.tmB, w_full, 0, P.bias_row0 + fb.chunk * NOUT);
       }
       __syncwarp();
     }
@@ -198,14 +193,11 @@ conv3x3_stream_kernel(const __grid_constant__ StreamParams P) {
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   {
-    // "ones" operand of the accumulator-init MMA: 128 rows x 64 channels, swizzle-128B K-major, value 1 in
-    // K columns 0 and 1 (they meet the hi / lo halves of the bias), 0 elsewhere
-    const uint32_t one2 = P.ep.is_bf16 ? 0x3F803F80u : 0x3C003C00u;
-    for (uint32_t ci = threadIdx.x; ci < 1024u; ci += kStreamThreads) {
-      const uint32_t r = ci >> 3, pc = ci & 7u;
-      sts128(ones_base + ci * 16u, pc == (r & 7u) ? one2 : 0u, 0u, 0u, 0u);
-    }
-    fence_proxy_async();
+    // fp32 bias of every output channel (alpha already folded in): the epilogue warps write it into the accumulator
+    // slots they own.  A constant of the launch, so it is read before the dependency wait.
+    float* sb = reinterpret_cast<float*>(smem_gen + (bias_base - smem_base));
+    const int nb = P.chunks * NOUT;
+    for (int i = threadIdx.x; i < nb; i += kStreamThreads) sb[i] = __ldg(P.bias_f + i);
   }
   tcgen05_before_sync();
   __syncthreads();
@@ -240,10 +232,9 @@ conv3x3_stream_kernel(const __grid_constant__ StreamParams P) {
           early_chunk = -1;  // already requested in the prologue
         } else if (elect_one()) {
           const int ntile = P.nkb * 3;
-          mbar_expect_tx(w_full, static_cast<uint32_t>(ntile) * kWTile + kBiasTile);
+          mbar_expect_tx(w_full, static_cast<uint32_t>(ntile) * kWTile);
           for (int t = 0; t < ntile; ++t)
             tma_load_2d(w_base + t * kWTile, &P.tmW, w_full, 0, (b.chunk * ntile + t) * 3 * NOUT);
-          tma_load_2d(bias_base, &P.tmB, w_full, 0, P.bias_row0 + b.chunk * NOUT);
         }
         __syncwarp();
         wph ^= 1;
@@ -271,14 +262,14 @@ conv3x3_stream_kernel(const __grid_constant__ StreamParams P) {
         const int nblk = y_hi - y_lo + 1;
         const int nA = sL + nblk <= S ? nblk : S - sL;  // the MMAs split where the ring wraps
         const int nB = nblk - nA;
-        uint32_t fresh = 0;  // up to 3 x {bit 7 valid, bit 6 parity, bit 5 wait, bits 0..4 slot}
+        uint32_t fresh = 0;  // up to 3 x {bit 7 valid, bit 6 parity of the slot's use count, bits 0..4 slot}
         {
           const int f_lo = (r == r0) ? y_lo : r + 1;
           int sh = 0;
           for (int y = f_lo; y <= y_hi; ++y, sh += 8) {
             int s2 = sL + (y - y_lo), k2 = kL;
             if (s2 >= S) { s2 -= S; ++k2; }
-            fresh |= (0x80u | (k2 > 0 ? 0x20u : 0u) | (((k2 & 1) ^ 1) ? 0x40u : 0u) | static_cast<uint32_t>(s2)) << sh;
+            fresh |= (0x80u | ((k2 & 1) ? 0x40u : 0u) | static_cast<uint32_t>(s2)) << sh;
           }
         }
         uint32_t c0 = 0xFFu, c1 = 0xFFu;  // accumulator slots completed by this input row
@@ -334,13 +325,11 @@ conv3x3_stream_kernel(const __grid_constant__ StreamParams P) {
     // with shuffles) so that ptxas keeps every descriptor in uniform registers; one elected lane issues the
     // tcgen05 instructions.  One thread feeds the tensor pipe and the pipe queues almost nothing, so every
     // instruction this warp executes between two MMAs is dead time for the pipe: the row bookkeeping comes
-    // precomputed from the producer warp (row records), and the next row's record, its fresh accumulator slots
-    // (wait for the epilogue's drain, bias-init MMA) are handled in the middle of the current row's last burst.
+    // precomputed from the producer warp (row records), and the next row's record and its fresh accumulator slots
+    // (wait for the epilogue's drain + bias re-initialisation) are handled in the middle of the current row's last burst.
     uint32_t as = 0, aph = 0, wph = 0;
     const int nkb = P.nkb;
     const bool do_mma = !(P.dbg_flags & 1);
-    const uint32_t idesc0 = P.idesc[0];
-    const uint64_t d_ones = sdesc(ones_base), d_bias = sdesc(bias_base);
     const uint32_t n_aslots = static_cast<uint32_t>(P.a_slots);
 
     uint32_t rc[kRecWords];
@@ -366,13 +355,9 @@ conv3x3_stream_kernel(const __grid_constant__ StreamParams P) {
       uint32_t f = rc[7];
 #pragma unroll
       for (int j = 0; j < 3; ++j, f >>= 8) {
-        if (f & 0x80u) {
-          const uint32_t s2 = f & 0x1Fu;
-          if (f & 0x20u) {  // the slot's first use needs no drain
-            mbar_wait_u(acc_empty + 8 * s2, (f >> 6) & 1u);
-            tcgen05_after_sync();
-          }
-          if (do_mma) umma_f16_elect(tmem_base + s2 * NOUT, d_ones, d_bias, idesc0, 0u);
+        if (f & 0x80u) {  // fresh slot: drained and re-initialised with the bias by the epilogue warps
+          mbar_wait_u(acc_empty + 8 * (f & 0x1Fu), (f >> 6) & 1u);
+          tcgen05_after_sync();
         }
       }
     };
@@ -470,6 +455,26 @@ conv3x3_stream_kernel(const __grid_constant__ StreamParams P) {
     int s = 0, k = 0, q = 0;
     int u = u0;
     Band b;
+    const int upc = P.n_img * P.strips * P.H;  // units (output rows of 128 pixels) per chunk
+    // Writes the bias row of `chunk_` into accumulator slot s_ (this warp's 32 TMEM lanes) and hands the slot to
+    // the MMA stream: every MMA accumulates, the slot's initial value IS the bias (exact fp32).
+    auto init_slot = [&](int s_, int chunk_) {
+      const uint32_t ta = tmem_base + (static_cast<uint32_t>(qd * 32) << 16) + static_cast<uint32_t>(s_ * NOUT);
+      const uint32_t ba = bias_base + static_cast<uint32_t>(chunk_ * NOUT) * 4u;
+#pragma unroll
+      for (int c = 0; c < NOUT; c += 16) {
+        uint32_t bv[16];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) lds128(ba + (c + 4 * i) * 4u, bv[4 * i], bv[4 * i + 1], bv[4 * i + 2], bv[4 * i + 3]);
+        tmem_st16p(ta + c, bv);
+      }
+      tmem_st_wait();
+      tcgen05_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_empty + 8 * s_);
+    };
+    // first use of every slot (output rows u0 .. u0+S-1; this warp's parity group)
+    for (int q0 = par; q0 < S && u0 + q0 < u1; q0 += 2) init_slot(q0, (u0 + q0) / upc);
     pdl_wait();  // residual loads and output stores touch tensors of the previous kernel
     while (next_band(P, u, u1, b)) {
       const int ax = b.strip * kTileW + m;
@@ -498,9 +503,12 @@ conv3x3_stream_kernel(const __grid_constant__ StreamParams P) {
 #pragma unroll
           for (int c = 0; c < NOUT; c += 16) tmem_ld16p(taddr + c, &raw[c]);
           tmem_ld_wait();
-          tcgen05_before_sync();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(acc_empty + 8 * s);  // slot free: the MMA stream may reuse it
+          {
+            // slot drained: re-initialise it with the bias of the output row that reuses it (S rows ahead in this
+            // CTA's unit order, possibly the next chunk) and release it to the MMA stream
+            const int ut = u - (b.ye - y) + S;
+            if (ut < u1) init_slot(s, ut / upc);
+          }
           if (!(P.dbg_flags & 4)) {
             if (fast) {
               // ---- activation, residuals, 16-bit pack into the warp's swizzled staging tile, TMA store

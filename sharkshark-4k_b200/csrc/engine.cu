@@ -265,8 +265,8 @@ std::string pack_weights(const ConvSpec& cs, const HostTensor& W, const HostTens
 struct StreamPacked {
   std::vector<uint16_t> w;
   std::vector<float> bias, slope;
+  std::vector<float> bias_f;  // bias with alpha (and the none_minus sign) folded in: initial value of the accumulators
   int nout = 0, chunks = 0, nkb = 0, npad_total = 0, a_slots = 0, acc_slots = 0;
-  int bias_row0 = 0;     // first row of the per-chunk bias tiles (appended after the weight tiles)
   float alpha_out = 1.f; // epilogue scale left after folding alpha into weights and bias
   uint8_t nks[kMaxSKB];
   uint8_t src_kb[kMaxSKB];  // 64-channel block of the source tensor read by K block i
@@ -279,6 +279,7 @@ bool stream_config(const ConvSpec& cs, StreamPacked* sp) {
   if (getenv("SS4K_NO_STREAM")) return false;
   if (cs.split && getenv("SS4K_NO_STREAM_SPLIT")) return false;
   const int npad = round_up(cs.cout, 16);
+  if (npad * 4 > kStreamBiasBytes) return false;
   // fp16 hi/lo split operands: three K blocks per 64 source channels: A_hi*W_hi, A_hi*W_lo, A_lo*W_hi
   const int nsplit = cs.split ? 3 : 1;
   const int nkb0 = (cs.cin + 63) / 64;
@@ -292,13 +293,13 @@ bool stream_config(const ConvSpec& cs, StreamPacked* sp) {
   for (int i = 0; i < nc; ++i) {
     const int nout = cand[i];
     if (npad % nout) continue;
-    const int wbytes = nkb * 9 * nout * 128 + nout * 128 /* bias tile */ + 128 * 128 /* ones tile */;
+    const int wbytes = nkb * 9 * nout * 128 + kStreamBiasBytes;
     const int stage = kStreamEpiWarps * round_up(32 * nout * 2, 1024);
     const int left = kSmemBytes - 2048 - wbytes - stage;
     const int slots = std::min(kMaxSASlots, left / kASlotBytes);
     if (slots < 3) continue;
     sp->nout = nout; sp->chunks = npad / nout; sp->nkb = nkb; sp->npad_total = npad;
-    sp->a_slots = slots; sp->acc_slots = std::min(kMaxAccSlots, kTmemCols / nout);
+    sp->a_slots = slots; sp->acc_slots = std::min(kMaxAccSlots, kTmemCols / nout) & ~1;  // even: rows alternate between two epilogue warp groups
     for (int kb = 0; kb < nkb; ++kb) {
       const int b0 = kb / nsplit, part = kb % nsplit;
       sp->nks[kb] = static_cast<uint8_t>((std::min(64, cs.cin - 64 * b0) + 15) / 16);
@@ -331,8 +332,7 @@ std::string pack_weights_stream(const ConvSpec& cs, const HostTensor& W, const H
   // (none, PReLU / LeakyReLU): fold alpha into weights and bias so the epilogue does not multiply
   const float fold = (cs.act != kActRelu6) ? cs.alpha : 1.f;
   out->alpha_out = (cs.act != kActRelu6) ? 1.f : cs.alpha;
-  out->bias_row0 = out->chunks * nkb * 9 * nout;
-  out->w.assign((static_cast<size_t>(out->bias_row0) + npad) * 64, 0);
+  out->w.assign(static_cast<size_t>(out->chunks) * nkb * 9 * nout * 64, 0);
   for (int ch = 0; ch < out->chunks; ++ch)
     for (int kb = 0; kb < nkb; ++kb)
       for (int kx = 0; kx < 3; ++kx)
@@ -349,14 +349,12 @@ std::string pack_weights_stream(const ConvSpec& cs, const HostTensor& W, const H
               out->w[row * 64 + cc] = out->whalf[kb] ? f2h(wv - h2f(hi, bf16), bf16) : hi;
             }
           }
-  // bias tiles: row = output channel, K column 0 = high half, column 1 = low half (the "ones" operand has 1 there)
+  // the accumulators start from the bias (fp32, written by the epilogue warps with tcgen05.st)
+  out->bias_f.assign(npad, 0.f);
   for (int row = 0; row < npad; ++row) {
     const int n = orow[row];
     if (n < 0 || !B) continue;
-    const float bv = (n < cs.neg_first ? -fold : fold) * B->data[n];
-    const uint16_t hi = f2h(bv, bf16);
-    out->w[(static_cast<size_t>(out->bias_row0) + row) * 64 + 0] = hi;
-    out->w[(static_cast<size_t>(out->bias_row0) + row) * 64 + 1] = f2h(bv - h2f(hi, bf16), bf16);
+    out->bias_f[row] = (n < cs.neg_first ? -fold : fold) * B->data[n];
   }
   out->bias.assign(npad, 0.f);
   out->slope.assign(npad, 1.f);
@@ -515,8 +513,8 @@ int materialize_stream(ss4k_ctx* ctx, const ConvSpec& cs, const HostTensor& W, c
   CK(ctx, cudaMalloc(&ex->d_w, pk.w.size() * 2));
   ex->w_bytes = pk.w.size() * 2;
   CK(ctx, cudaMemcpy(ex->d_w, pk.w.data(), pk.w.size() * 2, cudaMemcpyHostToDevice));
-  CK(ctx, cudaMalloc(&ex->d_bias, pk.bias.size() * 4));
-  CK(ctx, cudaMemcpy(ex->d_bias, pk.bias.data(), pk.bias.size() * 4, cudaMemcpyHostToDevice));
+  CK(ctx, cudaMalloc(&ex->d_bias, pk.bias_f.size() * 4));
+  CK(ctx, cudaMemcpy(ex->d_bias, pk.bias_f.data(), pk.bias_f.size() * 4, cudaMemcpyHostToDevice));
   CK(ctx, cudaMalloc(&ex->d_slope, pk.slope.size() * 4));
   CK(ctx, cudaMemcpy(ex->d_slope, pk.slope.data(), pk.slope.size() * 4, cudaMemcpyHostToDevice));
   const CUtensorMapDataType dt = bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
@@ -553,17 +551,7 @@ int materialize_stream(ss4k_ctx* ctx, const ConvSpec& cs, const HostTensor& W, c
                              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(ctx, SS4K_E_CUDA, fmt("cuTensorMapEncodeTiled(stream weights) failed: %d", (int)r));
   }
-  {  // bias tiles: same tensor, NOUT-row box
-    const cuuint64_t rows = pk.w.size() / 64;
-    cuuint64_t dims[2] = {64, rows};
-    cuuint64_t strides[1] = {128};
-    cuuint32_t box[2] = {64, static_cast<cuuint32_t>(pk.nout)};
-    cuuint32_t es[2] = {1, 1};
-    CUresult r = ctx->encode(&p.tmB, dt, 2, ex->d_w, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return fail(ctx, SS4K_E_CUDA, fmt("cuTensorMapEncodeTiled(stream bias) failed: %d", (int)r));
-  }
-  p.bias_row0 = pk.bias_row0;
+  p.bias_f = ex->d_bias;
   // fast epilogue: plain NHWC 16-bit output -> swizzled shared-memory tile -> TMA store
   p.fast_store = 0;
   if (cs.out_mode == kOutNHWC && cs.out_buf >= 0 && cs.out_lo_buf < 0 && cs.out_coff % 8 == 0 && cs.out_pitch % 8 == 0 &&
@@ -608,7 +596,7 @@ int materialize_stream(ss4k_ctx* ctx, const ConvSpec& cs, const HostTensor& W, c
     p.idesc[i] = (1u << 4) | (f << 7) | (f << 10) | (static_cast<uint32_t>((i + 1) * pk.nout >> 3) << 17) | (static_cast<uint32_t>(128 >> 4) << 24);
   p.err = ctx->err_dev;
   fill_epilogue(cs, bf16, bufptr, ex->d_bias, ex->d_slope, &p.ep, &ex->ext_out);
-  p.ep.bias = nullptr;                  // added by the accumulator-init MMA
+  p.ep.bias = nullptr;                  // the accumulators start from the bias (p.bias_f)
   p.ep.slope = S ? ex->d_slope : nullptr;
   p.ep.slope_const = cs.const_slope;
   p.ep.alpha = pk.alpha_out;            // folded into weights / bias when the activation allows
@@ -1172,11 +1160,13 @@ int ss4k_debug_pack(const ss4k_conv_desc* d, int in_pitch, int in_coff, int wper
     if (!stream_config(cs, &sp)) return fail(nullptr, SS4K_E_INVALID, "conv is not eligible for the row-streaming kernel");
     std::string es = pack_weights_stream(cs, W, bias_host ? &B : nullptr, slope_host ? &S : nullptr, bf16, &sp);
     if (!es.empty()) return fail(nullptr, SS4K_E_WEIGHTS, es);
-    std::string js = fmt("{\"kernel\":\"stream\",\"nout\":%d,\"chunks\":%d,\"nkb\":%d,\"npad\":%d,\"a_slots\":%d,\"acc_slots\":%d,\"bias_row0\":%d,\"nks\":[",
-                         sp.nout, sp.chunks, sp.nkb, sp.npad_total, sp.a_slots, sp.acc_slots, sp.chunks * sp.nkb * 9 * sp.nout);
+    std::string js = fmt("{\"kernel\":\"stream\",\"nout\":%d,\"chunks\":%d,\"nkb\":%d,\"npad\":%d,\"a_slots\":%d,\"acc_slots\":%d,\"nks\":[",
+                         sp.nout, sp.chunks, sp.nkb, sp.npad_total, sp.a_slots, sp.acc_slots);
     for (int i = 0; i < sp.nkb; ++i) js += fmt("%s%d", i ? "," : "", sp.nks[i]);
     js += "],\"bias\":[";
     for (size_t i = 0; i < sp.bias.size(); ++i) js += fmt("%s%.9g", i ? "," : "", sp.bias[i]);
+    js += "],\"bias_f\":[";
+    for (size_t i = 0; i < sp.bias_f.size(); ++i) js += fmt("%s%.9g", i ? "," : "", sp.bias_f[i]);
     js += "],\"slope\":[";
     for (size_t i = 0; i < sp.slope.size(); ++i) js += fmt("%s%.9g", i ? "," : "", sp.slope[i]);
     js += "]}";

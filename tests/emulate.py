@@ -202,9 +202,8 @@ def debug_pack_stream(lib, L, w, bias=None, slope=None, in_pitch=None, in_coff=0
     meta = json.loads(ctypes.string_at(js).decode())
     arr = (ctypes.c_float * cnt.value).from_address(pk.value)
     flat = torch.tensor(list(arr), dtype=torch.float32).reshape(-1, 64)
-    packed = flat[:meta["bias_row0"]].reshape(meta["chunks"], meta["nkb"], 3, 3, meta["nout"], 64)
-    # bias tiles [chunks][nout][64]: K column 0 = high half, column 1 = low half, the rest zero
-    meta["bias_tiles"] = flat[meta["bias_row0"]:].reshape(meta["chunks"], meta["nout"], 64)
+    packed = flat.reshape(meta["chunks"], meta["nkb"], 3, 3, meta["nout"], 64)
+    # meta["bias_f"]: fp32 bias with alpha folded in, [chunks * nout] -- the accumulators' initial value
     lib.ss4k_free(js)
     lib.ss4k_free(pk)
     return meta, packed
@@ -213,8 +212,8 @@ def debug_pack_stream(lib, L, w, bias=None, slope=None, in_pitch=None, in_coff=0
 def emulate_stream_conv(meta, packed, x_nhwc, grid, in_coff=0, acc_slots=None):
     """Mirror of conv3x3_stream_kernel's schedule: per-CTA bands of output rows, accumulator ring with
     vertically fused taps (one 'MMA' adds input row r into the slots of output rows r-1, r, r+1, split
-    where the ring wraps), zero-initialising first MMA, completion commits, in-order epilogue drain.
-    Fresh slots are initialised by the ones x bias-tile MMA.  Returns the accumulators [N, H, W, npad]
+    where the ring wraps), completion commits, in-order epilogue drain.  Fresh slots hold the bias row
+    (written by the epilogue warps after the drain), every MMA accumulates.  Returns the accumulators [N, H, W, npad]
     (alpha-folded conv + bias, before the activation)."""
     n_img, H, W, pitch = x_nhwc.shape
     nout, chunks, nkb, S = meta["nout"], meta["chunks"], meta["nkb"], acc_slots or meta["acc_slots"]
@@ -241,13 +240,12 @@ def emulate_stream_conv(meta, packed, x_nhwc, grid, in_coff=0, acc_slots=None):
                 y_lo, y_hi = max(r - 1, yb), min(r + 1, ye - 1)
                 b_lo, b_hi = y_lo - (r - 1), y_hi - (r - 1)
                 f_lo = y_lo if r == r0 else r + 1
-                ones = torch.zeros(128, 16, dtype=torch.float64)
-                ones[:, :2] = 1.0
+                bias_f = torch.tensor(meta["bias_f"], dtype=torch.float64)
                 for yy in range(f_lo, y_hi + 1):
                     s = (qs + yy - yb) % S
                     assert state[s] == "empty", ("accumulator slot not drained", cta, r, yy, s, state)
                     state[s] = "busy"
-                    tmem[s] = ones @ meta["bias_tiles"][chunk, :, :16].double().t()      # accumulate = 0
+                    tmem[s] = bias_f[chunk * nout:(chunk + 1) * nout].expand(128, nout).clone()   # tcgen05.st by the epilogue
 
                 s0 = (qs + (y_lo - yb)) % S
                 nblk = b_hi - b_lo + 1

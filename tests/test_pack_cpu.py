@@ -160,15 +160,14 @@ def test_stream_channel_offset_and_permutation(lib):
     assert torch.equal(got, want[..., perm])
 
 
-def test_stream_alpha_fold_and_bias_split(lib):
-    """alpha is folded into weights and bias for none / PReLU activations (not for ReLU6); a bias that is not
-    representable in fp16 is carried as hi + lo halves in K columns 0 / 1 of the bias tile."""
+def test_stream_alpha_fold_and_bias(lib):
+    """alpha is folded into weights and bias for none / PReLU activations (not for ReLU6); the bias is carried
+    in fp32 (the accumulators' initial value), so it need not be representable in fp16."""
     wt = _exact_weights(32, 64, 21)
     bias = torch.full((32,), 0.1234567)
     meta, packed = debug_pack_stream(lib, L, wt, bias=bias, alpha=0.25, act=1)
     assert torch.equal(packed[0, 0, 1, 1, :, :], (0.25 * wt[:, :, 1, 1]))
-    bt = meta["bias_tiles"][0]
-    assert abs((bt[:, 0] + bt[:, 1]).double() - 0.25 * 0.1234567).max().item() < 2e-8
-    assert torch.count_nonzero(bt[:, 2:]) == 0
+    bf = torch.tensor(meta["bias_f"])
+    assert bf.shape == (32,) and abs(bf.double() - 0.25 * 0.1234567).max().item() < 2e-8
     meta6, packed6 = debug_pack_stream(lib, L, wt, bias=bias, alpha=0.25, act=2)
     assert torch.equal(packed6[0, 0, 1, 1, :, :], wt[:, :, 1, 1])
