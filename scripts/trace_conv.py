@@ -14,7 +14,7 @@ for cin, cout, n in [(64, 32, 1), (160, 32, 1), (192, 64, 1), (64, 64, 1), (64, 
         tr = d.pop("trace")
         print(json.dumps(d))
         for t in tr[:2]:
-            print("   phases", t[:9])
+            print("   phases", t[:9], "setup: barriers", t[9], "tmem", t[10], "bias", t[11], "producer at dep wait", t[12], "after", t[13])
             for i in range(8):
                 q = t[16 + 6 * i: 22 + 6 * i]
                 print("   row", i, "start", q[0], " +issue8", q[1] - q[0], " +fetch", q[2] - q[1], " +prepare", q[3] - q[2], " +issue4", q[4] - q[3], " +commits", q[5] - q[4])

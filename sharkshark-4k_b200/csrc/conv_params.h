@@ -149,6 +149,13 @@ struct StreamParams {
   long long* trace;       // debug: per-CTA clock64 stamps [grid][64] (null in production)
   const void* next_w;     // packed weights of the next kernel of the plan (L2 prefetch), or null
   uint32_t next_w_bytes;
+  // dead-tensor discard (RRDB dense block): lines of a tensor that no later kernel reads are dropped from L2
+  // without write-back (discard.global.L2): 128-byte line l of every pixel with bit l of discard_mask set
+  void* discard_ptr;
+  uint32_t discard_pitch_bytes, discard_mask;
+  int64_t discard_npx;
+  int32_t l2_in, l2_out;  // L2 eviction priority of the activation loads / output stores: 0 normal, 1 evict_last
+                          // (re-read by the next convs of the dense block), 2 evict_first (dead after this conv)
 };
 
 }  // namespace ss4k

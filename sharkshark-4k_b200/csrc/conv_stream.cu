@@ -70,16 +70,16 @@ __device__ __forceinline__ uint64_t sdesc(uint32_t saddr) {
   return kSdescHi | static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4);
 }
 
-__device__ __forceinline__ void tma_store_4d(const CUtensorMap* tm, uint32_t src, int c0, int c1, int c2, int c3) {
-  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* tm, uint32_t src, int c0, int c1, int c2, int c3, uint64_t pol) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3, %4, %5}], [%1], %6;"
                :
-               : "l"(reinterpret_cast<uint64_t>(tm)), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "l"(reinterpret_cast<uint64_t>(tm)), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "l"(pol)
                : "memory");
 }
-__device__ __forceinline__ void tma_store_5d(const CUtensorMap* tm, uint32_t src, int c0, int c1, int c2, int c3, int c4) {
-  asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];"
+__device__ __forceinline__ void tma_store_5d(const CUtensorMap* tm, uint32_t src, int c0, int c1, int c2, int c3, int c4, uint64_t pol) {
+  asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3, %4, %5, %6}], [%1], %7;"
                :
-               : "l"(reinterpret_cast<uint64_t>(tm)), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+               : "l"(reinterpret_cast<uint64_t>(tm)), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "l"(pol)
                : "memory");
 }
 // programmatic dependent launch: let the next kernel of the stream start its prologue early / wait for the
@@ -119,6 +119,8 @@ __device__ __forceinline__ bool next_band(const StreamParams& P, int& u, int u1,
 
 }  // namespace
 
+static_assert(kMaxSASlots <= 16 && kMaxAccSlots <= 16, "barrier set-up assigns one lane per ring slot");
+
 template <int NOUT>
 __global__ void __launch_bounds__(kStreamThreads, 1)
 conv3x3_stream_kernel(const __grid_constant__ StreamParams P) {
@@ -149,26 +151,37 @@ conv3x3_stream_kernel(const __grid_constant__ StreamParams P) {
   if (warp == 0) SS4K_TRACE(0);
 
   pdl_launch_dependents();
+  {
+    // touch every 64-byte line of the parameter block at once: the first use of each field otherwise misses in the
+    // constant cache one after the other along the set-up path
+    const uint64_t* pw = reinterpret_cast<const uint64_t*>(&P);
+    uint64_t acc = 0;
+#pragma unroll
+    for (int i = 0; i < static_cast<int>(sizeof(StreamParams) / 64); ++i) acc ^= pw[i * 8];
+    asm volatile("" ::"l"(acc));
+  }
   const int u0 = static_cast<int>(static_cast<int64_t>(blockIdx.x) * P.total_units / gridDim.x);
   const int u1 = static_cast<int>(static_cast<int64_t>(blockIdx.x + 1) * P.total_units / gridDim.x);
   int early_chunk = -1;  // weights requested in the prologue (producer warp)
   if (warp == 0) {
+    // barrier set-up spread over the warp's lanes (58 dependent shared-memory operations from one lane were a
+    // visible part of the per-launch fixed cost)
     if (lane == 0) {
       prefetch_tmap(&P.tmA[0]);
       prefetch_tmap(&P.tmW);
       if (P.fast_store) prefetch_tmap(&P.tmO);
-      for (int i = 0; i < kMaxSASlots; ++i) {
-        mbar_init(a_full + 8 * i, 1);
-        mbar_init(a_empty + 8 * i, 1);
-      }
-      for (int i = 0; i < kMaxAccSlots; ++i) {
-        mbar_init(acc_full + 8 * i, 1);
-        mbar_init(acc_empty + 8 * i, 4);  // one arrive per epilogue warp of the row's parity group
-      }
       mbar_init(w_full, 1);
       mbar_init(w_empty, 1);
-      fence_barrier_init();
     }
+    if (lane < kMaxSASlots) {
+      mbar_init(a_full + 8 * lane, 1);
+      mbar_init(a_empty + 8 * lane, 1);
+    }
+    if (lane >= 16 && lane < 16 + kMaxAccSlots) {
+      mbar_init(acc_full + 8 * (lane - 16), 1);
+      mbar_init(acc_empty + 8 * (lane - 16), 4);  // one arrive per epilogue warp of the row's parity group
+    }
+    fence_barrier_init();
     __syncwarp();
     // the first chunk's weights are constants of the launch: request them before the rest of the set-up
     // (TMEM allocation, bias copy, block barrier) so that their latency overlaps it
@@ -185,28 +198,39 @@ conv3x3_stream_kernel(const __grid_constant__ StreamParams P) {
       }
       __syncwarp();
     }
+    SS4K_TRACE(9);
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
                  "r"(static_cast<uint32_t>(kTmemCols))
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    SS4K_TRACE(10);
   }
   {
     // fp32 bias of every output channel (alpha already folded in): the epilogue warps write it into the accumulator
     // slots they own.  A constant of the launch, so it is read before the dependency wait.
     float* sb = reinterpret_cast<float*>(smem_gen + (bias_base - smem_base));
     const int nb = P.chunks * NOUT;
-    for (int i = threadIdx.x; i < nb; i += kStreamThreads) sb[i] = __ldg(P.bias_f + i);
+    if (warp != 0)
+      for (int i = threadIdx.x - 32; i < nb; i += kStreamThreads - 32) sb[i] = __ldg(P.bias_f + i);
+    if (warp == 2) SS4K_TRACE(11);
   }
-  tcgen05_before_sync();
-  __syncthreads();
-  tcgen05_after_sync();
-  // this CTA owns all 512 TMEM columns (one CTA per SM), so the allocation starts at column 0 / lane 0;
-  // using the constant keeps TMEM addresses in uniform registers
-  if (*tmem_slot_ptr != 0u) __trap();
+  // Set-up barrier: the producer warp only ARRIVES (its barrier initialisation becomes visible to the others) and goes
+  // straight on to its loads -- it needs neither the TMEM allocation nor the bias copy, and its first activation
+  // load is the head of the per-launch critical path.
+  if (warp == 0) {
+    asm volatile("bar.arrive 1, %0;" ::"n"(kStreamThreads) : "memory");
+  } else {
+    tcgen05_before_sync();
+    asm volatile("bar.sync 1, %0;" ::"n"(kStreamThreads) : "memory");
+    tcgen05_after_sync();
+    // this CTA owns all 512 TMEM columns (one CTA per SM), so the allocation starts at column 0 / lane 0;
+    // using the constant keeps TMEM addresses in uniform registers
+    if (*tmem_slot_ptr != 0u) __trap();
+  }
   constexpr uint32_t tmem_base = 0u;
-  if (warp == 0) SS4K_TRACE(1);
+  if (warp == 1) SS4K_TRACE(1);
 
   const int S = P.acc_slots;
 
@@ -219,6 +243,7 @@ conv3x3_stream_kernel(const __grid_constant__ StreamParams P) {
     uint32_t as = 0, aph = 0, wph = 0;
     int loaded_chunk = -1;
     int u = u0;
+    const uint64_t pol_in = l2_policy(P.l2_in);
     Band b, nb;
     bool dep_ready = false;
     int sL = 0, kL = 0;  // accumulator ring position (slot, wrap count) of output row y_lo
@@ -241,11 +266,14 @@ conv3x3_stream_kernel(const __grid_constant__ StreamParams P) {
         loaded_chunk = b.chunk;
       }
       if (!dep_ready) {  // weights are constants; the activations belong to the previous kernel of the stream
+        SS4K_TRACE(12);
         pdl_wait();
         dep_ready = true;
+        SS4K_TRACE(13);
       }
-      const int r0 = b.yb > 0 ? b.yb - 1 : 0;
-      const int r1 = b.ye < P.H ? b.ye : P.H - 1;
+      // dbg_flags & 8: skip the band's halo rows (WRONG results at band boundaries; measures what they cost)
+      const int r0 = (b.yb > 0 && !(P.dbg_flags & 8)) ? b.yb - 1 : b.yb;
+      const int r1 = (b.ye < P.H && !(P.dbg_flags & 8)) ? b.ye : b.ye - 1;
       const int x0 = b.strip * kTileW - 1;
       int y_lo = b.yb;
       for (int r = r0; r <= r1; ++r) {
@@ -295,7 +323,7 @@ conv3x3_stream_kernel(const __grid_constant__ StreamParams P) {
               mbar_arrive(a_full + 8 * as);
             } else {
               mbar_expect_tx(a_full + 8 * as, kBoxW * kRowBytes);
-              tma_load_5d(a_base + as * kASlotBytes, &P.tmA[P.a_tm[kb]], a_full + 8 * as, 0, x0, P.a_kb[kb], r, b.n + P.n_in0);
+              tma_load_5d_hint(a_base + as * kASlotBytes, &P.tmA[P.a_tm[kb]], a_full + 8 * as, 0, x0, P.a_kb[kb], r, b.n + P.n_in0, pol_in);
             }
           }
           __syncwarp();
@@ -452,6 +480,7 @@ conv3x3_stream_kernel(const __grid_constant__ StreamParams P) {
     const uint32_t stage = stage_base + static_cast<uint32_t>(ew) * ((kStageWarp + 1023u) & ~1023u);
     const bool bf16 = E.is_bf16 != 0;
     const bool fast = P.fast_store != 0;
+    const uint64_t pol_out = l2_policy(P.l2_out);
     int s = 0, k = 0, q = 0;
     int u = u0;
     Band b;
@@ -476,6 +505,19 @@ conv3x3_stream_kernel(const __grid_constant__ StreamParams P) {
     // first use of every slot (output rows u0 .. u0+S-1; this warp's parity group)
     for (int q0 = par; q0 < S && u0 + q0 < u1; q0 += 2) init_slot(q0, (u0 + q0) / upc);
     pdl_wait();  // residual loads and output stores touch tensors of the previous kernel
+    if (P.discard_ptr != nullptr) {
+      // the previous dense block's x1..x4 (and x) are dead once its conv5 has completed: drop their dirty lines from
+      // L2 instead of letting them be written back to HBM (4 GB per 720p frame of pure write traffic otherwise)
+      const int64_t per = (P.discard_npx + gridDim.x - 1) / gridDim.x;
+      const int64_t p0 = per * blockIdx.x, p1 = p0 + per < P.discard_npx ? p0 + per : P.discard_npx;
+      uint8_t* const db = reinterpret_cast<uint8_t*>(P.discard_ptr);
+      for (int64_t p = p0 + (ew * 32 + lane); p < p1; p += kStreamEpiWarps * 32) {
+        uint8_t* const px = db + p * P.discard_pitch_bytes;
+#pragma unroll
+        for (int l = 0; l < 3; ++l)
+          if ((P.discard_mask >> l) & 1u) asm volatile("discard.global.L2 [%0], 128;" ::"l"(px + l * 128) : "memory");
+      }
+    }
     while (next_band(P, u, u1, b)) {
       const int ax = b.strip * kTileW + m;
       const bool valid = ax < P.W;
@@ -572,9 +614,9 @@ conv3x3_stream_kernel(const __grid_constant__ StreamParams P) {
                 if (P.fast_store == 2) {
 #pragma unroll
                   for (int ab = 0; ab < 4; ++ab)
-                    tma_store_5d(&P.tmO, stage, b.chunk * NOUT, ab & 1, b.strip * kTileW + qd * 32, ab >> 1, (b.n + P.n_out0) * P.H + y);
+                    tma_store_5d(&P.tmO, stage, b.chunk * NOUT, ab & 1, b.strip * kTileW + qd * 32, ab >> 1, (b.n + P.n_out0) * P.H + y, pol_out);
                 } else {
-                  tma_store_4d(&P.tmO, stage, b.chunk * NOUT, b.strip * kTileW + qd * 32, y, b.n + P.n_out0);
+                  tma_store_4d(&P.tmO, stage, b.chunk * NOUT, b.strip * kTileW + qd * 32, y, b.n + P.n_out0, pol_out);
                 }
                 bulk_commit();
               }
@@ -593,7 +635,9 @@ conv3x3_stream_kernel(const __grid_constant__ StreamParams P) {
       }
     }
     if (warp == 2) SS4K_TRACE(6);
-    if (fast && lane == 0) bulk_wait0();  // all output tiles written before the CTA releases its shared memory
+    // the staging tiles must have been read before the CTA releases its shared memory; the global writes themselves
+    // complete asynchronously and are ordered before the next kernel by grid completion (griddepcontrol.wait there)
+    if (fast && lane == 0) { if (P.dbg_flags & 16) bulk_wait0(); else bulk_wait_read0(); }
     if (warp == 2) SS4K_TRACE(7);
   }
 

@@ -591,6 +591,16 @@ int materialize_stream(ss4k_ctx* ctx, const ConvSpec& cs, const HostTensor& W, c
   p.chunks = pk.chunks;
   p.total_units = pk.chunks * cs.n * p.strips * cs.in_h;
   p.acc_slots = pk.acc_slots; p.a_slots = pk.a_slots;
+  p.l2_in = cs.l2_in; p.l2_out = cs.l2_out;
+  if (const char* e = getenv("SS4K_DBG_FLAGS")) {  // experiments only (see StreamParams::dbg_flags): RRDB trunk convs
+    if (cs.name.rfind("body.", 0) == 0) p.dbg_flags = atoi(e);
+  }
+  if (cs.discard_buf >= 0 && cs.discard_mask != 0) {
+    p.discard_ptr = bufptr(cs.discard_buf);
+    p.discard_pitch_bytes = static_cast<uint32_t>(cs.discard_pitch) * 2u;
+    p.discard_mask = static_cast<uint32_t>(cs.discard_mask);
+    p.discard_npx = cs.discard_npx;
+  }
   const uint32_t f = bf16 ? 1u : 0u;
   for (int i = 0; i < 3; ++i)
     p.idesc[i] = (1u << 4) | (f << 7) | (f << 10) | (static_cast<uint32_t>((i + 1) * pk.nout >> 3) << 17) | (static_cast<uint32_t>(128 >> 4) << 24);

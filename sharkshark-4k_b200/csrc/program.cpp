@@ -124,6 +124,15 @@ std::string build_rrdb(const PlanCfgLite& c, Program* P) {
     P->add_conv(u);
     P->flops -= u.flops();  // the duplicate is not algorithmic work
   }
+  // L2 eviction priorities of the dense block: the slab x|x1..x4 is re-read by every later
+  // conv of the block and dead after conv5.  Four digits: conv1-4 loads, conv1-4 stores, conv5 loads, conv5 stores
+  // (0 normal, 1 evict_last, 2 evict_first).
+  int hint[4] = {1, 1, 2, 1};
+  if (const char* e = getenv("SS4K_L2_HINTS")) {
+    for (int i = 0; i < 4 && e[i] >= '0' && e[i] <= '2'; ++i) hint[i] = e[i] - '0';
+  }
+  // dead-slab discard (conv_stream.cu): on unless SS4K_DISCARD=0
+  const bool use_discard = getenv("SS4K_DISCARD") == nullptr || atoi(getenv("SS4K_DISCARD")) != 0;
   for (int b = 0; b < nb; ++b) {
     for (int r = 0; r < 3; ++r) {
       const int cur = S[r], nxt = S[(r + 1) % 3];
@@ -132,10 +141,18 @@ std::string build_rrdb(const PlanCfgLite& c, Program* P) {
         ConvSpec v = base_conv(pre + std::to_string(k), cur, th, tw, slab, nf + (k - 1) * gc, gc);
         v.act = kActPRelu; v.const_slope = 0.2f;
         v.out_buf = cur; v.out_pitch = slab; v.out_coff = nf + (k - 1) * gc;
+        v.l2_in = hint[0]; v.l2_out = hint[1];
+        if (k == 1 && (b > 0 || r > 0) && use_discard) {
+          // the previous block's slab is dead after its conv5 (its x stays alive when it is the RRDB input, slab 0)
+          const int prev = (r + 2) % 3;
+          v.discard_buf = S[prev]; v.discard_mask = prev == 0 ? 6 : 7;
+          v.discard_pitch = slab; v.discard_npx = static_cast<long long>(c.n) * th * tw;
+        }
         P->add_conv(v);
       }
       ConvSpec v = base_conv(pre + "5", cur, th, tw, slab, slab, nf);
       v.out_buf = nxt; v.out_pitch = slab; v.out_coff = 0;
+      v.l2_in = hint[2]; v.l2_out = hint[3];
       v.res1_buf = cur; v.res1_pitch = slab; v.res1_coff = 0;
       if (r < 2) {
         v.alpha = 0.2f; v.beta1 = 1.f;                    // x5*0.2 + x

@@ -59,6 +59,11 @@ struct ConvSpec {
   int tshift = 0;                   // 1: temporal-shift scatter store with fold = `fold` (time == batch index)
   int in_ring = 0, out_ring = 0;    // BSVD streaming: images (ring slots) of the input / output tensors (0: n)
   int up2_store = 0;                // 1: store every output pixel 2x2 times: the destination is the nearest-x2 upsampled image
+  int discard_buf = kBufNone;       // tensor whose lines (bit l of discard_mask: 128-byte line l of every pixel) are dead:
+  int discard_mask = 0;             //   dropped from L2 without write-back by this conv (no later step reads them)
+  int discard_pitch = 0;            //   channel pitch of that tensor (16-bit elements; a multiple of 64 = whole lines)
+  long long discard_npx = 0;        //   its pixel count
+  int l2_in = 0, l2_out = 0;        // L2 eviction priority hints of the loads / stores (StreamParams::l2_in / l2_out)
   double flops() const;
 };
 
