@@ -254,7 +254,7 @@ def run_native(args, rank, world, local_rank):
         achieved = (k_fl / max(1, k_n)) / (k_us_timed * 1e-6) / 1e12
         achieved_events = k_fl / (k_ms / 1000) / 1e12
         traffic = None
-        tp = os.path.join(ROOT, "profiles", "r01_v4_dram_traffic_b1.json")
+        tp = os.path.join(ROOT, "profiles", "r01_v6_dram_traffic_b1.json")
         if B == 1 and os.path.isfile(tp):
             with open(tp) as f:
                 tk = json.load(f)["kernels"]
@@ -268,7 +268,7 @@ def run_native(args, rank, world, local_rank):
             "config": {"workload": "RRDBNet-23 x2 1280x720->2560x1440 (BASELINE.json configs[1])",
                        "frames_per_step_per_gpu": B, "in": "uint8 NHWC", "out": "uint8 NHWC",
                        "weights": "random init (upstream basicsr init, seed 0)",
-                       "l2": "no flush: one step moves > 60 GB through L2 and > 30 GB through HBM per frame (>> 126 MB L2); 3 input buffers rotated",
+                       "l2": "no flush: one frame reads and writes 118 MB slabs 69 times (13.5 GB through HBM per frame, >> 126 MB L2); 3 input buffers rotated",
                        "desc_mode": eng.desc_mode, "parallelism": f"frame-sharded x{world}",
                        "launch": "%d of %d kernels per step replay from one CUDA graph; programmatic dependent launch %s"
                                  % (plan.graph_steps, plan.launches, "off" if os.environ.get("SS4K_NO_PDL") else "on")},
@@ -282,7 +282,7 @@ def run_native(args, rank, world, local_rank):
                          "flops_per_launch_avg": k_fl / max(1, k_n), "kernel_share_of_step": share,
                          "achieved_unoverlapped": achieved_events, "avg_launch_us_unoverlapped": 1000 * k_ms / max(1, k_n),
                          "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum per launch, mean over the kernel's launches of one frame "
-                                         "(profiles/r01_v4_dram_traffic_b1.json; warm caches, batch 1)" if traffic else None,
+                                         "(profiles/r01_v6_dram_traffic_b1.json; one ncu pass, warm caches, batch 1)" if traffic else None,
                          "how": "avg launch duration = CUDA-event time of the timed region (graph replay) x the kernel's share of a step / "
                                 "its launches; share from CUDA events between every step of an un-graphed run on the launching stream "
                                 "(mean of %d runs; those serialised per-launch times give 'achieved_unoverlapped'); "

@@ -12,7 +12,7 @@ import torch
 from torch import nn
 
 from . import _lib as L
-from .engine import Engine
+from .engine import Engine, PlanCache
 
 
 def load_checkpoint(path):
@@ -67,23 +67,19 @@ class NativeBSVD(nn.Module):
 
     shift_num = 16  # BSVD.count_shift (model.py:582-588): 16 BiBufferConvs -> +-16 frame receptive field
 
-    def __init__(self, state_dict, device=0, act_mode=L.ACT_F16, out_dtype=torch.float32, use_graph=True):
+    def __init__(self, state_dict, device=0, act_mode=L.ACT_F16, out_dtype=torch.float32, use_graph=True, max_plans=12):
         super().__init__()
         self.engine = Engine.get(device)
         if act_mode == "auto":
             act_mode = pick_act_mode(state_dict)
         self.act_mode, self.out_dtype, self.use_graph = act_mode, out_dtype, use_graph
         self.net_id = self.engine.new_net(state_dict)
-        self._plans = {}
+        self._plans = PlanCache(max_plans)
 
     def _plan(self, t, h, w, in_fmt, out_fmt, noise=0.0):
-        key = (t, h, w, in_fmt, out_fmt, float(noise))
-        p = self._plans.get(key)
-        if p is None:
-            p = self.engine.plan(self.net_id, L.ARCH_BSVD, t, h, w, act_mode=self.act_mode, in_fmt=in_fmt,
-                                 out_fmt=out_fmt, use_graph=self.use_graph, bsvd_noise=noise)
-            self._plans[key] = p
-        return p
+        return self._plans.get((t, h, w, in_fmt, out_fmt, float(noise)), lambda: self.engine.plan(
+            self.net_id, L.ARCH_BSVD, t, h, w, act_mode=self.act_mode, in_fmt=in_fmt, out_fmt=out_fmt,
+            use_graph=self.use_graph, bsvd_noise=noise))
 
     def denoise_frames(self, frames, h, w, noise, nv12=False):
         """Frame-format entry: a clip of uint8 NHWC RGB frames ``[T,h,w,3]`` or NV12 frames ``[T, h*w*3/2]`` (CUDA) ->

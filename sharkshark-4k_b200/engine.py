@@ -125,6 +125,37 @@ def plan_dry(cfg):
         lib.ss4k_free(out)
 
 
+class PlanCache:
+    """Shape-keyed LRU cache of engine plans.  A plan owns its workspaces (about 2 GB for RRDBNet at 720p), so a
+    caller that sees arbitrary shapes -- the reference's still-image server drives the same service with one plan
+    per image size (src/sharkshark/image_server/image_pipeline.py:54-64) -- must not keep every plan alive: the
+    least recently used plan is destroyed once `max_plans` are cached."""
+
+    def __init__(self, max_plans=8):
+        self.max_plans = max(1, int(max_plans))
+        self._d = {}        # insertion order == recency order
+        self.evictions = 0
+
+    def get(self, key, make):
+        p = self._d.pop(key, None)
+        if p is None:
+            while len(self._d) >= self.max_plans:
+                old = self._d.pop(next(iter(self._d)))
+                self.evictions += 1
+                close = getattr(old, "close", None)
+                if close is not None:
+                    close()
+            p = make()
+        self._d[key] = p
+        return p
+
+    def __len__(self):
+        return len(self._d)
+
+    def __contains__(self, key):
+        return key in self._d
+
+
 _OUT_DTYPES = {L.FMT_F32_NCHW: torch.float32, L.FMT_F16_NCHW: torch.float16, L.FMT_U8_NHWC: torch.uint8}
 
 

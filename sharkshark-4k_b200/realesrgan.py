@@ -15,7 +15,7 @@ import torch
 from torch import nn
 
 from . import _lib as L
-from .engine import Engine
+from .engine import Engine, PlanCache
 
 
 @dataclass
@@ -64,7 +64,7 @@ class _NativeNet(nn.Module):
     arch = None
 
     def __init__(self, state_dict, scale, depth, device=0, act_mode=L.ACT_F16, tile=0, tile_pad=10,
-                 out_dtype=torch.float32, use_graph=True):
+                 out_dtype=torch.float32, use_graph=True, max_plans=12):
         super().__init__()
         self.engine = Engine.get(device)
         self.scale, self.depth, self.act_mode = scale, depth, act_mode
@@ -73,17 +73,12 @@ class _NativeNet(nn.Module):
         self.out_dtype = out_dtype
         self.use_graph = use_graph
         self.net_id = self.engine.new_net(state_dict)
-        self._plans = {}
+        self._plans = PlanCache(max_plans)
 
     def _plan(self, n, h, w, in_fmt, out_fmt):
-        key = (n, h, w, in_fmt, out_fmt)
-        p = self._plans.get(key)
-        if p is None:
-            p = self.engine.plan(self.net_id, self.arch, n, h, w, scale=self.scale, depth=self.depth,
-                                 tile=0, tile_pad=self.tile_pad, act_mode=self.act_mode, in_fmt=in_fmt,
-                                 out_fmt=out_fmt, use_graph=self.use_graph)
-            self._plans[key] = p
-        return p
+        return self._plans.get((n, h, w, in_fmt, out_fmt), lambda: self.engine.plan(
+            self.net_id, self.arch, n, h, w, scale=self.scale, depth=self.depth, tile=0, tile_pad=self.tile_pad,
+            act_mode=self.act_mode, in_fmt=in_fmt, out_fmt=out_fmt, use_graph=self.use_graph))
 
     def plan_for(self, x):
         n, _, h, w = x.shape

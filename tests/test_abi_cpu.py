@@ -47,3 +47,27 @@ def test_product_package_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cpp", ".h", ".cuh", ".inc")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), f
+
+
+def test_plan_cache_lru():
+    """Shape-keyed plan cache (still-image server path, image_pipeline.py:54-64: one plan per image size): the least
+    recently used plan is closed once max_plans are alive."""
+    from ss4k_b200.engine import PlanCache
+
+    closed = []
+
+    class FakePlan:
+        def __init__(self, k):
+            self.k = k
+
+        def close(self):
+            closed.append(self.k)
+
+    c = PlanCache(max_plans=2)
+    a = c.get("a", lambda: FakePlan("a"))
+    c.get("b", lambda: FakePlan("b"))
+    assert c.get("a", lambda: FakePlan("a2")) is a          # hit, and "a" becomes the most recent
+    c.get("c", lambda: FakePlan("c"))                       # evicts "b"
+    assert closed == ["b"] and "a" in c and "c" in c and len(c) == 2 and c.evictions == 1
+    c.get("b", lambda: FakePlan("b"))                       # evicts "a"
+    assert closed == ["b", "a"]

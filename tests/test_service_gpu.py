@@ -100,3 +100,27 @@ def test_proc_job_recieved_roundtrip(engine):
     job = service.UpscalerQueueEntry(frames=_frames(1, 40, 72, 4).cuda(), step=7)
     out = svc.proc_job_recieved(job)
     assert out.step == 7 and tuple(out.frames.shape) == (1, 160, 288, 3) and out.frames.dtype == torch.uint8
+
+
+def test_image_server_shapes_lru(engine):
+    """The still-image server drives the same service with arbitrary image sizes (image_pipeline.py:54-64:
+    lr_level=3, batch_size=1, lr_hr_resize=False; one job per image): one engine plan per shape, the least recently
+    used plan is destroyed once max_plans are cached, and a re-planned shape reproduces its first result bit for bit."""
+    torch.manual_seed(0)
+    net = srvgg.SRVGGNetCompact(3, 3, 64, 16, 4).eval()
+    svc = service.FsrcnnUpscalerService(lr_level=3, device=0, denoising=False, model_name='realesr-animevideov3',
+                                        state_dict=net.state_dict(), batch_size=1, lr_hr_resize=False)
+    svc.proc_init()
+    svc.model._plans.max_plans = 2
+    shapes = [(40, 56), (72, 96), (33, 130), (40, 56)]
+    outs = []
+    for i, (h, w) in enumerate(shapes):
+        frames = _frames(1, h, w, 10 + (i % 3))
+        got = svc.upscale(frames.cuda())
+        torch.cuda.synchronize()
+        assert got.shape == (1, 4 * h, 4 * w, 3)
+        want = glue.upscale_multi(frames, net, lr_shape=(720, 1280), output_shape=None, lr_hr_resize=False)
+        _cmp(got, want)
+        outs.append(got.cpu())
+    assert svc.model._plans.evictions >= 2 and len(svc.model._plans) == 2
+    assert torch.equal(outs[0], outs[3])
