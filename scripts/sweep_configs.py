@@ -29,11 +29,11 @@ def main():
     if "cfg3" in which or "cfg4" in which:
         net2 = rrdbnet.RRDBNet(3, 3, 2, 64, 23, 32).eval()
         sr = realesrgan.NativeRRDBNet(net2.state_dict(), scale=2, num_block=23, device=0)
-        for name, (h, w), tile in (("cfg3", (720, 1280), 0), ("cfg4", (1080, 1920), 512)):
+        for name, (h, w), tile in (("cfg3", (720, 1280), 0), ("cfg4", (1080, 1920), 512), ("cfg4", (1080, 1920), 492), ("cfg4", (1080, 1920), 0)):
             if name not in which:
                 continue
             F = 8
-            for mode, sd in (("f16 (trained-like weights x0.5)", obsvd.build_bsvd32(0, weight_scale=0.5)), ("f16 split (constructor init)", obsvd.build_bsvd32(0))):
+            for mode, sd in (("f16 (trained-like weights x0.5)", obsvd.build_bsvd32(0, weight_scale=0.5)), ("f16 split (constructor init)", obsvd.build_bsvd32(0)))[:1 if (name == "cfg4" and tile != 512) else 2]:
                 den = nbsvd.NativeBSVD(sd, device=0, act_mode="auto", out_dtype=torch.float16)
                 srm = sr if tile == 0 else realesrgan.NativeRRDBNet(net2.state_dict(), scale=2, num_block=23, device=0, tile=tile, tile_pad=10)
                 srm.out_dtype = torch.float16
@@ -71,7 +71,8 @@ def main():
         net4 = rrdbnet.RRDBNet(3, 3, 4, 64, 23, 32).eval()
         h, w = 1080, 1920
         x = torch.rand(1, 3, h, w, device="cuda")
-        for tile in (0, 1024, 512, 256):
+        # 1004 / 492 / 236: tile + 2 * tile_pad is a multiple of the kernel's 128-pixel strip (no partly filled strip)
+        for tile in (0, 1024, 1004, 512, 492, 256, 236):
             m = realesrgan.NativeRRDBNet(net4.state_dict(), scale=4, num_block=23, device=0, tile=tile, tile_pad=10)
             m.out_dtype = torch.float16
             t = ev_time(lambda: m(x), 2)
