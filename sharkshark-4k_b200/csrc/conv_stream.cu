@@ -620,6 +620,24 @@ conv3x3_stream_kernel(const __grid_constant__ StreamParams P) {
                 }
                 bulk_commit();
               }
+            } else if (NOUT == 16 && E.out_mode == kOutU8NHWC && E.cout == 3 && E.act == kActNone && E.alpha == 1.0f &&
+                       E.res1 == nullptr && E.res2 == nullptr && __all_sync(0xffffffffu, valid)) {
+              // uint8 RGB frame store (last conv of the nets): the warp's 32 pixels are 96 contiguous bytes; assemble
+              // them into 24 words with shuffles instead of three strided byte stores per thread
+              uint32_t px = 0;
+#pragma unroll
+              for (int i = 0; i < 3; ++i) {
+                float f = fminf(fmaxf(__uint_as_float(raw[i]), 0.f), 1.f) * 255.f;
+                if (E.round_u8) f = rintf(f);
+                px |= static_cast<uint32_t>(static_cast<uint8_t>(f)) << (8 * i);
+              }
+              const int p0 = (4 * lane) / 3, sh = 4 * lane - 3 * p0;  // word `lane` starts `sh` bytes into pixel p0
+              const uint32_t lo = __shfl_sync(0xffffffffu, px, p0 & 31), hi = __shfl_sync(0xffffffffu, px, (p0 + 1) & 31);
+              const uint64_t two = static_cast<uint64_t>(lo) | (static_cast<uint64_t>(hi) << 24);
+              if (lane < 24) {
+                const size_t pix0 = (static_cast<size_t>(b.n) * E.out_h + y) * E.out_w + b.strip * kTileW + qd * 32;
+                reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(E.out) + pix0 * 3)[lane] = static_cast<uint32_t>(two >> (8 * sh));
+              }
             } else if (valid) {
 #pragma unroll
               for (int c = 0; c < NOUT; c += 16) {
