@@ -124,17 +124,28 @@ constexpr int kASlotBytes = 17408;  // 130 * 128 rounded up to the 1024-byte swi
 
 constexpr int kStreamBiasBytes = 1024;  // fp32 bias of every output channel (<= 256 padded channels per conv)
 
+// How a fresh accumulator slot gets its initial value (the bias):
+//   NOUT <= 48: the epilogue warp that drained the slot writes the fp32 bias row back with tcgen05.st (the MMA stream is
+//               the bound of these variants: no issue slot, no operand traffic spent on it);
+//   NOUT == 64: a ones[128x16] x bias_tile[NOUT x 16] MMA issued by the MMA warp (this variant is bound by its epilogue
+//               warps -- 2.3 k clk per row against 1.15 k clk of MMAs -- so the 0.5 k clk of tcgen05.st per row cost
+//               13 % there while the tensor pipe has the slack).
+constexpr bool stream_bias_mma(int nout) { return nout == 64; }
+constexpr int kStreamOnesBytes = 128 * 128;  // "ones" operand tile of the bias MMA
+
 constexpr int kStreamEpiWarps = 8;  // two per TMEM lane quarter, alternating output rows
 constexpr int kStreamThreads = 32 * (2 + kStreamEpiWarps);
 
 struct StreamParams {
   CUtensorMap tmA[2];   // 5-D (64, W, channel block, H, N), box (64, 130, 1, 1, 1), swizzle 128B
-  CUtensorMap tmW;      // 2-D (64, rows), box (64, 3*NOUT): rows = [chunk][kb][kx][2-ky][NOUT]
+  CUtensorMap tmW;      // 2-D (64, rows), box (64, 3*NOUT): rows = [chunk][kb][kx][2-ky][NOUT], then bias tiles (NOUT == 64)
+  CUtensorMap tmB;      // same tensor, box (64, NOUT): the per-chunk bias tile (bias hi/lo in K columns 0/1; NOUT == 64)
   CUtensorMap tmO;      // NHWC output, 4-D (C, W, H, N), box (NOUT, 32, 1, 1), swizzled: TMA store of the fast path
   Epilogue ep;
   int32_t fast_store;   // 1: plain NHWC output -> registers -> swizzled smem tile -> TMA store;
                         // 2: the same tile stored four times through a 5-D (C, b, W, a, N*H) map: nearest-x2 upsample
   const float* bias_f;  // [chunks * NOUT] fp32 bias with alpha folded in: the accumulators' initial value
+  int32_t bias_row0;    // first row of the bias tiles inside the weight tensor (NOUT == 64)
   uint8_t a_kb[kMaxSKB];  // source 64-channel block of K block i
   uint8_t a_tm[kMaxSKB];  // which activation tensor map
   uint8_t nks[kMaxSKB];   // 16-channel k-steps to issue (1..4)

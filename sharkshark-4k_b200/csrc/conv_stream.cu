@@ -129,8 +129,12 @@ conv3x3_stream_kernel(const __grid_constant__ StreamParams P) {
   constexpr uint32_t kStageWarp = 32u * NOUT * 2u;   // one epilogue warp's 32-pixel output tile
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t w_base = smem_base;
-  const uint32_t bias_base = w_base + static_cast<uint32_t>(P.nkb) * 3u * kWTile;  // fp32 bias of every chunk
-  const uint32_t a_base = bias_base + kStreamBiasBytes;
+  // after the weights: fp32 bias of every chunk (tcgen05.st initialisation), or bias tile + ones tile (bias MMA)
+  constexpr bool kBiasMMA = stream_bias_mma(NOUT);
+  constexpr uint32_t kBiasTile = NOUT * 128u;
+  const uint32_t bias_base = w_base + static_cast<uint32_t>(P.nkb) * 3u * kWTile;
+  const uint32_t ones_base = bias_base + kBiasTile;
+  const uint32_t a_base = kBiasMMA ? ones_base + kStreamOnesBytes : bias_base + kStreamBiasBytes;
   const uint32_t stage_base = a_base + static_cast<uint32_t>(P.a_slots) * kASlotBytes;
   const uint32_t bar_base = stage_base + kStreamEpiWarps * ((kStageWarp + 1023u) & ~1023u);
   const uint32_t a_full = bar_base;
@@ -169,6 +173,7 @@ conv3x3_stream_kernel(const __grid_constant__ StreamParams P) {
     if (lane == 0) {
       prefetch_tmap(&P.tmA[0]);
       prefetch_tmap(&P.tmW);
+      if (kBiasMMA) prefetch_tmap(&P.tmB);
       if (P.fast_store) prefetch_tmap(&P.tmO);
       mbar_init(w_full, 1);
       mbar_init(w_empty, 1);
@@ -192,9 +197,10 @@ conv3x3_stream_kernel(const __grid_constant__ StreamParams P) {
       early_chunk = fb.chunk;
       if (elect_one()) {
         const int ntile = P.nkb * 3;
-        mbar_expect_tx(w_full, static_cast<uint32_t>(ntile) * kWTile);
+        mbar_expect_tx(w_full, static_cast<uint32_t>(ntile) * kWTile + (kBiasMMA ? kBiasTile : 0u));
         for (int t = 0; t < ntile; ++t)
           tma_load_2d(w_base + t * kWTile, &P.tmW, w_full, 0, (fb.chunk * ntile + t) * 3 * NOUT);
+        if (kBiasMMA) tma_load_2d(bias_base, &P.tmB, w_full, 0, P.bias_row0 + fb.chunk * NOUT);
       }
       __syncwarp();
     }
@@ -210,10 +216,22 @@ conv3x3_stream_kernel(const __grid_constant__ StreamParams P) {
   {
     // fp32 bias of every output channel (alpha already folded in): the epilogue warps write it into the accumulator
     // slots they own.  A constant of the launch, so it is read before the dependency wait.
-    float* sb = reinterpret_cast<float*>(smem_gen + (bias_base - smem_base));
-    const int nb = P.chunks * NOUT;
-    if (warp != 0)
-      for (int i = threadIdx.x - 32; i < nb; i += kStreamThreads - 32) sb[i] = __ldg(P.bias_f + i);
+    if (kBiasMMA) {
+      // "ones" operand of the accumulator-init MMA: 128 rows x 64 channels, swizzle-128B K-major, value 1 in K
+      // columns 0 and 1 (they meet the hi / lo halves of the bias in the bias tile), 0 elsewhere
+      const uint32_t one2 = P.ep.is_bf16 ? 0x3F803F80u : 0x3C003C00u;
+      if (warp != 0)
+        for (uint32_t ci = threadIdx.x - 32; ci < 1024u; ci += kStreamThreads - 32) {
+          const uint32_t r = ci >> 3, pc = ci & 7u;
+          sts128(ones_base + ci * 16u, pc == (r & 7u) ? one2 : 0u, 0u, 0u, 0u);
+        }
+      fence_proxy_async();
+    } else {
+      float* sb = reinterpret_cast<float*>(smem_gen + (bias_base - smem_base));
+      const int nb = P.chunks * NOUT;
+      if (warp != 0)
+        for (int i = threadIdx.x - 32; i < nb; i += kStreamThreads - 32) sb[i] = __ldg(P.bias_f + i);
+    }
     if (warp == 2) SS4K_TRACE(11);
   }
   // Set-up barrier: the producer warp only ARRIVES (its barrier initialisation becomes visible to the others) and goes
@@ -257,9 +275,10 @@ conv3x3_stream_kernel(const __grid_constant__ StreamParams P) {
           early_chunk = -1;  // already requested in the prologue
         } else if (elect_one()) {
           const int ntile = P.nkb * 3;
-          mbar_expect_tx(w_full, static_cast<uint32_t>(ntile) * kWTile);
+          mbar_expect_tx(w_full, static_cast<uint32_t>(ntile) * kWTile + (kBiasMMA ? kBiasTile : 0u));
           for (int t = 0; t < ntile; ++t)
             tma_load_2d(w_base + t * kWTile, &P.tmW, w_full, 0, (b.chunk * ntile + t) * 3 * NOUT);
+          if (kBiasMMA) tma_load_2d(bias_base, &P.tmB, w_full, 0, P.bias_row0 + b.chunk * NOUT);
         }
         __syncwarp();
         wph ^= 1;
@@ -383,9 +402,10 @@ conv3x3_stream_kernel(const __grid_constant__ StreamParams P) {
       uint32_t f = rc[7];
 #pragma unroll
       for (int j = 0; j < 3; ++j, f >>= 8) {
-        if (f & 0x80u) {  // fresh slot: drained and re-initialised with the bias by the epilogue warps
+        if (f & 0x80u) {  // fresh slot: drained (and, NOUT <= 48, re-initialised with the bias) by the epilogue warps
           mbar_wait_u(acc_empty + 8 * (f & 0x1Fu), (f >> 6) & 1u);
           tcgen05_after_sync();
+          if (kBiasMMA && do_mma) umma_f16_elect(tmem_base + (f & 0x1Fu) * NOUT, sdesc(ones_base), sdesc(bias_base), P.idesc[0], 0u);
         }
       }
     };
@@ -490,14 +510,16 @@ conv3x3_stream_kernel(const __grid_constant__ StreamParams P) {
     auto init_slot = [&](int s_, int chunk_) {
       const uint32_t ta = tmem_base + (static_cast<uint32_t>(qd * 32) << 16) + static_cast<uint32_t>(s_ * NOUT);
       const uint32_t ba = bias_base + static_cast<uint32_t>(chunk_ * NOUT) * 4u;
+      if (!kBiasMMA) {
 #pragma unroll
-      for (int c = 0; c < NOUT; c += 16) {
-        uint32_t bv[16];
+        for (int c = 0; c < NOUT; c += 16) {
+          uint32_t bv[16];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) lds128(ba + (c + 4 * i) * 4u, bv[4 * i], bv[4 * i + 1], bv[4 * i + 2], bv[4 * i + 3]);
-        tmem_st16p(ta + c, bv);
+          for (int i = 0; i < 4; ++i) lds128(ba + (c + 4 * i) * 4u, bv[4 * i], bv[4 * i + 1], bv[4 * i + 2], bv[4 * i + 3]);
+          tmem_st16p(ta + c, bv);
+        }
+        tmem_st_wait();
       }
-      tmem_st_wait();
       tcgen05_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(acc_empty + 8 * s_);

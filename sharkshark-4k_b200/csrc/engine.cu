@@ -267,6 +267,7 @@ struct StreamPacked {
   std::vector<float> bias, slope;
   std::vector<float> bias_f;  // bias with alpha (and the none_minus sign) folded in: initial value of the accumulators
   int nout = 0, chunks = 0, nkb = 0, npad_total = 0, a_slots = 0, acc_slots = 0;
+  int bias_row0 = 0;     // rows of weight tiles == first row of the bias tiles (bias-MMA variant)
   float alpha_out = 1.f; // epilogue scale left after folding alpha into weights and bias
   uint8_t nks[kMaxSKB];
   uint8_t src_kb[kMaxSKB];  // 64-channel block of the source tensor read by K block i
@@ -293,7 +294,7 @@ bool stream_config(const ConvSpec& cs, StreamPacked* sp) {
   for (int i = 0; i < nc; ++i) {
     const int nout = cand[i];
     if (npad % nout) continue;
-    const int wbytes = nkb * 9 * nout * 128 + kStreamBiasBytes;
+    const int wbytes = nkb * 9 * nout * 128 + (stream_bias_mma(nout) ? nout * 128 + kStreamOnesBytes : kStreamBiasBytes);
     const int stage = kStreamEpiWarps * round_up(32 * nout * 2, 1024);
     const int left = kSmemBytes - 2048 - wbytes - stage;
     const int slots = std::min(kMaxSASlots, left / kASlotBytes);
@@ -332,7 +333,11 @@ std::string pack_weights_stream(const ConvSpec& cs, const HostTensor& W, const H
   // (none, PReLU / LeakyReLU): fold alpha into weights and bias so the epilogue does not multiply
   const float fold = (cs.act != kActRelu6) ? cs.alpha : 1.f;
   out->alpha_out = (cs.act != kActRelu6) ? 1.f : cs.alpha;
-  out->w.assign(static_cast<size_t>(out->chunks) * nkb * 9 * nout * 64, 0);
+  // weight tiles, then (bias-MMA variant) one bias tile per chunk: row = output channel, K column 0 = high half,
+  // column 1 = low half of the bias (the "ones" operand has 1 there)
+  const size_t wrows = static_cast<size_t>(out->chunks) * nkb * 9 * nout;
+  out->bias_row0 = static_cast<int>(wrows);
+  out->w.assign((wrows + (stream_bias_mma(nout) ? npad : 0)) * 64, 0);
   for (int ch = 0; ch < out->chunks; ++ch)
     for (int kb = 0; kb < nkb; ++kb)
       for (int kx = 0; kx < 3; ++kx)
@@ -355,6 +360,11 @@ std::string pack_weights_stream(const ConvSpec& cs, const HostTensor& W, const H
     const int n = orow[row];
     if (n < 0 || !B) continue;
     out->bias_f[row] = (n < cs.neg_first ? -fold : fold) * B->data[n];
+    if (stream_bias_mma(nout)) {
+      const uint16_t hi = f2h(out->bias_f[row], bf16);
+      out->w[(wrows + row) * 64 + 0] = hi;
+      out->w[(wrows + row) * 64 + 1] = f2h(out->bias_f[row] - h2f(hi, bf16), bf16);
+    }
   }
   out->bias.assign(npad, 0.f);
   out->slope.assign(npad, 1.f);
@@ -552,6 +562,18 @@ int materialize_stream(ss4k_ctx* ctx, const ConvSpec& cs, const HostTensor& W, c
     if (r != CUDA_SUCCESS) return fail(ctx, SS4K_E_CUDA, fmt("cuTensorMapEncodeTiled(stream weights) failed: %d", (int)r));
   }
   p.bias_f = ex->d_bias;
+  p.bias_row0 = pk.bias_row0;
+  p.tmB = p.tmW;
+  if (stream_bias_mma(pk.nout)) {  // bias tiles: same tensor, NOUT-row box
+    const cuuint64_t rows = pk.w.size() / 64;
+    cuuint64_t dims[2] = {64, rows};
+    cuuint64_t strides[1] = {128};
+    cuuint32_t box[2] = {64, static_cast<cuuint32_t>(pk.nout)};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = ctx->encode(&p.tmB, dt, 2, ex->d_w, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(ctx, SS4K_E_CUDA, fmt("cuTensorMapEncodeTiled(stream bias) failed: %d", (int)r));
+  }
   // fast epilogue: plain NHWC 16-bit output -> swizzled shared-memory tile -> TMA store
   p.fast_store = 0;
   if (cs.out_mode == kOutNHWC && cs.out_buf >= 0 && cs.out_lo_buf < 0 && cs.out_coff % 8 == 0 && cs.out_pitch % 8 == 0 &&
@@ -1170,8 +1192,8 @@ int ss4k_debug_pack(const ss4k_conv_desc* d, int in_pitch, int in_coff, int wper
     if (!stream_config(cs, &sp)) return fail(nullptr, SS4K_E_INVALID, "conv is not eligible for the row-streaming kernel");
     std::string es = pack_weights_stream(cs, W, bias_host ? &B : nullptr, slope_host ? &S : nullptr, bf16, &sp);
     if (!es.empty()) return fail(nullptr, SS4K_E_WEIGHTS, es);
-    std::string js = fmt("{\"kernel\":\"stream\",\"nout\":%d,\"chunks\":%d,\"nkb\":%d,\"npad\":%d,\"a_slots\":%d,\"acc_slots\":%d,\"nks\":[",
-                         sp.nout, sp.chunks, sp.nkb, sp.npad_total, sp.a_slots, sp.acc_slots);
+    std::string js = fmt("{\"kernel\":\"stream\",\"nout\":%d,\"chunks\":%d,\"nkb\":%d,\"npad\":%d,\"a_slots\":%d,\"acc_slots\":%d,\"w_rows\":%d,\"nks\":[",
+                         sp.nout, sp.chunks, sp.nkb, sp.npad_total, sp.a_slots, sp.acc_slots, sp.bias_row0);
     for (int i = 0; i < sp.nkb; ++i) js += fmt("%s%d", i ? "," : "", sp.nks[i]);
     js += "],\"bias\":[";
     for (size_t i = 0; i < sp.bias.size(); ++i) js += fmt("%s%.9g", i ? "," : "", sp.bias[i]);
