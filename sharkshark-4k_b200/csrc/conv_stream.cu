@@ -501,6 +501,22 @@ conv3x3_stream_kernel(const __grid_constant__ StreamParams P) {
     const bool bf16 = E.is_bf16 != 0;
     const bool fast = P.fast_store != 0;
     const uint64_t pol_out = l2_policy(P.l2_out);
+    // Specialised epilogue arithmetic of the fast path.  The general form decides activation kind, slope source,
+    // alpha, residuals and 16-bit type per 8-channel group (about 20 instructions per value); the three shapes the
+    // nets actually use are 2-4 instructions per value:
+    //   1 LeakyReLU with a constant slope in [0, 1], no residual      (RDB conv1-4, upsampling convs)
+    //   2 PReLU with per-channel slopes, no residual                  (SRVGG body)
+    //   3 no activation, alpha folded into the weights, 0-2 residuals (RDB conv5, conv_body)
+    int emode = 0;
+    if (fast && !bf16 && E.alpha == 1.0f) {
+      if (E.act == kActPRelu && E.slope == nullptr && E.res1 == nullptr && E.res2 == nullptr && E.slope_const >= 0.f &&
+          E.slope_const <= 1.f)
+        emode = 1;
+      else if (E.act == kActPRelu && E.slope != nullptr && E.res1 == nullptr && E.res2 == nullptr)
+        emode = 2;
+      else if (E.act == kActNone)
+        emode = 3;
+    }
     int s = 0, k = 0, q = 0;
     int u = u0;
     Band b;
@@ -578,6 +594,67 @@ conv3x3_stream_kernel(const __grid_constant__ StreamParams P) {
               // ---- activation, residuals, 16-bit pack into the warp's swizzled staging tile, TMA store
               if (lane == 0) bulk_wait_read0();  // this warp's previous store has finished reading the tile
               __syncwarp();
+              const uint32_t srow = stage + lane * (NOUT * 2u);
+              // swizzled 16-byte chunk position inside the [32 pixels][NOUT] tile (matches tmO's swizzle mode)
+              const uint32_t sxor = NOUT == 64 ? (lane & 7u) : (NOUT == 32 ? ((lane >> 1) & 3u) : (NOUT == 16 ? ((lane >> 2) & 1u) : 0u));
+              auto h2 = [](float a, float c) -> uint32_t {
+                const __half2 h = __floats2half2_rn(a, c);
+                return *reinterpret_cast<const uint32_t*>(&h);
+              };
+              if (emode == 1) {
+                const float sl = E.slope_const;
+#pragma unroll
+                for (int j = 0; j < NOUT / 8; ++j) {
+                  float v[8];
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) {
+                    const float a = __uint_as_float(raw[8 * j + i]);
+                    v[i] = fmaxf(a, a * sl);  // == a >= 0 ? a : a * sl for 0 <= sl <= 1
+                  }
+                  sts128(srow + ((static_cast<uint32_t>(j) ^ sxor) << 4), h2(v[0], v[1]), h2(v[2], v[3]), h2(v[4], v[5]), h2(v[6], v[7]));
+                }
+              } else if (emode == 2) {
+#pragma unroll
+                for (int j = 0; j < NOUT / 8; ++j) {
+                  const float4* sp = reinterpret_cast<const float4*>(E.slope + b.chunk * NOUT + 8 * j);
+                  const float4 sa = __ldg(sp), sb = __ldg(sp + 1);
+                  const float sl[8] = {sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w};
+                  float v[8];
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) {
+                    const float a = __uint_as_float(raw[8 * j + i]);
+                    v[i] = fmaf(fminf(a, 0.f), sl[i], fmaxf(a, 0.f));
+                  }
+                  sts128(srow + ((static_cast<uint32_t>(j) ^ sxor) << 4), h2(v[0], v[1]), h2(v[2], v[3]), h2(v[4], v[5]), h2(v[6], v[7]));
+                }
+              } else if (emode == 3) {
+                const float b1 = E.beta1, b2 = E.beta2;
+#pragma unroll
+                for (int j = 0; j < NOUT / 8; ++j) {
+                  float v[8];
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(raw[8 * j + i]);
+                  if (has_r1) {
+                    const uint32_t w4[4] = {r1v[j].x, r1v[j].y, r1v[j].z, r1v[j].w};
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                      const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w4[i]));
+                      v[2 * i] = fmaf(b1, f.x, v[2 * i]);
+                      v[2 * i + 1] = fmaf(b1, f.y, v[2 * i + 1]);
+                    }
+                  }
+                  if (has_r2) {
+                    const uint32_t w4[4] = {r2v[j].x, r2v[j].y, r2v[j].z, r2v[j].w};
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                      const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w4[i]));
+                      v[2 * i] = fmaf(b2, f.x, v[2 * i]);
+                      v[2 * i + 1] = fmaf(b2, f.y, v[2 * i + 1]);
+                    }
+                  }
+                  sts128(srow + ((static_cast<uint32_t>(j) ^ sxor) << 4), h2(v[0], v[1]), h2(v[2], v[3]), h2(v[4], v[5]), h2(v[6], v[7]));
+                }
+              } else
 #pragma unroll
               for (int j = 0; j < NOUT / 8; ++j) {
                 float v[8];
