@@ -67,6 +67,48 @@ __global__ void chan_stats_kernel(Img im, double* __restrict__ sums /* [N*C][2] 
   }
 }
 
+// half NCHW planes (the net's output): 16-byte loads, no index arithmetic -- the plane is contiguous.  Same
+// accumulation type as the general kernel (every element is added in double).
+__global__ void chan_stats_half_kernel(const uint4* __restrict__ img, size_t vec_per_plane, double* __restrict__ sums) {
+  const int nc = blockIdx.y;
+  const uint4* p = img + static_cast<size_t>(nc) * vec_per_plane;
+  double s = 0.0, q = 0.0;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < vec_per_plane;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const uint4 v = __ldg(p + i);
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[k]));
+      s += f.x;
+      q += static_cast<double>(f.x) * f.x;
+      s += f.y;
+      q += static_cast<double>(f.y) * f.y;
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    q += __shfl_xor_sync(0xffffffffu, q, o);
+  }
+  __shared__ double sh[2][32];
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) { sh[0][w] = s; sh[1][w] = q; }
+  __syncthreads();
+  if (w == 0) {
+    const int nw = blockDim.x >> 5;
+    s = l < nw ? sh[0][l] : 0.0;
+    q = l < nw ? sh[1][l] : 0.0;
+    for (int o = 16; o > 0; o >>= 1) {
+      s += __shfl_xor_sync(0xffffffffu, s, o);
+      q += __shfl_xor_sync(0xffffffffu, q, o);
+    }
+    if (l == 0) {
+      atomicAdd(&sums[2 * nc], s);
+      atomicAdd(&sums[2 * nc + 1], q);
+    }
+  }
+}
+
 // affine map of the distribution match: hr' = a*hr + b with a = std_lr / (std_hr + 1e-8), b = mean_lr - a*mean_hr
 // (unbiased std like torch.Tensor.std)
 __device__ __forceinline__ void match_coeffs(const double* hr_sums, const double* lr_sums, int nc, double cnt_hr,
@@ -133,16 +175,40 @@ __global__ void blur_diff_kernel(const float* __restrict__ hb, const float* __re
   diff[idx] = acc;
 }
 
+// 32 consecutive RGB pixels of one warp -> 96 contiguous bytes: 24 word stores assembled with shuffles instead of
+// three strided byte stores per thread.  px = b0 | b1 << 8 | b2 << 16; dst = address of lane 0's pixel (4-byte
+// aligned); every lane of the warp must call this.
+__device__ __forceinline__ void store_rgb_row32(uint8_t* dst, uint32_t px) {
+  const int lane = threadIdx.x & 31;
+  const int p0 = (4 * lane) / 3, sh = 4 * lane - 3 * p0;  // word `lane` starts `sh` bytes into pixel p0
+  const uint32_t lo = __shfl_sync(0xffffffffu, px, p0 & 31), hi = __shfl_sync(0xffffffffu, px, (p0 + 1) & 31);
+  const uint64_t two = static_cast<uint64_t>(lo) | (static_cast<uint64_t>(hi) << 24);
+  if (lane < 24) reinterpret_cast<uint32_t*>(dst)[lane] = static_cast<uint32_t>(two >> (8 * sh));
+}
+
 // ---- finalise: clamp(a*hr + b - bilinear_up(diff), 0, 1) -> uint8 NHWC (truncating) or float NCHW ----------
 __global__ void finalize_kernel(Img hr, const float* __restrict__ diff, int dh, int dw, const double* hr_sums,
                                 const double* lr_sums, double cnt_hr, double cnt_lr, uint8_t* __restrict__ out_u8,
                                 float* __restrict__ out_f32, int round_u8) {
   const size_t total = static_cast<size_t>(hr.N) * hr.H * hr.W;
-  const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (idx >= total) return;
-  const int x = static_cast<int>(idx % hr.W);
-  const int y = static_cast<int>((idx / hr.W) % hr.H);
-  const int n = static_cast<int>(idx / (static_cast<size_t>(hr.W) * hr.H));
+  const size_t idx0 = static_cast<size_t>(blockIdx.x) * blockDim.x;
+  const size_t idx = idx0 + threadIdx.x;
+  // the match coefficients (double precision, with square roots) once per block and image, not per pixel: a block
+  // of 256 consecutive pixels touches at most two images
+  __shared__ float coef[2][4][2];
+  const size_t plane = static_cast<size_t>(hr.W) * hr.H;
+  const int n_first = static_cast<int>(idx0 / plane);
+  const bool shared_coef = hr.C <= 4 && plane >= blockDim.x;
+  if (threadIdx.x < 2 * hr.C && shared_coef) {
+    const int k = threadIdx.x / hr.C, c = threadIdx.x - k * hr.C;
+    if (n_first + k < hr.N) match_coeffs(hr_sums, lr_sums, (n_first + k) * hr.C + c, cnt_hr, cnt_lr, &coef[k][c][0], &coef[k][c][1]);
+  }
+  __syncthreads();
+  const bool live = idx < total;
+  const size_t idc = live ? idx : total - 1;
+  const int x = static_cast<int>(idc % hr.W);
+  const int y = static_cast<int>((idc / hr.W) % hr.H);
+  const int n = static_cast<int>(idc / plane);
   // bilinear, align_corners=False (area_pixel_compute_source_index): src = (dst + 0.5) * in/out - 0.5, clamped at 0
   int y0 = 0, y1 = 0, x0 = 0, x1 = 0;
   float ly = 0.f, lx = 0.f;
@@ -156,10 +222,14 @@ __global__ void finalize_kernel(Img hr, const float* __restrict__ diff, int dh, 
     x1 = x0 < dw - 1 ? x0 + 1 : x0;
     ly = sy - y0; lx = sx - x0;
   }
+  // whole warp inside the image list and 3 channels: the uint8 row goes out as packed words
+  const bool packed = out_u8 != nullptr && hr.C == 3 && __all_sync(0xffffffffu, live) && reinterpret_cast<uintptr_t>(out_u8) % 4 == 0;
+  uint32_t px = 0;
   for (int c = 0; c < hr.C; ++c) {
     const int nc = n * hr.C + c;
     float a, b;
-    match_coeffs(hr_sums, lr_sums, nc, cnt_hr, cnt_lr, &a, &b);
+    if (shared_coef) { a = coef[n - n_first][c][0]; b = coef[n - n_first][c][1]; }
+    else match_coeffs(hr_sums, lr_sums, nc, cnt_hr, cnt_lr, &a, &b);
     float v = a * hr.at(n, c, y, x) + b;
     if (diff != nullptr) {
       const float* d = diff + static_cast<size_t>(nc) * dh * dw;
@@ -171,11 +241,13 @@ __global__ void finalize_kernel(Img hr, const float* __restrict__ diff, int dh, 
     if (out_u8 != nullptr) {
       float f = v * 255.f;
       if (round_u8) f = rintf(f);
-      out_u8[idx * hr.C + c] = static_cast<uint8_t>(f);
-    } else {
+      if (packed) px |= static_cast<uint32_t>(static_cast<uint8_t>(f)) << (8 * c);
+      else if (live) out_u8[idx * hr.C + c] = static_cast<uint8_t>(f);
+    } else if (live) {
       out_f32[((static_cast<size_t>(n) * hr.C + c) * hr.H + y) * hr.W + x] = v;
     }
   }
+  if (packed) store_rgb_row32(out_u8 + (idx - (threadIdx.x & 31)) * 3, px);
 }
 
 // ---- bicubic resize (A = -0.75, align_corners=False, clamped taps) of a float NCHW image -> clamp -> uint8 NHWC ----
@@ -239,8 +311,10 @@ finalize_bicubic_u8_kernel(Img hr, const float* __restrict__ diff, int dh, int d
   const int px0 = static_cast<int>(floorf((ox0 + 0.5f) * fx - 0.5f)) - 1;
   const int px1 = static_cast<int>(floorf((ox1 + 0.5f) * fx - 0.5f)) + 2;
   const int ph = py1 - py0 + 1, pw = px1 - px0 + 1;  // host guarantees ph <= kFbMaxH, pw <= kFbMaxW
-  float ma[3], mb[3];
-  for (int c = 0; c < 3; ++c) match_coeffs(hr_sums, lr_sums, n * hr.C + c, cnt_hr, cnt_lr, &ma[c], &mb[c]);
+  __shared__ float coef[3][2];  // match coefficients: double precision with square roots, once per block
+  if (threadIdx.x < 3) match_coeffs(hr_sums, lr_sums, n * hr.C + threadIdx.x, cnt_hr, cnt_lr, &coef[threadIdx.x][0], &coef[threadIdx.x][1]);
+  __syncthreads();
+  const float ma[3] = {coef[0][0], coef[1][0], coef[2][0]}, mb[3] = {coef[0][1], coef[1][1], coef[2][1]};
   for (int i = threadIdx.x; i < ph * pw; i += kFbTw * kFbTh) {
     const int ry = i / pw, rx = i - ry * pw;
     const int y = min(max(py0 + ry, 0), H - 1), x = min(max(px0 + rx, 0), W - 1);  // clamped taps (border replicate)
@@ -266,7 +340,10 @@ finalize_bicubic_u8_kernel(Img hr, const float* __restrict__ diff, int dh, int d
   }
   __syncthreads();
   const int x = ox0 + (threadIdx.x % kFbTw), y = oy0 + (threadIdx.x / kFbTw);
-  if (x >= OW || y >= OH) return;
+  // a warp is one 32-pixel output row of the tile: packed word stores when the whole row is inside the image
+  const bool live = x < OW && y < OH;
+  const bool packed = __all_sync(0xffffffffu, live) && (static_cast<size_t>(OW) * 3) % 4 == 0 && reinterpret_cast<uintptr_t>(out) % 4 == 0;
+  if (!live && !packed) return;
   const float A = -0.75f;
   const float sy = (y + 0.5f) * fy - 0.5f, sx = (x + 0.5f) * fx - 0.5f;
   const int iy = static_cast<int>(floorf(sy)), ix = static_cast<int>(floorf(sx));
@@ -274,6 +351,7 @@ finalize_bicubic_u8_kernel(Img hr, const float* __restrict__ diff, int dh, int d
   const float wy[4] = {cubic2(ty + 1.f, A), cubic1(ty, A), cubic1(1.f - ty, A), cubic2(2.f - ty, A)};
   const float wx[4] = {cubic2(tx + 1.f, A), cubic1(tx, A), cubic1(1.f - tx, A), cubic2(2.f - tx, A)};
   const size_t oidx = (static_cast<size_t>(n) * OH + y) * OW + x;
+  uint32_t px = 0;
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
     float acc = 0.f;
@@ -287,8 +365,10 @@ finalize_bicubic_u8_kernel(Img hr, const float* __restrict__ diff, int dh, int d
     }
     float f = fminf(fmaxf(acc, 0.f), 1.f) * 255.f;
     if (round_u8) f = rintf(f);
-    out[oidx * 3 + c] = static_cast<uint8_t>(f);
+    if (packed) px |= static_cast<uint32_t>(static_cast<uint8_t>(f)) << (8 * c);
+    else out[oidx * 3 + c] = static_cast<uint8_t>(f);
   }
+  if (packed) store_rgb_row32(out + (oidx - (threadIdx.x & 31)) * 3, px);
 }
 
 // ---- 3x3 depthwise reflect "sharpen" + clamp, optional blend with another image (float NCHW in/out) ----------
@@ -326,6 +406,12 @@ int ss4k_glue_chan_stats(const void* img, int fmt, int n, int c, int h, int w, d
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (cudaMemsetAsync(sums_dev, 0, sizeof(double) * 2 * n * c, st) != cudaSuccess) return SS4K_E_CUDA;
   const size_t total = static_cast<size_t>(h) * w;
+  if (fmt == 1 && total % 8 == 0 && reinterpret_cast<uintptr_t>(img) % 16 == 0) {
+    const size_t vec = total / 8;
+    const unsigned gx = static_cast<unsigned>(std::min<size_t>((vec + 255) / 256, std::max(1, 1184 / (n * c))));  // ~8 blocks per SM in all
+    chan_stats_half_kernel<<<dim3(gx, static_cast<unsigned>(n * c)), 256, 0, st>>>(reinterpret_cast<const uint4*>(img), vec, sums_dev);
+    return cudaGetLastError() == cudaSuccess ? SS4K_OK : SS4K_E_CUDA;
+  }
   dim3 grid(static_cast<unsigned>(std::min<size_t>((total + 1023) / 1024, 296)), static_cast<unsigned>(n * c));
   chan_stats_kernel<<<grid, 256, 0, st>>>(Img{img, fmt, n, c, h, w}, sums_dev);
   return cudaGetLastError() == cudaSuccess ? SS4K_OK : SS4K_E_CUDA;
