@@ -737,6 +737,33 @@ conv3x3_stream_kernel(const __grid_constant__ StreamParams P) {
                 const size_t pix0 = (static_cast<size_t>(b.n) * E.out_h + y) * E.out_w + b.strip * kTileW + qd * 32;
                 reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(E.out) + pix0 * 3)[lane] = static_cast<uint32_t>(two >> (8 * sh));
               }
+            } else if (NOUT == 48 && E.out_mode == kOutPSNCHWF16 && E.ps_r == 4 && E.cout == 48 && E.act == kActNone &&
+                       E.alpha == 1.0f && E.res1 == nullptr && E.res2 == nullptr && !bf16) {
+              // PixelShuffle(4) into half NCHW (+ nearest-upsampled base image): SRVGGNetCompact's last conv
+              // (factory.py:69-82).  Conv channel c*16 + a*4 + b of pixel (y, x) is out[n, c, 4y + a, 4x + b]: for one
+              // (c, a) a thread owns 4 consecutive output pixels (8 bytes) and a warp 256 contiguous bytes.
+              if (valid) {
+                const size_t pixi = (static_cast<size_t>(b.n) * E.out_h + y) * E.out_w + ax;
+                const int OH = 4 * E.out_h, OW = 4 * E.out_w;
+                __half* const o = reinterpret_cast<__half*>(E.out);
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                  float base = 0.f;
+                  if (E.base != nullptr)
+                    base = __half2float(reinterpret_cast<const __half*>(E.base)[pixi * E.base_pitch + c]);
+#pragma unroll
+                  for (int a4 = 0; a4 < 4; ++a4) {
+                    const int ch = c * 16 + a4 * 4;
+                    const __half2 lo = __floats2half2_rn(__uint_as_float(raw[ch]) + base, __uint_as_float(raw[ch + 1]) + base);
+                    const __half2 hi = __floats2half2_rn(__uint_as_float(raw[ch + 2]) + base, __uint_as_float(raw[ch + 3]) + base);
+                    uint2 w2;
+                    w2.x = *reinterpret_cast<const uint32_t*>(&lo);
+                    w2.y = *reinterpret_cast<const uint32_t*>(&hi);
+                    const size_t oi = ((static_cast<size_t>(b.n) * 3 + c) * OH + (4 * y + a4)) * OW + 4 * static_cast<size_t>(ax);
+                    *reinterpret_cast<uint2*>(o + oi) = w2;
+                  }
+                }
+              }
             } else if (valid) {
 #pragma unroll
               for (int c = 0; c < NOUT; c += 16) {
