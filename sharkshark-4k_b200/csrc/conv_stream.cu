@@ -507,6 +507,7 @@ conv3x3_stream_kernel(const __grid_constant__ StreamParams P) {
     //   1 LeakyReLU with a constant slope in [0, 1], no residual      (RDB conv1-4, upsampling convs)
     //   2 PReLU with per-channel slopes, no residual                  (SRVGG body)
     //   3 no activation, alpha folded into the weights, 0-2 residuals (RDB conv5, conv_body)
+    //   4 ReLU6, no residual                                          (BSVD body)
     int emode = 0;
     if (fast && !bf16 && E.alpha == 1.0f) {
       if (E.act == kActPRelu && E.slope == nullptr && E.res1 == nullptr && E.res2 == nullptr && E.slope_const >= 0.f &&
@@ -516,6 +517,8 @@ conv3x3_stream_kernel(const __grid_constant__ StreamParams P) {
         emode = 2;
       else if (E.act == kActNone)
         emode = 3;
+      else if (E.act == kActRelu6 && E.res1 == nullptr && E.res2 == nullptr)
+        emode = 4;
     }
     int s = 0, k = 0, q = 0;
     int u = u0;
@@ -625,6 +628,14 @@ conv3x3_stream_kernel(const __grid_constant__ StreamParams P) {
                     const float a = __uint_as_float(raw[8 * j + i]);
                     v[i] = fmaf(fminf(a, 0.f), sl[i], fmaxf(a, 0.f));
                   }
+                  sts128(srow + ((static_cast<uint32_t>(j) ^ sxor) << 4), h2(v[0], v[1]), h2(v[2], v[3]), h2(v[4], v[5]), h2(v[6], v[7]));
+                }
+              } else if (emode == 4) {
+#pragma unroll
+                for (int j = 0; j < NOUT / 8; ++j) {
+                  float v[8];
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) v[i] = fminf(fmaxf(__uint_as_float(raw[8 * j + i]), 0.f), 6.f);
                   sts128(srow + ((static_cast<uint32_t>(j) ^ sxor) << 4), h2(v[0], v[1]), h2(v[2], v[3]), h2(v[4], v[5]), h2(v[6], v[7]));
                 }
               } else if (emode == 3) {
@@ -761,6 +772,60 @@ conv3x3_stream_kernel(const __grid_constant__ StreamParams P) {
                     w2.y = *reinterpret_cast<const uint32_t*>(&hi);
                     const size_t oi = ((static_cast<size_t>(b.n) * 3 + c) * OH + (4 * y + a4)) * OW + 4 * static_cast<size_t>(ax);
                     *reinterpret_cast<uint2*>(o + oi) = w2;
+                  }
+                }
+              }
+            } else if ((E.out_mode == kOutNHWC || E.out_mode == kOutPS2NHWC) && !E.up2_store && E.alpha == 1.0f &&
+                       E.res2 == nullptr && E.res1_nch == 0 && E.out_lo == nullptr && E.res1_lo_off == 0 && !bf16 &&
+                       (E.act == kActRelu6 || E.act == kActNone) && (E.res1 == nullptr || E.beta1 == 1.0f)) {
+              // BSVD stores (bsvd/model.py:43-52, 231-323): ReLU6 or linear, optional PixelShuffle(2) (weights'
+              // output channels pre-permuted to (a, b, c)), optional skip add at the output pixel, optional temporal-
+              // shift scatter (channels [0, fold) go to frame t-1's tensor, [fold, 2 fold) to frame t+1's).  Same
+              // arithmetic as epilogue_chunk, decided once per 8-channel group instead of per value.
+              if (valid) {
+                const int t = E.t0 + b.n;
+                const int cq = E.cout >> 2;
+                const bool ps2 = E.out_mode == kOutPS2NHWC;
+                const bool relu6 = E.act == kActRelu6;
+                uint16_t* const o16 = reinterpret_cast<uint16_t*>(E.out);
+#pragma unroll
+                for (int j = 0; j < NOUT / 8; ++j) {
+                  const int ch0 = b.chunk * NOUT + 8 * j;
+                  if (ch0 >= E.cout) break;  // padded output channels
+                  int oy = y, ox = ax, oc = ch0;
+                  if (ps2) {
+                    const int ab = ch0 / cq;
+                    oc = ch0 - ab * cq;
+                    oy = 2 * y + (ab >> 1);
+                    ox = 2 * ax + (ab & 1);
+                  }
+                  const size_t po = (static_cast<size_t>(b.n) * E.out_h + oy) * E.out_w + ox;
+                  float v[8];
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) {
+                    const float a = __uint_as_float(raw[8 * j + i]);
+                    v[i] = relu6 ? fminf(fmaxf(a, 0.f), 6.f) : a;
+                  }
+                  if (E.res1 != nullptr) {
+                    const uint4 r = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(E.res1) + po * E.res1_pitch + E.res1_coff + oc);
+                    const uint32_t w4[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                      const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w4[i]));
+                      v[2 * i] += f.x;
+                      v[2 * i + 1] += f.y;
+                    }
+                  }
+                  int64_t delta = 0;
+                  bool ok = true;
+                  if (E.fold > 0) {
+                    if (oc < E.fold) { delta = E.off_prev; ok = t > 0; }
+                    else if (oc < 2 * E.fold) { delta = E.off_next; ok = t < E.t_count - 1; }
+                  }
+                  if (ok) {
+                    uint4 q4;
+                    q4.x = pack2(v[0], v[1], false); q4.y = pack2(v[2], v[3], false); q4.z = pack2(v[4], v[5], false); q4.w = pack2(v[6], v[7], false);
+                    *reinterpret_cast<uint4*>(o16 + static_cast<int64_t>(po * E.out_pitch + E.out_coff + oc) + delta) = q4;
                   }
                 }
               }
