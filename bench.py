@@ -254,7 +254,7 @@ def run_native(args, rank, world, local_rank):
         achieved = (k_fl / max(1, k_n)) / (k_us_timed * 1e-6) / 1e12
         achieved_events = k_fl / (k_ms / 1000) / 1e12
         traffic = None
-        tp = os.path.join(ROOT, "profiles", "r01_v6_dram_traffic_b1.json")
+        tp = os.path.join(ROOT, "profiles", "r01_v7_dram_traffic_b1.json")
         if B == 1 and os.path.isfile(tp):
             with open(tp) as f:
                 tk = json.load(f)["kernels"]
@@ -282,7 +282,7 @@ def run_native(args, rank, world, local_rank):
                          "flops_per_launch_avg": k_fl / max(1, k_n), "kernel_share_of_step": share,
                          "achieved_unoverlapped": achieved_events, "avg_launch_us_unoverlapped": 1000 * k_ms / max(1, k_n),
                          "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum per launch, mean over the kernel's launches of one frame "
-                                         "(profiles/r01_v6_dram_traffic_b1.json; one ncu pass, warm caches, batch 1)" if traffic else None,
+                                         "(profiles/r01_v7_dram_traffic_b1.json; one ncu pass, warm caches, batch 1)" if traffic else None,
                          "how": "avg launch duration = CUDA-event time of the timed region (graph replay) x the kernel's share of a step / "
                                 "its launches; share from CUDA events between every step of an un-graphed run on the launching stream "
                                 "(mean of %d runs; those serialised per-launch times give 'achieved_unoverlapped'); "
