@@ -294,7 +294,7 @@ __global__ void bicubic_u8_kernel(const float* __restrict__ in, int N, int C, in
 //      into shared memory (about 5 evaluations per output pixel at a 2x downscale), then every thread runs its 4x4
 //      bicubic from there.  Same arithmetic as finalize_kernel followed by bicubic_u8_kernel
 //      (fsrcnn_upscaler.py:214-233).  Source patch limit kFbMaxH x kFbMaxW (downscale factors up to 2).
-constexpr int kFbTw = 32, kFbTh = 8, kFbMaxW = 72, kFbMaxH = 24;
+constexpr int kFbTw = 32, kFbTh = 8, kFbMaxW = 72, kFbMaxH = 24, kFbDiffRows = 6;
 __global__ void __launch_bounds__(kFbTw * kFbTh)
 finalize_bicubic_u8_kernel(Img hr, const float* __restrict__ diff, int dh, int dw, const double* hr_sums,
                            const double* lr_sums, double cnt_hr, double cnt_lr, uint8_t* __restrict__ out,
@@ -315,6 +315,71 @@ finalize_bicubic_u8_kernel(Img hr, const float* __restrict__ diff, int dh, int d
   if (threadIdx.x < 3) match_coeffs(hr_sums, lr_sums, n * hr.C + threadIdx.x, cnt_hr, cnt_lr, &coef[threadIdx.x][0], &coef[threadIdx.x][1]);
   __syncthreads();
   const float ma[3] = {coef[0][0], coef[1][0], coef[2][0]}, mb[3] = {coef[0][1], coef[1][1], coef[2][1]};
+  // The bilinear up-sampling of the low-resolution colour difference is separable: interpolate the few diff rows the
+  // patch touches along x once per column (dxs), then every patch element needs two shared-memory reads and one
+  // lerp per channel instead of twelve global loads and nine lerps.  Same operations in the same order as
+  // finalize_kernel (top / bottom row lerps along x, then the lerp along y), so the results are bit-identical.
+  __shared__ float dxs[3][kFbDiffRows][kFbMaxW];
+  __shared__ int col_x[kFbMaxW];
+  int dy_lo = 0;
+  bool staged = diff != nullptr;
+  if (diff != nullptr) {
+    const float ry_scale = static_cast<float>(dh) / H, rx_scale = static_cast<float>(dw) / W;
+    {  // diff rows touched by the patch (rows are monotonic in y)
+      float s0 = (min(max(py0, 0), H - 1) + 0.5f) * ry_scale - 0.5f, s1 = (min(max(py1, 0), H - 1) + 0.5f) * ry_scale - 0.5f;
+      s0 = s0 < 0.f ? 0.f : s0;
+      s1 = s1 < 0.f ? 0.f : s1;
+      dy_lo = static_cast<int>(s0);
+      const int y0l = static_cast<int>(s1);
+      const int dy_hi = y0l < dh - 1 ? y0l + 1 : y0l;
+      staged = dy_hi - dy_lo + 1 <= kFbDiffRows;
+    }
+    if (staged) {
+      for (int i = threadIdx.x; i < kFbDiffRows * pw; i += kFbTw * kFbTh) {
+        const int r = i / pw, rx = i - r * pw;
+        const int x = min(max(px0 + rx, 0), W - 1);
+        if (r == 0) col_x[rx] = x;
+        float sx = (x + 0.5f) * rx_scale - 0.5f;
+        sx = sx < 0.f ? 0.f : sx;
+        const int x0 = static_cast<int>(sx);
+        const int x1 = x0 < dw - 1 ? x0 + 1 : x0;
+        const float lx = sx - x0;
+        const int yy = dy_lo + r < dh ? dy_lo + r : dh - 1;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const float* d = diff + static_cast<size_t>(n * hr.C + c) * dh * dw + static_cast<size_t>(yy) * dw;
+          dxs[c][r][rx] = d[x0] * (1.f - lx) + d[x1] * lx;
+        }
+      }
+      __syncthreads();
+    }
+  }
+  if (diff == nullptr || staged) {
+    for (int i = threadIdx.x; i < ph * pw; i += kFbTw * kFbTh) {
+      const int ry = i / pw, rx = i - ry * pw;
+      const int y = min(max(py0 + ry, 0), H - 1);
+      int r0 = 0, r1 = 0, x;
+      float ly = 0.f;
+      if (diff != nullptr) {
+        float sy = (y + 0.5f) * (static_cast<float>(dh) / H) - 0.5f;
+        sy = sy < 0.f ? 0.f : sy;
+        const int y0 = static_cast<int>(sy);
+        const int y1 = y0 < dh - 1 ? y0 + 1 : y0;
+        ly = sy - y0;
+        r0 = y0 - dy_lo;
+        r1 = y1 - dy_lo;
+        x = col_x[rx];
+      } else {
+        x = min(max(px0 + rx, 0), W - 1);
+      }
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        float sub = 0.f;
+        if (diff != nullptr) sub = dxs[c][r0][rx] * (1.f - ly) + dxs[c][r1][rx] * ly;
+        patch[c][ry][rx] = fminf(fmaxf(ma[c] * hr.at(n, c, y, x) + mb[c] - sub, 0.f), 1.f);
+      }
+    }
+  } else
   for (int i = threadIdx.x; i < ph * pw; i += kFbTw * kFbTh) {
     const int ry = i / pw, rx = i - ry * pw;
     const int y = min(max(py0 + ry, 0), H - 1), x = min(max(px0 + rx, 0), W - 1);  // clamped taps (border replicate)
