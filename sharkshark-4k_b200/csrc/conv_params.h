@@ -155,7 +155,9 @@ struct StreamParams {
   int32_t acc_slots, a_slots;
   uint32_t idesc[3];      // instruction descriptors for N = NOUT, 2*NOUT, 3*NOUT
   int32_t* err;
-  int32_t dbg_flags;
+  int32_t dbg_flags;      // profiling experiments (scripts/bench_conv.py, SS4K_DBG_FLAGS): 1 skip MMA issue, 2 skip TMA
+                          // loads, 4 epilogue without math / stores, 8 skip band halo rows (WRONG results), 16 full
+                          // completion wait on the last output tiles, 64 trace rows stamped by epilogue warp 2
   int32_t n_in0, n_out0;  // added to the image coordinate of TMA loads / stores (BSVD streaming: ring slots)
   long long* trace;       // debug: per-CTA clock64 stamps [grid][64] (null in production)
   const void* next_w;     // packed weights of the next kernel of the plan (L2 prefetch), or null

@@ -138,3 +138,21 @@ def test_u8_boundary_and_host_path(engine):
     out_host = torch.empty(2, 80, 128, 3, dtype=torch.uint8).pin_memory()
     plan.run_host(frames.pin_memory(), out_host)
     assert torch.equal(out_host, got)
+
+
+def test_rrdbnet_uint8_frames_ragged_width(engine):
+    """uint8 NHWC frames in / out through the engine plan (the service and bench boundary) at a width that is not a
+    multiple of the 32-pixel store rows: packed word stores where a warp's row is complete, byte stores at the ragged
+    edge (csrc/conv_stream.cu, last conv)."""
+    torch.manual_seed(3)
+    net = rrdbnet.RRDBNet(3, 3, 2, 64, 2, 32).eval()
+    frames = torch.randint(0, 256, (2, 44, 150, 3), dtype=torch.uint8)
+    with torch.no_grad():
+        want = net(frames.permute(0, 3, 1, 2).float() / 255.0).clamp(0, 1)
+    model = realesrgan.NativeRRDBNet(net.state_dict(), scale=2, num_block=2, device=0)
+    plan = model._plan(2, 44, 150, L.FMT_U8_NHWC, L.FMT_U8_NHWC)
+    got = plan.run(frames.cuda()).cpu()
+    assert got.shape == (2, 88, 300, 3) and got.dtype == torch.uint8
+    d = (got.permute(0, 3, 1, 2).float() - want * 255.0)
+    # truncating quantisation (fsrcnn_upscaler.py:233): got == floor(255 * y) up to the fp16 error of y
+    assert d.max().item() <= 0.6 and d.min().item() >= -1.6, (d.min().item(), d.max().item())
