@@ -167,6 +167,11 @@ struct StreamParams {
   void* discard_ptr;
   uint32_t discard_pitch_bytes, discard_mask;
   int64_t discard_npx;
+  // K blocks whose source channels were written at least two kernels ago (dense block: everything but the previous
+  // conv's 32 growth channels): their slabs may be loaded before griddepcontrol.wait.  Sound only when this kernel and
+  // the two before it fill every SM with one CTA: a CTA of this kernel then runs only after some CTA of the previous
+  // kernel has exited, i.e. has itself waited for the kernel before that to complete and flush.
+  uint32_t early_kb_mask;
   int32_t l2_in, l2_out;  // L2 eviction priority of the activation loads / output stores: 0 normal, 1 evict_last
                           // (re-read by the next convs of the dense block), 2 evict_first (dead after this conv)
 };

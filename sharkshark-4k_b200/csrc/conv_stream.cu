@@ -284,7 +284,9 @@ conv3x3_stream_kernel(const __grid_constant__ StreamParams P) {
         wph ^= 1;
         loaded_chunk = b.chunk;
       }
-      if (!dep_ready) {  // weights are constants; the activations belong to the previous kernel of the stream
+      // (weights are constants; the activations belong to earlier kernels of the stream: the dependency wait sits in
+      //  front of the first load that may touch the PREVIOUS kernel's output, see StreamParams::early_kb_mask)
+      if (!dep_ready && P.early_kb_mask == 0u) {
         SS4K_TRACE(12);
         pdl_wait();
         dep_ready = true;
@@ -330,6 +332,12 @@ conv3x3_stream_kernel(const __grid_constant__ StreamParams P) {
                                ((r == r0 && new_chunk) ? kRecNewChunk : 0u) |
                                ((r == r1 && has_next && nb.chunk != b.chunk) ? kRecFreeW : 0u);
         for (int kb = 0; kb < P.nkb; ++kb) {
+          if (!dep_ready && !((P.early_kb_mask >> kb) & 1u)) {
+            SS4K_TRACE(12);
+            pdl_wait();
+            dep_ready = true;
+            SS4K_TRACE(13);
+          }
           mbar_wait_u(a_empty + 8 * as, aph ^ 1);
           if (elect_one()) {
             if (kb == 0) {

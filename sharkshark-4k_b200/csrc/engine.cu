@@ -967,6 +967,24 @@ int ss4k_plan_create(ss4k_ctx* ctx, const ss4k_plan_cfg* cfg, ss4k_plan** out_pl
     int rc = materialize_conv(ctx, cs, w->second, B, S, cfg->act_mode, bufptr, &pl->convs.back());
     if (rc != SS4K_OK) { ss4k_plan_destroy(pl.release()); return rc; }
   }
+  // Early activation loads (StreamParams::early_kb_mask): K blocks that only read channels written at least two steps
+  // ago are requested before the dependency wait.  Needs this conv and the two launches before it to be streaming convs
+  // that fill every SM (see conv_params.h).
+  if (getenv("SS4K_NO_EARLY_LOAD") == nullptr) {
+    for (size_t si = 2; si < P.steps.size(); ++si) {
+      if (P.steps[si].kind != 1 || P.steps[si - 1].kind != 1 || P.steps[si - 2].kind != 1) continue;
+      ConvExec& c = pl->convs[pl->step_conv[si]];
+      const ConvExec& p1 = pl->convs[pl->step_conv[si - 1]];
+      const ConvExec& p2 = pl->convs[pl->step_conv[si - 2]];
+      const ConvSpec& cs = P.steps[si].conv;
+      if (!c.stream || !p1.stream || !p2.stream || c.grid != ctx->nsm || p1.grid != ctx->nsm || p2.grid != ctx->nsm) continue;
+      if (cs.old_cin <= 0 || cs.split) continue;
+      uint32_t mask = 0;
+      for (int kb = 0; kb < c.sp.nkb; ++kb)
+        if (c.sp.a_tm[kb] == 0 && (c.sp.a_kb[kb] + 1) * 64 <= cs.old_cin) mask |= 1u << kb;
+      c.sp.early_kb_mask = mask;
+    }
+  }
   // each streaming conv prefetches the next conv's packed weights into L2 (the last one: the first conv's, for the next frame)
   if (getenv("SS4K_NO_W_PREFETCH") == nullptr) {
     const int nc = static_cast<int>(pl->convs.size());

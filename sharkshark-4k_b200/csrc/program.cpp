@@ -142,6 +142,7 @@ std::string build_rrdb(const PlanCfgLite& c, Program* P) {
         v.act = kActPRelu; v.const_slope = 0.2f;
         v.out_buf = cur; v.out_pitch = slab; v.out_coff = nf + (k - 1) * gc;
         v.l2_in = hint[0]; v.l2_out = hint[1];
+        if (k >= 2) v.old_cin = nf + (k - 2) * gc;   // everything but conv(k-1)'s growth channels
         if (k == 1 && (b > 0 || r > 0) && use_discard) {
           // the previous block's slab is dead after its conv5 (its x stays alive when it is the RRDB input, slab 0)
           const int prev = (r + 2) % 3;
@@ -153,6 +154,7 @@ std::string build_rrdb(const PlanCfgLite& c, Program* P) {
       ConvSpec v = base_conv(pre + "5", cur, th, tw, slab, slab, nf);
       v.out_buf = nxt; v.out_pitch = slab; v.out_coff = 0;
       v.l2_in = hint[2]; v.l2_out = hint[3];
+      v.old_cin = nf + 3 * gc;
       v.res1_buf = cur; v.res1_pitch = slab; v.res1_coff = 0;
       if (r < 2) {
         v.alpha = 0.2f; v.beta1 = 1.f;                    // x5*0.2 + x

@@ -63,6 +63,7 @@ struct ConvSpec {
   int discard_mask = 0;             //   dropped from L2 without write-back by this conv (no later step reads them)
   int discard_pitch = 0;            //   channel pitch of that tensor (16-bit elements; a multiple of 64 = whole lines)
   long long discard_npx = 0;        //   its pixel count
+  int old_cin = 0;                  // input channels [0, old_cin) were written at least two steps ago (StreamParams::early_kb_mask)
   int l2_in = 0, l2_out = 0;        // L2 eviction priority hints of the loads / stores (StreamParams::l2_in / l2_out)
   double flops() const;
 };
