@@ -134,6 +134,13 @@ int ss4k_run(ss4k_plan* plan, const void* in_dev, void* out_dev, void* cuda_stre
 /* run with host buffers (pinned or pageable): H2D copy, run, D2H copy, stream-ordered on an
  * internal stream; returns after the result is in out_host. */
 int ss4k_run_host(ss4k_plan* plan, const void* in_host, void* out_host);
+/* the same as a software pipeline over successive frames (the reference's producer / consumer queues,
+ * src/sharkshark/pipeline.py:61-138): the call returns once the work is queued; the H2D copy of call i+1 and the D2H
+ * copy of call i-1 overlap the kernels of call i (two device staging slots, copy streams of their own).  in_host /
+ * out_host (pinned) must stay valid, and out_host unread, until ss4k_plan_host_sync returns; at most two calls'
+ * out_host buffers are in flight, so alternate between two. */
+int ss4k_run_host_async(ss4k_plan* plan, const void* in_host, void* out_host);
+int ss4k_plan_host_sync(ss4k_plan* plan);
 int ss4k_plan_io_bytes(const ss4k_plan* plan, int64_t* in_bytes, int64_t* out_bytes);
 /* measurement entry (bench.py roofline): one run of the plan without its CUDA graph, a CUDA event between
  * every step on `cuda_stream`.  ms[i] = device time of step i, flops[i] = its algorithmic FLOPs,

@@ -47,6 +47,8 @@ SYMBOLS = {
     "ss4k_free": (None, [_vp]),
     "ss4k_run": (_i, [_vp, _vp, _vp, _vp]),
     "ss4k_run_host": (_i, [_vp, _vp, _vp]),
+    "ss4k_run_host_async": (_i, [_vp, _vp, _vp]),
+    "ss4k_plan_host_sync": (_i, [_vp]),
     "ss4k_plan_io_bytes": (_i, [_vp, ctypes.POINTER(_i64), ctypes.POINTER(_i64)]),
     "ss4k_plan_profile": (_i, [_vp, _vp, _vp, _vp, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_double),
                                ctypes.POINTER(ctypes.c_int32), _i]),

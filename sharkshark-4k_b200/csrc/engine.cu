@@ -742,6 +742,15 @@ struct ss4k_plan {
   int graph_first = -1, graph_last = -1;  // [first, last] step range inside the graph
   void* stage_in = nullptr;   // device staging for ss4k_run_host
   void* stage_out = nullptr;
+  // software pipeline of ss4k_run_host_async: two staging slots, copy streams, hand-over events
+  struct HostPipe {
+    void* in[2] = {nullptr, nullptr};
+    void* out[2] = {nullptr, nullptr};
+    cudaStream_t h2d = nullptr, d2h = nullptr;
+    cudaEvent_t in_ready[2] = {nullptr, nullptr}, out_ready[2] = {nullptr, nullptr}, out_copied[2] = {nullptr, nullptr};
+    uint64_t calls = 0;
+    bool init = false;
+  } pipe;
   int64_t in_bytes = 0, out_bytes = 0;
 };
 
@@ -911,6 +920,15 @@ int ss4k_plan_destroy(ss4k_plan* pl) {
   if (pl->graph) cudaGraphExecDestroy(pl->graph);
   for (auto& c : pl->convs) free_conv(c);
   for (void* b : pl->bufs) if (b) cudaFree(b);
+  if (pl->pipe.init) {
+    cudaStreamSynchronize(pl->pipe.h2d);
+    cudaStreamSynchronize(pl->pipe.d2h);
+    for (int i = 0; i < 2; ++i) {
+      cudaFree(pl->pipe.in[i]); cudaFree(pl->pipe.out[i]);
+      cudaEventDestroy(pl->pipe.in_ready[i]); cudaEventDestroy(pl->pipe.out_ready[i]); cudaEventDestroy(pl->pipe.out_copied[i]);
+    }
+    cudaStreamDestroy(pl->pipe.h2d); cudaStreamDestroy(pl->pipe.d2h);
+  }
   if (pl->stage_in) cudaFree(pl->stage_in);
   if (pl->stage_out) cudaFree(pl->stage_out);
   delete pl;
@@ -1083,6 +1101,54 @@ int ss4k_run_host(ss4k_plan* pl, const void* in_host, void* out_host) {
   return check_kernel_health(ctx, cudaStreamSynchronize(ctx->stream), "ss4k_run_host");
 }
 
+
+// Pipelined host path: call i uses staging slot i & 1.  H2D on its own stream (after the kernels of call i-2 have
+// consumed the slot), the plan on the engine stream, D2H on its own stream (after which the slot's output buffer may be
+// overwritten by call i+2).
+int ss4k_run_host_async(ss4k_plan* pl, const void* in_host, void* out_host) {
+  if (!pl || !in_host || !out_host) return fail(pl ? pl->ctx : nullptr, SS4K_E_INVALID, "null argument to ss4k_run_host_async");
+  ss4k_ctx* ctx = pl->ctx;
+  auto& pp = pl->pipe;
+  if (!pp.init) {
+    CK(ctx, cudaStreamCreateWithFlags(&pp.h2d, cudaStreamNonBlocking));
+    CK(ctx, cudaStreamCreateWithFlags(&pp.d2h, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+      CK(ctx, cudaMalloc(&pp.in[i], pl->in_bytes + 256));
+      CK(ctx, cudaMalloc(&pp.out[i], pl->out_bytes + 256));
+      CK(ctx, cudaEventCreateWithFlags(&pp.in_ready[i], cudaEventDisableTiming));
+      CK(ctx, cudaEventCreateWithFlags(&pp.out_ready[i], cudaEventDisableTiming));
+      CK(ctx, cudaEventCreateWithFlags(&pp.out_copied[i], cudaEventDisableTiming));
+    }
+    pp.init = true;
+  }
+  const int s = static_cast<int>(pp.calls & 1);
+  const bool reused = pp.calls >= 2;
+  ++pp.calls;
+  if (reused) CK(ctx, cudaStreamWaitEvent(pp.h2d, pp.out_ready[s], 0));  // call i-2's kernels have read in[s]
+  CK(ctx, cudaMemcpyAsync(pp.in[s], in_host, pl->in_bytes, cudaMemcpyHostToDevice, pp.h2d));
+  CK(ctx, cudaEventRecord(pp.in_ready[s], pp.h2d));
+  CK(ctx, cudaStreamWaitEvent(ctx->stream, pp.in_ready[s], 0));
+  if (reused) CK(ctx, cudaStreamWaitEvent(ctx->stream, pp.out_copied[s], 0));  // call i-2's result has left out[s]
+  int rc = ss4k_run(pl, pp.in[s], pp.out[s], ctx->stream);
+  if (rc != SS4K_OK) return rc;
+  CK(ctx, cudaEventRecord(pp.out_ready[s], ctx->stream));
+  CK(ctx, cudaStreamWaitEvent(pp.d2h, pp.out_ready[s], 0));
+  CK(ctx, cudaMemcpyAsync(out_host, pp.out[s], pl->out_bytes, cudaMemcpyDeviceToHost, pp.d2h));
+  CK(ctx, cudaEventRecord(pp.out_copied[s], pp.d2h));
+  return SS4K_OK;
+}
+
+int ss4k_plan_host_sync(ss4k_plan* pl) {
+  if (!pl) return fail(nullptr, SS4K_E_INVALID, "null plan");
+  ss4k_ctx* ctx = pl->ctx;
+  if (pl->pipe.init) {
+    CK(ctx, cudaStreamSynchronize(pl->pipe.h2d));
+    int rc = check_kernel_health(ctx, cudaStreamSynchronize(ctx->stream), "ss4k_plan_host_sync");
+    if (rc != SS4K_OK) return rc;
+    CK(ctx, cudaStreamSynchronize(pl->pipe.d2h));
+  }
+  return SS4K_OK;
+}
 
 // Per-step timing of one plan run (no CUDA graph): a CUDA event between every step on `cuda_stream`.
 // kind[i]: 0 prep / layout kernel, 1 row-streaming conv kernel, 2 tile conv kernel.  Returns the number of steps.

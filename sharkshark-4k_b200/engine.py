@@ -216,6 +216,16 @@ class Plan:
                                        ctypes.c_void_p(out_host.data_ptr())), self.engine.h)
         return out_host
 
+    def run_host_async(self, x_host, out_host):
+        """Pipelined form of run_host: queues H2D + run + D2H and returns; successive calls overlap their copies with
+        each other's kernels.  Alternate between two pinned `out_host` buffers and call host_sync() before reading."""
+        assert not x_host.is_cuda and not out_host.is_cuda
+        L.check(self.lib.ss4k_run_host_async(self.h, ctypes.c_void_p(x_host.data_ptr()),
+                                             ctypes.c_void_p(out_host.data_ptr())), self.engine.h)
+
+    def host_sync(self):
+        L.check(self.lib.ss4k_plan_host_sync(self.h), self.engine.h)
+
     def close(self):
         if self.h:
             self.lib.ss4k_plan_destroy(self.h)

@@ -83,3 +83,28 @@ def test_translation_equivariance_of_the_interior(model, dy, dx):
     diff = (a - b).abs().max().item()
     print(f"shift ({dy},{dx}): interior max |diff| {diff:.2e}")
     assert diff <= 2.0 / 255
+
+
+def test_run_host_async_matches_run_host(engine):
+    """The pipelined host path (ss4k_run_host_async: H2D, kernels and D2H of neighbouring frames overlap on three
+    streams, two staging slots) returns bit for bit what the serial ss4k_run_host returns, frame by frame."""
+    import torch
+    from ss4k_b200 import _lib as L, realesrgan
+    from oracle import rrdbnet
+    torch.manual_seed(5)
+    net = rrdbnet.RRDBNet(3, 3, 2, 64, 2, 32).eval()
+    model = realesrgan.NativeRRDBNet(net.state_dict(), scale=2, num_block=2, device=0)
+    plan = model._plan(1, 96, 160, L.FMT_U8_NHWC, L.FMT_U8_NHWC)
+    frames = [torch.randint(0, 256, (1, 96, 160, 3), dtype=torch.uint8).pin_memory() for _ in range(5)]
+    want = []
+    for f in frames:
+        o = torch.empty(1, 192, 320, 3, dtype=torch.uint8).pin_memory()
+        plan.run_host(f, o)
+        want.append(o.clone())
+    outs = [torch.empty(1, 192, 320, 3, dtype=torch.uint8).pin_memory() for _ in range(5)]
+    for f, o in zip(frames, outs):
+        plan.run_host_async(f, o)
+    plan.host_sync()
+    for w, o in zip(want, outs):
+        assert torch.equal(w, o)
+    assert not torch.equal(want[0], want[1])
