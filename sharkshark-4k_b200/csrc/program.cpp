@@ -263,6 +263,8 @@ std::string Program::to_json() const {
       js_kv(o, "base_buf", c.base_buf); js_kv(o, "base_pitch", c.base_pitch); js_kv(o, "wperm", c.wperm);
       js_kv(o, "neg_first", c.neg_first); js_kv(o, "res1_nch", c.res1_nch); js_kv(o, "tshift", c.tshift);
       js_kv(o, "up2_store", c.up2_store);
+      js_kv(o, "old_cin", c.old_cin); js_kv(o, "l2_in", c.l2_in); js_kv(o, "l2_out", c.l2_out);
+      js_kv(o, "discard_buf", c.discard_buf); js_kv(o, "discard_mask", c.discard_mask);
       js_kv(o, "split", c.split, true);
     }
     o << "}" << (i + 1 < steps.size() ? "," : "");

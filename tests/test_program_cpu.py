@@ -86,3 +86,59 @@ def test_bsvd_program(lib, frames):
     # algorithmic FLOPs: 272.0 GMAC per 1280x720 frame
     p720 = ss4k_b200.plan_dry(ss4k_b200.make_cfg(0, L.ARCH_BSVD, 1, 720, 1280))
     assert abs(p720["flops"] / 2e9 - 271.99) < 0.05
+
+
+def test_rrdb_memory_management_is_sound(lib):
+    """L2 management of the dense block checked against a liveness analysis of the program:
+    * a conv that DISCARDS 128-byte lines of a slab (discard_buf / discard_mask: line l = channels [64 l, 64 l + 64))
+      must come after the last step that reads those channels and before the next step that writes them;
+    * old_cin (channels a conv may load before the dependency wait) must only cover channels whose last writer is at
+      least two steps back."""
+    prog = ss4k_b200.plan_dry(ss4k_b200.make_cfg(0, L.ARCH_RRDB, 1, 32, 48, scale=2, depth=3))
+    steps = prog["steps"]
+    convs = [(i, s) for i, s in enumerate(steps) if s["kind"] == "conv"]
+
+    def reads(s):   # (buf, c0, c1) ranges read by a conv: input channels and residuals
+        r = [(s["in_buf"], s["in_coff"], s["in_coff"] + s["cin"])]
+        if s["res1_buf"] >= 0:
+            r.append((s["res1_buf"], s["res1_coff"], s["res1_coff"] + s["cout"]))
+        if s["res2_buf"] >= 0:
+            r.append((s["res2_buf"], s["res2_coff"], s["res2_coff"] + s["cout"]))
+        return r
+
+    def writes(s):
+        return (s["out_buf"], s["out_coff"], s["out_coff"] + s["cout"])
+
+    def overlap(a, b):
+        return a[0] == b[0] and a[1] < b[2] and b[1] < a[2]
+
+    n_discards = 0
+    for i, s in convs:
+        if s["discard_buf"] >= 0 and s["discard_mask"]:
+            n_discards += 1
+            for l in range(3):
+                if not (s["discard_mask"] >> l) & 1:
+                    continue
+                dead = (s["discard_buf"], 64 * l, 64 * l + 64)
+                # every later step that reads these channels must be preceded by a writer that comes after the discard
+                rewritten = set()
+                for j, t in convs:
+                    if j < i:
+                        continue
+                    for r in reads(t):
+                        if overlap(r, dead):
+                            lo, hi = max(r[1], dead[1]), min(r[2], dead[2])
+                            assert all(c in rewritten for c in range(lo, hi)), (s["name"], "discards", dead, "read by", t["name"])
+                    w = writes(t)
+                    if overlap(w, dead):
+                        rewritten.update(range(max(w[1], dead[1]), min(w[2], dead[2])))
+        if s["old_cin"] > 0:
+            # last writer of every channel in [0, old_cin) of the input tensor is at least two conv steps back
+            pos = [k for k, (j, _) in enumerate(convs) if j == i][0]
+            prev = convs[pos - 1][1]
+            w = writes(prev)
+            assert not overlap(w, (s["in_buf"], s["in_coff"], s["in_coff"] + s["old_cin"])), (s["name"], prev["name"])
+            assert s["old_cin"] <= s["cin"]
+    assert n_discards == 3 * 3 - 1          # every RDB but the first drops its predecessor's slab
+    hints = {(s["l2_in"], s["l2_out"]) for _, s in convs if s["name"].startswith("body.")}
+    assert hints == {(1, 1), (2, 1)}
