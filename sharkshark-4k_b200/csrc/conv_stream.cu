@@ -17,13 +17,23 @@
 //     stream never drains between rows, and the epilogue warps retire output row y as soon as input
 //     row y+1 has been accumulated.  Rows are split evenly over the persistent grid (one CTA per SM).
 //   * all weights of the conv (every K block and tap) stay resident in shared memory.
-//   * accumulator slots are (re-)initialised WITH THE BIAS by the epilogue warps (tcgen05.st of the fp32 bias row
-//     right after they drained the slot with tcgen05.ld), so every MMA accumulates, the issuing warp spends no
-//     instruction on zero-initialisation and the bias costs no shared-memory operand traffic.
+//   * accumulator slots start from the bias, so every MMA accumulates: the 16/32/48-wide variants have the epilogue
+//     warp that drained a slot (tcgen05.ld) write the fp32 bias row back (tcgen05.st) -- no issue slot, no operand
+//     traffic; the 64-wide variant, whose tensor pipe has the slack, uses a ones x bias-tile MMA (conv_params.h,
+//     stream_bias_mma).
 //   * warp 0 = TMA producer and row planner, warp 1 = MMA issuer, warps 2..9 = epilogue, two warps per TMEM lane
 //     quarter taking alternate output rows: TMEM -> registers -> activation / scaled residual adds ->
-//     16-bit pack -> swizzled shared-memory tile -> TMA store (plain NHWC outputs), or the generic
-//     path (PixelShuffle / NCHW / uint8 / temporal-shift scatter / hi+lo split stores).
+//     16-bit pack -> swizzled shared-memory tile -> TMA store (plain NHWC outputs).  The epilogue warps share the
+//     SM's four schedulers with the MMA-issuing warp, so their arithmetic is specialised per shape (`emode`: 2-4
+//     instructions per value instead of ~20 for the general form); uint8 RGB rows, PixelShuffle(4) into half NCHW
+//     and BSVD's ReLU6 / PixelShuffle(2) + skip / temporal-shift scatter stores have lean paths of their own, the
+//     rest (NCHW float, hi+lo split stores, ...) goes through epilogue_chunk.
+//   * memory system: L2 eviction-priority hints on the TMA loads / stores and discard of dead slab lines (dense
+//     block); K blocks that only read channels of older kernels are requested before the
+//     dependency wait (early_kb_mask); the next kernel's weights are prefetched into L2.
+//   * NOTE for maintainers: a 64-bit integer division or any out-of-line call in this kernel makes ptxas give up
+//     the uniform registers of the MMA issue loop (R2UR count 69 -> 270, -30 %): check
+//     `cuobjdump -sass libss4k.so | grep -c R2UR` for the <32> variant after every change.
 //   * row records: the accumulator-ring bookkeeping of every input row (which slots it touches first / completes,
 //     where the ring wraps, descriptors, chunk switches) is computed by the producer warp and travels with the
 //     row's first activation slab as a 32-byte record; the issuing warp reads the NEXT row's record and waits for
