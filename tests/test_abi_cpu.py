@@ -71,3 +71,23 @@ def test_plan_cache_lru():
     assert closed == ["b"] and "a" in c and "c" in c and len(c) == 2 and c.evictions == 1
     c.get("b", lambda: FakePlan("b"))                       # evicts "a"
     assert closed == ["b", "a"]
+
+
+def test_mma_issue_loop_keeps_uniform_registers():
+    """Code-generation guard for csrc/conv_stream.cu: the MMA-issuing warp's loop must keep its descriptors in uniform
+    registers.  A 64-bit division or an out-of-line call anywhere in the kernel makes ptxas fall back to vector
+    registers + R2UR moves in front of every tcgen05.mma (measured: 69 -> 270 R2UR, -30 % frames/s)."""
+    import shutil
+    import subprocess
+    import pytest
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not available")
+    so = os.path.join(ROOT, "sharkshark-4k_b200", "csrc", "libss4k.so")
+    sass = subprocess.run(["cuobjdump", "-sass", so], capture_output=True, text=True, timeout=600).stdout
+    blocks = sass.split("Function : ")
+    body = [b for b in blocks if b.startswith("_ZN4ss4k21conv3x3_stream_kernelILi32E")]
+    assert body, "conv3x3_stream_kernel<32> not found in the library"
+    n_mma = body[0].count("UTCHMMA")
+    n_r2ur = body[0].count("R2UR")
+    assert n_mma >= 24, n_mma
+    assert n_r2ur <= 120, f"{n_r2ur} R2UR instructions: the issue loop lost its uniform registers"
