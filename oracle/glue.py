@@ -1,6 +1,7 @@
 """Service glue restated as pure functions (oracle; test infrastructure only).
 
-Follows /root/reference/src/upscale/fsrcnn_upscaler.py line by line, keeping its quirks:
+Follows /root/reference/src/upscale/fsrcnn_upscaler.py line by line, keeping its quirks (PINNED: reproduces the uint8
+outputs of the reference's own code bit for bit, tests/golden/glue.npz, tests/test_oracle_cpu.py::test_glue_golden):
   blur_ker :20-52, sharpen_ker :54-84, upscale_multi :168-233, upscale_single :235-326
   (unbiased std, +1e-8, bicubic-always resize because ``output_shape[0] >= batch dim``, truncating uint8).
 fp16 autocast of the reference is NOT emulated: the oracle is the fp32 meaning of the same graph.

@@ -72,3 +72,65 @@ def cpu_shims():
     finally:
         torch.zeros = real_zeros
         torch.Tensor.cuda = real_cuda
+
+
+def load_fsrcnn_service_code():
+    """The reference's OWN service glue, compiled from its source text: ``blur_ker``, ``sharpen_ker`` and the methods
+    ``upscale`` / ``upscale_multi`` / ``upscale_single`` of ``FsrcnnUpscalerService``
+    (src/upscale/fsrcnn_upscaler.py:20-84,144-326).
+
+    The module itself cannot be imported (top-level ``matplotlib`` / ``tqdm`` and relative imports of all three model
+    factories), so the function and method definitions are cut out of its AST unchanged and
+    executed in a namespace that holds what they use (torch, F, math, time).  Returns that namespace; the class has
+    no base and no ``__init__`` -- build instances with ``object.__new__`` and set the attributes the methods read."""
+    import ast
+    import math
+    import time
+    with open(os.path.join(REF_ROOT, "src/upscale/fsrcnn_upscaler.py")) as f:
+        tree = ast.parse(f.read())
+    keep = []
+    for node in tree.body:
+        if isinstance(node, ast.FunctionDef) and node.name in ("blur_ker", "sharpen_ker"):
+            keep.append(node)
+        elif isinstance(node, ast.ClassDef) and node.name == "FsrcnnUpscalerService":
+            node.bases, node.keywords, node.decorator_list = [], [], []
+            node.body = [n for n in node.body if isinstance(n, ast.FunctionDef) and
+                         n.name in ("upscale", "upscale_multi", "upscale_single")]
+            keep.append(node)
+    assert len(keep) == 3, [getattr(k, "name", None) for k in keep]
+    mod = ast.Module(body=keep, type_ignores=[])
+    ns = {"torch": torch, "F": torch.nn.functional, "math": math, "time": time}
+    exec(compile(mod, os.path.join(REF_ROOT, "src/upscale/fsrcnn_upscaler.py"), "exec"), ns)
+    return ns
+
+
+class _NullProfiler:
+    def start(self, name):
+        pass
+
+    def end(self, name):
+        pass
+
+
+def make_reference_service(ns, model, lr_shape, output_shape=None, lr_hr_resize=True, denoise_model=None,
+                           denoise_rate=1.0):
+    """An instance of the reference's FsrcnnUpscalerService (see load_fsrcnn_service_code) wired like proc_init
+    (fsrcnn_upscaler.py:118-139) but on the CPU in fp32: the stencil modules are the reference's blur_ker / sharpen_ker
+    without the ``.half()`` (torch.cuda.amp.autocast is a no-op without a GPU), the nets are the callables given."""
+    svc = object.__new__(ns["FsrcnnUpscalerService"])
+    svc.lr_shape, svc.output_shape, svc.lr_hr_resize = tuple(lr_shape), output_shape, lr_hr_resize
+    svc.device = torch.device("cpu")
+    svc.upscaler_model = "realesrgan"
+    svc.single_mode = False
+    svc.denoising = denoise_model is not None
+    svc.denoise_rate = denoise_rate
+    svc.profiler = _NullProfiler()
+    svc.model = model
+    svc.lr_prev = None
+    svc.match_blur = ns["blur_ker"](kernel_size=8 * 2 + 1, sigma=8.0)
+    if denoise_model is not None:
+        svc.denoise_model = denoise_model
+        svc.denoise_blur = ns["blur_ker"]()
+        svc.denoise_sharpen = ns["sharpen_ker"](strength=0.00002)
+        svc.denoise_sharpen_hr = ns["sharpen_ker"](strength=0.00007)
+    return svc

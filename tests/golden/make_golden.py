@@ -8,6 +8,8 @@ outputs of the reference nn.Modules themselves, imported by file path:
   bsvd32_f5.npz  : BSVD(chns=[32,64,128], mid_ch=32, interm_ch=30, relu6, norm none).forward on a
                    5-frame clip   src/upscale/model/bsvd/model.py:467-588 (config bsvd/factory.py:31-35)
   bsvd32_f1.npz  : the same net on a 1-frame clip (what the service feeds, fsrcnn_upscaler.py:277)
+  glue.npz       : uint8 outputs of the reference's own FsrcnnUpscalerService.upscale_multi / upscale_single code
+                   (fsrcnn_upscaler.py:168-326, compiled from its source text) around weight-free stand-in nets
 Each file holds the seeded input, the reference fp32 CPU output and per-tensor weight checksums
 (sum, sum of squares) so that tests can rebuild the weights from the seed through oracle/ and prove
 they are the reference's weights without shipping megabytes.
@@ -23,6 +25,26 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, ROOT)
 
 from oracle import reference_import as ri  # noqa: E402
+
+
+GLUE_MULTI_CASES = (((720, 1280), None), ((48, 64), (100, 140)), ((48, 64), None))
+GLUE_SINGLE_LR, GLUE_SINGLE_OUT = (48, 64), (100, 140)
+
+
+def glue_models():
+    """Stand-in nets for the glue fixtures: an x2 'upscaler' and a 'denoiser' that need no weights."""
+    import torch.nn.functional as F
+    model = lambda t: F.interpolate(t.float(), scale_factor=2, mode="bicubic", align_corners=False) * 0.9 + 0.04  # noqa: E731
+    den = lambda x: x[:, :, :3] * 0.97 + 0.01  # noqa: E731
+    return model, den
+
+
+def glue_frames():
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(7)
+    base = torch.rand(2, 13, 17, 3, generator=g)
+    smooth = F.interpolate(base.permute(0, 3, 1, 2), size=(96, 128), mode="bilinear").permute(0, 2, 3, 1)
+    return (smooth * 255 + torch.randn(2, 96, 128, 3, generator=g) * 6).clamp(0, 255).to(torch.uint8)
 
 
 def checksums(sd):
@@ -57,6 +79,24 @@ def main():
         k, c = checksums(net.state_dict())
         np.savez_compressed(os.path.join(HERE, f"bsvd32_f{frames}.npz"), x=x.numpy(), y=y.numpy(), keys=k, sums=c,
                             seed=0)
+    # service glue: the reference's OWN upscale_multi / upscale_single code (fsrcnn_upscaler.py:168-326), cut out of its
+    # source (oracle/reference_import.py::load_fsrcnn_service_code), run on the CPU in fp32 around stand-in nets that
+    # tests can rebuild without weights (glue_models below)
+    import warnings
+    warnings.simplefilter("ignore")  # torch.cuda.amp.autocast without a GPU
+    ns = ri.load_fsrcnn_service_code()
+    model, den = glue_models()
+    frames = glue_frames()
+    out = {"frames": frames.numpy()}
+    for i, (lr_shape, out_shape) in enumerate(GLUE_MULTI_CASES):
+        svc = ri.make_reference_service(ns, model, lr_shape, out_shape)
+        out[f"multi{i}"] = svc.upscale_multi(frames.clone()).numpy()
+    for i, use_den in enumerate((False, True)):
+        svc = ri.make_reference_service(ns, model, GLUE_SINGLE_LR, GLUE_SINGLE_OUT, denoise_model=den if use_den else None,
+                                        denoise_rate=0.75)
+        for fi in range(2):   # two consecutive frames: first-frame and steady-state noise maps (:262,269)
+            out[f"single{i}_{fi}"] = svc.upscale_single(frames[fi].clone()).numpy()
+    np.savez_compressed(os.path.join(HERE, "glue.npz"), **out)
     print("golden fixtures written to", HERE)
 
 

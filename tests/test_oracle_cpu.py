@@ -5,6 +5,8 @@
     from the seed (checksums) and reproduce the outputs.
   * when /root/reference is present (build container only, never the GPU box) the restatements are
     additionally compared with the live reference modules on fresh seeds.
+  * the service glue (oracle/glue.py) is pinned to the reference's own upscale_multi / upscale_single code, cut out of
+    src/upscale/fsrcnn_upscaler.py by its AST (the module itself cannot be imported) and run on the CPU in fp32.
   * RRDBNet lives in un-vendored pip `basicsr`: pinned only by its known-answer parameter counts and
     state-dict key names -> parity unpinned, stated in DESIGN.md.
 """
@@ -121,7 +123,66 @@ def test_glue_kernels_match_reference_formulas():
     assert out.dtype == torch.uint8 and tuple(out.shape) == (2, 48, 64, 3)
 
 
+def _glue_cases():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(GOLD, "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    return mg
+
+
+def _same_u8(got, want):
+    """uint8 outputs of two fp32 evaluations of the same graph: equal, up to a truncation flip of one level on a
+    vanishing fraction of the values when the accumulation order of a library kernel differs between builds."""
+    d = (torch.as_tensor(got).int() - torch.as_tensor(want).int()).abs()
+    assert d.max().item() <= 1 and (d > 0).float().mean().item() <= 1e-3, (d.max().item(), (d > 0).float().mean().item())
+
+
+def test_glue_golden():
+    """oracle/glue.py against the uint8 outputs of the reference's OWN upscale_multi / upscale_single code
+    (fsrcnn_upscaler.py:168-326, compiled from its source text by tests/golden/make_golden.py): area downscale branch,
+    mean / std match, local colour match, bicubic resize, truncating uint8; single-frame path with and without the
+    denoise branch, first and second frame."""
+    mg = _glue_cases()
+    g = np.load(os.path.join(GOLD, "glue.npz"))
+    frames = torch.from_numpy(g["frames"])
+    assert torch.equal(frames, mg.glue_frames())
+    model, den = mg.glue_models()
+    for i, (lr_shape, out_shape) in enumerate(mg.GLUE_MULTI_CASES):
+        _same_u8(glue.upscale_multi(frames.clone(), model, lr_shape=lr_shape, output_shape=out_shape), g[f"multi{i}"])
+    for i, use_den in enumerate((False, True)):
+        for fi in range(2):
+            got = glue.upscale_single(frames[fi].clone(), model, lr_shape=mg.GLUE_SINGLE_LR, output_shape=mg.GLUE_SINGLE_OUT,
+                                      denoise_model=den if use_den else None, denoise_rate=0.75, first_frame=fi == 0)
+            _same_u8(got, g[f"single{i}_{fi}"])
+
+
 # ---------------------------------------------------------------- live reference (build container)
+@needs_ref
+def test_glue_matches_live_reference():
+    """The same comparison against the reference's code executed live, on other shapes and seeds."""
+    import warnings
+    import torch.nn.functional as F
+    warnings.simplefilter("ignore")
+    ns = ri.load_fsrcnn_service_code()
+    model = lambda t: F.interpolate(t.float(), scale_factor=4, mode="bilinear", align_corners=False) * 0.8 + 0.1  # noqa: E731
+    den = lambda x: x[:, :, :3] * 0.9 + 0.05  # noqa: E731
+    frames = torch.randint(0, 256, (3, 40, 72, 3), dtype=torch.uint8, generator=torch.Generator().manual_seed(11))
+    for lr_shape, out_shape, resize in (((720, 1280), None, True), ((20, 36), (75, 133), True), ((20, 36), (75, 133), False)):
+        svc = ri.make_reference_service(ns, model, lr_shape, out_shape, lr_hr_resize=resize)
+        _same_u8(glue.upscale_multi(frames.clone(), model, lr_shape=lr_shape, output_shape=out_shape, lr_hr_resize=resize),
+                 svc.upscale_multi(frames.clone()))
+    svc = ri.make_reference_service(ns, model, (20, 36), (90, 150), denoise_model=den, denoise_rate=0.5)
+    for fi in range(3):
+        want = svc.upscale_single(frames[fi].clone())
+        got = glue.upscale_single(frames[fi].clone(), model, lr_shape=(20, 36), output_shape=(90, 150), denoise_model=den,
+                                  denoise_rate=0.5, first_frame=fi == 0)
+        _same_u8(got, want)
+    # blur_ker / sharpen_ker weights
+    assert torch.equal(ns["blur_ker"](kernel_size=17, sigma=8.0).weight.data, glue.blur_weight(17, 8.0))
+    assert torch.allclose(ns["sharpen_ker"](strength=0.00007).weight.data, glue.sharpen_weight(0.00007), atol=0, rtol=0)
+
+
 @needs_ref
 def test_srvgg_matches_live_reference():
     fac = ri.load_realesrgan_factory()
