@@ -766,6 +766,25 @@ conv3x3_stream_kernel(const __grid_constant__ StreamParams P) {
                 const size_t pix0 = (static_cast<size_t>(b.n) * E.out_h + y) * E.out_w + b.strip * kTileW + qd * 32;
                 reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(E.out) + pix0 * 3)[lane] = static_cast<uint32_t>(two >> (8 * sh));
               }
+            } else if (NOUT == 16 && (E.out_mode == kOutNCHWF16 || E.out_mode == kOutNCHWF32) && E.cout <= 4 &&
+                       E.act == kActNone && E.alpha == 1.0f && E.res2 == nullptr && E.res1_lo_off == 0 && !bf16) {
+              // few-channel planar output (last conv of RRDBNet / BSVD at the model boundary, optional residual on the
+              // first res1_nch channels: BSVD none_minus, bsvd/model.py:436-442): one coalesced store per channel
+              if (valid) {
+                const size_t plane = static_cast<size_t>(E.out_h) * E.out_w;
+                const size_t o0 = static_cast<size_t>(b.n) * E.cout * plane + static_cast<size_t>(y) * E.out_w + ax;
+                const uint16_t* rp = E.res1 != nullptr ? reinterpret_cast<const uint16_t*>(E.res1) + pix * E.res1_pitch + E.res1_coff : nullptr;
+                const int nres = E.res1 == nullptr ? 0 : (E.res1_nch > 0 ? E.res1_nch : E.cout);
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                  if (c < E.cout) {
+                    float v = __uint_as_float(raw[c]);
+                    if (c < nres) v = fmaf(E.beta1, __half2float(*reinterpret_cast<const __half*>(rp + c)), v);
+                    if (E.out_mode == kOutNCHWF16) reinterpret_cast<__half*>(E.out)[o0 + c * plane] = __float2half_rn(v);
+                    else reinterpret_cast<float*>(E.out)[o0 + c * plane] = v;
+                  }
+                }
+              }
             } else if (NOUT == 48 && E.out_mode == kOutPSNCHWF16 && E.ps_r == 4 && E.cout == 48 && E.act == kActNone &&
                        E.alpha == 1.0f && E.res1 == nullptr && E.res2 == nullptr && !bf16) {
               // PixelShuffle(4) into half NCHW (+ nearest-upsampled base image): SRVGGNetCompact's last conv
