@@ -587,9 +587,25 @@ conv3x3_stream_kernel(const __grid_constant__ StreamParams P) {
           const size_t pix = (static_cast<size_t>(b.n) * E.out_h + y) * E.out_w + ax;
           const bool has_r1 = fast && E.res1 != nullptr, has_r2 = fast && E.res2 != nullptr;
           if (has_r1 && valid) {
-            const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(E.res1) + pix * E.res1_pitch + E.res1_coff + b.chunk * NOUT);
+            if (E.res1_nch > 0) {
+              // residual on the first res1_nch (<= 8) channels of the conv only (BSVD none_minus, bsvd/model.py:436-442):
+              // one 16-byte load for channel group 0 of chunk 0, the other channels' halves masked to +0
 #pragma unroll
-            for (int j = 0; j < NOUT / 8; ++j) r1v[j] = rp[j];
+              for (int j = 0; j < NOUT / 8; ++j) r1v[j] = make_uint4(0u, 0u, 0u, 0u);
+              if (b.chunk == 0) {
+                uint4 t = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(E.res1) + pix * E.res1_pitch + E.res1_coff);
+                const int nch = E.res1_nch;
+                t.x &= (nch > 0 ? 0xFFFFu : 0u) | (nch > 1 ? 0xFFFF0000u : 0u);
+                t.y &= (nch > 2 ? 0xFFFFu : 0u) | (nch > 3 ? 0xFFFF0000u : 0u);
+                t.z &= (nch > 4 ? 0xFFFFu : 0u) | (nch > 5 ? 0xFFFF0000u : 0u);
+                t.w &= (nch > 6 ? 0xFFFFu : 0u) | (nch > 7 ? 0xFFFF0000u : 0u);
+                r1v[0] = t;
+              }
+            } else {
+              const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(E.res1) + pix * E.res1_pitch + E.res1_coff + b.chunk * NOUT);
+#pragma unroll
+              for (int j = 0; j < NOUT / 8; ++j) r1v[j] = rp[j];
+            }
           }
           if (has_r2 && valid) {
             const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(E.res2) + pix * E.res2_pitch + E.res2_coff + b.chunk * NOUT);

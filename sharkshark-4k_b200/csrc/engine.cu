@@ -577,7 +577,7 @@ int materialize_stream(ss4k_ctx* ctx, const ConvSpec& cs, const HostTensor& W, c
   // fast epilogue: plain NHWC 16-bit output -> swizzled shared-memory tile -> TMA store
   p.fast_store = 0;
   if (cs.out_mode == kOutNHWC && cs.out_buf >= 0 && cs.out_lo_buf < 0 && cs.out_coff % 8 == 0 && cs.out_pitch % 8 == 0 &&
-      !cs.tshift && cs.res1_nch == 0 &&
+      !cs.tshift && (cs.res1_nch == 0 || (cs.res1_nch <= 8 && cs.res1_pitch >= 8 && cs.res1_coff % 8 == 0 && cs.res1_lo_buf < 0)) &&
       (pk.nout == 16 || pk.nout == 32 || pk.nout == 64) && getenv("SS4K_NO_FAST_STORE") == nullptr) {
     const cuuint64_t eb = 2;
     const int cavail = std::min(cs.out_pitch - cs.out_coff, pk.npad_total);
