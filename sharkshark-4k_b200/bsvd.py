@@ -122,6 +122,21 @@ class NativeBSVD(nn.Module):
         s.close()
         return torch.cat(outs, dim=0)
 
+    def close(self):
+        """Destroy the cached plans and release the engine's host copy of the weights (ss4k_clear_weights)."""
+        for p in list(self._plans._d.values()):
+            p.close()
+        self._plans._d.clear()
+        if self.net_id is not None:
+            self.engine.release_net(self.net_id)
+            self.net_id = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
     def reset(self):
         """Every forward() is a complete clip, so there is no state to reset (model.py:482-484,579)."""
 

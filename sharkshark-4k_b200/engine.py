@@ -59,6 +59,11 @@ class Engine:
                                                L.DT_F32, shape, t.ndim), self.h)
         return net_id
 
+    def release_net(self, net_id):
+        """Drop the host (fp32) copy of a net's weights; plans already created keep their packed device weights."""
+        if self.h:
+            self.lib.ss4k_clear_weights(self.h, net_id)
+
     def plan(self, net_id, arch, n, h, w, scale=4, depth=0, tile=0, tile_pad=10, act_mode=L.ACT_F16,
              in_fmt=L.FMT_F32_NCHW, out_fmt=L.FMT_F32_NCHW, use_graph=True, bsvd_noise=0.0):
         cfg = make_cfg(net_id, arch, n, h, w, scale, depth, tile, tile_pad, act_mode, in_fmt, out_fmt, use_graph)

@@ -1,0 +1,106 @@
+"""Denoise + upscale of a frame chunk: the hot path of the reference's live-stream configuration in one call.
+
+Reference composition: src/upscale/fsrcnn_upscaler.py:245-300 (``upscale_single``: BSVD denoiser in front of the
+RealESRGAN upscaler, one decoded frame at a time); BASELINE.json configs[2] runs it on an NV12 stream with the
+denoiser seeing the frames as ONE temporal stream (BSVD.forward over the chunk, src/upscale/model/bsvd/model.py:515-524)
+and the chunks sharded across GPUs with the 16-frame temporal halo (``sharding.bsvd_chunks``).
+
+    NV12 / uint8 RGB frames [T, ...]  --BSVD clip (T frames)-->  half NCHW [T,3,H,W]
+        --owned frames only-->  RRDBNet / SRVGG, one frame per engine run  -->  uint8 NHWC [n_own, sH, sW, 3]
+
+Both stages are engine plans (CUDA graphs of tcgen05 convs) behind the C ABI; colour decode, /255 and the noise map
+(0.1 * denoise_rate, fsrcnn_upscaler.py:262) are produced by the BSVD plan's layout kernel.  torch supplies device
+buffers, streams and pinned host memory only.
+"""
+import torch
+
+from . import _lib as L
+
+
+class DenoiseUpscalePipeline:
+    def __init__(self, denoiser, upscaler, h, w, noise, nv12=True, out_fmt=L.FMT_U8_NHWC):
+        self.den, self.sr = denoiser, upscaler
+        self.h, self.w, self.noise, self.nv12 = h, w, float(noise), nv12
+        self.out_fmt = out_fmt
+        self.device = denoiser.engine.device
+        self.sr_plan = upscaler._plan(1, h, w, L.FMT_F16_NCHW, out_fmt)
+        self._den_out_dtype = denoiser.out_dtype
+        self._copy_stream = None
+        self._slots = {}
+        self._calls = 0
+
+    # ------------------------------------------------------------------ plans
+    def den_plan(self, t):
+        in_fmt = L.FMT_NV12 if self.nv12 else L.FMT_U8_NHWC
+        return self.den._plan(t, self.h, self.w, in_fmt, L.FMT_F16_NCHW, self.noise)
+
+    def frame_bytes_in(self):
+        return self.h * self.w * 3 // 2 if self.nv12 else self.h * self.w * 3
+
+    def out_frame_shape(self):
+        return tuple(self.sr_plan.out_shape()[1:])
+
+    def new_output(self, n_own):
+        dt = {L.FMT_U8_NHWC: torch.uint8, L.FMT_F16_NCHW: torch.float16, L.FMT_F32_NCHW: torch.float32}[self.out_fmt]
+        return torch.empty((n_own,) + self.out_frame_shape(), device=self.device, dtype=dt)
+
+    def flops(self, t, n_own):
+        return self.den_plan(t).flops + n_own * self.sr_plan.flops
+
+    def launches(self, t, n_own):
+        return self.den_plan(t).launches + n_own * self.sr_plan.launches
+
+    # ------------------------------------------------------------------ device-resident path
+    def run(self, frames, own=None, out=None, after_frame=None):
+        """frames: CUDA uint8 chunk [T, h*w*3/2] (NV12) or [T,h,w,3]; own: slice of the chunk whose frames are
+        upscaled (default: all); returns [n_own, sH, sW, 3] uint8 (stream-ordered, no sync)."""
+        t = frames.shape[0]
+        own = own if own is not None else slice(0, t)
+        lo, hi, _ = own.indices(t)
+        den = self.den_plan(t).run(frames.contiguous())          # [T,3,H,W] half
+        if out is None:
+            out = self.new_output(hi - lo)
+        for i in range(lo, hi):
+            self.sr_plan.run(den[i:i + 1], out[i - lo:i - lo + 1])
+            if after_frame is not None:
+                after_frame(i - lo)
+        return out
+
+    # ------------------------------------------------------------------ host path (pinned buffers in / out)
+    def run_host(self, frames_host, own, out_host):
+        """Pinned host chunk in, pinned host frames out.  The H2D copy, both nets and the D2H copies are queued and the
+        call returns; the D2H copy of frame i overlaps the upscaling of frame i+1 (copy stream) and consecutive
+        calls alternate between two device staging slots.  Call ``host_sync()`` before reading ``out_host``."""
+        assert not frames_host.is_cuda and not out_host.is_cuda
+        t = frames_host.shape[0]
+        lo, hi, _ = own.indices(t)
+        key = (t, hi - lo)
+        if key not in self._slots:
+            self._slots[key] = [{"in": torch.empty(frames_host.shape, dtype=torch.uint8, device=self.device),
+                                 "out": self.new_output(hi - lo), "copied": None} for _ in range(2)]
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(self.device)
+        slot = self._slots[key][self._calls & 1]
+        self._calls += 1
+        cur = torch.cuda.current_stream(self.device)
+        if slot["copied"] is not None:
+            cur.wait_event(slot["copied"])                        # the slot's previous result has left the device
+        slot["in"].copy_(frames_host, non_blocking=True)
+
+        def after(i):
+            ev = torch.cuda.Event()
+            ev.record(cur)
+            self._copy_stream.wait_event(ev)
+            with torch.cuda.stream(self._copy_stream):
+                out_host[i].copy_(slot["out"][i], non_blocking=True)
+
+        self.run(slot["in"], own, slot["out"], after_frame=after)
+        done = torch.cuda.Event()
+        done.record(self._copy_stream)
+        slot["copied"] = done
+        return out_host
+
+    def host_sync(self):
+        torch.cuda.current_stream(self.device).synchronize()
+        if self._copy_stream is not None:
+            self._copy_stream.synchronize()

@@ -133,6 +133,21 @@ class _NativeNet(nn.Module):
     def float(self):
         return self
 
+    def close(self):
+        """Destroy the cached plans and release the engine's host copy of the weights (ss4k_clear_weights)."""
+        for p in list(self._plans._d.values()):
+            p.close()
+        self._plans._d.clear()
+        if self.net_id is not None:
+            self.engine.release_net(self.net_id)
+            self.net_id = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
 
 class NativeSRVGG(_NativeNet):
     """SRVGGNetCompact (factory.py:18-82) on the native engine."""
@@ -161,23 +176,35 @@ def build_model(factor=4, device=0, input_shape=(720, 1280), batch_size=8, denoi
     if name not in MODEL_ZOO:
         raise ValueError(f"unknown model_name {name}")
     arch, netscale, depth = MODEL_ZOO[name]
+    # DNI (factory.py:152-157): 'realesr-general-x4v3' with denoise_strength != 1 ALWAYS blends the general and the
+    # wdn weights in the reference; a missing second weight set is an error here, never a silent un-blended net.
+    needs_dni = name == 'realesr-general-x4v3' and args.denoise_strength != 1
+    dni_weight = [args.denoise_strength, 1 - args.denoise_strength]
     if state_dict is None:
         path = args.model_path or os.path.join('weights', name + '.pth')
         if isinstance(path, (list, tuple)):
             sds = [load_checkpoint(p) for p in path]
-            state_dict = dni(sds[0], sds[1], [args.denoise_strength, 1 - args.denoise_strength])
+            state_dict = dni(sds[0], sds[1], dni_weight)
         else:
             if not os.path.isfile(path):
                 raise FileNotFoundError(f"{path}: weights are downloaded at run time by the reference "
                                         "(factory.py:140-150); pass state_dict= or args.model_path")
             state_dict = load_checkpoint(path)
-            if name == 'realesr-general-x4v3' and args.denoise_strength != 1:
+            if needs_dni:
                 wdn = path.replace('realesr-general-x4v3', 'realesr-general-wdn-x4v3')
-                if os.path.isfile(wdn):
-                    state_dict = dni(state_dict, load_checkpoint(wdn),
-                                     [args.denoise_strength, 1 - args.denoise_strength])
+                if wdn == path or not os.path.isfile(wdn):
+                    raise FileNotFoundError(
+                        f"{wdn}: model 'realesr-general-x4v3' with denoise_strength {args.denoise_strength} != 1 blends "
+                        "the general and the wdn weights (factory.py:152-157); the wdn checkpoint is missing")
+                state_dict = dni(state_dict, load_checkpoint(wdn), dni_weight)
     elif isinstance(state_dict, (list, tuple)):
-        state_dict = dni(state_dict[0], state_dict[1], [args.denoise_strength, 1 - args.denoise_strength])
+        if len(state_dict) != 2:
+            raise ValueError("state_dict=(general, wdn): exactly two weight sets")
+        state_dict = dni(state_dict[0], state_dict[1], dni_weight)
+    elif needs_dni:
+        raise ValueError(
+            f"model 'realesr-general-x4v3' with denoise_strength {args.denoise_strength} != 1 needs both weight sets: "
+            "pass state_dict=(general_state_dict, wdn_state_dict) (the reference always blends them, factory.py:152-157)")
     # depth follows the weights actually supplied (the zoo entry is the published architecture)
     if arch == L.ARCH_RRDB:
         blocks = {int(k.split('.')[1]) for k in state_dict if k.startswith('body.') and '.rdb1.conv1.weight' in k}

@@ -68,7 +68,7 @@ class FsrcnnUpscalerService:
     def __init__(self, lr_level=3, device=0, on_queue=None, denoising=True, denoise_rate=1.0,
                  upscaler_model='realesrgan', batch_size=1, jit_mode=None, lr_hr_resize=True,
                  model_name=None, state_dict=None, denoise_state_dict=None, act_mode=L.ACT_F16,
-                 denoise_act_mode="auto"):
+                 denoise_act_mode="auto", single_mode=None):
         self.lr_shape = self.LR_SHAPES[lr_level]
         self.scale = 4
         self.denoise_rate = denoise_rate
@@ -77,7 +77,9 @@ class FsrcnnUpscalerService:
         self.on_queue = on_queue
         self.output_shape = None
         self.upscaler_model = upscaler_model
-        self.single_mode = upscaler_model != 'realesrgan'      # :109 (quirk kept; force with single_mode=True)
+        # :109 makes single_mode = (upscaler_model != 'realesrgan'), which only the FSRCNN model (out of scope here) can
+        # reach; the keyword selects the per-frame denoise + upscale path (upscale_single) for the RealESRGAN models
+        self.single_mode = (upscaler_model != 'realesrgan') if single_mode is None else bool(single_mode)
         self.denoising = denoising
         self.batch_size = batch_size
         self.jit_mode = jit_mode
@@ -107,11 +109,17 @@ class FsrcnnUpscalerService:
         self.model.out_dtype = torch.float16        # the reference's JitWrapper returns fp16 (factory.py:242-245)
         self.engine = Engine.get(self.device.index or 0)
         self.lib = self.engine.lib
-        if self.denoising:
-            self.denoise_model = native_bsvd.build_model(device=self.device.index or 0, input_shape=self.lr_shape,
-                                                         state_dict=self.denoise_state_dict, act_mode=self.denoise_act_mode)
+        # only upscale_single uses the denoiser (fsrcnn_upscaler.py:245-284): the multi-frame default must not need a
+        # BSVD checkpoint, so it is built here for single_mode and on first use otherwise
+        self.denoise_model = None
+        if self.denoising and self.single_mode:
+            self._build_denoiser()
         self.match_blur = gaussian_kernel(8 * 2 + 1, 8.0).to(self.device)     # :138
         self._sums = {}
+
+    def _build_denoiser(self):
+        self.denoise_model = native_bsvd.build_model(device=self.device.index or 0, input_shape=self.lr_shape,
+                                                     state_dict=self.denoise_state_dict, act_mode=self.denoise_act_mode)
 
     def proc_cleanup(self):
         pass
@@ -224,6 +232,8 @@ class FsrcnnUpscalerService:
             x[0, 0, :3].copy_(lr_before[0])
             x[0, 0, 3].fill_(0.05 if first else 0.1 * self.denoise_rate)       # :262,269
             self.profiler.start('fsrcnn.denoise')
+            if self.denoise_model is None:
+                self._build_denoiser()
             den = self.denoise_model(x)[:, -1]                                 # :277  (F = 1 clip)
             lr = torch.empty(1, 3, lh, lw, dtype=torch.float32, device=self.device)
             L.check(self.lib.ss4k_glue_sharpen_blend(_ptr(den), _fmt(den), 1, 3, lh, lw, 0.00002, 0.8, _ptr(lr_before), 0,

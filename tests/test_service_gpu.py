@@ -82,8 +82,7 @@ def test_upscale_single_denoise_then_rrdb(engine):
     want1 = glue.upscale_single(frames[1], net, (360, 640), (720, 1280), den, 0.75, False)
     svc = service.FsrcnnUpscalerService(lr_level=0, device=0, denoising=True, denoise_rate=0.75,
                                         model_name='RealESRGAN_x2plus', state_dict=net.state_dict(),
-                                        denoise_state_dict=sd)
-    svc.single_mode = True
+                                        denoise_state_dict=sd, single_mode=True)
     svc.proc_init()
     svc.output_shape = (720, 1280)
     got = svc.upscale(frames.cuda())
