@@ -63,8 +63,9 @@ def match_local_colour(hr, lr, factor=8):
     return hr
 
 
-def upscale_multi(frames_u8, model, lr_shape, output_shape=None, lr_hr_resize=True):
-    """frames_u8 [N,H,W,3] uint8 -> uint8 [N,H',W',3]  (fsrcnn_upscaler.py:168-233)."""
+def upscale_multi(frames_u8, model, lr_shape, output_shape=None, lr_hr_resize=True, return_float=False):
+    """frames_u8 [N,H,W,3] uint8 -> uint8 [N,H',W',3]  (fsrcnn_upscaler.py:168-233).
+    return_float: also return the float frame (x 255, NHWC) in front of the truncating ``.to(torch.uint8)``."""
     with torch.no_grad():
         img = frames_u8.permute(0, 3, 1, 2) / 255.0
         lr = img
@@ -79,7 +80,8 @@ def upscale_multi(frames_u8, model, lr_shape, output_shape=None, lr_hr_resize=Tr
             mode = "bicubic" if output_shape[0] >= hr.shape[0] else "area"
             hr = F.interpolate(hr, size=output_shape, mode=mode)
         hr = torch.clamp(hr, 0, 1)
-        return (hr * 255).permute(0, 2, 3, 1).to(torch.uint8)
+        q = (hr * 255).permute(0, 2, 3, 1)
+        return (q.to(torch.uint8), q) if return_float else q.to(torch.uint8)
 
 
 def denoise_frame(frame_chw, denoise_model, denoise_rate, first_frame):
@@ -95,7 +97,7 @@ def denoise_frame(frame_chw, denoise_model, denoise_rate, first_frame):
 
 
 def upscale_single(frame_u8, model, lr_shape, output_shape=None, denoise_model=None, denoise_rate=1.0,
-                   first_frame=True):
+                   first_frame=True, return_float=False):
     """frame_u8 [H,W,3] uint8 -> uint8 [H',W',3]  (fsrcnn_upscaler.py:235-326, realesrgan branch).
     denoise_model: callable [1,1,4,H,W] -> [1,1,3,H,W] or None (denoising=False)."""
     with torch.no_grad():
@@ -117,4 +119,5 @@ def upscale_single(frame_u8, model, lr_shape, output_shape=None, denoise_model=N
         if output_shape is not None:
             out = F.interpolate(out, size=output_shape, mode="bicubic")                  # :316-325 (bicubic in practice)
         out = torch.clamp(out, 0, 1)
-        return (out * 255)[0].permute(1, 2, 0).to(torch.uint8)
+        q = (out * 255)[0].permute(1, 2, 0)
+        return (q.to(torch.uint8), q) if return_float else q.to(torch.uint8)

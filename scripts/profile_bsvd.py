@@ -9,8 +9,9 @@ from ss4k_b200 import bsvd as nbsvd, engine as E
 from oracle import bsvd as obsvd
 
 F = int(sys.argv[1]) if len(sys.argv) > 1 else 8
-sd = obsvd.build_bsvd32(0, weight_scale=0.5)
-den = nbsvd.NativeBSVD(sd, device=0, act_mode=L.ACT_F16, out_dtype=torch.float16)
+SPLIT = len(sys.argv) > 2 and sys.argv[2] == "split"
+sd = obsvd.build_bsvd32(0, weight_scale=1.0 if SPLIT else 0.5)
+den = nbsvd.NativeBSVD(sd, device=0, act_mode=L.ACT_F16_SPLIT if SPLIT else L.ACT_F16, out_dtype=torch.float16)
 x = torch.rand(1, F, 4, 720, 1280, device="cuda")
 y = den(x); torch.cuda.synchronize()
 plan = list(den._plans._d.values())[0]

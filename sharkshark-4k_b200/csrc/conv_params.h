@@ -174,6 +174,15 @@ struct StreamParams {
   uint32_t early_kb_mask;
   int32_t l2_in, l2_out;  // L2 eviction priority of the activation loads / output stores: 0 normal, 1 evict_last
                           // (re-read by the next convs of the dense block), 2 evict_first (dead after this conv)
+  // Stride-2 convs (BSVD DownBlock, bsvd/model.py:262-263).  The input is read through its pixel-PAIR view
+  // (2C channels = [even pixel | odd pixel], W/2 pairs per row): output pixel x needs pair x-1 (odd half, kx = 0) and
+  // pair x (even half kx = 1, odd half kx = 2) -> two horizontal shifts with k-step masks instead of three taps.
+  // Vertically, input row r feeds output row r/2 (ky = 1) when r is even and output rows (r-1)/2 (ky = 2), (r+1)/2
+  // (ky = 0) when r is odd: the weight tile stacks its N blocks as [ky2 | ky0 | ky1] so that both cases are one MMA.
+  // H, W are the OUTPUT grid; the activation tensor map has 2 H rows of W pairs.
+  int32_t stride2;
+  int32_t nkx;                // weight tiles (horizontal shifts) per K block: 3, or 2 for stride 2
+  uint8_t ksm[kMaxSKB][2];    // stride 2: 4-bit mask of the 16-channel k-steps to issue per (K block, shift)
 };
 
 }  // namespace ss4k

@@ -142,7 +142,7 @@ conv3x3_stream_kernel(const __grid_constant__ StreamParams P) {
   // after the weights: fp32 bias of every chunk (tcgen05.st initialisation), or bias tile + ones tile (bias MMA)
   constexpr bool kBiasMMA = stream_bias_mma(NOUT);
   constexpr uint32_t kBiasTile = NOUT * 128u;
-  const uint32_t bias_base = w_base + static_cast<uint32_t>(P.nkb) * 3u * kWTile;
+  const uint32_t bias_base = w_base + static_cast<uint32_t>(P.nkb * P.nkx) * kWTile;
   const uint32_t ones_base = bias_base + kBiasTile;
   const uint32_t a_base = kBiasMMA ? ones_base + kStreamOnesBytes : bias_base + kStreamBiasBytes;
   const uint32_t stage_base = a_base + static_cast<uint32_t>(P.a_slots) * kASlotBytes;
@@ -206,7 +206,7 @@ conv3x3_stream_kernel(const __grid_constant__ StreamParams P) {
       next_band(P, uu, u1, fb);
       early_chunk = fb.chunk;
       if (elect_one()) {
-        const int ntile = P.nkb * 3;
+        const int ntile = P.nkb * P.nkx;
         mbar_expect_tx(w_full, static_cast<uint32_t>(ntile) * kWTile + (kBiasMMA ? kBiasTile : 0u));
         for (int t = 0; t < ntile; ++t)
           tma_load_2d(w_base + t * kWTile, &P.tmW, w_full, 0, (fb.chunk * ntile + t) * 3 * NOUT);
@@ -284,7 +284,7 @@ conv3x3_stream_kernel(const __grid_constant__ StreamParams P) {
         if (b.chunk == early_chunk) {
           early_chunk = -1;  // already requested in the prologue
         } else if (elect_one()) {
-          const int ntile = P.nkb * 3;
+          const int ntile = P.nkb * P.nkx;
           mbar_expect_tx(w_full, static_cast<uint32_t>(ntile) * kWTile + (kBiasMMA ? kBiasTile : 0u));
           for (int t = 0; t < ntile; ++t)
             tma_load_2d(w_base + t * kWTile, &P.tmW, w_full, 0, (b.chunk * ntile + t) * 3 * NOUT);
@@ -303,40 +303,65 @@ conv3x3_stream_kernel(const __grid_constant__ StreamParams P) {
         SS4K_TRACE(13);
       }
       // dbg_flags & 8: skip the band's halo rows (WRONG results at band boundaries; measures what they cost)
-      const int r0 = (b.yb > 0 && !(P.dbg_flags & 8)) ? b.yb - 1 : b.yb;
-      const int r1 = (b.ye < P.H && !(P.dbg_flags & 8)) ? b.ye : b.ye - 1;
+      const bool s2 = P.stride2 != 0;
+      int r0, r1;
+      if (s2) {  // output rows [yb, ye) read input rows [2 yb - 1, 2 ye - 1]
+        r0 = b.yb > 0 ? 2 * b.yb - 1 : 0;
+        r1 = 2 * b.ye - 1;
+      } else {
+        r0 = (b.yb > 0 && !(P.dbg_flags & 8)) ? b.yb - 1 : b.yb;
+        r1 = (b.ye < P.H && !(P.dbg_flags & 8)) ? b.ye : b.ye - 1;
+      }
       const int x0 = b.strip * kTileW - 1;
       int y_lo = b.yb;
       for (int r = r0; r <= r1; ++r) {
-        // ---- the row's record
-        {
-          const int y = r - 1 > b.yb ? r - 1 : b.yb;
-          if (y != y_lo) {
-            y_lo = y;
-            if (++sL == S) { sL = 0; ++kL; }
+        // ---- the row's record: output rows [y_lo, y_hi] receive this input row, the first through weight block b_lo
+        int y_first, y_hi, b_lo, f_lo;
+        bool done_lo;  // this input row completes output row y_lo
+        if (s2) {
+          if (r & 1) {
+            const int ya = (r - 1) >> 1;  // ky = 2 for row ya (block 0), ky = 0 for row ya + 1 (block 1)
+            y_first = ya > b.yb ? ya : b.yb;
+            y_hi = ya + 1 < b.ye - 1 ? ya + 1 : b.ye - 1;
+            b_lo = y_first - ya;
+            f_lo = ya + 1;
+            done_lo = ya >= b.yb;
+          } else {                        // ky = 1 (block 2)
+            y_first = y_hi = r >> 1;
+            b_lo = 2;
+            f_lo = y_hi + 1;
+            done_lo = false;
           }
+        } else {
+          y_first = r - 1 > b.yb ? r - 1 : b.yb;
+          y_hi = r + 1 < b.ye - 1 ? r + 1 : b.ye - 1;
+          b_lo = y_first - (r - 1);  // weight row block (block = 2 - ky) of output row y_lo
+          f_lo = r + 1;
+          done_lo = r - 1 >= b.yb;
         }
-        const int y_hi = r + 1 < b.ye - 1 ? r + 1 : b.ye - 1;
-        const int b_lo = y_lo - (r - 1);  // weight row block (block = 2 - ky) of output row y_lo
+        if (y_first != y_lo) {
+          y_lo = y_first;
+          if (++sL == S) { sL = 0; ++kL; }
+        }
+        if (r == r0) f_lo = y_lo;
         const int nblk = y_hi - y_lo + 1;
         const int nA = sL + nblk <= S ? nblk : S - sL;  // the MMAs split where the ring wraps
         const int nB = nblk - nA;
         uint32_t fresh = 0;  // up to 3 x {bit 7 valid, bit 6 parity of the slot's use count, bits 0..4 slot}
         {
-          const int f_lo = (r == r0) ? y_lo : r + 1;
           int sh = 0;
           for (int y = f_lo; y <= y_hi; ++y, sh += 8) {
-            int s2 = sL + (y - y_lo), k2 = kL;
-            if (s2 >= S) { s2 -= S; ++k2; }
-            fresh |= (0x80u | ((k2 & 1) ? 0x40u : 0u) | static_cast<uint32_t>(s2)) << sh;
+            int s2_ = sL + (y - y_lo), k2 = kL;
+            if (s2_ >= S) { s2_ -= S; ++k2; }
+            fresh |= (0x80u | ((k2 & 1) ? 0x40u : 0u) | static_cast<uint32_t>(s2_)) << sh;
           }
         }
         uint32_t c0 = 0xFFu, c1 = 0xFFu;  // accumulator slots completed by this input row
-        if (r - 1 >= b.yb) c0 = static_cast<uint32_t>(sL);
-        if (r == r1 && r <= b.ye - 1) {  // image bottom: row H-1 has no row below it
-          int s2 = sL + (r - y_lo);
-          if (s2 >= S) s2 -= S;
-          c1 = static_cast<uint32_t>(s2);
+        if (done_lo) c0 = static_cast<uint32_t>(sL);
+        if (!s2 && r == r1 && r <= b.ye - 1) {  // image bottom: row H-1 has no row below it
+          int s2_ = sL + (r - y_lo);
+          if (s2_ >= S) s2_ -= S;
+          c1 = static_cast<uint32_t>(s2_);
         }
         const uint32_t flags = static_cast<uint32_t>(nB) | ((r == r1 && !has_next) ? kRecLast : 0u) |
                                ((r == r0 && new_chunk) ? kRecNewChunk : 0u) |
@@ -452,7 +477,7 @@ conv3x3_stream_kernel(const __grid_constant__ StreamParams P) {
           }
           // descriptor low words (address >> 4): per-MMA offsets are compile-time constants
           const uint32_t a_lo = (a_base + as * kASlotBytes) >> 4;
-          const uint32_t w_lo = (w_base + static_cast<uint32_t>(kb * 3) * kWTile) >> 4;
+          const uint32_t w_lo = (w_base + static_cast<uint32_t>(kb * P.nkx) * kWTile) >> 4;
           const uint32_t wA_lo = w_lo + woffA, wB_lo = w_lo + woffB;
           const int nks = P.nks[kb];
           const uint32_t as_cur = as;
@@ -462,6 +487,24 @@ conv3x3_stream_kernel(const __grid_constant__ StreamParams P) {
             umma_f16_lo(colA, a_lo + ((KX) * kRowBytes + (KS) * 32) / 16, wA_lo + ((KX) * kWTile + (KS) * 32) / 16, idA, 1u); \
             if (wrap) umma_f16_lo(tmem_base, a_lo + ((KX) * kRowBytes + (KS) * 32) / 16, wB_lo + ((KX) * kWTile + (KS) * 32) / 16, idB, 1u); \
           }
+          if (P.stride2) {
+            // pixel-pair view: shift 0 = pair x-1 (odd half only), shift 1 = pair x; k-steps from the per-shift masks
+            const uint32_t m0 = P.ksm[kb][0], m1 = P.ksm[kb][1];
+            if (do_mma) {
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks)
+                if ((m0 >> ks) & 1u) SS4K_MMA(0, ks)
+            }
+            if (kb == nkb - 1 && overlap) {
+              fetch(as, aph);
+              prepare();
+            }
+            if (do_mma) {
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks)
+                if ((m1 >> ks) & 1u) SS4K_MMA(1, ks)
+            }
+          } else {
           if (do_mma) {
             if (nks == 4) {
               SS4K_MMA(0, 0) SS4K_MMA(0, 1) SS4K_MMA(0, 2) SS4K_MMA(0, 3)
@@ -490,6 +533,7 @@ conv3x3_stream_kernel(const __grid_constant__ StreamParams P) {
               for (int ks = 0; ks < 3; ++ks)
                 if (ks < nks) SS4K_MMA(2, ks)
             }
+          }
           }
 #undef SS4K_MMA
           umma_commit_elect(a_empty + 8 * as_cur);  // slab reusable once these MMAs have read it

@@ -273,18 +273,26 @@ struct StreamPacked {
   uint8_t src_kb[kMaxSKB];  // 64-channel block of the source tensor read by K block i
   uint8_t src_tm[kMaxSKB];  // 0: the tensor itself (high halves in split mode), 1: its low-half twin
   uint8_t whalf[kMaxSKB];   // 0: weights (high halves), 1: low halves of the weights
+  int stride2 = 0, nkx = 3;
+  uint8_t ksm[kMaxSKB][2];  // stride 2: k-step masks per (K block, horizontal shift)
 };
 
 bool stream_config(const ConvSpec& cs, StreamPacked* sp) {
-  if (cs.mode != kModeConv3 || cs.in_coff % 8 || cs.in_pitch % 8) return false;
+  const bool s2 = cs.mode == kModeS2;
+  if (cs.mode != kModeConv3 && !s2) return false;
+  if (cs.in_coff % 8 || cs.in_pitch % 8) return false;
+  // stride 2 reads the pixel-pair view (2 * pitch channels per pair, 64-channel K blocks): pitch 32 or a multiple of 64
+  if (s2 && (cs.in_coff != 0 || (2 * cs.in_pitch) % 64 || cs.cin > cs.in_pitch || cs.in_h % 2 || cs.in_w % 2)) return false;
+  if (s2 && getenv("SS4K_NO_STREAM_S2")) return false;
   if (getenv("SS4K_NO_STREAM")) return false;
   if (cs.split && getenv("SS4K_NO_STREAM_SPLIT")) return false;
   const int npad = round_up(cs.cout, 16);
   if (npad * 4 > kStreamBiasBytes) return false;
   // fp16 hi/lo split operands: three K blocks per 64 source channels: A_hi*W_hi, A_hi*W_lo, A_lo*W_hi
   const int nsplit = cs.split ? 3 : 1;
-  const int nkb0 = (cs.cin + 63) / 64;
+  const int nkb0 = s2 ? 2 * cs.in_pitch / 64 : (cs.cin + 63) / 64;
   const int nkb = nkb0 * nsplit;
+  const int nkx = s2 ? 2 : 3;
   if (nkb > kMaxSKB) return false;
   int cand[4], nc = 0;
   if (npad <= 64) cand[nc++] = npad;
@@ -294,19 +302,32 @@ bool stream_config(const ConvSpec& cs, StreamPacked* sp) {
   for (int i = 0; i < nc; ++i) {
     const int nout = cand[i];
     if (npad % nout) continue;
-    const int wbytes = nkb * 9 * nout * 128 + (stream_bias_mma(nout) ? nout * 128 + kStreamOnesBytes : kStreamBiasBytes);
+    const int wbytes = nkb * nkx * 3 * nout * 128 + (stream_bias_mma(nout) ? nout * 128 + kStreamOnesBytes : kStreamBiasBytes);
     const int stage = kStreamEpiWarps * round_up(32 * nout * 2, 1024);
     const int left = kSmemBytes - 2048 - wbytes - stage;
     const int slots = std::min(kMaxSASlots, left / kASlotBytes);
     if (slots < 3) continue;
     sp->nout = nout; sp->chunks = npad / nout; sp->nkb = nkb; sp->npad_total = npad;
+    sp->stride2 = s2 ? 1 : 0; sp->nkx = nkx;
     sp->a_slots = slots; sp->acc_slots = std::min(kMaxAccSlots, kTmemCols / nout) & ~1;  // even: rows alternate between two epilogue warp groups
     for (int kb = 0; kb < nkb; ++kb) {
       const int b0 = kb / nsplit, part = kb % nsplit;
-      sp->nks[kb] = static_cast<uint8_t>((std::min(64, cs.cin - 64 * b0) + 15) / 16);
+      sp->nks[kb] = static_cast<uint8_t>(s2 ? 4 : (std::min(64, cs.cin - 64 * b0) + 15) / 16);
       sp->src_kb[kb] = static_cast<uint8_t>(b0);
       sp->src_tm[kb] = part == 2 ? 1 : 0;
       sp->whalf[kb] = part == 1 ? 1 : 0;
+      sp->ksm[kb][0] = sp->ksm[kb][1] = 0;
+      if (s2) {
+        // merged channel m = b0*64 + cc of the pair view: half = m / pitch (0 even pixel, 1 odd pixel), c = m % pitch.
+        // shift 0 (pair x-1): odd half with kx = 0; shift 1 (pair x): even half kx = 1, odd half kx = 2.
+        for (int ks = 0; ks < 4; ++ks) {
+          const int m = b0 * 64 + ks * 16;
+          const int half = m / cs.in_pitch, c = m % cs.in_pitch;
+          if (c >= cs.cin) continue;
+          if (half == 1) sp->ksm[kb][0] |= static_cast<uint8_t>(1u << ks);
+          sp->ksm[kb][1] |= static_cast<uint8_t>(1u << ks);
+        }
+      }
     }
     return true;
   }
@@ -335,21 +356,36 @@ std::string pack_weights_stream(const ConvSpec& cs, const HostTensor& W, const H
   out->alpha_out = (cs.act != kActRelu6) ? 1.f : cs.alpha;
   // weight tiles, then (bias-MMA variant) one bias tile per chunk: row = output channel, K column 0 = high half,
   // column 1 = low half of the bias (the "ones" operand has 1 there)
-  const size_t wrows = static_cast<size_t>(out->chunks) * nkb * 9 * nout;
+  const int nkx = out->nkx;
+  const size_t wrows = static_cast<size_t>(out->chunks) * nkb * nkx * 3 * nout;
   out->bias_row0 = static_cast<int>(wrows);
   out->w.assign((wrows + (stream_bias_mma(nout) ? npad : 0)) * 64, 0);
+  // vertical tap of N block `blk`: stride 1 stacks [ky2 | ky1 | ky0] (block = 2 - ky); stride 2 stacks [ky2 | ky0 | ky1]
+  static const int ky_s1[3] = {2, 1, 0}, ky_s2[3] = {2, 0, 1};
   for (int ch = 0; ch < out->chunks; ++ch)
     for (int kb = 0; kb < nkb; ++kb)
-      for (int kx = 0; kx < 3; ++kx)
+      for (int kx = 0; kx < nkx; ++kx)
         for (int blk = 0; blk < 3; ++blk)
           for (int co = 0; co < nout; ++co) {
             const int n = orow[ch * nout + co];
             if (n < 0) continue;
-            const size_t row = ((((static_cast<size_t>(ch) * nkb + kb) * 3 + kx) * 3 + blk) * nout + co);
+            const size_t row = ((((static_cast<size_t>(ch) * nkb + kb) * nkx + kx) * 3 + blk) * nout + co);
             for (int cc = 0; cc < 64; ++cc) {
-              const int c = out->src_kb[kb] * 64 + cc;
-              if (c >= cs.cin) break;
-              const float wv = (n < cs.neg_first ? -fold : fold) * W.data[((static_cast<size_t>(n) * cs.cin + c) * 3 + (2 - blk)) * 3 + kx];
+              int c, wkx;
+              if (out->stride2) {
+                const int m = out->src_kb[kb] * 64 + cc;
+                const int half = m / cs.in_pitch;
+                c = m % cs.in_pitch;
+                if (half > 1 || c >= cs.cin) continue;
+                if (kx == 0) { if (half == 0) continue; wkx = 0; }   // pair x-1: its odd pixel is input column 2x-1
+                else wkx = half == 0 ? 1 : 2;                        // pair x: columns 2x and 2x+1
+              } else {
+                c = out->src_kb[kb] * 64 + cc;
+                if (c >= cs.cin) break;
+                wkx = kx;
+              }
+              const int ky = out->stride2 ? ky_s2[blk] : ky_s1[blk];
+              const float wv = (n < cs.neg_first ? -fold : fold) * W.data[((static_cast<size_t>(n) * cs.cin + c) * 3 + ky) * 3 + wkx];
               const uint16_t hi = f2h(wv, bf16);
               out->w[row * 64 + cc] = out->whalf[kb] ? f2h(wv - h2f(hi, bf16), bf16) : hi;
             }
@@ -529,13 +565,16 @@ int materialize_stream(ss4k_ctx* ctx, const ConvSpec& cs, const HostTensor& W, c
   CK(ctx, cudaMemcpy(ex->d_slope, pk.slope.data(), pk.slope.size() * 4, cudaMemcpyHostToDevice));
   const CUtensorMapDataType dt = bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
   {  // activations: (64 channels, W, channel block, H, N) starting at channel in_coff
+    //              stride 2: the pixel-pair view (64 channels, W/2 pairs, block of the 2*pitch merged channels, H, N)
     const cuuint64_t eb = 2;
     const int avail = cs.in_pitch - cs.in_coff;
-    const int nkb0 = (cs.cin + 63) / 64;  // 64-channel blocks of the source tensor (split mode: 3 K blocks each)
-    cuuint64_t dims[5] = {static_cast<cuuint64_t>(nkb0 == 1 ? std::min(64, avail) : 64), static_cast<cuuint64_t>(cs.in_w),
+    const bool s2 = pk.stride2 != 0;
+    const int nkb0 = s2 ? 2 * cs.in_pitch / 64 : (cs.cin + 63) / 64;  // 64-channel blocks of the source (split mode: 3 K blocks each)
+    cuuint64_t dims[5] = {static_cast<cuuint64_t>(s2 ? 64 : (nkb0 == 1 ? std::min(64, avail) : 64)),
+                          static_cast<cuuint64_t>(s2 ? cs.in_w / 2 : cs.in_w),
                           static_cast<cuuint64_t>(nkb0), static_cast<cuuint64_t>(cs.in_h),
                           static_cast<cuuint64_t>(cs.in_ring ? cs.in_ring : cs.n)};
-    cuuint64_t strides[4] = {cs.in_pitch * eb, 128, static_cast<cuuint64_t>(cs.in_w) * cs.in_pitch * eb,
+    cuuint64_t strides[4] = {(s2 ? 2 : 1) * cs.in_pitch * eb, 128, static_cast<cuuint64_t>(cs.in_w) * cs.in_pitch * eb,
                              static_cast<cuuint64_t>(cs.in_h) * cs.in_w * cs.in_pitch * eb};
     cuuint32_t box[5] = {64, static_cast<cuuint32_t>(kBoxW), 1, 1, 1};
     cuuint32_t es[5] = {1, 1, 1, 1, 1};
@@ -608,10 +647,12 @@ int materialize_stream(ss4k_ctx* ctx, const ConvSpec& cs, const HostTensor& W, c
   }
   p.nkb = pk.nkb;
   for (int kb = 0; kb < pk.nkb; ++kb) { p.a_kb[kb] = pk.src_kb[kb]; p.a_tm[kb] = pk.src_tm[kb]; p.nks[kb] = pk.nks[kb]; }
-  p.n_img = cs.n; p.H = cs.in_h; p.W = cs.in_w;
-  p.strips = (cs.in_w + kTileW - 1) / kTileW;
+  p.stride2 = pk.stride2; p.nkx = pk.nkx;
+  for (int kb = 0; kb < pk.nkb; ++kb) { p.ksm[kb][0] = pk.ksm[kb][0]; p.ksm[kb][1] = pk.ksm[kb][1]; }
+  p.n_img = cs.n; p.H = pk.stride2 ? cs.in_h / 2 : cs.in_h; p.W = pk.stride2 ? cs.in_w / 2 : cs.in_w;  // the output grid
+  p.strips = (p.W + kTileW - 1) / kTileW;
   p.chunks = pk.chunks;
-  p.total_units = pk.chunks * cs.n * p.strips * cs.in_h;
+  p.total_units = pk.chunks * cs.n * p.strips * p.H;
   p.acc_slots = pk.acc_slots; p.a_slots = pk.a_slots;
   p.l2_in = cs.l2_in; p.l2_out = cs.l2_out;
   if (const char* e = getenv("SS4K_DBG_FLAGS")) {  // experiments only (see StreamParams::dbg_flags): RRDB trunk convs
@@ -1279,6 +1320,10 @@ int ss4k_debug_pack(const ss4k_conv_desc* d, int in_pitch, int in_coff, int wper
     std::string js = fmt("{\"kernel\":\"stream\",\"nout\":%d,\"chunks\":%d,\"nkb\":%d,\"npad\":%d,\"a_slots\":%d,\"acc_slots\":%d,\"w_rows\":%d,\"nks\":[",
                          sp.nout, sp.chunks, sp.nkb, sp.npad_total, sp.a_slots, sp.acc_slots, sp.bias_row0);
     for (int i = 0; i < sp.nkb; ++i) js += fmt("%s%d", i ? "," : "", sp.nks[i]);
+    js += fmt("],\"stride2\":%d,\"nkx\":%d,\"ksm\":[", sp.stride2, sp.nkx);
+    for (int i = 0; i < sp.nkb; ++i) js += fmt("%s[%d,%d]", i ? "," : "", sp.ksm[i][0], sp.ksm[i][1]);
+    js += "],\"src_kb\":[";
+    for (int i = 0; i < sp.nkb; ++i) js += fmt("%s%d", i ? "," : "", sp.src_kb[i]);
     js += "],\"bias\":[";
     for (size_t i = 0; i < sp.bias.size(); ++i) js += fmt("%s%.9g", i ? "," : "", sp.bias[i]);
     js += "],\"bias_f\":[";

@@ -183,12 +183,13 @@ def run_program(prog, sd, x, quant=None):
 
 
 # ------------------------------------------------------------------------------------------------
-def debug_pack_stream(lib, L, w, bias=None, slope=None, in_pitch=None, in_coff=0, wperm=0, act_mode=0, act=0, alpha=1.0):
+def debug_pack_stream(lib, L, w, bias=None, slope=None, in_pitch=None, in_coff=0, wperm=0, act_mode=0, act=0, alpha=1.0,
+                      mode=0):
     """Weight layout + configuration of the row-streaming kernel (csrc/conv_stream.cu)."""
     cout, cin = w.shape[:2]
     d = L.ConvDesc()
     d.struct_size = ctypes.sizeof(L.ConvDesc)
-    d.n, d.h, d.w, d.cin, d.cout, d.mode, d.act_mode = 1, 8, 8, cin, cout, 0, act_mode
+    d.n, d.h, d.w, d.cin, d.cout, d.mode, d.act_mode = 1, 8, 8, cin, cout, mode, act_mode
     d.act, d.alpha = act, alpha
     d.reserved[6] = 1
     if in_pitch is None:
@@ -202,7 +203,7 @@ def debug_pack_stream(lib, L, w, bias=None, slope=None, in_pitch=None, in_coff=0
     meta = json.loads(ctypes.string_at(js).decode())
     arr = (ctypes.c_float * cnt.value).from_address(pk.value)
     flat = torch.tensor(list(arr), dtype=torch.float32).reshape(-1, 64)
-    packed = flat[:meta["w_rows"]].reshape(meta["chunks"], meta["nkb"], 3, 3, meta["nout"], 64)
+    packed = flat[:meta["w_rows"]].reshape(meta["chunks"], meta["nkb"], meta["nkx"], 3, meta["nout"], 64)
     # (the 64-wide variant appends one bias tile per chunk: bias hi / lo halves in K columns 0 / 1, for its bias MMA)
     meta["bias_tiles"] = flat[meta["w_rows"]:]
     # meta["bias_f"]: fp32 bias with alpha folded in, [chunks * nout] -- the accumulators' initial value
@@ -272,6 +273,84 @@ def emulate_stream_conv(meta, packed, x_nhwc, grid, in_coff=0, acc_slots=None):
                 if r == r1 and r <= ye - 1:
                     done.append(r)
                 for yy in done:           # commit -> epilogue drains (in order) -> slot free
+                    s = (qs + yy - yb) % S
+                    assert state[s] == "busy"
+                    x0 = strip * 128
+                    wv = min(128, W - x0)
+                    out[n, yy, x0:x0 + wv, chunk * nout:(chunk + 1) * nout] = tmem[s, :wv]
+                    state[s] = "empty"
+            qs = (qs + ye - yb) % S
+        assert all(st == "empty" for st in state)
+    assert not torch.isnan(out).any()
+    return out
+
+
+def emulate_stream_conv_s2(meta, packed, x_nhwc, grid, acc_slots=None):
+    """Mirror of conv3x3_stream_kernel's STRIDE-2 schedule (StreamParams::stride2): the input is read through its
+    pixel-pair view (2*pitch channels per pair), two horizontal shifts with k-step masks, N blocks [ky2 | ky0 | ky1]:
+    an odd input row feeds output rows (r-1)/2 and (r+1)/2 with one 'MMA', an even row feeds row r/2.
+    Returns the accumulators [N, H/2, W/2, npad]."""
+    n_img, Hin, Win, pitch = x_nhwc.shape
+    H, W = Hin // 2, Win // 2
+    nout, chunks, nkb, S = meta["nout"], meta["chunks"], meta["nkb"], acc_slots or meta["acc_slots"]
+    assert meta["stride2"] == 1 and meta["nkx"] == 2
+    strips = (W + 127) // 128
+    total = chunks * n_img * strips * H
+    out = torch.full((n_img, H, W, chunks * nout), float("nan"), dtype=torch.float64)
+    nblk_src = 2 * pitch // 64
+    pairs = x_nhwc.double().reshape(n_img, Hin, W, 2 * pitch)
+    xpad = torch.zeros(n_img, Hin, strips * 128 + 2, nblk_src * 64, dtype=torch.float64)
+    xpad[:, :, 1:W + 1] = pairs                      # pair -1 / >= W read zeros (TMA OOB fill)
+    bias_f = torch.tensor(meta["bias_f"], dtype=torch.float64)
+    g = min(grid, total)
+    for cta in range(g):
+        u, u1 = cta * total // g, (cta + 1) * total // g
+        tmem = torch.zeros(S, 128, nout, dtype=torch.float64)
+        state = ["empty"] * S
+        qs = 0
+        while u < u1:
+            t = u
+            y = t % H; t //= H
+            strip = t % strips; t //= strips
+            n = t % n_img; chunk = t // n_img
+            yb, ye = y, min(H, y + (u1 - u))
+            u += ye - yb
+            r0, r1 = (2 * yb - 1 if yb > 0 else 0), 2 * ye - 1
+            for r in range(r0, r1 + 1):
+                if r & 1:
+                    ya = (r - 1) // 2
+                    y_lo, y_hi = max(ya, yb), min(ya + 1, ye - 1)
+                    b_lo, f_lo, done = y_lo - ya, ya + 1, ([ya] if ya >= yb else [])
+                else:
+                    y_lo = y_hi = r // 2
+                    b_lo, f_lo, done = 2, y_hi + 1, []
+                if r == r0:
+                    f_lo = y_lo
+                for yy in range(f_lo, y_hi + 1):
+                    s = (qs + yy - yb) % S
+                    assert state[s] == "empty", ("accumulator slot not drained", cta, r, yy, s, state)
+                    state[s] = "busy"
+                    tmem[s] = bias_f[chunk * nout:(chunk + 1) * nout].expand(128, nout).clone()
+                s0 = (qs + (y_lo - yb)) % S
+                nblk = y_hi - y_lo + 1
+                nA = nblk if s0 + nblk <= S else S - s0
+                ops = [(s0, b_lo, nA)] + ([(0, b_lo + nA, nblk - nA)] if nblk > nA else [])
+                for kb in range(nkb):
+                    c0 = meta["src_kb"][kb] * 64
+                    slab = xpad[n, r, strip * 128:strip * 128 + 130, c0:c0 + 64]
+                    for sh in range(2):
+                        a_full = slab[sh:sh + 128]
+                        for ks in range(4):
+                            if not (meta["ksm"][kb][sh] >> ks) & 1:
+                                continue
+                            a = a_full[:, ks * 16:(ks + 1) * 16]
+                            for (sa, b0, nb_) in ops:
+                                wt = packed[chunk, kb, sh, b0:b0 + nb_, :, ks * 16:(ks + 1) * 16].double()
+                                d = torch.einsum("mk,bnk->bmn", a, wt)
+                                for i in range(nb_):
+                                    assert state[sa + i] == "busy"
+                                    tmem[sa + i] += d[i]
+                for yy in done:
                     s = (qs + yy - yb) % S
                     assert state[s] == "busy"
                     x0 = strip * 128

@@ -39,18 +39,44 @@ def _frames(n, seed=1234):
     return (x + 0.05 * torch.randn(n, 3, H, W, generator=g)).clamp(0, 1)
 
 
-def test_rrdbnet_x2_720p_full_frame_vs_oracle(model, net):
+@pytest.fixture(scope="module")
+def full_frame(net):
     x = _frames(1)
     torch.set_num_threads(os.cpu_count() or 1)
     with torch.no_grad():
         want = net(x).clamp(0, 1)
-    got = model(x.cuda()).float().cpu().clamp(0, 1)
-    assert tuple(got.shape) == (1, 3, 2 * H, 2 * W)
+    return x, want
+
+
+def _gate(got, want):
     mse = torch.mean((got - want) ** 2).item()
     psnr = 99.0 if mse == 0 else -10 * math.log10(mse)
-    maxabs = (got - want).abs().max().item() * 255
-    print(f"RRDBNet-23 x2 1280x720 full frame: PSNR {psnr:.1f} dB, max|err| {maxabs:.3f}/255")
+    return psnr, (got - want).abs().max().item() * 255
+
+
+def test_rrdbnet_x2_720p_full_frame_vs_oracle(model, full_frame):
+    x, want = full_frame
+    got = model(x.cuda()).float().cpu().clamp(0, 1)
+    assert tuple(got.shape) == (1, 3, 2 * H, 2 * W)
+    psnr, maxabs = _gate(got, want)
+    print(f"RRDBNet-23 x2 1280x720 full frame (fp16 operands): PSNR {psnr:.1f} dB, max|err| {maxabs:.3f}/255")
     assert psnr >= 50 and maxabs <= 2.0
+
+
+def test_rrdbnet_x2_720p_bf16_report(engine, net, full_frame):
+    """BASELINE.json configs[1] says "bf16": run it at net level on the whole frame and REPORT it.  SURVEY.md H2 predicts
+    that bf16 operands miss the max-abs gate on RRDBNet (8 mantissa bits through 351 convs) -- which is why fp16 is the
+    engine's default; the test is an expected failure whose message carries the measured numbers."""
+    x, want = full_frame
+    m16 = realesrgan.NativeRRDBNet(net.state_dict(), scale=2, num_block=23, device=0, act_mode=L.ACT_BF16)
+    got = m16(x.cuda()).float().cpu().clamp(0, 1)
+    m16.close()
+    psnr, maxabs = _gate(got, want)
+    msg = f"RRDBNet-23 x2 1280x720 full frame (bf16 operands): PSNR {psnr:.1f} dB, max|err| {maxabs:.3f}/255"
+    print(msg)
+    assert psnr >= 40, msg          # a broken bf16 path is a failure, a precision miss is the expected outcome
+    if not (psnr >= 50 and maxabs <= 2.0):
+        pytest.xfail(msg + " -- bf16 misses the north-star gate as predicted (SURVEY.md H2); fp16 is the default")
 
 
 def test_batch_invariance_and_determinism(model):
@@ -66,8 +92,11 @@ def test_batch_invariance_and_determinism(model):
 
 @pytest.mark.parametrize("dy,dx", [(2, 0), (0, 2), (6, 130), (14, 4)])
 def test_translation_equivariance_of_the_interior(model, dy, dx):
-    """out(shift(x))[interior] == shift(out(x))[interior]; the margin covers the shifted-in border region's reach.
-    fp16 accumulation order is position independent (same K order per pixel), so the match is exact."""
+    """out(shift(x))[interior] ~= shift(out(x))[interior].  The arithmetic of a pixel does not depend on its position
+    (same K order per pixel whatever strip / band / accumulator slot it lands in), so the only difference between the two
+    runs is the zero padding that moved with the shift: the receptive field (about 350 trunk pixels) is larger than the
+    256-pixel margin, but border influence decays fast through the 0.2-scaled residual blocks.  Asserted: the interior
+    agrees within the north-star tolerance (2/255); a strip- or band-boundary bug shows up as an O(1) difference."""
     x = _frames(1, seed=3).cuda()
     plan = model._plan(1, H, W, L.FMT_F32_NCHW, L.FMT_F16_NCHW)
     ref = plan.run(x).clone()

@@ -122,7 +122,7 @@ def test_tile_config_budget(lib, desc_mode):
 
 
 # ---------------------------------------------------------------- row-streaming kernel (conv_stream.cu)
-from tests.emulate import debug_pack_stream, emulate_stream_conv  # noqa: E402
+from tests.emulate import debug_pack_stream, emulate_stream_conv, emulate_stream_conv_s2  # noqa: E402
 
 
 @pytest.mark.parametrize("cin,cout,h,w,n,grid,slots", [
@@ -171,3 +171,30 @@ def test_stream_alpha_fold_and_bias(lib):
     assert bf.shape == (32,) and abs(bf.double() - 0.25 * 0.1234567).max().item() < 2e-8
     meta6, packed6 = debug_pack_stream(lib, L, wt, bias=bias, alpha=0.25, act=2)
     assert torch.equal(packed6[0, 0, 1, 1, :, :], wt[:, :, 1, 1])
+
+
+@pytest.mark.parametrize("cin,cout,h,w,n,grid,slots", [
+    (32, 64, 16, 40, 1, 148, None),     # BSVD downc0: one K block = [even pixel 32 ch | odd pixel 32 ch]
+    (64, 128, 12, 300, 2, 7, None),     # BSVD downc1: two K blocks, two 64-wide chunks, two strips
+    (32, 64, 44, 24, 1, 3, 4),          # long bands, small ring -> wraps inside the two-row windows
+    (64, 64, 8, 520, 1, 5, 3),          # minimal ring, three strips
+])
+def test_stream_schedule_stride2(lib, cin, cout, h, w, n, grid, slots):
+    """Stride-2 convs on the row-streaming kernel (pixel-pair view, [ky2 | ky0 | ky1] weight blocks)."""
+    wt = _exact_weights(cout, cin, 31)
+    x = torch.randint(-8, 9, (n, cin, h, w), generator=torch.Generator().manual_seed(32)).float() / 8
+    bias = torch.randint(-64, 65, (cout,), generator=torch.Generator().manual_seed(33)).float() / 32
+    meta, packed = debug_pack_stream(lib, L, wt, bias=bias, mode=2, in_pitch=cin)
+    assert meta["stride2"] == 1 and meta["nkb"] == 2 * cin // 64
+    got = emulate_stream_conv_s2(meta, packed, _nhwc(x, cin), grid, acc_slots=slots)
+    want = F.conv2d(x.double(), wt.double(), bias.double(), stride=2, padding=1).permute(0, 2, 3, 1)
+    assert torch.equal(got[..., :cout], want)
+
+
+def test_stream_stride2_split_blocks(lib):
+    """fp16 hi/lo split operands on the stride-2 path: three K blocks per merged 64-channel block."""
+    wt = _exact_weights(64, 32, 41)
+    meta, packed = debug_pack_stream(lib, L, wt, mode=2, in_pitch=32, act_mode=L.ACT_F16_SPLIT)
+    assert meta["nkb"] == 3 and meta["src_kb"] == [0, 0, 0] and meta["ksm"] == [[12, 15]] * 3
+    assert torch.equal(packed[0, 0], packed[0, 2])          # A_hi*W_hi and A_lo*W_hi share the weight tile
+    assert torch.count_nonzero(packed[0, 1]) == 0             # exactly representable weights: the low halves are zero

@@ -10,9 +10,19 @@ pytestmark = pytest.mark.gpu
 
 
 def _cmp(got, want, max_lsb=3, mean_lsb=0.6):
-    assert got.dtype == torch.uint8 and got.shape == want.shape, (got.shape, want.shape)
-    d = (got.cpu().int() - want.int()).abs()
-    print(f"uint8 diff: mean {d.float().mean().item():.3f}, max {d.max().item()}, >1 LSB {100.0 * (d > 1).float().mean().item():.3f}%")
+    """``want`` = (uint8 frame, float frame x 255 in front of the truncating cast) from the oracle glue.
+    The north-star gate is on the FLOAT frame: |engine - oracle| <= 2/255.  The engine truncates like the reference
+    (fsrcnn_upscaler.py:233), so its uint8 value g = floor(q_engine) lies in (q_oracle - 3, q_oracle + 2]: that interval is
+    what is asserted.  On the uint8 frames it allows 3 LSB (|floor(a) - floor(b)| <= floor(|a - b|) + 1), the third LSB
+    being the truncation flip of a value next to an integer boundary, never a larger float error."""
+    want_u8, want_q = want
+    assert got.dtype == torch.uint8 and got.shape == want_u8.shape, (got.shape, want_u8.shape)
+    g = got.cpu()
+    d = (g.int() - want_u8.int()).abs()
+    e = g.float() - want_q
+    print(f"uint8 diff: mean {d.float().mean().item():.3f}, max {d.max().item()}, >1 LSB {100.0 * (d > 1).float().mean().item():.3f}%; "
+          f"uint8 - oracle float: [{e.min().item():.3f}, {e.max().item():.3f}]")
+    assert e.max().item() <= 2.0 and e.min().item() > -3.0
     assert d.max().item() <= max_lsb and d.float().mean().item() <= mean_lsb
 
 
@@ -28,7 +38,7 @@ def test_upscale_multi_rrdb_x2(engine):
     torch.manual_seed(0)
     net = rrdbnet.RRDBNet(3, 3, 2, 64, 2, 32).eval()
     frames = _frames(2, 96, 160, 1)
-    want = glue.upscale_multi(frames, net, lr_shape=(720, 1280), output_shape=(192, 320))
+    want = glue.upscale_multi(frames, net, lr_shape=(720, 1280), output_shape=(192, 320), return_float=True)
     svc = service.FsrcnnUpscalerService(lr_level=3, device=0, denoising=False, model_name='RealESRGAN_x2plus',
                                         state_dict=net.state_dict(), batch_size=2)
     svc.proc_init()
@@ -44,7 +54,7 @@ def test_upscale_multi_srvgg_x4_bicubic_down(engine):
     torch.manual_seed(0)
     net = srvgg.SRVGGNetCompact(3, 3, 64, 16, 4).eval()
     frames = _frames(1, 2 * 360, 2 * 640, 2)
-    want = glue.upscale_multi(frames, net, lr_shape=(360, 640), output_shape=(720, 1280))
+    want = glue.upscale_multi(frames, net, lr_shape=(360, 640), output_shape=(720, 1280), return_float=True)
     svc = service.FsrcnnUpscalerService(lr_level=0, device=0, denoising=False, model_name='realesr-animevideov3',
                                         state_dict=net.state_dict())
     svc.proc_init()
@@ -60,7 +70,7 @@ def test_upscale_multi_resize_factors(engine, out_shape):
     torch.manual_seed(0)
     net = srvgg.SRVGGNetCompact(3, 3, 64, 16, 4).eval()
     frames = _frames(2, 90, 160, 5)
-    want = glue.upscale_multi(frames, net, lr_shape=(720, 1280), output_shape=out_shape)
+    want = glue.upscale_multi(frames, net, lr_shape=(720, 1280), output_shape=out_shape, return_float=True)
     svc = service.FsrcnnUpscalerService(lr_level=3, device=0, denoising=False, model_name='realesr-animevideov3',
                                         state_dict=net.state_dict(), batch_size=2)
     svc.proc_init()
@@ -78,8 +88,8 @@ def test_upscale_single_denoise_then_rrdb(engine):
     sd = bsvd.build_bsvd32(0, weight_scale=0.5)
     frames = _frames(2, 360, 640, 3)
     den = lambda x: bsvd.bsvd_forward(sd, x)  # noqa: E731
-    want0 = glue.upscale_single(frames[0], net, (360, 640), (720, 1280), den, 0.75, True)
-    want1 = glue.upscale_single(frames[1], net, (360, 640), (720, 1280), den, 0.75, False)
+    want0 = glue.upscale_single(frames[0], net, (360, 640), (720, 1280), den, 0.75, True, return_float=True)
+    want1 = glue.upscale_single(frames[1], net, (360, 640), (720, 1280), den, 0.75, False, return_float=True)
     svc = service.FsrcnnUpscalerService(lr_level=0, device=0, denoising=True, denoise_rate=0.75,
                                         model_name='RealESRGAN_x2plus', state_dict=net.state_dict(),
                                         denoise_state_dict=sd, single_mode=True)
@@ -118,7 +128,7 @@ def test_image_server_shapes_lru(engine):
         got = svc.upscale(frames.cuda())
         torch.cuda.synchronize()
         assert got.shape == (1, 4 * h, 4 * w, 3)
-        want = glue.upscale_multi(frames, net, lr_shape=(720, 1280), output_shape=None, lr_hr_resize=False)
+        want = glue.upscale_multi(frames, net, lr_shape=(720, 1280), output_shape=None, lr_hr_resize=False, return_float=True)
         _cmp(got, want)
         outs.append(got.cpu())
     assert svc.model._plans.evictions >= 2 and len(svc.model._plans) == 2
