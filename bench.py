@@ -4,8 +4,9 @@
 Default workload = BASELINE.json configs[2] (the configuration the metric "frames/s 720p->1440p denoise+SR" is quoted
 on; it fits one GPU):
   synthetic NV12 1280x720 stream -> BSVD-32 temporal denoiser over a chunk of `--clip` frames (reference constructor
-  init -> fp16 hi/lo split precision, the parity configuration) -> RRDBNet-23 x2 on every owned frame -> uint8 RGB
-  2560x1440.  A step = one chunk of `--clip` owned frames per GPU.
+  init -> fp16 hi/lo split precision, the parity configuration) -> sharpen / clamp / 0.8-0.2 blend with the decoded
+  frame (fsrcnn_upscaler.py:278-281) -> RRDBNet-23 x2 on every owned frame -> uint8 RGB 2560x1440.
+  A step = one chunk of `--clip` owned frames per GPU.
   N > 1 (torchrun): the global clip of N*clip frames is sharded into contiguous chunks with the denoiser's 16-frame
   temporal halo (sharding.bsvd_chunks): halo frames are decoded and denoised redundantly, only owned frames are
   upscaled; the finished uint8 frames are gathered to rank 0 (the encoder rank) over NCCL inside every step.
@@ -127,8 +128,7 @@ def synth_nv12(t0, t1, device, variant=0):
 def cpu_frame_cfg3(net, bsd, crop_h=FRAME_H):
     """One frame of cfg3 on the host cores in fp32: NV12 decode -> BSVD (one-frame clip) -> RRDBNet x2.  Returns seconds.
     crop_h < 720 times a band of the frame (bounded sample), full width."""
-    import numpy as np
-    from oracle import bsvd, colour
+    from oracle import bsvd, colour, glue
     torch.set_num_threads(os.cpu_count() or 1)
     nv = synth_nv12(0, 1, torch.device("cpu")).numpy()
     t0 = time.perf_counter()
@@ -136,7 +136,8 @@ def cpu_frame_cfg3(net, bsd, crop_h=FRAME_H):
         rgb = torch.from_numpy(colour.nv12_to_rgb(nv, FRAME_H, FRAME_W))[:, :, :crop_h]
         x = torch.cat([rgb, torch.full((1, 1, crop_h, FRAME_W), NOISE)], dim=1)[None]
         den = bsvd.bsvd_forward(bsd, x)[0]
-        hr = net(den)
+        den = torch.clamp(glue.depthwise_reflect(den.reshape(3, 1, crop_h, FRAME_W), glue.sharpen_weight(0.00002)).reshape(1, 3, crop_h, FRAME_W), 0, 1)
+        hr = net(den * 0.8 + 0.2 * rgb)                 # fsrcnn_upscaler.py:278-281
         (hr.clamp(0, 1) * 255).to(torch.uint8)
     return time.perf_counter() - t0
 
@@ -386,8 +387,9 @@ def run_native_cfg3(args, rank, world, local_rank):
     den_plan = pipe.den_plan(T)
     den_out = den_plan.new_output()
     prof_den = den_plan.profile(chunks_dev[0], den_out)
-    prof_sr = pipe.sr_plan.profile(den_out[0:1].contiguous(), out_dev[0:1])
-    prof_sr = pipe.sr_plan.profile(den_out[0:1].contiguous(), out_dev[0:1])
+    lr0 = pipe._lr[F][0:1]
+    prof_sr = pipe.sr_plan.profile(lr0, out_dev[0:1])
+    prof_sr = pipe.sr_plan.profile(lr0, out_dev[0:1])
     torch.cuda.synchronize()
     den_ms = sum(m for m, _, _ in prof_den)
     sr_ms = sum(m for m, _, _ in prof_sr)

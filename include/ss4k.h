@@ -124,6 +124,11 @@ double ss4k_plan_flops(const ss4k_plan* plan);
 int ss4k_plan_launches(const ss4k_plan* plan);
 /* how many of those steps replay from the plan's CUDA graph (0: graph capture unavailable / disabled) */
 int ss4k_plan_graph_steps(const ss4k_plan* plan);
+/* steps of the layer program (== entries ss4k_plan_profile returns; a fused residual dense block -- basicsr
+ * ResidualDenseBlock, reached from realesrgan/factory.py:113-125 -- is five steps but one launch) */
+int ss4k_plan_steps(const ss4k_plan* plan);
+/* residual dense blocks that run as one fused launch each (0: the trunk runs conv by conv) */
+int ss4k_plan_fused_blocks(const ss4k_plan* plan);
 /* JSON description of the layer program (buffers, convs, epilogues); malloc'd, free with ss4k_free.
  * Works without a GPU when the plan was built with ss4k_plan_dry (host-side planner only). */
 int ss4k_plan_dry(const ss4k_plan_cfg* cfg, char** out_json);

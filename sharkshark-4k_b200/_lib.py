@@ -43,6 +43,8 @@ SYMBOLS = {
     "ss4k_plan_flops": (ctypes.c_double, [_vp]),
     "ss4k_plan_launches": (_i, [_vp]),
     "ss4k_plan_graph_steps": (_i, [_vp]),
+    "ss4k_plan_steps": (_i, [_vp]),
+    "ss4k_plan_fused_blocks": (_i, [_vp]),
     "ss4k_plan_dry": (_i, [ctypes.POINTER(PlanCfg), ctypes.POINTER(_vp)]),
     "ss4k_free": (None, [_vp]),
     "ss4k_run": (_i, [_vp, _vp, _vp, _vp]),

@@ -185,4 +185,52 @@ struct StreamParams {
   uint8_t ksm[kMaxSKB][2];    // stride 2: 4-bit mask of the 16-channel k-steps to issue per (K block, shift)
 };
 
+
+// ------------------------------------------------------------------------------------------------
+// Fused residual dense block (rdb_fused.cu): the five convs of one basicsr ResidualDenseBlock
+// (conv1..4: 64+32k -> 32 + LeakyReLU(0.2) into the slab's growth channels; conv5: 192 -> 64, x5*0.2 + x [+ RRDB residual])
+// as ONE persistent launch.  A CTA keeps its band of output rows through the phases; what one phase reads from the
+// previous one is guarded by per-CTA progress counters in global memory instead of a kernel boundary.
+constexpr int kRdbPhases = 5;
+constexpr int kRdbNout = 32;
+constexpr int kRdbMaxWTiles = 9;     // K blocks x horizontal taps of the widest phase (192 input channels)
+constexpr int kRdbCtrPerCta = 8;     // one progress counter per epilogue warp
+
+struct RdbPhase {
+  int32_t nkb;          // 64-channel K blocks read by this conv
+  int32_t nks_last;     // 16-channel k-steps of the last K block (the others issue 4)
+  int32_t chunks;       // 32-wide output chunks (conv5: 2)
+  int32_t w_row0;       // first row of the phase's weight tiles in the packed weight tensor
+  int32_t bias0;        // offset of the phase's bias in bias_f
+  int32_t out_c0;       // first output channel in the destination tensor (TMA store coordinate)
+  int32_t out_map;      // 0: this block's slab, 1: the next block's slab
+  int32_t total_units;  // chunks * n_img * strips * H output rows of 128 pixels
+  int32_t l2_in, l2_out;
+};
+
+struct RdbParams {
+  CUtensorMap tmA;      // this block's slab, 5-D (64, W, channel block, H, N), box (64, 130, 1, 1, 1), swizzle 128B
+  CUtensorMap tmW;      // packed weights of the five convs, 2-D (64, rows), box (64, 96)
+  CUtensorMap tmO[2];   // 4-D (C, W, H, N), box (32, 32, 1, 1), swizzle 64B: this slab / the next slab
+  RdbPhase ph[kRdbPhases];
+  const float* bias_f;  // fp32 bias of every phase / chunk, alpha folded in (the accumulators' initial value)
+  float slope;          // LeakyReLU slope of conv1..4
+  float beta1, beta2;   // conv5: out = acc + beta1 * res1 + beta2 * res2
+  const void* res1;     // this slab's x (NHWC 16-bit, pitch res1_pitch)
+  const void* res2;     // the RRDB input (third block of an RRDB), or null
+  int32_t res1_pitch, res1_coff, res2_pitch, res2_coff;
+  int32_t n_img, H, W, strips;
+  int32_t acc_slots, a_slots;
+  uint32_t idesc[3];
+  uint32_t* ctr_use;    // progress counters of this launch: [grid][kRdbCtrPerCta] rows completed per epilogue warp
+  uint32_t* ctr_zero;   // the buffer the NEXT fused launch uses: cleared by this one
+  void* discard_ptr;    // dead-tensor discard (see StreamParams)
+  uint32_t discard_pitch_bytes, discard_mask;
+  int64_t discard_npx;
+  const void* next_w;   // packed weights of the next launch (L2 prefetch), or null
+  uint32_t next_w_bytes;
+  int32_t* err;
+  int32_t dbg_flags;    // 1: ignore the progress counters (WRONG results; measures what the dependency waits cost)
+};
+
 }  // namespace ss4k

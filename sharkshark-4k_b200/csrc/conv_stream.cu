@@ -970,6 +970,22 @@ cudaError_t conv_stream_prepare() {
 }
 
 template <int NOUT>
+static int occupancy_one() {
+  int n = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, conv3x3_stream_kernel<NOUT>, kStreamThreads, kSmemBytes) != cudaSuccess) return 0;
+  return n;
+}
+int conv_stream_max_ctas_per_sm(int nout) {
+  switch (nout) {
+    case 16: return occupancy_one<16>();
+    case 32: return occupancy_one<32>();
+    case 48: return occupancy_one<48>();
+    case 64: return occupancy_one<64>();
+    default: return 0;
+  }
+}
+
+template <int NOUT>
 static cudaError_t launch_one(const StreamParams& p, int grid, cudaStream_t stream, bool pdl) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);

@@ -12,6 +12,12 @@ cudaError_t conv_tc_launch(const ConvParams& p, int grid, cudaStream_t stream);
 // conv_stream.cu
 cudaError_t conv_stream_prepare();
 cudaError_t conv_stream_launch(const StreamParams& p, int nout, int grid, cudaStream_t stream, bool pdl);
+int conv_stream_max_ctas_per_sm(int nout);  // resident CTAs per SM of the variant (early activation loads need exactly 1)
+
+// rdb_fused.cu: the five convs of a residual dense block as one persistent launch
+cudaError_t rdb_fused_prepare();
+int rdb_fused_max_ctas_per_sm();
+cudaError_t rdb_fused_launch(const RdbParams& p, int grid, cudaStream_t stream, bool pdl);
 
 // elementwise.cu
 // in_fmt: SS4K_FMT_* ; out: [N, H/us, W/us, pitch] 16-bit NHWC (out_lo: low halves for split mode or null)

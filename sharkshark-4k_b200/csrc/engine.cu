@@ -106,6 +106,10 @@ int round_up(int a, int b) { return (a + b - 1) / b * b; }
 struct ConvExec {
   ConvParams p;
   StreamParams sp;      // row-streaming kernel (conv_stream.cu) when `stream` is set
+  RdbParams rp;         // fused residual dense block (rdb_fused.cu) when `fused` is set: this step launches conv1..5
+  bool fused = false;
+  bool skip = false;    // conv2..5 of a fused block: no launch of their own
+  double fused_flops = 0;
   bool stream = false;
   int nout = 0;         // accumulator slot width of the streaming kernel
   int grid = 0;
@@ -680,6 +684,8 @@ int materialize_stream(ss4k_ctx* ctx, const ConvSpec& cs, const HostTensor& W, c
 const bool g_use_pdl = getenv("SS4K_NO_PDL") == nullptr;
 
 cudaError_t launch_exec(const ConvExec& c, void* ext_out, cudaStream_t st) {
+  if (c.skip) return cudaSuccess;
+  if (c.fused) return rdb_fused_launch(c.rp, c.grid, st, g_use_pdl);
   if (c.stream) {
     if (c.ext_out) {
       StreamParams p = c.sp;
@@ -781,6 +787,8 @@ struct ss4k_plan {
   std::vector<int> step_conv;   // step index -> conv index (or -1)
   cudaGraphExec_t graph = nullptr;
   int graph_first = -1, graph_last = -1;  // [first, last] step range inside the graph
+  uint32_t* d_ctr = nullptr;  // progress counters of the fused residual dense blocks (3 rotating buffers)
+  int n_fused = 0;
   void* stage_in = nullptr;   // device staging for ss4k_run_host
   void* stage_out = nullptr;
   // software pipeline of ss4k_run_host_async: two staging slots, copy streams, hand-over events
@@ -819,9 +827,144 @@ int run_step(ss4k_plan* pl, int si, const void* in_dev, void* out_dev, cudaStrea
     ctx->launches++;
   } else {
     ConvExec& c = pl->convs[pl->step_conv[si]];
+    if (c.skip) return SS4K_OK;
     CK(ctx, launch_exec(c, out_dev, st));
     ctx->launches++;
   }
+  return SS4K_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fused residual dense blocks: every run of five trunk convs body.B.rdbR.conv1..conv5 becomes one launch of
+// rdb_fused_kernel (rdb_fused.cu).  Built from the five materialised streaming convs: their packed weights and biases
+// are concatenated, their tensor maps / epilogue constants re-used.
+int fuse_rdbs(ss4k_plan* pl) {
+  ss4k_ctx* ctx = pl->ctx;
+  if (getenv("SS4K_NO_RDB_FUSE") != nullptr || pl->cfg.act_mode != SS4K_ACT_F16) return SS4K_OK;
+  if (rdb_fused_max_ctas_per_sm() != 1) return SS4K_OK;   // the progress-counter waits need one co-resident CTA per SM
+  Program& P = pl->prog;
+  const int ns = static_cast<int>(P.steps.size());
+  std::vector<int> groups;
+  auto ends_with = [](const std::string& a, const std::string& b) { return a.size() >= b.size() && a.compare(a.size() - b.size(), b.size(), b) == 0; };
+  for (int si = 0; si + 4 < ns; ++si) {
+    if (P.steps[si].kind != 1) continue;
+    const std::string& nm = P.steps[si].conv.name;
+    if (nm.rfind("body.", 0) != 0 || !ends_with(nm, ".conv1")) continue;
+    const std::string pre = nm.substr(0, nm.size() - 1);
+    bool ok = true;
+    for (int k = 0; k < 5 && ok; ++k) {
+      const Step& st = P.steps[si + k];
+      if (st.kind != 1 || st.conv.name != pre + std::to_string(k + 1)) { ok = false; break; }
+      const ConvExec& c = pl->convs[pl->step_conv[si + k]];
+      const ConvSpec& cs = st.conv;
+      ok = c.stream && !c.fused && !c.skip && c.nout == kRdbNout && !cs.split && c.grid == ctx->nsm && c.sp.fast_store == 1 &&
+           c.sp.chunks == (k == 4 ? 2 : 1) && cs.in_buf == P.steps[si].conv.in_buf && cs.in_coff == 0 &&
+           cs.cin == 64 + 32 * k && cs.in_pitch == 192 && cs.out_pitch == 192 && !c.sp.stride2 &&
+           (k == 4 ? (cs.out_coff == 0 && cs.res1_buf == cs.in_buf) : (cs.out_buf == cs.in_buf && cs.out_coff == 64 + 32 * k));
+    }
+    if (!ok) continue;
+    const StreamParams& s0 = pl->convs[pl->step_conv[si]].sp;
+    const int64_t total0 = static_cast<int64_t>(s0.n_img) * s0.strips * s0.H;
+    if (total0 < 2 * ctx->nsm || (2 * total0 + 1) * ctx->nsm >= (1ll << 31)) continue;
+    groups.push_back(si);
+    si += 4;
+  }
+  const int ng = static_cast<int>(groups.size());
+  if (ng < 2) return SS4K_OK;
+  const size_t ctr_elems = static_cast<size_t>(ctx->nsm) * kRdbCtrPerCta;
+  CK(ctx, cudaMalloc(&pl->d_ctr, 3 * ctr_elems * sizeof(uint32_t)));
+  CK(ctx, cudaMemset(pl->d_ctr, 0, 3 * ctr_elems * sizeof(uint32_t)));
+  // counter buffer of launch g: g % 3, except that the last launch must also differ from the first (graph replay wraps)
+  auto buf_of = [&](int g) { return (g == ng - 1 && ng % 3 == 1) ? 1 : g % 3; };
+  const CUtensorMapDataType dt = CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  for (int gi = 0; gi < ng; ++gi) {
+    const int si = groups[gi];
+    ConvExec* c[5];
+    for (int k = 0; k < 5; ++k) c[k] = &pl->convs[pl->step_conv[si + k]];
+    const ConvSpec& cs1 = P.steps[si].conv;
+    const ConvSpec& cs5 = P.steps[si + 4].conv;
+    RdbParams rp;
+    memset(&rp, 0, sizeof(rp));
+    // ---- weights and biases of the five convs, back to back
+    size_t wtot = 0, btot = 0;
+    for (int k = 0; k < 5; ++k) { wtot += c[k]->w_bytes; btot += static_cast<size_t>(c[k]->sp.chunks) * kRdbNout; }
+    void* d_w = nullptr;
+    float* d_b = nullptr;
+    CK(ctx, cudaMalloc(&d_w, wtot));
+    CK(ctx, cudaMalloc(&d_b, btot * sizeof(float)));
+    size_t woff = 0, boff = 0;
+    double flops = 0;
+    for (int k = 0; k < 5; ++k) {
+      CK(ctx, cudaMemcpy(reinterpret_cast<uint8_t*>(d_w) + woff, c[k]->d_w, c[k]->w_bytes, cudaMemcpyDeviceToDevice));
+      const size_t nb = static_cast<size_t>(c[k]->sp.chunks) * kRdbNout;
+      CK(ctx, cudaMemcpy(d_b + boff, c[k]->d_bias, nb * sizeof(float), cudaMemcpyDeviceToDevice));
+      RdbPhase& ph = rp.ph[k];
+      const StreamParams& sp = c[k]->sp;
+      ph.nkb = sp.nkb;
+      ph.nks_last = sp.nks[sp.nkb - 1];
+      for (int kb = 0; kb + 1 < sp.nkb; ++kb)
+        if (sp.nks[kb] != 4) return fail(ctx, SS4K_E_INVALID, "fuse_rdbs: partial K block in front of the last one");
+      if (sp.nkb * 3 > kRdbMaxWTiles) return fail(ctx, SS4K_E_INVALID, "fuse_rdbs: too many weight tiles");
+      ph.chunks = sp.chunks;
+      ph.w_row0 = static_cast<int32_t>(woff / 128);
+      ph.bias0 = static_cast<int32_t>(boff);
+      ph.out_c0 = P.steps[si + k].conv.out_coff;
+      ph.out_map = k == 4 ? 1 : 0;
+      ph.total_units = sp.total_units;
+      ph.l2_in = sp.l2_in; ph.l2_out = sp.l2_out;
+      woff += c[k]->w_bytes;
+      boff += nb;
+      flops += P.steps[si + k].conv.flops();
+    }
+    rp.tmA = c[4]->sp.tmA[0];   // conv5 reads all three 64-channel blocks of the slab
+    {
+      cuuint64_t dims[2] = {64, static_cast<cuuint64_t>(wtot / 128)};
+      cuuint64_t strides[1] = {128};
+      cuuint32_t box[2] = {64, static_cast<cuuint32_t>(3 * kRdbNout)};
+      cuuint32_t es[2] = {1, 1};
+      CUresult r = ctx->encode(&rp.tmW, dt, 2, d_w, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) return fail(ctx, SS4K_E_CUDA, fmt("cuTensorMapEncodeTiled(fused weights) failed: %d", (int)r));
+    }
+    for (int m = 0; m < 2; ++m) {  // whole-slab output maps: this block's slab (growth channels), the next block's slab (x)
+      const ConvSpec& cs = m == 0 ? cs1 : cs5;
+      const cuuint64_t eb = 2;
+      cuuint64_t dims[4] = {static_cast<cuuint64_t>(cs.out_pitch), static_cast<cuuint64_t>(cs.out_w), static_cast<cuuint64_t>(cs.out_h),
+                            static_cast<cuuint64_t>(cs.n)};
+      cuuint64_t strides[3] = {cs.out_pitch * eb, static_cast<cuuint64_t>(cs.out_w) * cs.out_pitch * eb,
+                               static_cast<cuuint64_t>(cs.out_h) * cs.out_w * cs.out_pitch * eb};
+      cuuint32_t box[4] = {static_cast<cuuint32_t>(kRdbNout), 32, 1, 1};
+      cuuint32_t es[4] = {1, 1, 1, 1};
+      CUresult r = ctx->encode(&rp.tmO[m], dt, 4, pl->bufs[cs.out_buf], dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                               CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) return fail(ctx, SS4K_E_CUDA, fmt("cuTensorMapEncodeTiled(fused output) failed: %d", (int)r));
+    }
+    rp.bias_f = d_b;
+    rp.slope = c[0]->sp.ep.slope_const;
+    const Epilogue& e5 = c[4]->sp.ep;
+    rp.beta1 = e5.beta1; rp.beta2 = e5.beta2;
+    rp.res1 = e5.res1; rp.res1_pitch = e5.res1_pitch; rp.res1_coff = e5.res1_coff;
+    rp.res2 = e5.res2; rp.res2_pitch = e5.res2_pitch; rp.res2_coff = e5.res2_coff;
+    rp.n_img = c[0]->sp.n_img; rp.H = c[0]->sp.H; rp.W = c[0]->sp.W; rp.strips = c[0]->sp.strips;
+    rp.acc_slots = c[0]->sp.acc_slots;
+    rp.a_slots = std::min(kMaxSASlots, (kSmemBytes - 2048 - kRdbMaxWTiles * 3 * kRdbNout * 128 - kStreamBiasBytes -
+                                        kStreamEpiWarps * round_up(32 * kRdbNout * 2, 1024)) / kASlotBytes);
+    for (int i = 0; i < 3; ++i) rp.idesc[i] = c[0]->sp.idesc[i];
+    rp.ctr_use = pl->d_ctr + static_cast<size_t>(buf_of(gi)) * ctr_elems;
+    rp.ctr_zero = pl->d_ctr + static_cast<size_t>(buf_of((gi + 1) % ng)) * ctr_elems;
+    rp.discard_ptr = c[0]->sp.discard_ptr; rp.discard_pitch_bytes = c[0]->sp.discard_pitch_bytes;
+    rp.discard_mask = c[0]->sp.discard_mask; rp.discard_npx = c[0]->sp.discard_npx;
+    rp.err = ctx->err_dev;
+    if (const char* e = getenv("SS4K_RDB_DBG")) rp.dbg_flags = atoi(e);
+    // the group's first exec now owns the fused weights; the others launch nothing
+    for (int k = 0; k < 5; ++k) { free_conv(*c[k]); c[k]->skip = k > 0; c[k]->sp.next_w = nullptr; }
+    c[0]->fused = true;
+    c[0]->fused_flops = flops;
+    c[0]->rp = rp;
+    c[0]->d_w = d_w; c[0]->w_bytes = wtot; c[0]->d_bias = d_b;
+    c[0]->grid = ctx->nsm;
+  }
+  pl->n_fused = ng;
   return SS4K_OK;
 }
 
@@ -873,6 +1016,7 @@ int ss4k_create(int device_id, ss4k_ctx** out_ctx) {
   CK(nullptr, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
   CK(nullptr, conv_tc_prepare());
   CK(nullptr, conv_stream_prepare());
+  CK(nullptr, rdb_fused_prepare());
   const char* force = getenv("SS4K_DESC_MODE");
   if (force && *force) {
     ctx->desc_mode = atoi(force);
@@ -972,6 +1116,7 @@ int ss4k_plan_destroy(ss4k_plan* pl) {
   }
   if (pl->stage_in) cudaFree(pl->stage_in);
   if (pl->stage_out) cudaFree(pl->stage_out);
+  if (pl->d_ctr) cudaFree(pl->d_ctr);
   delete pl;
   return SS4K_OK;
 }
@@ -1026,6 +1171,10 @@ int ss4k_plan_create(ss4k_ctx* ctx, const ss4k_plan_cfg* cfg, ss4k_plan** out_pl
     int rc = materialize_conv(ctx, cs, w->second, B, S, cfg->act_mode, bufptr, &pl->convs.back());
     if (rc != SS4K_OK) { ss4k_plan_destroy(pl.release()); return rc; }
   }
+  {
+    int rc = fuse_rdbs(pl.get());
+    if (rc != SS4K_OK) { ss4k_plan_destroy(pl.release()); return rc; }
+  }
   // Early activation loads (StreamParams::early_kb_mask): K blocks that only read channels written at least two steps
   // ago are requested before the dependency wait.  Needs this conv and the two launches before it to be streaming convs
   // that fill every SM (see conv_params.h).
@@ -1036,24 +1185,29 @@ int ss4k_plan_create(ss4k_ctx* ctx, const ss4k_plan_cfg* cfg, ss4k_plan** out_pl
       const ConvExec& p1 = pl->convs[pl->step_conv[si - 1]];
       const ConvExec& p2 = pl->convs[pl->step_conv[si - 2]];
       const ConvSpec& cs = P.steps[si].conv;
+      if (c.fused || c.skip || p1.fused || p1.skip || p2.fused || p2.skip) continue;
       if (!c.stream || !p1.stream || !p2.stream || c.grid != ctx->nsm || p1.grid != ctx->nsm || p2.grid != ctx->nsm) continue;
       if (cs.old_cin <= 0 || cs.split) continue;
+      // the argument above needs exactly one resident CTA per SM
+      if (conv_stream_max_ctas_per_sm(c.nout) != 1) continue;
       uint32_t mask = 0;
       for (int kb = 0; kb < c.sp.nkb; ++kb)
         if (c.sp.a_tm[kb] == 0 && (c.sp.a_kb[kb] + 1) * 64 <= cs.old_cin) mask |= 1u << kb;
       c.sp.early_kb_mask = mask;
     }
   }
-  // each streaming conv prefetches the next conv's packed weights into L2 (the last one: the first conv's, for the next frame)
+  // each launch prefetches the next launch's packed weights into L2 (the last one: the first conv's, for the next frame)
   if (getenv("SS4K_NO_W_PREFETCH") == nullptr) {
-    const int nc = static_cast<int>(pl->convs.size());
+    std::vector<ConvExec*> live;
+    for (auto& c : pl->convs)
+      if (!c.skip) live.push_back(&c);
+    const int nc = static_cast<int>(live.size());
     for (int i = 0; i < nc; ++i) {
-      ConvExec& c = pl->convs[i];
-      const ConvExec& nx = pl->convs[(i + 1) % nc];
-      if (c.stream && nx.stream && nx.d_w != nullptr && nc > 1) {
-        c.sp.next_w = nx.d_w;
-        c.sp.next_w_bytes = static_cast<uint32_t>(nx.w_bytes);
-      }
+      ConvExec& c = *live[i];
+      const ConvExec& nx = *live[(i + 1) % nc];
+      if (nc < 2 || nx.d_w == nullptr || !(nx.stream || nx.fused)) continue;
+      if (c.fused) { c.rp.next_w = nx.d_w; c.rp.next_w_bytes = static_cast<uint32_t>(nx.w_bytes); }
+      else if (c.stream) { c.sp.next_w = nx.d_w; c.sp.next_w_bytes = static_cast<uint32_t>(nx.w_bytes); }
     }
   }
   pl->in_bytes = fmt_bytes(P.in_fmt, P.in_n, P.in_c, P.in_h, P.in_w);
@@ -1103,8 +1257,17 @@ int ss4k_plan_out_shape(const ss4k_plan* pl, int32_t out_nchw[4]) {
   return SS4K_OK;
 }
 double ss4k_plan_flops(const ss4k_plan* pl) { return pl ? pl->prog.flops : 0.0; }
-int ss4k_plan_launches(const ss4k_plan* pl) { return pl ? static_cast<int>(pl->prog.steps.size()) : 0; }
-int ss4k_plan_graph_steps(const ss4k_plan* pl) { return (pl && pl->graph) ? pl->graph_last - pl->graph_first + 1 : 0; }
+static int live_steps(const ss4k_plan* pl, int first, int last) {
+  int n = 0;
+  for (int si = first; si <= last; ++si)
+    if (!(pl->prog.steps[si].kind == 1 && pl->convs[pl->step_conv[si]].skip)) ++n;
+  return n;
+}
+// kernels one run launches (a fused residual dense block is one launch for five convs)
+int ss4k_plan_launches(const ss4k_plan* pl) { return pl ? live_steps(pl, 0, static_cast<int>(pl->prog.steps.size()) - 1) : 0; }
+int ss4k_plan_graph_steps(const ss4k_plan* pl) { return (pl && pl->graph) ? live_steps(pl, pl->graph_first, pl->graph_last) : 0; }
+int ss4k_plan_steps(const ss4k_plan* pl) { return pl ? static_cast<int>(pl->prog.steps.size()) : 0; }
+int ss4k_plan_fused_blocks(const ss4k_plan* pl) { return pl ? pl->n_fused : 0; }
 int ss4k_plan_io_bytes(const ss4k_plan* pl, int64_t* in_bytes, int64_t* out_bytes) {
   if (!pl) return SS4K_E_INVALID;
   if (in_bytes) *in_bytes = pl->in_bytes;
@@ -1120,7 +1283,7 @@ int ss4k_run(ss4k_plan* pl, const void* in_dev, void* out_dev, void* cuda_stream
   for (int si = 0; si < ns; ++si) {
     if (pl->graph && si == pl->graph_first) {
       CK(ctx, cudaGraphLaunch(pl->graph, st));
-      ctx->launches += pl->graph_last - pl->graph_first + 1;
+      ctx->launches += live_steps(pl, pl->graph_first, pl->graph_last);
       si = pl->graph_last;
       continue;
     }
@@ -1214,6 +1377,11 @@ int ss4k_plan_profile(ss4k_plan* pl, const void* in_dev, void* out_dev, void* cu
     const Step& s = pl->prog.steps[si];
     flops[si] = s.kind == 1 ? s.conv.flops() : 0.0;
     kind[si] = s.kind == 0 ? 0 : (pl->convs[pl->step_conv[si]].stream ? 1 : 2);
+    if (s.kind == 1) {
+      const ConvExec& c = pl->convs[pl->step_conv[si]];
+      if (c.fused) { kind[si] = 3; flops[si] = c.fused_flops; }   // one launch for the block's five convs
+      else if (c.skip) { kind[si] = 4; flops[si] = 0.0; }         // part of the fused launch in front of it
+    }
   }
   for (auto& e : ev) cudaEventDestroy(e);
   return rc == SS4K_OK ? ns : rc;

@@ -27,6 +27,14 @@ struct Img {
   __device__ __forceinline__ float at(int n, int c, int y, int x) const {
     if (fmt == 0) return reinterpret_cast<const float*>(p)[((static_cast<size_t>(n) * C + c) * H + y) * W + x];
     if (fmt == 1) return __half2float(reinterpret_cast<const __half*>(p)[((static_cast<size_t>(n) * C + c) * H + y) * W + x]);
+    if (fmt == 3) {  // NV12 frame (Y plane + interleaved UV), BT.709 limited range, nearest chroma: same arithmetic as prep_kernel
+      const uint8_t* frame = reinterpret_cast<const uint8_t*>(p) + static_cast<size_t>(n) * (static_cast<size_t>(H) * W * 3 / 2);
+      const float yy = (static_cast<float>(frame[static_cast<size_t>(y) * W + x]) - 16.f) * (1.f / 219.f);
+      const uint8_t* uv = frame + static_cast<size_t>(H) * W + static_cast<size_t>(y >> 1) * W + (x & ~1);
+      const float cb = (static_cast<float>(uv[0]) - 128.f) * (1.f / 224.f), cr = (static_cast<float>(uv[1]) - 128.f) * (1.f / 224.f);
+      const float v = c == 0 ? yy + 1.5748f * cr : (c == 1 ? yy - 0.187324f * cb - 0.468124f * cr : yy + 1.8556f * cb);
+      return fminf(fmaxf(v, 0.f), 1.f);
+    }
     return static_cast<float>(reinterpret_cast<const uint8_t*>(p)[((static_cast<size_t>(n) * H + y) * W + x) * C + c]) / 255.0f;
   }
 };
@@ -530,7 +538,7 @@ int ss4k_glue_bicubic_u8(const float* in, int n, int c, int h, int w, uint8_t* o
 
 int ss4k_glue_sharpen_blend(const void* x, int fmt, int n, int c, int h, int w, float strength, float opacity, const void* other,
                             int other_fmt, float* out, void* stream) {
-  if (!x || !out || fmt < 0 || fmt > 2) return SS4K_E_INVALID;
+  if (!x || !out || fmt < 0 || fmt > 2 || (other && (other_fmt < 0 || other_fmt > 3))) return SS4K_E_INVALID;
   // sharpen_ker (fsrcnn_upscaler.py:54-84): (sharp*s + identity*(1-s)) / sum, sharp = [-1..9..-1]
   const float center = 9.f * strength + (1.f - strength), side = -strength;
   const float sum = center + 8.f * side;

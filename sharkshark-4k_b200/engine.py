@@ -178,6 +178,8 @@ class Plan:
         self.flops = self.lib.ss4k_plan_flops(h)
         self.launches = self.lib.ss4k_plan_launches(h)
         self.graph_steps = self.lib.ss4k_plan_graph_steps(h)
+        self.steps = self.lib.ss4k_plan_steps(h)
+        self.fused_blocks = self.lib.ss4k_plan_fused_blocks(h)
         ib, ob = ctypes.c_int64(), ctypes.c_int64()
         self.lib.ss4k_plan_io_bytes(h, ctypes.byref(ib), ctypes.byref(ob))
         self.in_bytes, self.out_bytes = ib.value, ob.value
@@ -202,10 +204,11 @@ class Plan:
 
     def profile(self, x, out=None):
         """One un-graphed run with a CUDA event between every step: list of (ms, flops, kind) per step
-        (kind 0 layout/colour kernel, 1 row-streaming conv kernel, 2 tile conv kernel)."""
+        (kind 0 layout/colour kernel, 1 row-streaming conv kernel, 2 tile conv kernel, 3 fused residual dense block =
+        five convs in one launch, 4 a conv that is part of the fused launch in front of it: no time of its own)."""
         if out is None:
             out = self.new_output()
-        cap = self.launches + 8
+        cap = self.steps + 8
         ms, fl, kd = (ctypes.c_float * cap)(), (ctypes.c_double * cap)(), (ctypes.c_int32 * cap)()
         st = ctypes.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)
         n = self.lib.ss4k_plan_profile(self.h, ctypes.c_void_p(x.data_ptr()), ctypes.c_void_p(out.data_ptr()), st,

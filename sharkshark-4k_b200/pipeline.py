@@ -6,12 +6,16 @@ denoiser seeing the frames as ONE temporal stream (BSVD.forward over the chunk, 
 and the chunks sharded across GPUs with the 16-frame temporal halo (``sharding.bsvd_chunks``).
 
     NV12 / uint8 RGB frames [T, ...]  --BSVD clip (T frames)-->  half NCHW [T,3,H,W]
-        --owned frames only-->  RRDBNet / SRVGG, one frame per engine run  -->  uint8 NHWC [n_own, sH, sW, 3]
+        --owned frames: 0.8 * clamp(sharpen(denoised), 0, 1) + 0.2 * decoded frame   (fsrcnn_upscaler.py:278-281)
+        -->  RRDBNet / SRVGG, one frame per engine run  -->  uint8 NHWC [n_own, sH, sW, 3]
 
-Both stages are engine plans (CUDA graphs of tcgen05 convs) behind the C ABI; colour decode, /255 and the noise map
-(0.1 * denoise_rate, fsrcnn_upscaler.py:262) are produced by the BSVD plan's layout kernel.  torch supplies device
-buffers, streams and pinned host memory only.
+Both nets are engine plans (CUDA graphs of tcgen05 convs) behind the C ABI; colour decode, /255 and the noise map
+(0.1 * denoise_rate, fsrcnn_upscaler.py:262) are produced by the BSVD plan's layout kernel, the sharpen / clamp / blend
+between the nets by the service glue kernel (csrc/glue.cu, which decodes the NV12 frame for the blend itself).  torch
+supplies device buffers, streams and pinned host memory only.
 """
+import ctypes
+
 import torch
 
 from . import _lib as L
@@ -23,7 +27,9 @@ class DenoiseUpscalePipeline:
         self.h, self.w, self.noise, self.nv12 = h, w, float(noise), nv12
         self.out_fmt = out_fmt
         self.device = denoiser.engine.device
-        self.sr_plan = upscaler._plan(1, h, w, L.FMT_F16_NCHW, out_fmt)
+        self.sr_plan = upscaler._plan(1, h, w, L.FMT_F32_NCHW, out_fmt)
+        self.lib = denoiser.engine.lib
+        self._lr = {}
         self._den_out_dtype = denoiser.out_dtype
         self._copy_stream = None
         self._slots = {}
@@ -57,13 +63,24 @@ class DenoiseUpscalePipeline:
         t = frames.shape[0]
         own = own if own is not None else slice(0, t)
         lo, hi, _ = own.indices(t)
-        den = self.den_plan(t).run(frames.contiguous())          # [T,3,H,W] half
+        frames = frames.contiguous()
+        den = self.den_plan(t).run(frames)                        # [T,3,H,W] half
         if out is None:
             out = self.new_output(hi - lo)
-        for i in range(lo, hi):
-            self.sr_plan.run(den[i:i + 1], out[i - lo:i - lo + 1])
+        n_own = hi - lo
+        lr = self._lr.get(n_own)
+        if lr is None:
+            lr = self._lr[n_own] = torch.empty(n_own, 3, self.h, self.w, dtype=torch.float32, device=self.device)
+        # denoised -> 3x3 reflect sharpen(2e-5) + clamp -> 0.8 * . + 0.2 * original frame (fsrcnn_upscaler.py:278-281)
+        st = ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        src = frames[lo:hi]
+        L.check(self.lib.ss4k_glue_sharpen_blend(ctypes.c_void_p(den[lo:hi].data_ptr()), 1, n_own, 3, self.h, self.w,
+                                                 0.00002, 0.8, ctypes.c_void_p(src.data_ptr()), 3 if self.nv12 else 2,
+                                                 ctypes.c_void_p(lr.data_ptr()), st), self.den.engine.h)
+        for i in range(n_own):
+            self.sr_plan.run(lr[i:i + 1], out[i:i + 1])
             if after_frame is not None:
-                after_frame(i - lo)
+                after_frame(i)
         return out
 
     # ------------------------------------------------------------------ host path (pinned buffers in / out)

@@ -57,3 +57,45 @@ def gather_frames(local, n_frames, dst=0, group=None):
     if rank != dst:
         return None
     return torch.cat([bufs[r][:hi - lo] for r, (lo, hi) in enumerate(shards)], dim=0)
+
+
+class StreamChunker:
+    """Chunk + halo bookkeeping for a LIVE (unbounded) stream: frames arrive one batch after another, chunk k owns
+    frames [k L, (k+1) L) and goes to GPU k % world; it can be dispatched as soon as its trailing halo has arrived
+    (frame (k+1) L + halo - 1), i.e. the sharded denoiser adds L + halo frames of latency, not a whole clip.  At the
+    end of the stream the last chunks are clipped to the frames that exist (zero features beyond the clip, like the
+    reference's drain, src/upscale/model/bsvd/model.py:555-569)."""
+
+    def __init__(self, world, chunk_len, halo=BSVD_HALO):
+        assert world >= 1 and chunk_len >= 1 and halo >= 0
+        self.world, self.chunk_len, self.halo = world, chunk_len, halo
+        self.frames = 0        # frames received so far
+        self.next_chunk = 0    # first chunk not dispatched yet
+        self.closed = False
+
+    def _chunk(self, k, total):
+        lo, hi = k * self.chunk_len, min((k + 1) * self.chunk_len, total)
+        return Chunk(lo, hi, max(0, lo - self.halo), min(total, hi + self.halo))
+
+    def push(self, n_frames):
+        """n_frames more frames arrived; returns the (rank, Chunk) pairs that became dispatchable."""
+        assert not self.closed
+        self.frames += n_frames
+        out = []
+        while (self.next_chunk + 1) * self.chunk_len + self.halo <= self.frames:
+            out.append((self.next_chunk % self.world, self._chunk(self.next_chunk, 1 << 62)))
+            self.next_chunk += 1
+        return out
+
+    def finish(self):
+        """End of the stream: the remaining chunks, clipped to the clip length."""
+        self.closed = True
+        out = []
+        while self.next_chunk * self.chunk_len < self.frames:
+            out.append((self.next_chunk % self.world, self._chunk(self.next_chunk, self.frames)))
+            self.next_chunk += 1
+        return out
+
+    def oldest_needed(self):
+        """First frame a future chunk still needs: everything before it may be released by the frame store."""
+        return max(0, self.next_chunk * self.chunk_len - self.halo)

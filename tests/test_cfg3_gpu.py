@@ -1,6 +1,7 @@
 """The headline configuration (BASELINE.json configs[2]) on the GPU, full 1280x720 frames:
 NV12 stream -> BSVD-32 temporal denoiser over the chunk (reference constructor init, fp16 hi/lo split precision)
--> RRDBNet-23 x2 on the owned frame -> 2560x1440, through ``pipeline.DenoiseUpscalePipeline`` (the call bench.py times),
+-> sharpen / clamp / 0.8-0.2 blend with the decoded frame (fsrcnn_upscaler.py:278-281) -> RRDBNet-23 x2 on the owned frame
+-> 2560x1440, through ``pipeline.DenoiseUpscalePipeline`` (the call bench.py times),
 against the CPU oracle chain oracle.colour -> oracle.bsvd -> oracle.rrdbnet on the same seeded frames and weights.
 
 Gate (BASELINE.json north_star): PSNR >= 50 dB and max |err| <= 2/255 on clamped [0,1] RGB, compared BEFORE the uint8
@@ -17,7 +18,7 @@ from ss4k_b200 import _lib as L
 from ss4k_b200 import bsvd as native_bsvd
 from ss4k_b200 import realesrgan, sharding
 from ss4k_b200.pipeline import DenoiseUpscalePipeline
-from oracle import bsvd, colour, rrdbnet
+from oracle import bsvd, colour, glue, rrdbnet
 
 pytestmark = pytest.mark.gpu
 
@@ -63,7 +64,10 @@ def test_cfg3_720p_chunk_vs_oracle(nets):
         rgb = torch.from_numpy(colour.nv12_to_rgb(nv, H, W))                        # [T,3,H,W]
         x = torch.cat([rgb, torch.full((T, 1, H, W), NOISE)], dim=1)[None]          # [1,T,4,H,W]
         den_want = bsvd.bsvd_forward(bsd, x)[0]                                      # [T,3,H,W]
-        want = rr(den_want[own])
+        # glue between the nets (fsrcnn_upscaler.py:278-281): sharpen(2e-5) + clamp, 0.8 * den + 0.2 * original
+        d = den_want[own]
+        d = torch.clamp(glue.depthwise_reflect(d.reshape(-1, 1, H, W), glue.sharpen_weight(0.00002)).reshape(d.shape), 0, 1)
+        want = rr(d * 0.8 + 0.2 * rgb[own])
     frames = torch.from_numpy(nv).cuda()
     pf = DenoiseUpscalePipeline(den, sr, H, W, NOISE, nv12=True, out_fmt=L.FMT_F16_NCHW)
     got = pf.run(frames, own)
