@@ -129,6 +129,8 @@ int ss4k_plan_graph_steps(const ss4k_plan* plan);
 int ss4k_plan_steps(const ss4k_plan* plan);
 /* residual dense blocks that run as one fused launch each (0: the trunk runs conv by conv) */
 int ss4k_plan_fused_blocks(const ss4k_plan* plan);
+/* debug: per-CTA producer statistics of the fused launches of a plan created with SS4K_RDB_TRACE=1 */
+int64_t ss4k_debug_rdb_trace(ss4k_plan* plan, long long* out, int64_t cap);
 /* JSON description of the layer program (buffers, convs, epilogues); malloc'd, free with ss4k_free.
  * Works without a GPU when the plan was built with ss4k_plan_dry (host-side planner only). */
 int ss4k_plan_dry(const ss4k_plan_cfg* cfg, char** out_json);

@@ -788,6 +788,7 @@ struct ss4k_plan {
   cudaGraphExec_t graph = nullptr;
   int graph_first = -1, graph_last = -1;  // [first, last] step range inside the graph
   uint32_t* d_ctr = nullptr;  // progress counters of the fused residual dense blocks (3 rotating buffers)
+  long long* d_rdb_trace = nullptr;  // SS4K_RDB_TRACE=1: producer statistics of every fused launch [n_fused][nsm][16]
   int n_fused = 0;
   void* stage_in = nullptr;   // device staging for ss4k_run_host
   void* stage_out = nullptr;
@@ -864,8 +865,11 @@ int fuse_rdbs(ss4k_plan* pl) {
     }
     if (!ok) continue;
     const StreamParams& s0 = pl->convs[pl->step_conv[si]].sp;
-    const int64_t total0 = static_cast<int64_t>(s0.n_img) * s0.strips * s0.H;
-    if (total0 < 2 * ctx->nsm || (2 * total0 + 1) * ctx->nsm >= (1ll << 31)) continue;
+    // strips x bands with the same band boundaries in every strip, one CTA per (image, strip, band): worth it only if
+    // that grid fills the GPU and a band has a few rows on each side of the half-band shift
+    const int nstrip = s0.n_img * s0.strips;
+    const int bands = nstrip > 0 ? std::min(ctx->nsm / nstrip, s0.H / 4) : 0;
+    if (bands < 1 || nstrip * bands * 100 < ctx->nsm * 94) continue;
     groups.push_back(si);
     si += 4;
   }
@@ -874,6 +878,10 @@ int fuse_rdbs(ss4k_plan* pl) {
   const size_t ctr_elems = static_cast<size_t>(ctx->nsm) * kRdbCtrPerCta;
   CK(ctx, cudaMalloc(&pl->d_ctr, 3 * ctr_elems * sizeof(uint32_t)));
   CK(ctx, cudaMemset(pl->d_ctr, 0, 3 * ctr_elems * sizeof(uint32_t)));
+  if (getenv("SS4K_RDB_TRACE") != nullptr) {
+    CK(ctx, cudaMalloc(&pl->d_rdb_trace, static_cast<size_t>(ng) * ctx->nsm * 16 * sizeof(long long)));
+    CK(ctx, cudaMemset(pl->d_rdb_trace, 0, static_cast<size_t>(ng) * ctx->nsm * 16 * sizeof(long long)));
+  }
   // counter buffer of launch g: g % 3, except that the last launch must also differ from the first (graph replay wraps)
   auto buf_of = [&](int g) { return (g == ng - 1 && ng % 3 == 1) ? 1 : g % 3; };
   const CUtensorMapDataType dt = CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
@@ -894,28 +902,35 @@ int fuse_rdbs(ss4k_plan* pl) {
     CK(ctx, cudaMalloc(&d_b, btot * sizeof(float)));
     size_t woff = 0, boff = 0;
     double flops = 0;
+    int np = 0;   // phases: conv1..4, then conv5's two 32-wide output chunks
     for (int k = 0; k < 5; ++k) {
       CK(ctx, cudaMemcpy(reinterpret_cast<uint8_t*>(d_w) + woff, c[k]->d_w, c[k]->w_bytes, cudaMemcpyDeviceToDevice));
       const size_t nb = static_cast<size_t>(c[k]->sp.chunks) * kRdbNout;
       CK(ctx, cudaMemcpy(d_b + boff, c[k]->d_bias, nb * sizeof(float), cudaMemcpyDeviceToDevice));
-      RdbPhase& ph = rp.ph[k];
       const StreamParams& sp = c[k]->sp;
-      ph.nkb = sp.nkb;
-      ph.nks_last = sp.nks[sp.nkb - 1];
       for (int kb = 0; kb + 1 < sp.nkb; ++kb)
         if (sp.nks[kb] != 4) return fail(ctx, SS4K_E_INVALID, "fuse_rdbs: partial K block in front of the last one");
       if (sp.nkb * 3 > kRdbMaxWTiles) return fail(ctx, SS4K_E_INVALID, "fuse_rdbs: too many weight tiles");
-      ph.chunks = sp.chunks;
-      ph.w_row0 = static_cast<int32_t>(woff / 128);
-      ph.bias0 = static_cast<int32_t>(boff);
-      ph.out_c0 = P.steps[si + k].conv.out_coff;
-      ph.out_map = k == 4 ? 1 : 0;
-      ph.total_units = sp.total_units;
-      ph.l2_in = sp.l2_in; ph.l2_out = sp.l2_out;
+      const size_t chunk_rows = static_cast<size_t>(sp.nkb) * 9 * kRdbNout;   // [kb][kx][2-ky][32] rows of 64 channels
+      for (int ch = 0; ch < sp.chunks; ++ch, ++np) {
+        RdbPhase& ph = rp.ph[np];
+        ph.nkb = sp.nkb;
+        ph.nks_last = sp.nks[sp.nkb - 1];
+        ph.w_row0 = static_cast<int32_t>(woff / 128 + ch * chunk_rows);
+        ph.bias0 = static_cast<int32_t>(boff) + ch * kRdbNout;
+        ph.out_c0 = P.steps[si + k].conv.out_coff + ch * kRdbNout;
+        ph.out_map = k == 4 ? 1 : 0;
+        ph.dep = k == 0 ? -1 : k - 1;     // conv(k+1) reads what conv(k) wrote; both chunks of conv5 read conv4's rows
+        ph.shift = (np & 1) && k < 4 ? 1 : 0;
+        ph.residual = k == 4 ? 1 : 0;
+        ph.res_c = ch * kRdbNout;
+        ph.l2_in = sp.l2_in; ph.l2_out = sp.l2_out;
+      }
       woff += c[k]->w_bytes;
       boff += nb;
       flops += P.steps[si + k].conv.flops();
     }
+    if (np != kRdbPhases) return fail(ctx, SS4K_E_INVALID, "fuse_rdbs: unexpected phase count");
     rp.tmA = c[4]->sp.tmA[0];   // conv5 reads all three 64-channel blocks of the slab
     {
       cuuint64_t dims[2] = {64, static_cast<cuuint64_t>(wtot / 128)};
@@ -946,6 +961,8 @@ int fuse_rdbs(ss4k_plan* pl) {
     rp.res1 = e5.res1; rp.res1_pitch = e5.res1_pitch; rp.res1_coff = e5.res1_coff;
     rp.res2 = e5.res2; rp.res2_pitch = e5.res2_pitch; rp.res2_coff = e5.res2_coff;
     rp.n_img = c[0]->sp.n_img; rp.H = c[0]->sp.H; rp.W = c[0]->sp.W; rp.strips = c[0]->sp.strips;
+    rp.bands = std::min(ctx->nsm / (rp.n_img * rp.strips), rp.H / 4);
+    rp.half = (rp.H / rp.bands) / 2;
     rp.acc_slots = c[0]->sp.acc_slots;
     rp.a_slots = std::min(kMaxSASlots, (kSmemBytes - 2048 - kRdbMaxWTiles * 3 * kRdbNout * 128 - kStreamBiasBytes -
                                         kStreamEpiWarps * round_up(32 * kRdbNout * 2, 1024)) / kASlotBytes);
@@ -956,13 +973,14 @@ int fuse_rdbs(ss4k_plan* pl) {
     rp.discard_mask = c[0]->sp.discard_mask; rp.discard_npx = c[0]->sp.discard_npx;
     rp.err = ctx->err_dev;
     if (const char* e = getenv("SS4K_RDB_DBG")) rp.dbg_flags = atoi(e);
+    if (pl->d_rdb_trace != nullptr) rp.trace = pl->d_rdb_trace + static_cast<size_t>(gi) * ctx->nsm * 16;
     // the group's first exec now owns the fused weights; the others launch nothing
     for (int k = 0; k < 5; ++k) { free_conv(*c[k]); c[k]->skip = k > 0; c[k]->sp.next_w = nullptr; }
     c[0]->fused = true;
     c[0]->fused_flops = flops;
     c[0]->rp = rp;
     c[0]->d_w = d_w; c[0]->w_bytes = wtot; c[0]->d_bias = d_b;
-    c[0]->grid = ctx->nsm;
+    c[0]->grid = rp.n_img * rp.strips * rp.bands;
   }
   pl->n_fused = ng;
   return SS4K_OK;
@@ -1117,6 +1135,7 @@ int ss4k_plan_destroy(ss4k_plan* pl) {
   if (pl->stage_in) cudaFree(pl->stage_in);
   if (pl->stage_out) cudaFree(pl->stage_out);
   if (pl->d_ctr) cudaFree(pl->d_ctr);
+  if (pl->d_rdb_trace) cudaFree(pl->d_rdb_trace);
   delete pl;
   return SS4K_OK;
 }
@@ -1268,6 +1287,15 @@ int ss4k_plan_launches(const ss4k_plan* pl) { return pl ? live_steps(pl, 0, stat
 int ss4k_plan_graph_steps(const ss4k_plan* pl) { return (pl && pl->graph) ? live_steps(pl, pl->graph_first, pl->graph_last) : 0; }
 int ss4k_plan_steps(const ss4k_plan* pl) { return pl ? static_cast<int>(pl->prog.steps.size()) : 0; }
 int ss4k_plan_fused_blocks(const ss4k_plan* pl) { return pl ? pl->n_fused : 0; }
+// debug (plans created with SS4K_RDB_TRACE=1): producer statistics of the fused launches, [n_fused][nsm][16] int64
+int64_t ss4k_debug_rdb_trace(ss4k_plan* pl, long long* out, int64_t cap) {
+  if (!pl || !out || pl->d_rdb_trace == nullptr) return 0;
+  const int64_t n = static_cast<int64_t>(pl->n_fused) * pl->ctx->nsm * 16;
+  if (cap < n) return -n;
+  if (cudaDeviceSynchronize() != cudaSuccess) return 0;
+  if (cudaMemcpy(out, pl->d_rdb_trace, n * sizeof(long long), cudaMemcpyDeviceToHost) != cudaSuccess) return 0;
+  return n;
+}
 int ss4k_plan_io_bytes(const ss4k_plan* pl, int64_t* in_bytes, int64_t* out_bytes) {
   if (!pl) return SS4K_E_INVALID;
   if (in_bytes) *in_bytes = pl->in_bytes;

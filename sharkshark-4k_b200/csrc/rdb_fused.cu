@@ -6,15 +6,26 @@
 //     x1 = lrelu(conv1(x)); x2 = lrelu(conv2(cat(x, x1))); ... ; x5 = conv5(cat(x, x1..x4)); return x5 * 0.2 + x
 //
 // Why: at one 720p frame per step a trunk conv is 12 output rows per SM; the kernel boundary between two convs (grid
-// drain, launch, barrier / TMEM set-up, weight load, first TMA round trip) cost 5.3 us of a 25-55 us conv, 19 % of the
-// trunk.  Here a CTA (one per SM) keeps its band of output rows through the five convs
-// ("phases"): barriers, TMEM and the accumulator ring are set up once, the activation-slab / accumulator pipelines keep
-// running across a phase change, and the only thing a phase waits for is DATA: the rows of the previous phase it reads
-// (its own band plus one halo row / one halo pixel column of the neighbouring bands), published by the epilogue warps
-// of the CTA that wrote them through per-warp progress counters in global memory (release / acquire at gpu scope, a
-// proxy fence on both sides because the data moves through TMA).  Dependencies only point to earlier phases and all
-// CTAs are co-resident (grid == SM count, one CTA per SM), so the waits cannot deadlock; they are bounded (trap after
-// 4 s) like every other wait of the engine.
+// drain, launch, barrier / TMEM set-up, weight load, first TMA round trip) cost 5.3 us of a 25-55 us conv (DESIGN.md
+// section 4.1).  Here the frame is cut into column strips x row bands with the same band boundaries in every strip, one
+// CTA per (image, strip, band), all co-resident (grid <= SM count, one CTA per SM).  A CTA keeps its band through six
+// phases (conv1..4, conv5 as two 32-wide chunks): barriers, TMEM and the accumulator ring are set up once and the
+// activation-slab / accumulator pipelines keep running across a phase change.  What a phase reads from an earlier one
+// (its own band plus one halo row and one halo pixel column of the neighbouring bands) is guarded by per-warp progress
+// counters in global memory, published by the epilogue warps of the CTA that wrote the rows (release / acquire at gpu
+// scope, a proxy fence on both sides because the data moves through TMA).
+//
+// A phase boundary only stays free if nobody has to WAIT for those counters: store completion + release + acquire +
+// TMA round trip is as long as a kernel boundary.  So every other phase shifts the bands up by half a band (rows
+// falling off the top wrap to the bottom of the same strip): the first and last rows of a phase then depend on rows
+// the previous phase produced in the MIDDLE of its bands, half a band (6 rows, > 10 us) earlier, and because the bands
+// are aligned across strips the horizontal neighbours are at the same row at the same time.  Dependencies only point
+// to earlier phases, so the waits cannot deadlock; they are bounded (trap after 4 s) like every wait of the engine.
+//
+// Weights stream through a ring of three K-block groups (3 x 36 KB, what the widest conv needs): the producer requests
+// the next phase's groups as soon as the slots they go into have been released by the current phase's LAST row (the
+// MMA warp commits a slot right after that row's MMAs on it), so phase 1 is fully resident before phase 0 ends and the
+// later phases trickle in behind the last row instead of waiting for the whole previous phase to drain.
 //
 // Inside a phase everything is conv_stream.cu's scheme (see there): M = 128 pixels of a row, N = 3 vertical taps x 32
 // output channels, K = 64-channel blocks x 3 horizontal taps; accumulator ring in TMEM initialised with the fp32 bias by
@@ -35,6 +46,7 @@ namespace {
 constexpr int NOUT = kRdbNout;
 constexpr uint32_t kWTile = 3u * NOUT * 128u;      // one (K block, horizontal tap) weight tile
 constexpr uint32_t kStageWarp = 32u * NOUT * 2u;   // one epilogue warp's 32-pixel output tile (2 KB)
+constexpr int kWGroups = kRdbMaxWTiles / 3;        // weight ring: K-block groups of three tiles resident at a time
 
 __device__ __forceinline__ uint32_t elect_one_f() {
   uint32_t pred;
@@ -84,39 +96,50 @@ constexpr uint32_t kRecLast = 4u, kRecNewW = 8u, kRecFreeW = 16u;
 constexpr uint32_t kRecWords = 8u;
 
 struct Band {
-  int p, chunk, n, strip, yb, ye;
+  int p, yb, ye;
 };
-// Walks a CTA's output rows through the phases: units of a phase are output rows in (chunk, n, strip, y) order, split
-// evenly over the grid; a band is a run of rows inside one strip.
+// This CTA's place in the frame: image n, column strip, rows [v0, v1) of the strip in band coordinates.  In a shifted
+// phase band coordinate v is image row v - half (mod H): the band moves up, what falls off the top wraps to the bottom.
+struct Place {
+  int n, strip, v0, v1;
+};
+__device__ __forceinline__ Place cta_place(const RdbParams& P, unsigned cta) {
+  Place pl;
+  const int B = P.bands;
+  const int sj = static_cast<int>(cta) / B, bi = static_cast<int>(cta) - sj * B;
+  pl.n = sj / P.strips;
+  pl.strip = sj - pl.n * P.strips;
+  pl.v0 = bi * P.H / B;
+  pl.v1 = (bi + 1) * P.H / B;
+  return pl;
+}
 struct Cursor {
-  int p, u, u1;
+  int p, k;   // phase, rows of the phase already handed out
 };
-__device__ __forceinline__ int cta_u0(const RdbParams& P, int p, unsigned cta) {
-  return static_cast<int>(static_cast<uint32_t>(cta) * static_cast<uint32_t>(P.ph[p].total_units) / gridDim.x);
+// A band that contains the wrap point of a shifted phase (band coordinate v < half, i.e. the strip's first band) starts
+// `rot` rows into its range and takes the wrapped rows LAST: they depend on the rows the strip's last band finished the
+// previous phase with.
+__device__ __forceinline__ int band_rot(const RdbParams& P, int p, int v0) {
+  return (P.ph[p].shift && v0 < P.half) ? P.half - v0 : 0;
 }
-__device__ __forceinline__ void cursor_init(const RdbParams& P, Cursor& c) {
-  c.p = 0;
-  c.u = cta_u0(P, 0, blockIdx.x);
-  c.u1 = cta_u0(P, 0, blockIdx.x + 1);
-}
-__device__ __forceinline__ bool next_band(const RdbParams& P, Cursor& c, Band& b) {
-  while (c.u >= c.u1) {
+// next run of consecutive image rows of this CTA, phase after phase
+__device__ __forceinline__ bool next_band(const RdbParams& P, const Place& pl, Cursor& c, Band& b) {
+  const int nrows = pl.v1 - pl.v0;
+  if (c.k >= nrows) {
     if (++c.p >= kRdbPhases) return false;
-    c.u = cta_u0(P, c.p, blockIdx.x);
-    c.u1 = cta_u0(P, c.p, blockIdx.x + 1);
+    c.k = 0;
   }
-  int t = c.u;
-  const int y = t % P.H;
-  t /= P.H;
-  b.strip = t % P.strips;
-  t /= P.strips;
-  b.n = t % P.n_img;
-  b.chunk = t / P.n_img;
+  const int off = P.ph[c.p].shift ? P.half : 0;
+  const int rot = band_rot(P, c.p, pl.v0);
+  int v, cnt;
+  if (c.k < nrows - rot) { v = pl.v0 + rot + c.k; cnt = nrows - rot - c.k; }
+  else { v = pl.v0 + (c.k - (nrows - rot)); cnt = nrows - c.k; }
+  int y = v - off;
+  if (y < 0) y += P.H;   // the wrapped piece: rows at the bottom of the strip
   b.p = c.p;
   b.yb = y;
-  const int rem = c.u1 - c.u;
-  b.ye = rem < P.H - y ? y + rem : P.H;
-  c.u += b.ye - b.yb;
+  b.ye = y + cnt;
+  c.k += cnt;
   return true;
 }
 
@@ -135,9 +158,10 @@ rdb_fused_kernel(const __grid_constant__ RdbParams P) {
   const uint32_t a_empty = a_full + 8 * kMaxSASlots;
   const uint32_t acc_full = a_empty + 8 * kMaxSASlots;
   const uint32_t acc_empty = acc_full + 8 * kMaxAccSlots;
-  const uint32_t w_full = acc_empty + 8 * kMaxAccSlots;
-  const uint32_t w_empty = w_full + 8;
-  const uint32_t tmem_slot = w_empty + 8;
+  // weights live in a ring of kWGroups slots, one slot = the three horizontal-tap tiles of one K block (36 KB)
+  const uint32_t wg_full = acc_empty + 8 * kMaxAccSlots;
+  const uint32_t wg_empty = wg_full + 8 * kWGroups;
+  const uint32_t tmem_slot = wg_empty + 8 * kWGroups;
   const uint32_t rec_base = tmem_slot + 32;  // row records, one per activation slab slot
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
@@ -154,22 +178,18 @@ rdb_fused_kernel(const __grid_constant__ RdbParams P) {
     asm volatile("" ::"l"(acc));
   }
   const int S = P.acc_slots;
-  // rows this CTA owns per phase (cumulative): position q of its output-row sequence belongs to phase p when cum[p] <= q < cum[p+1]
-  int cum[kRdbPhases + 1];
-  cum[0] = 0;
-#pragma unroll
-  for (int p = 0; p < kRdbPhases; ++p) cum[p + 1] = cum[p] + cta_u0(P, p, blockIdx.x + 1) - cta_u0(P, p, blockIdx.x);
+  const Place pl = cta_place(P, blockIdx.x);
+  const int nrows = pl.v1 - pl.v0;            // rows of this CTA per phase; position q of its output-row sequence is phase q / nrows
+  const int qtot = nrows * kRdbPhases;
 
-  bool early_w = false;
   if (warp == 0) {
     if (lane == 0) {
       prefetch_tmap(&P.tmA);
       prefetch_tmap(&P.tmW);
       prefetch_tmap(&P.tmO[0]);
       prefetch_tmap(&P.tmO[1]);
-      mbar_init(w_full, 1);
-      mbar_init(w_empty, 1);
     }
+    if (lane < 2 * kWGroups) mbar_init(wg_full + 8 * lane, 1);   // wg_full[0..2], wg_empty[0..2] are contiguous
     if (lane < kMaxSASlots) {
       mbar_init(a_full + 8 * lane, 1);
       mbar_init(a_empty + 8 * lane, 1);
@@ -180,16 +200,6 @@ rdb_fused_kernel(const __grid_constant__ RdbParams P) {
     }
     fence_barrier_init();
     __syncwarp();
-    // phase 0's weights are constants of the launch: request them before the rest of the set-up
-    if (cum[1] > 0) {
-      early_w = true;
-      if (elect_one_f()) {
-        const int ntile = P.ph[0].nkb * 3;
-        mbar_expect_tx(w_full, static_cast<uint32_t>(ntile) * kWTile);
-        for (int t = 0; t < ntile; ++t) tma_load_2d_f(w_base + t * kWTile, &P.tmW, w_full, 0, P.ph[0].w_row0 + t * 3 * NOUT);
-      }
-      __syncwarp();
-    }
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
@@ -199,7 +209,7 @@ rdb_fused_kernel(const __grid_constant__ RdbParams P) {
   }
   {
     float* sb = reinterpret_cast<float*>(smem_gen + (bias_base - smem_base));
-    const int nb = P.ph[kRdbPhases - 1].bias0 + P.ph[kRdbPhases - 1].chunks * NOUT;
+    const int nb = P.ph[kRdbPhases - 1].bias0 + NOUT;
     if (warp != 0)
       for (int i = threadIdx.x - 32; i < nb; i += kStreamThreads - 32) sb[i] = __ldg(P.bias_f + i);
   }
@@ -215,67 +225,103 @@ rdb_fused_kernel(const __grid_constant__ RdbParams P) {
 
   if (warp == 0) {
     // ======================================================= TMA producer + row planner + dependency tracker
-    uint32_t as = 0, aph = 0, wph = 0;
-    int loaded_w = -1;  // phase * 4 + chunk of the weights in shared memory
-    bool dep_ready = false;
-    int sL = 0, kL = 0;
-    const uint32_t G = gridDim.x;
-    const uint32_t total0 = static_cast<uint32_t>(P.ph[0].total_units);  // unit space of the single-chunk phases 0..3
-    const bool use_ctr = !(P.dbg_flags & 1);
-    Cursor cur;
-    cursor_init(P, cur);
-    Band b, nb;
-    bool has = next_band(P, cur, b);
-    while (has) {
-      const bool has_next = next_band(P, cur, nb);
-      const RdbPhase& ph = P.ph[b.p];
-      const int wid = b.p * 4 + b.chunk;
-      const bool new_w = wid != loaded_w;
-      if (new_w) {
-        mbar_wait_u(w_empty, wph ^ 1);
-        if (early_w) {
-          early_w = false;  // phase 0: already requested in the prologue
-        } else if (elect_one_f()) {
-          const int ntile = ph.nkb * 3;
-          mbar_expect_tx(w_full, static_cast<uint32_t>(ntile) * kWTile);
-          for (int t = 0; t < ntile; ++t)
-            tma_load_2d_f(w_base + t * kWTile, &P.tmW, w_full, 0, ph.w_row0 + (b.chunk * ntile + t) * 3 * NOUT);
+    uint32_t as = 0, aph = 0;
+    int loaded_w = -1;  // phase whose first row has been planned (kRecNewW goes with it)
+    // ---- weight stream: K-block groups of all phases, in order, through the ring of kWGroups slots
+    int gl = 0, gl_p = 0, gl_kb = 0;   // next group to request: index in the launch, its phase, its K block
+    int gtot = 0;
+#pragma unroll
+    for (int i = 0; i < kRdbPhases; ++i) gtot += P.ph[i].nkb;
+    // requests every group whose slot is free; never blocks (every spin loop of this warp calls it: the MMA warp may be
+    // waiting for weights whose slot was released while this warp is waiting for something else)
+    auto try_weights = [&]() {
+      while (gl < gtot) {
+        const int slot = gl % kWGroups;
+        if (gl >= kWGroups && !mbar_try_wait(wg_empty + 8 * slot, static_cast<uint32_t>((gl / kWGroups - 1) & 1))) return;
+        if (elect_one_f()) {
+          mbar_expect_tx(wg_full + 8 * slot, 3u * kWTile);
+#pragma unroll
+          for (int t = 0; t < 3; ++t)
+            tma_load_2d_f(w_base + static_cast<uint32_t>(slot * 3 + t) * kWTile, &P.tmW, wg_full + 8 * slot, 0,
+                          P.ph[gl_p].w_row0 + (gl_kb * 3 + t) * 3 * NOUT);
         }
         __syncwarp();
-        wph ^= 1;
-        loaded_w = wid;
+        ++gl;
+        if (++gl_kb == P.ph[gl_p].nkb) { gl_kb = 0; ++gl_p; }
       }
+    };
+    // waits for an mbarrier phase while keeping the weight stream going; bounded like every wait of the engine
+    auto wait_bar = [&](uint32_t bar, uint32_t parity) {
+      if (mbar_try_wait(bar, parity)) return;
+      const uint64_t t0 = globaltimer_ns();
+      while (!mbar_try_wait(bar, parity)) {
+        try_weights();
+        if (globaltimer_ns() - t0 > 4000000000ull) asm volatile("trap;");
+      }
+    };
+    try_weights();   // weights are constants of the launch: phase 0 and phase 1 are requested before anything else
+    bool dep_ready = false;
+    int sL = 0, kL = 0;
+    const bool use_ctr = !(P.dbg_flags & 1);
+    const int B = P.bands, H = P.H;
+    long long n_wait = 0, clk_wait = 0, n_poll = 0, clk_poll = 0, clk_aempty = 0, ph_start[kRdbPhases] = {0, 0, 0, 0, 0, 0};
+    const long long clk_begin = clock64();
+    const bool tracing = P.trace != nullptr;
+    Cursor cur;
+    cur.p = 0; cur.k = 0;
+    Band b, nb;
+    bool has = next_band(P, pl, cur, b);
+    while (has) {
+      const bool has_next = next_band(P, pl, cur, nb);
+      const RdbPhase& ph = P.ph[b.p];
+      const bool new_w = b.p != loaded_w;
+      loaded_w = b.p;
       if (!dep_ready) {  // x was written by the previous launch
         pdl_wait_f();
         dep_ready = true;
       }
       const uint64_t pol_in = l2_policy(ph.l2_in);
+      int gbase = 0;   // index of the phase's first weight group in the launch
+#pragma unroll
+      for (int i = 0; i < kRdbPhases; ++i)
+        if (i < b.p) gbase += P.ph[i].nkb;
       const int r0 = b.yb > 0 ? b.yb - 1 : b.yb;
-      const int r1 = b.ye < P.H ? b.ye : b.ye - 1;
-      const int x0 = b.strip * kTileW - 1;
+      const int r1 = b.ye < H ? b.ye : b.ye - 1;
+      const int x0 = pl.strip * kTileW - 1;
       int y_lo = b.yb;
-      // rows [ok_lo, ok_hi) of strips strip-1, strip, strip+1 written by phase p-1 are known to be complete
+      // rows [ok_lo, ok_hi) of strips strip-1, strip, strip+1 written by phase ph.dep are known to be complete
       int ok_lo[3] = {0, 0, 0}, ok_hi[3] = {0, 0, 0};
+      const int dep = ph.dep;
+      const int doff = dep >= 0 && P.ph[dep >= 0 ? dep : 0].shift ? P.half : 0;
       for (int r = r0; r <= r1; ++r) {
-        // ---- the rows of the previous phase this input row reads (its growth channels; older channels follow by
-        //      induction: a CTA publishes its rows phase after phase in the same order)
-        if (b.p > 0 && use_ctr) {
+        // ---- the rows of phase `dep` this input row reads (the newest input channels; older channels follow by
+        //      transitivity: a row is published after everything it was computed from had been acquired)
+        if (dep >= 0 && use_ctr) {
           bool polled = false;
 #pragma unroll
           for (int d = 0; d < 3; ++d) {
-            const int s2 = b.strip + d - 1;
+            const int s2 = pl.strip + d - 1;
             if (s2 < 0 || s2 >= P.strips) continue;
             if (r >= ok_lo[d] && r < ok_hi[d]) continue;
-            const uint32_t base = static_cast<uint32_t>(b.n * P.strips + s2) * static_cast<uint32_t>(P.H);
-            const uint32_t u = base + static_cast<uint32_t>(r);
-            const uint32_t j = ((u + 1u) * G - 1u) / total0;         // owner of unit u: u0(j) <= u < u0(j+1)
-            const uint32_t uj0 = j * total0 / G, uj1 = (j + 1u) * total0 / G;
-            const uint32_t qbase = static_cast<uint32_t>(b.p - 1) * (uj1 - uj0);  // the owner's sequence position of its first row of phase p-1
-            const uint32_t q = qbase + (u - uj0);
+            int v = r + doff;                                          // band coordinate of image row r in phase dep
+            if (v >= H) v -= H;
+            const int bi = ((v + 1) * B - 1) / H;                      // owner band: v0(bi) <= v < v0(bi + 1)
+            const int vj0 = bi * H / B, vj1 = (bi + 1) * H / B;
+            const uint32_t j = static_cast<uint32_t>((pl.n * P.strips + s2) * B + bi);
+            const int nj = vj1 - vj0;
+            const int rot = band_rot(P, dep, vj0);
+            int pos = v - vj0 - rot;                                   // the owner's processing position of this row inside the phase
+            if (pos < 0) pos += nj;
+            const int piece_end = v >= vj0 + rot ? vj1 : vj0 + rot;    // rows up to here follow v in the owner's order
+            const uint32_t qbase = static_cast<uint32_t>(dep * nj);    // the owner's sequence position of its first row of phase dep
+            const uint32_t q = qbase + static_cast<uint32_t>(pos);
             const uint32_t* cp = P.ctr_use + j * kRdbCtrPerCta + (lane & 7);
             uint32_t V;
-            const uint64_t t0 = globaltimer_ns();
-            for (;;) {
+            uint64_t t0 = 0;
+            long long c0 = 0;
+            const long long cp0 = tracing ? clock64() : 0;
+            ++n_poll;
+            for (int it = 0;; ++it) {
               const uint32_t c = ld_acquire_u32(cp);
               // counters 0..3: rows with even sequence position, 4..7: odd (one per TMEM lane quarter)
               uint32_t m = c;
@@ -284,6 +330,8 @@ rdb_fused_kernel(const __grid_constant__ RdbParams P) {
               const uint32_t c_even = __shfl_sync(0xffffffffu, m, 0), c_odd = __shfl_sync(0xffffffffu, m, 4);
               V = min(2u * c_even, 2u * c_odd + 1u);                  // sequence positions < V are complete
               if (q < V) break;
+              try_weights();
+              if (it == 0) { t0 = globaltimer_ns(); c0 = clock64(); ++n_wait; }
               if (globaltimer_ns() - t0 > 4000000000ull) {   // bounded like every wait of the engine (no out-of-line call here)
                 if (P.err != nullptr && lane == 0) {
                   P.err[0] = 900 + b.p; P.err[1] = static_cast<int32_t>(blockIdx.x); P.err[2] = static_cast<int32_t>(j); P.err[3] = static_cast<int32_t>(q);
@@ -292,12 +340,14 @@ rdb_fused_kernel(const __grid_constant__ RdbParams P) {
                 asm volatile("trap;");
               }
             }
+            if (c0 != 0) clk_wait += clock64() - c0;
+            if (tracing) clk_poll += clock64() - cp0;
             polled = true;
-            uint32_t hi = uj0 + (V - qbase);                          // units of the owner verified so far (phase p-1)
-            hi = min(hi, uj1);
-            hi = min(hi, base + static_cast<uint32_t>(P.H));
+            int hi_v = v + (static_cast<int>(V - qbase) - pos);          // rows of the owner verified so far, band coordinates
+            hi_v = hi_v < piece_end ? hi_v : piece_end;
+            int hi_r = r + (hi_v - v);
             ok_lo[d] = r;
-            ok_hi[d] = static_cast<int>(hi - base);
+            ok_hi[d] = hi_r < H ? hi_r : H;
           }
           if (polled) fence_proxy_async_all();   // the acquired data was written through the async proxy and is read by TMA
           __syncwarp();
@@ -332,12 +382,21 @@ rdb_fused_kernel(const __grid_constant__ RdbParams P) {
           if (s2 >= S) s2 -= S;
           c1 = static_cast<uint32_t>(s2);
         }
-        const bool w_changes = has_next && (nb.p * 4 + nb.chunk) != wid;
+        const bool w_changes = !has_next || nb.p != b.p;   // the phase's last row releases its weight slots
         const uint32_t flags = static_cast<uint32_t>(nB) | ((r == r1 && !has_next) ? kRecLast : 0u) |
                                ((r == r0 && new_w) ? kRecNewW : 0u) | ((r == r1 && w_changes) ? kRecFreeW : 0u) |
-                               (static_cast<uint32_t>(ph.nkb) << 8) | (static_cast<uint32_t>(ph.nks_last) << 12);
+                               (static_cast<uint32_t>(ph.nkb) << 8) | (static_cast<uint32_t>(ph.nks_last) << 12) |
+                               (static_cast<uint32_t>(gbase) << 16);
+        if (tracing && ph_start[b.p] == 0) ph_start[b.p] = clock64() - clk_begin;
         for (int kb = 0; kb < ph.nkb; ++kb) {
-          mbar_wait_u(a_empty + 8 * as, aph ^ 1);
+          try_weights();
+          if (tracing) {
+            const long long ca = clock64();
+            wait_bar(a_empty + 8 * as, aph ^ 1);
+            clk_aempty += clock64() - ca;
+          } else {
+            wait_bar(a_empty + 8 * as, aph ^ 1);
+          }
           if (elect_one_f()) {
             if (kb == 0) {
               const uint32_t ra = rec_base + as * (kRecWords * 4u);
@@ -346,7 +405,7 @@ rdb_fused_kernel(const __grid_constant__ RdbParams P) {
               sts128_f(ra + 16, static_cast<uint32_t>((b_lo + nA) * NOUT * 128) >> 4, flags, c0 | (c1 << 8), fresh);
             }
             mbar_expect_tx(a_full + 8 * as, kBoxW * kRowBytes);
-            tma_load_5d_hint(a_base + as * kASlotBytes, &P.tmA, a_full + 8 * as, 0, x0, kb, r, b.n, pol_in);
+            tma_load_5d_hint(a_base + as * kASlotBytes, &P.tmA, a_full + 8 * as, 0, x0, kb, r, pl.n, pol_in);
           }
           __syncwarp();
           if (++as == static_cast<uint32_t>(P.a_slots)) { as = 0; aph ^= 1; }
@@ -356,6 +415,12 @@ rdb_fused_kernel(const __grid_constant__ RdbParams P) {
       if (sL >= S) { sL -= S; ++kL; }
       b = nb;
       has = has_next;
+    }
+    if (tracing && lane == 0) {
+      long long* t = P.trace + blockIdx.x * 16;
+      t[0] = n_wait; t[1] = clk_wait; t[2] = n_poll; t[3] = clk_poll; t[4] = clk_aempty; t[5] = clock64() - clk_begin;
+#pragma unroll
+      for (int i = 0; i < kRdbPhases; ++i) t[6 + i] = ph_start[i];
     }
     if (P.next_w != nullptr && lane == 0) {
       const uint32_t per = ((P.next_w_bytes + gridDim.x - 1) / gridDim.x + 15u) & ~15u;
@@ -368,7 +433,7 @@ rdb_fused_kernel(const __grid_constant__ RdbParams P) {
     }
   } else if (warp == 1) {
     // ======================================================= MMA issuer (conv_stream.cu's loop; K blocks per row from the record)
-    uint32_t as = 0, aph = 0, wph = 0;
+    uint32_t as = 0, aph = 0;
     const uint32_t n_aslots = static_cast<uint32_t>(P.a_slots);
     uint32_t rc[kRecWords];
     auto fetch = [&](uint32_t slot, uint32_t ph) {
@@ -383,10 +448,6 @@ rdb_fused_kernel(const __grid_constant__ RdbParams P) {
       rc[6] = __shfl_sync(0xffffffffu, v6, 0); rc[7] = __shfl_sync(0xffffffffu, v7, 0);
     };
     auto prepare = [&]() {
-      if (rc[5] & kRecNewW) {
-        mbar_wait_u(w_full, wph);
-        wph ^= 1;
-      }
       tcgen05_after_sync();
       uint32_t f = rc[7];
 #pragma unroll
@@ -397,7 +458,7 @@ rdb_fused_kernel(const __grid_constant__ RdbParams P) {
         }
       }
     };
-    if (cum[kRdbPhases] > 0) {
+    {
       fetch(0, 0);
       prepare();
       bool last = false;
@@ -406,7 +467,8 @@ rdb_fused_kernel(const __grid_constant__ RdbParams P) {
         const uint32_t flags = rc[5], cc = rc[6];
         const bool wrap = (flags & 3u) != 0;
         last = (flags & kRecLast) != 0;
-        const bool overlap = !last && !(flags & kRecFreeW);
+        const bool overlap = !last;
+        const int gbase = static_cast<int>((flags >> 16) & 15u);
         const int nkb = static_cast<int>((flags >> 8) & 15u);
         const int nks_last = static_cast<int>((flags >> 12) & 7u);
         for (int kb = 0; kb < nkb; ++kb) {
@@ -414,8 +476,16 @@ rdb_fused_kernel(const __grid_constant__ RdbParams P) {
             mbar_wait_u(a_full + 8 * as, aph);
             tcgen05_after_sync();
           }
+          // this K block's weights: group gbase + kb of the launch, ring slot (gbase + kb) % kWGroups; the phase's first row
+          // waits for them, its last row hands the slot back
+          const int wg = gbase + kb;
+          const uint32_t wslot = static_cast<uint32_t>(wg % kWGroups);
+          if (flags & kRecNewW) {
+            mbar_wait_u(wg_full + 8 * wslot, static_cast<uint32_t>((wg / kWGroups) & 1));
+            tcgen05_after_sync();
+          }
           const uint32_t a_lo = (a_base + as * kASlotBytes) >> 4;
-          const uint32_t w_lo = (w_base + static_cast<uint32_t>(kb * 3) * kWTile) >> 4;
+          const uint32_t w_lo = (w_base + wslot * 3u * kWTile) >> 4;
           const uint32_t wA_lo = w_lo + woffA, wB_lo = w_lo + woffB;
           const int nks = kb == nkb - 1 ? nks_last : 4;
           const uint32_t as_cur = as;
@@ -449,10 +519,10 @@ rdb_fused_kernel(const __grid_constant__ RdbParams P) {
           }
 #undef SS4K_MMA
           umma_commit_elect(a_empty + 8 * as_cur);
+          if (flags & kRecFreeW) umma_commit_elect(wg_empty + 8 * wslot);
         }
         if ((cc & 0xFFu) != 0xFFu) umma_commit_elect(acc_full + 8 * (cc & 0xFFu));
         if (((cc >> 8) & 0xFFu) != 0xFFu) umma_commit_elect(acc_full + 8 * ((cc >> 8) & 0xFFu));
-        if (flags & kRecFreeW) umma_commit_elect(w_empty);
         if (!last && !overlap) {
           fetch(as, aph);
           prepare();
@@ -468,15 +538,7 @@ rdb_fused_kernel(const __grid_constant__ RdbParams P) {
     const uint32_t stage = stage_base + static_cast<uint32_t>(ew) * ((kStageWarp + 1023u) & ~1023u);
     uint32_t* const my_ctr = P.ctr_use + blockIdx.x * kRdbCtrPerCta + ew;
     // bias offset of the row at sequence position qq of this CTA
-    auto bias_of = [&](int qq) -> int {
-      int p = 0;
-#pragma unroll
-      for (int i = 1; i < kRdbPhases; ++i)
-        if (qq >= cum[i]) p = i;
-      const int u = cta_u0(P, p, blockIdx.x) + (qq - cum[p]);
-      const int upc = P.n_img * P.strips * P.H;
-      return P.ph[p].bias0 + (u / upc) * NOUT;
-    };
+    auto bias_of = [&](int qq) -> int { return P.ph[qq / nrows].bias0; };
     auto init_slot = [&](int s_, int boff) {
       const uint32_t ta = tmem_base + (static_cast<uint32_t>(qd * 32) << 16) + static_cast<uint32_t>(s_ * NOUT);
       const uint32_t ba = bias_base + static_cast<uint32_t>(boff) * 4u;
@@ -492,7 +554,6 @@ rdb_fused_kernel(const __grid_constant__ RdbParams P) {
       __syncwarp();
       if (lane == 0) mbar_arrive(acc_empty + 8 * s_);
     };
-    const int qtot = cum[kRdbPhases];
     for (int q0 = par; q0 < S && q0 < qtot; q0 += 2) init_slot(q0, bias_of(q0));
     pdl_wait_f();  // residual loads and output stores touch tensors of the previous launch
     // clear the counters of the NEXT fused launch (its buffer is used neither by this launch nor by the previous one)
@@ -515,26 +576,27 @@ rdb_fused_kernel(const __grid_constant__ RdbParams P) {
     int s = 0, k = 0, q = 0;
     uint32_t pending = 0;  // rows of this warp whose TMA store has been issued but not yet published
     Cursor cur;
-    cursor_init(P, cur);
+    cur.p = 0; cur.k = 0;
     Band b;
     const float sl = P.slope, b1 = P.beta1, b2 = P.beta2;
     const bool has_r2 = P.res2 != nullptr;
-    while (next_band(P, cur, b)) {
+    const int ax = pl.strip * kTileW + m;
+    const bool valid = ax < P.W;
+    while (next_band(P, pl, cur, b)) {
       const RdbPhase& ph = P.ph[b.p];
-      const int ax = b.strip * kTileW + m;
-      const bool valid = ax < P.W;
       const uint64_t pol_out = l2_policy(ph.l2_out);
-      const bool last_phase = b.p == kRdbPhases - 1;
+      const bool last_phase = ph.residual != 0;
+      const int q_end = (b.p + 1) * nrows;   // sequence position of the first row of the next phase
       for (int y = b.yb; y < b.ye; ++y, ++q) {
         if ((q & 1) == par) {
           uint4 r1v[NOUT / 8], r2v[NOUT / 8];
           if (last_phase && valid) {
-            const size_t pix = (static_cast<size_t>(b.n) * P.H + y) * P.W + ax;
-            const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(P.res1) + pix * P.res1_pitch + P.res1_coff + b.chunk * NOUT);
+            const size_t pix = (static_cast<size_t>(pl.n) * P.H + y) * P.W + ax;
+            const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(P.res1) + pix * P.res1_pitch + P.res1_coff + ph.res_c);
 #pragma unroll
             for (int j = 0; j < NOUT / 8; ++j) r1v[j] = rp[j];
             if (has_r2) {
-              const uint4* rq = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(P.res2) + pix * P.res2_pitch + P.res2_coff + b.chunk * NOUT);
+              const uint4* rq = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(P.res2) + pix * P.res2_pitch + P.res2_coff + ph.res_c);
 #pragma unroll
               for (int j = 0; j < NOUT / 8; ++j) r2v[j] = rq[j];
             }
@@ -598,16 +660,16 @@ rdb_fused_kernel(const __grid_constant__ RdbParams P) {
           fence_proxy_async();
           __syncwarp();
           if (lane == 0) {
-            tma_store_4d_f(&P.tmO[ph.out_map], stage, ph.out_c0 + b.chunk * NOUT, b.strip * kTileW + qd * 32, y, b.n, pol_out);
+            tma_store_4d_f(&P.tmO[ph.out_map], stage, ph.out_c0, pl.strip * kTileW + qd * 32, y, pl.n, pol_out);
             bulk_commit_f();
-            // this warp's last row of the phase: publish at once, the next phase of some CTA is waiting for it
-            if (q + 2 >= cum[b.p + 1]) {
+            // this warp's last row of the phase: publish at once (nothing later of this warp would do it in time)
+            if (q + 2 >= q_end) {
               bulk_wait0_f();
               fence_proxy_async_all();
               red_release_add(my_ctr, 1u);
             }
           }
-          pending = (q + 2 >= cum[b.p + 1]) ? 0u : 1u;
+          pending = (q + 2 >= q_end) ? 0u : 1u;
         }
         if (++s == S) { s = 0; ++k; }
       }
