@@ -586,7 +586,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--workload", default="cfg3", choices=["cfg3", "cfg2"])
-    ap.add_argument("--clip", type=int, default=32, help="cfg3: owned frames per GPU per step")
+    ap.add_argument("--clip", type=int, default=48, help="cfg3: owned frames per GPU per step")
     ap.add_argument("--bsvd", default="split", choices=["split", "f16", "auto"],
                     help="cfg3: split = reference constructor init in fp16 hi/lo split precision (parity configuration); "
                          "f16 = trained-like weights (constructor init x 0.5), single-MMA fp16")

@@ -89,7 +89,10 @@ typedef struct ss4k_plan_cfg {
   int32_t in_fmt;      /* SS4K_FMT_*                                          */
   int32_t out_fmt;     /* SS4K_FMT_* (U8: clamp to [0,1], *255, truncate like fsrcnn_upscaler.py:233) */
   int32_t use_graph;   /* 1: capture the per-frame launch sequence in a CUDA graph */
-  int32_t reserved[8]; /* [0]: BSVD with a 3-channel frame format (SS4K_FMT_U8_NHWC / SS4K_FMT_NV12): bit pattern of the
+  int32_t reserved[8]; /* [1]: RealESRGANer pre_pad (factory.py:95): reflect pad on the right / bottom before tiling, cropped
+                        *      off the output; the x2 nets also get RealESRGANer's reflect mod-2 pad for odd sizes.  tile,
+                        *      tile_pad, pre_pad are applied INSIDE the plan: crops of one shape run as one batch.
+                        * [0]: BSVD with a 3-channel frame format (SS4K_FMT_U8_NHWC / SS4K_FMT_NV12): bit pattern of the
                         * float noise level written into the 4th input channel (0.1 * denoise_rate,
                         * fsrcnn_upscaler.py:262); with the float / half NCHW formats the caller supplies 4 channels */
 } ss4k_plan_cfg;

@@ -118,3 +118,23 @@ def tile_process(model, img, scale, tile, tile_pad):
             out[:, :, sy * scale:ey * scale, sx * scale:ex * scale] = \
                 o[:, :, oy0:oy0 + (ey - sy) * scale, ox0:ox0 + (ex - sx) * scale]
     return out
+
+
+def enhance_tensor(model, img, scale, tile=0, tile_pad=10, pre_pad=0):
+    """RealESRGANer.pre_process -> process / tile_process -> post_process on a float tensor [B,3,H,W]
+    (realesrgan/utils.py @5ca1078): reflect pre_pad on the right / bottom, reflect mod-2 pad for the
+    x2 net, tiles with tile_pad, then both pads cropped off the output (x scale)."""
+    import torch.nn.functional as F
+    if pre_pad:
+        img = F.pad(img, (0, pre_pad, 0, pre_pad), "reflect")
+    mod_h = mod_w = 0
+    if scale == 2:
+        _, _, h, w = img.shape
+        mod_h, mod_w = (2 - h % 2) % 2, (2 - w % 2) % 2
+        if mod_h or mod_w:
+            img = F.pad(img, (0, mod_w, 0, mod_h), "reflect")
+    out = tile_process(model, img, scale, tile, tile_pad) if tile > 0 else model(img)
+    _, _, h, w = out.shape
+    out = out[:, :, 0:h - mod_h * scale, 0:w - mod_w * scale]
+    _, _, h, w = out.shape
+    return out[:, :, 0:h - pre_pad * scale, 0:w - pre_pad * scale]

@@ -2,6 +2,7 @@
 counters, clocks spent waiting for them / for free activation slabs, clock at which every phase starts."""
 import ctypes, os, sys
 os.environ["SS4K_RDB_TRACE"] = "1"
+os.environ["SS4K_RDB_FUSE"] = "1"
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import numpy as np

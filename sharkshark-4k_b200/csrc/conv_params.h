@@ -135,6 +135,7 @@ constexpr int kStreamOnesBytes = 128 * 128;  // "ones" operand tile of the bias 
 
 constexpr int kStreamEpiWarps = 8;  // two per TMEM lane quarter, alternating output rows
 constexpr int kStreamThreads = 32 * (2 + kStreamEpiWarps);
+constexpr int kRdbThreads = kStreamThreads;                 // fused residual dense block kernel: same warp roles
 
 struct StreamParams {
   CUtensorMap tmA[2];   // 5-D (64, W, channel block, H, N), box (64, 130, 1, 1, 1), swizzle 128B

@@ -1,5 +1,6 @@
 #pragma once
 #include <cuda_runtime.h>
+#include <stdint.h>
 
 #include "conv_params.h"
 
@@ -18,6 +19,19 @@ int conv_stream_max_ctas_per_sm(int nout);  // resident CTAs per SM of the varia
 cudaError_t rdb_fused_prepare();
 int rdb_fused_max_ctas_per_sm();
 cudaError_t rdb_fused_launch(const RdbParams& p, int grid, cudaStream_t stream, bool pdl);
+
+// tiled inference: one padded crop of the (reflect-padded) frame and where its un-padded centre goes in the output
+struct TileBox {
+  int32_t src_y, src_x;       // top-left of the padded crop in the input frame
+  int32_t off_y, off_x;       // top-left of the un-padded centre inside the net's output for the crop (pixels of the output grid)
+  int32_t dst_y, dst_x;       // where it goes in the output frame
+  int32_t paste_h, paste_w;   // its size (clipped to the output frame by the kernel)
+};
+// fmt: SS4K_FMT_F32_NCHW / F16_NCHW / U8_NHWC; crops are stored as a batch [box * N + n] of hc x wc images in the same format
+cudaError_t tile_gather_launch(int fmt, const void* in, void* out, const TileBox* boxes_dev, int nbox, int N, int C, int H,
+                               int W, int pre_pad, int hc, int wc, cudaStream_t s);
+cudaError_t tile_paste_launch(int fmt, const void* crops, void* out, const TileBox* boxes_dev, int nbox, int N, int C, int hco,
+                              int wco, int OH, int OW, cudaStream_t s);
 
 // elementwise.cu
 // in_fmt: SS4K_FMT_* ; out: [N, H/us, W/us, pitch] 16-bit NHWC (out_lo: low halves for split mode or null)

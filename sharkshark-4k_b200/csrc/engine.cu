@@ -308,7 +308,7 @@ bool stream_config(const ConvSpec& cs, StreamPacked* sp) {
     if (npad % nout) continue;
     const int wbytes = nkb * nkx * 3 * nout * 128 + (stream_bias_mma(nout) ? nout * 128 + kStreamOnesBytes : kStreamBiasBytes);
     const int stage = kStreamEpiWarps * round_up(32 * nout * 2, 1024);
-    const int left = kSmemBytes - 2048 - wbytes - stage;
+    const int left = kSmemBytes - 3072 - wbytes - stage;  // 1 KB alignment slack + barriers, row records, row_ready ring
     const int slots = std::min(kMaxSASlots, left / kASlotBytes);
     if (slots < 3) continue;
     sp->nout = nout; sp->chunks = npad / nout; sp->nkb = nkb; sp->npad_total = npad;
@@ -802,6 +802,16 @@ struct ss4k_plan {
     bool init = false;
   } pipe;
   int64_t in_bytes = 0, out_bytes = 0;
+  // tiled inference (cfg.tile / tile_pad / pre_pad, RealESRGANer semantics): one sub-plan per padded-crop shape class
+  struct TileClass {
+    int hc = 0, wc = 0, count = 0;
+    ss4k_plan* sub = nullptr;
+    TileBox* d_boxes = nullptr;
+    void* d_in = nullptr;
+    void* d_out = nullptr;
+  };
+  std::vector<TileClass> tiles;
+  bool tiled = false;
 };
 
 namespace {
@@ -841,7 +851,11 @@ int run_step(ss4k_plan* pl, int si, const void* in_dev, void* out_dev, cudaStrea
 // are concatenated, their tensor maps / epilogue constants re-used.
 int fuse_rdbs(ss4k_plan* pl) {
   ss4k_ctx* ctx = pl->ctx;
-  if (getenv("SS4K_NO_RDB_FUSE") != nullptr || pl->cfg.act_mode != SS4K_ACT_F16) return SS4K_OK;
+  // Opt-in (SS4K_RDB_FUSE=1): measured on B200 the fused launch is correct (bit-identical) but not faster than the
+  // conv-by-conv trunk with programmatic dependent launch -- the convs are bound by the shared-memory port inside every
+  // row, not by their boundaries (profiles/r02_*).
+  const char* fuse_env = getenv("SS4K_RDB_FUSE");
+  if (fuse_env == nullptr || atoi(fuse_env) == 0 || pl->cfg.act_mode != SS4K_ACT_F16) return SS4K_OK;
   if (rdb_fused_max_ctas_per_sm() != 1) return SS4K_OK;   // the progress-counter waits need one co-resident CTA per SM
   Program& P = pl->prog;
   const int ns = static_cast<int>(P.steps.size());
@@ -1120,6 +1134,12 @@ int ss4k_plan_dry(const ss4k_plan_cfg* cfg, char** out_json) {
 
 int ss4k_plan_destroy(ss4k_plan* pl) {
   if (!pl) return SS4K_OK;
+  for (auto& t : pl->tiles) {
+    if (t.sub) ss4k_plan_destroy(t.sub);
+    if (t.d_boxes) cudaFree(t.d_boxes);
+    if (t.d_in) cudaFree(t.d_in);
+    if (t.d_out) cudaFree(t.d_out);
+  }
   if (pl->graph) cudaGraphExecDestroy(pl->graph);
   for (auto& c : pl->convs) free_conv(c);
   for (void* b : pl->bufs) if (b) cudaFree(b);
@@ -1140,10 +1160,20 @@ int ss4k_plan_destroy(ss4k_plan* pl) {
   return SS4K_OK;
 }
 
+static int create_tiled_plan(ss4k_ctx* ctx, const ss4k_plan_cfg* cfg, ss4k_plan** out_plan);
+
 int ss4k_plan_create(ss4k_ctx* ctx, const ss4k_plan_cfg* cfg, ss4k_plan** out_plan) {
   if (!ctx || !cfg || !out_plan) return fail(ctx, SS4K_E_INVALID, "null argument");
   *out_plan = nullptr;
   CK(ctx, cudaSetDevice(ctx->device));
+  if (cfg->arch != SS4K_ARCH_BSVD) {
+    // RealESRGANer options (factory.py:93-95): tile / tile_pad / pre_pad, and the reflect mod-pad of the x2 nets
+    const int pre_pad = cfg->reserved[1];
+    const bool mod2 = cfg->arch == SS4K_ARCH_RRDB && cfg->scale == 2 && (((cfg->h + pre_pad) | (cfg->w + pre_pad)) & 1);
+    const bool one_tile = cfg->tile > 0 && cfg->tile >= cfg->h && cfg->tile >= cfg->w;   // a single tile is the frame itself
+    if (pre_pad < 0 || cfg->tile < 0 || cfg->tile_pad < 0) return fail(ctx, SS4K_E_INVALID, "negative tile / tile_pad / pre_pad");
+    if ((cfg->tile > 0 && !one_tile) || pre_pad > 0 || mod2) return create_tiled_plan(ctx, cfg, out_plan);
+  }
   std::unique_ptr<ss4k_plan> pl(new ss4k_plan());
   pl->ctx = ctx;
   pl->cfg = *cfg;
@@ -1262,6 +1292,73 @@ int ss4k_plan_create(ss4k_ctx* ctx, const ss4k_plan_cfg* cfg, ss4k_plan** out_pl
   return SS4K_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Tiled plans: RealESRGANer.pre_process (reflect pre_pad, mod-2 pad of the x2 nets), tile_process (grid of
+// ceil(W/tile) x ceil(H/tile) tiles, each crop expanded by tile_pad and clamped to the padded frame, un-padded centre
+// pasted, no blending) and post_process (pads cropped off) -- SURVEY.md Appendix B; reached from
+// realesrgan/factory.py:93-95,160-169.  Crops of one shape are independent images: they run as ONE batch per class.
+static int create_tiled_plan(ss4k_ctx* ctx, const ss4k_plan_cfg* cfg, ss4k_plan** out_plan) {
+  if (cfg->in_fmt == SS4K_FMT_NV12) return fail(ctx, SS4K_E_INVALID, "tiled inference takes RGB frames (float / half NCHW or uint8 NHWC)");
+  const int s = cfg->scale;
+  const int pre_pad = cfg->reserved[1];
+  int Hp = cfg->h + pre_pad, Wp = cfg->w + pre_pad;
+  if (cfg->arch == SS4K_ARCH_RRDB && s == 2) { Hp += Hp & 1; Wp += Wp & 1; }
+  if (Hp - cfg->h >= cfg->h || Wp - cfg->w >= cfg->w) return fail(ctx, SS4K_E_INVALID, "pre_pad must be smaller than the frame (reflect padding)");
+  const int tile = cfg->tile > 0 ? cfg->tile : std::max(Hp, Wp);
+  const int pad = cfg->tile > 0 ? cfg->tile_pad : 0;
+  std::unique_ptr<ss4k_plan> pl(new ss4k_plan());
+  pl->ctx = ctx;
+  pl->cfg = *cfg;
+  pl->tiled = true;
+  Program& P = pl->prog;
+  P.in_fmt = cfg->in_fmt; P.out_fmt = cfg->out_fmt;
+  P.in_n = cfg->n; P.in_c = 3; P.in_h = cfg->h; P.in_w = cfg->w;
+  P.out_n = cfg->n; P.out_c = 3; P.out_h = cfg->h * s; P.out_w = cfg->w * s;
+  std::map<std::pair<int, int>, std::vector<TileBox>> classes;
+  const int tx = (Wp + tile - 1) / tile, ty = (Hp + tile - 1) / tile;
+  for (int y = 0; y < ty; ++y)
+    for (int x = 0; x < tx; ++x) {
+      const int sx = x * tile, sy = y * tile;
+      const int ex = std::min(sx + tile, Wp), ey = std::min(sy + tile, Hp);
+      const int sxp = std::max(sx - pad, 0), exp_ = std::min(ex + pad, Wp);
+      const int syp = std::max(sy - pad, 0), eyp = std::min(ey + pad, Hp);
+      TileBox b;
+      b.src_y = syp; b.src_x = sxp;
+      b.off_y = (sy - syp) * s; b.off_x = (sx - sxp) * s;
+      b.dst_y = sy * s; b.dst_x = sx * s;
+      b.paste_h = (ey - sy) * s; b.paste_w = (ex - sx) * s;
+      classes[std::make_pair(eyp - syp, exp_ - sxp)].push_back(b);
+    }
+  for (auto& kv : classes) {
+    ss4k_plan::TileClass tc;
+    tc.hc = kv.first.first; tc.wc = kv.first.second; tc.count = static_cast<int>(kv.second.size());
+    ss4k_plan_cfg sub = *cfg;
+    sub.tile = 0; sub.reserved[1] = 0;
+    sub.n = cfg->n * tc.count; sub.h = tc.hc; sub.w = tc.wc;
+    pl->tiles.push_back(tc);
+    ss4k_plan::TileClass& t = pl->tiles.back();
+    int rc = ss4k_plan_create(ctx, &sub, &t.sub);
+    if (rc != SS4K_OK) {
+      const std::string why = ctx->err;
+      ss4k_plan_destroy(pl.release());
+      return fail(ctx, rc, fmt("tile class %dx%d: %s", tc.hc, tc.wc, why.c_str()));
+    }
+    cudaError_t ce = cudaMalloc(&t.d_boxes, kv.second.size() * sizeof(TileBox));
+    if (ce == cudaSuccess) ce = cudaMemcpy(t.d_boxes, kv.second.data(), kv.second.size() * sizeof(TileBox), cudaMemcpyHostToDevice);
+    if (ce == cudaSuccess) ce = cudaMalloc(&t.d_in, t.sub->in_bytes + 256);
+    if (ce == cudaSuccess) ce = cudaMalloc(&t.d_out, t.sub->out_bytes + 256);
+    if (ce != cudaSuccess) {
+      ss4k_plan_destroy(pl.release());
+      return fail(ctx, SS4K_E_NOMEM, fmt("tiled plan buffers: %s", cudaGetErrorString(ce)));
+    }
+    P.flops += t.sub->prog.flops;
+  }
+  pl->in_bytes = fmt_bytes(P.in_fmt, P.in_n, P.in_c, P.in_h, P.in_w);
+  pl->out_bytes = fmt_bytes(P.out_fmt, P.out_n, P.out_c, P.out_h, P.out_w);
+  *out_plan = pl.release();
+  return SS4K_OK;
+}
+
 int ss4k_rgb_to_nv12(ss4k_ctx* ctx, const void* rgb_dev, void* nv12_dev, int n, int h, int w, void* cuda_stream) {
   if (!ctx || !rgb_dev || !nv12_dev || n <= 0 || h <= 0 || w <= 0) return fail(ctx, SS4K_E_INVALID, "bad argument to ss4k_rgb_to_nv12");
   if (h % 2 || w % 4) return fail(ctx, SS4K_E_INVALID, "ss4k_rgb_to_nv12 needs h % 2 == 0 and w % 4 == 0");
@@ -1283,8 +1380,18 @@ static int live_steps(const ss4k_plan* pl, int first, int last) {
   return n;
 }
 // kernels one run launches (a fused residual dense block is one launch for five convs)
-int ss4k_plan_launches(const ss4k_plan* pl) { return pl ? live_steps(pl, 0, static_cast<int>(pl->prog.steps.size()) - 1) : 0; }
-int ss4k_plan_graph_steps(const ss4k_plan* pl) { return (pl && pl->graph) ? live_steps(pl, pl->graph_first, pl->graph_last) : 0; }
+int ss4k_plan_launches(const ss4k_plan* pl) {
+  if (!pl) return 0;
+  int n = live_steps(pl, 0, static_cast<int>(pl->prog.steps.size()) - 1);
+  for (const auto& t : pl->tiles) n += ss4k_plan_launches(t.sub) + 2;   // + gather and paste of the tile class
+  return n;
+}
+int ss4k_plan_graph_steps(const ss4k_plan* pl) {
+  if (!pl) return 0;
+  int n = pl->graph ? live_steps(pl, pl->graph_first, pl->graph_last) : 0;
+  for (const auto& t : pl->tiles) n += ss4k_plan_graph_steps(t.sub);
+  return n;
+}
 int ss4k_plan_steps(const ss4k_plan* pl) { return pl ? static_cast<int>(pl->prog.steps.size()) : 0; }
 int ss4k_plan_fused_blocks(const ss4k_plan* pl) { return pl ? pl->n_fused : 0; }
 // debug (plans created with SS4K_RDB_TRACE=1): producer statistics of the fused launches, [n_fused][nsm][16] int64
@@ -1307,6 +1414,18 @@ int ss4k_run(ss4k_plan* pl, const void* in_dev, void* out_dev, void* cuda_stream
   if (!pl || !in_dev || !out_dev) return fail(pl ? pl->ctx : nullptr, SS4K_E_INVALID, "null argument to ss4k_run");
   ss4k_ctx* ctx = pl->ctx;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(cuda_stream);
+  if (pl->tiled) {
+    const Program& P = pl->prog;
+    for (auto& t : pl->tiles) {
+      CK(ctx, tile_gather_launch(P.in_fmt, in_dev, t.d_in, t.d_boxes, t.count, P.in_n, 3, P.in_h, P.in_w, pl->cfg.reserved[1], t.hc, t.wc, st));
+      int rc = ss4k_run(t.sub, t.d_in, t.d_out, cuda_stream);
+      if (rc != SS4K_OK) return rc;
+      CK(ctx, tile_paste_launch(P.out_fmt, t.d_out, out_dev, t.d_boxes, t.count, P.in_n, 3, t.sub->prog.out_h, t.sub->prog.out_w,
+                                P.out_h, P.out_w, st));
+      ctx->launches += 2;
+    }
+    return SS4K_OK;
+  }
   const int ns = static_cast<int>(pl->prog.steps.size());
   for (int si = 0; si < ns; ++si) {
     if (pl->graph && si == pl->graph_first) {
@@ -1388,6 +1507,7 @@ int ss4k_plan_profile(ss4k_plan* pl, const void* in_dev, void* out_dev, void* cu
                       int32_t* kind, int cap) {
   if (!pl || !in_dev || !out_dev || !ms || !flops || !kind) return fail(pl ? pl->ctx : nullptr, SS4K_E_INVALID, "null argument to ss4k_plan_profile");
   ss4k_ctx* ctx = pl->ctx;
+  if (pl->tiled) return fail(ctx, SS4K_E_INVALID, "ss4k_plan_profile: profile the tile classes' shapes as plans of their own");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(cuda_stream);
   const int ns = static_cast<int>(pl->prog.steps.size());
   if (cap < ns) return fail(ctx, SS4K_E_INVALID, "ss4k_plan_profile: arrays too small");

@@ -46,6 +46,7 @@ namespace {
 constexpr int NOUT = kRdbNout;
 constexpr uint32_t kWTile = 3u * NOUT * 128u;      // one (K block, horizontal tap) weight tile
 constexpr uint32_t kStageWarp = 32u * NOUT * 2u;   // one epilogue warp's 32-pixel output tile (2 KB)
+constexpr int kInFlight = 2;                       // TMA stores per epilogue warp that may still be in flight when older rows are published
 constexpr int kWGroups = kRdbMaxWTiles / 3;        // weight ring: K-block groups of three tiles resident at a time
 
 __device__ __forceinline__ uint32_t elect_one_f() {
@@ -80,6 +81,21 @@ __device__ __forceinline__ void bulk_wait0_f() { asm volatile("cp.async.bulk.wai
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 __device__ __forceinline__ void sts128_f(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+// non-blocking phase test (mbarrier.try_wait may suspend the thread up to a system-dependent time limit: a polling loop
+// that also has other things to look after must not use it)
+__device__ __forceinline__ uint32_t mbar_test_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, P1;\n\t"
+      "}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok;
 }
 __device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p) {
   uint32_t v;
@@ -145,7 +161,7 @@ __device__ __forceinline__ bool next_band(const RdbParams& P, const Place& pl, C
 
 }  // namespace
 
-__global__ void __launch_bounds__(kStreamThreads, 1)
+__global__ void __launch_bounds__(kRdbThreads, 1)
 rdb_fused_kernel(const __grid_constant__ RdbParams P) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -211,13 +227,13 @@ rdb_fused_kernel(const __grid_constant__ RdbParams P) {
     float* sb = reinterpret_cast<float*>(smem_gen + (bias_base - smem_base));
     const int nb = P.ph[kRdbPhases - 1].bias0 + NOUT;
     if (warp != 0)
-      for (int i = threadIdx.x - 32; i < nb; i += kStreamThreads - 32) sb[i] = __ldg(P.bias_f + i);
+      for (int i = threadIdx.x - 32; i < nb; i += kRdbThreads - 32) sb[i] = __ldg(P.bias_f + i);
   }
   if (warp == 0) {
-    asm volatile("bar.arrive 1, %0;" ::"n"(kStreamThreads) : "memory");
+    asm volatile("bar.arrive 1, %0;" ::"n"(kRdbThreads) : "memory");
   } else {
     tcgen05_before_sync();
-    asm volatile("bar.sync 1, %0;" ::"n"(kStreamThreads) : "memory");
+    asm volatile("bar.sync 1, %0;" ::"n"(kRdbThreads) : "memory");
     tcgen05_after_sync();
     if (*tmem_slot_ptr != 0u) __trap();  // one CTA per SM owns all 512 columns: the allocation starts at column 0
   }
@@ -237,7 +253,7 @@ rdb_fused_kernel(const __grid_constant__ RdbParams P) {
     auto try_weights = [&]() {
       while (gl < gtot) {
         const int slot = gl % kWGroups;
-        if (gl >= kWGroups && !mbar_try_wait(wg_empty + 8 * slot, static_cast<uint32_t>((gl / kWGroups - 1) & 1))) return;
+        if (gl >= kWGroups && !mbar_test_wait(wg_empty + 8 * slot, static_cast<uint32_t>((gl / kWGroups - 1) & 1))) return;
         if (elect_one_f()) {
           mbar_expect_tx(wg_full + 8 * slot, 3u * kWTile);
 #pragma unroll
@@ -252,11 +268,11 @@ rdb_fused_kernel(const __grid_constant__ RdbParams P) {
     };
     // waits for an mbarrier phase while keeping the weight stream going; bounded like every wait of the engine
     auto wait_bar = [&](uint32_t bar, uint32_t parity) {
-      if (mbar_try_wait(bar, parity)) return;
+      if (mbar_test_wait(bar, parity)) return;
       const uint64_t t0 = globaltimer_ns();
-      while (!mbar_try_wait(bar, parity)) {
+      for (uint32_t it = 0; !mbar_test_wait(bar, parity); ++it) {
         try_weights();
-        if (globaltimer_ns() - t0 > 4000000000ull) asm volatile("trap;");
+        if ((it & 1023u) == 1023u && globaltimer_ns() - t0 > 4000000000ull) asm volatile("trap;");
       }
     };
     try_weights();   // weights are constants of the launch: phase 0 and phase 1 are requested before anything else
@@ -289,67 +305,67 @@ rdb_fused_kernel(const __grid_constant__ RdbParams P) {
       const int r1 = b.ye < H ? b.ye : b.ye - 1;
       const int x0 = pl.strip * kTileW - 1;
       int y_lo = b.yb;
-      // rows [ok_lo, ok_hi) of strips strip-1, strip, strip+1 written by phase ph.dep are known to be complete
-      int ok_lo[3] = {0, 0, 0}, ok_hi[3] = {0, 0, 0};
+      // rows [ok_lo, ok_hi) written by phase ph.dep are known to be complete in this strip and its two neighbours
+      int ok_lo = 0, ok_hi = 0;
       const int dep = ph.dep;
       const int doff = dep >= 0 && P.ph[dep >= 0 ? dep : 0].shift ? P.half : 0;
       for (int r = r0; r <= r1; ++r) {
+        try_weights();
         // ---- the rows of phase `dep` this input row reads (the newest input channels; older channels follow by
-        //      transitivity: a row is published after everything it was computed from had been acquired)
-        if (dep >= 0 && use_ctr) {
-          bool polled = false;
-#pragma unroll
-          for (int d = 0; d < 3; ++d) {
-            const int s2 = pl.strip + d - 1;
-            if (s2 < 0 || s2 >= P.strips) continue;
-            if (r >= ok_lo[d] && r < ok_hi[d]) continue;
-            int v = r + doff;                                          // band coordinate of image row r in phase dep
-            if (v >= H) v -= H;
-            const int bi = ((v + 1) * B - 1) / H;                      // owner band: v0(bi) <= v < v0(bi + 1)
-            const int vj0 = bi * H / B, vj1 = (bi + 1) * H / B;
-            const uint32_t j = static_cast<uint32_t>((pl.n * P.strips + s2) * B + bi);
-            const int nj = vj1 - vj0;
-            const int rot = band_rot(P, dep, vj0);
-            int pos = v - vj0 - rot;                                   // the owner's processing position of this row inside the phase
-            if (pos < 0) pos += nj;
-            const int piece_end = v >= vj0 + rot ? vj1 : vj0 + rot;    // rows up to here follow v in the owner's order
-            const uint32_t qbase = static_cast<uint32_t>(dep * nj);    // the owner's sequence position of its first row of phase dep
-            const uint32_t q = qbase + static_cast<uint32_t>(pos);
-            const uint32_t* cp = P.ctr_use + j * kRdbCtrPerCta + (lane & 7);
-            uint32_t V;
-            uint64_t t0 = 0;
-            long long c0 = 0;
-            const long long cp0 = tracing ? clock64() : 0;
-            ++n_poll;
-            for (int it = 0;; ++it) {
-              const uint32_t c = ld_acquire_u32(cp);
-              // counters 0..3: rows with even sequence position, 4..7: odd (one per TMEM lane quarter)
-              uint32_t m = c;
-              m = min(m, __shfl_xor_sync(0xffffffffu, m, 1));
-              m = min(m, __shfl_xor_sync(0xffffffffu, m, 2));
-              const uint32_t c_even = __shfl_sync(0xffffffffu, m, 0), c_odd = __shfl_sync(0xffffffffu, m, 4);
-              V = min(2u * c_even, 2u * c_odd + 1u);                  // sequence positions < V are complete
-              if (q < V) break;
-              try_weights();
-              if (it == 0) { t0 = globaltimer_ns(); c0 = clock64(); ++n_wait; }
-              if (globaltimer_ns() - t0 > 4000000000ull) {   // bounded like every wait of the engine (no out-of-line call here)
-                if (P.err != nullptr && lane == 0) {
-                  P.err[0] = 900 + b.p; P.err[1] = static_cast<int32_t>(blockIdx.x); P.err[2] = static_cast<int32_t>(j); P.err[3] = static_cast<int32_t>(q);
-                  __threadfence_system();
-                }
-                asm volatile("trap;");
+        //      transitivity: a row is published after everything it was computed from had been acquired).  The bands are
+        //      aligned across strips, so the three owners (this strip and its neighbours) sit at the same band / position:
+        //      their 3 x 8 counters are read by 24 lanes at once, one L2 round trip per poll.
+        if (dep >= 0 && use_ctr && !(r >= ok_lo && r < ok_hi)) {
+          int v = r + doff;                                          // band coordinate of image row r in phase dep
+          if (v >= H) v -= H;
+          const int bi = ((v + 1) * B - 1) / H;                      // owner band: v0(bi) <= v < v0(bi + 1)
+          const int vj0 = bi * H / B, vj1 = (bi + 1) * H / B;
+          const int nj = vj1 - vj0;
+          const int rot = band_rot(P, dep, vj0);
+          int pos = v - vj0 - rot;                                   // the owners' processing position of this row inside the phase
+          if (pos < 0) pos += nj;
+          const int piece_end = v >= vj0 + rot ? vj1 : vj0 + rot;    // rows up to here follow v in the owners' order
+          const uint32_t qbase = static_cast<uint32_t>(dep * nj);    // sequence position of the owners' first row of phase dep
+          const uint32_t q = qbase + static_cast<uint32_t>(pos);
+          const int d = lane >> 3;                                   // lanes 0..7: strip - 1, 8..15: strip, 16..23: strip + 1
+          const int s2 = pl.strip + d - 1;
+          const bool act = d < 3 && s2 >= 0 && s2 < P.strips;
+          const uint32_t j = static_cast<uint32_t>((pl.n * P.strips + (act ? s2 : pl.strip)) * B + bi);
+          const uint32_t* cp = P.ctr_use + j * kRdbCtrPerCta + (lane & 7);
+          uint32_t V;
+          uint64_t t0 = 0;
+          long long c0 = 0;
+          const long long cp0 = tracing ? clock64() : 0;
+          ++n_poll;
+          for (int it = 0;; ++it) {
+            const uint32_t c = act ? ld_acquire_u32(cp) : 0x3FFFFFFFu;
+            // counters 0..3 of a CTA: rows with even sequence position, 4..7: odd (one per TMEM lane quarter)
+            uint32_t m = c;
+            m = min(m, __shfl_xor_sync(0xffffffffu, m, 1));
+            m = min(m, __shfl_xor_sync(0xffffffffu, m, 2));
+            const uint32_t c_even = __shfl_sync(0xffffffffu, m, lane & 24), c_odd = __shfl_sync(0xffffffffu, m, (lane & 24) + 4);
+            V = min(2u * c_even, 2u * c_odd + 1u);                  // sequence positions < V are complete (per owner)
+            V = min(V, __shfl_xor_sync(0xffffffffu, V, 8));
+            V = min(V, __shfl_xor_sync(0xffffffffu, V, 16));          // ... in all three strips
+            if (q < V) break;
+            try_weights();
+            if (it == 0) { t0 = globaltimer_ns(); c0 = clock64(); ++n_wait; }
+            if (globaltimer_ns() - t0 > 4000000000ull) {   // bounded like every wait of the engine (no out-of-line call here)
+              if (P.err != nullptr && lane == 0) {
+                P.err[0] = 900 + b.p; P.err[1] = static_cast<int32_t>(blockIdx.x); P.err[2] = static_cast<int32_t>(bi); P.err[3] = static_cast<int32_t>(q);
+                __threadfence_system();
               }
+              asm volatile("trap;");
             }
-            if (c0 != 0) clk_wait += clock64() - c0;
-            if (tracing) clk_poll += clock64() - cp0;
-            polled = true;
-            int hi_v = v + (static_cast<int>(V - qbase) - pos);          // rows of the owner verified so far, band coordinates
-            hi_v = hi_v < piece_end ? hi_v : piece_end;
-            int hi_r = r + (hi_v - v);
-            ok_lo[d] = r;
-            ok_hi[d] = hi_r < H ? hi_r : H;
           }
-          if (polled) fence_proxy_async_all();   // the acquired data was written through the async proxy and is read by TMA
+          if (c0 != 0) clk_wait += clock64() - c0;
+          if (tracing) clk_poll += clock64() - cp0;
+          int hi_v = v + (static_cast<int>(V - qbase) - pos);          // rows of the owners verified so far, band coordinates
+          hi_v = hi_v < piece_end ? hi_v : piece_end;
+          const int hi_r = r + (hi_v - v);
+          ok_lo = r;
+          ok_hi = hi_r < H ? hi_r : H;
+          fence_proxy_async_all();   // the acquired data was written through the async proxy and is read by TMA
           __syncwarp();
         }
         // ---- the row's record (see conv_stream.cu)
@@ -574,7 +590,7 @@ rdb_fused_kernel(const __grid_constant__ RdbParams P) {
       return *reinterpret_cast<const uint32_t*>(&h);
     };
     int s = 0, k = 0, q = 0;
-    uint32_t pending = 0;  // rows of this warp whose TMA store has been issued but not yet published
+    uint32_t issued = 0, published = 0;  // rows of this warp whose TMA store has been committed / announced in its counter
     Cursor cur;
     cur.p = 0; cur.k = 0;
     Band b;
@@ -586,7 +602,6 @@ rdb_fused_kernel(const __grid_constant__ RdbParams P) {
       const RdbPhase& ph = P.ph[b.p];
       const uint64_t pol_out = l2_policy(ph.l2_out);
       const bool last_phase = ph.residual != 0;
-      const int q_end = (b.p + 1) * nrows;   // sequence position of the first row of the next phase
       for (int y = b.yb; y < b.ye; ++y, ++q) {
         if ((q & 1) == par) {
           uint4 r1v[NOUT / 8], r2v[NOUT / 8];
@@ -601,6 +616,21 @@ rdb_fused_kernel(const __grid_constant__ RdbParams P) {
               for (int j = 0; j < NOUT / 8; ++j) r2v[j] = rq[j];
             }
           }
+          // Never go to sleep on unannounced rows: if the accumulator is not ready yet (this warp has run dry), wait
+          // for the stores in flight and publish them first.  Costs nothing while rows keep coming, and it is what makes
+          // the protocol deadlock-free for any geometry: a CTA that waits for data holds nothing back.
+          if (issued > published) {
+            uint32_t ready = lane == 0 ? mbar_test_wait(acc_full + 8 * s, static_cast<uint32_t>(k & 1)) : 0u;
+            ready = __shfl_sync(0xffffffffu, ready, 0);
+            if (!ready) {
+              if (lane == 0) {
+                bulk_wait0_f();
+                fence_proxy_async_all();
+                red_release_add(my_ctr, issued - published);
+              }
+              published = issued;
+            }
+          }
           mbar_wait_u(acc_full + 8 * s, k & 1);
           tcgen05_after_sync();
           const uint32_t taddr = tmem_base + (static_cast<uint32_t>(qd * 32) << 16) + static_cast<uint32_t>(s * NOUT);
@@ -609,13 +639,8 @@ rdb_fused_kernel(const __grid_constant__ RdbParams P) {
           for (int c = 0; c < NOUT; c += 16) tmem_ld16p(taddr + c, &raw[c]);
           tmem_ld_wait();
           if (q + S < qtot) init_slot(s, bias_of(q + S));
-          // the previous row's store of this warp: complete (not just read) so that the row can be published
-          if (lane == 0 && pending) {
-            bulk_wait0_f();
-            fence_proxy_async_all();
-            red_release_add(my_ctr, pending);
-          }
-          pending = 0;
+          // the staging tile is free once this warp's previous store has READ it (publication waits for completion: below)
+          if (lane == 0) bulk_wait_read0_f();
           __syncwarp();
           const uint32_t srow = stage + lane * (NOUT * 2u);
           const uint32_t sxor = (lane >> 1) & 3u;  // swizzle-64B position of the 16-byte chunk inside the [32 pixels][32 ch] tile
@@ -662,18 +687,25 @@ rdb_fused_kernel(const __grid_constant__ RdbParams P) {
           if (lane == 0) {
             tma_store_4d_f(&P.tmO[ph.out_map], stage, ph.out_c0, pl.strip * kTileW + qd * 32, y, pl.n, pol_out);
             bulk_commit_f();
-            // this warp's last row of the phase: publish at once (nothing later of this warp would do it in time)
-            if (q + 2 >= q_end) {
-              bulk_wait0_f();
+            // Publication: a row may be announced once its store is COMPLETE (global writes performed), which takes a few
+            // thousand clocks: waiting for the newest store would make every row pay that latency.  Up to kInFlight
+            // stores stay in flight; everything older is complete and gets published (the shifted schedule gives every
+            // dependency half a band of slack, and this warp keeps storing rows until well after the last row anyone
+            // waits for -- conv4's -- so nothing is left unpublished).
+            asm volatile("cp.async.bulk.wait_group %0;" ::"n"(kInFlight) : "memory");
+            if (issued + 1 > published + kInFlight) {
               fence_proxy_async_all();
-              red_release_add(my_ctr, 1u);
+              red_release_add(my_ctr, issued + 1 - kInFlight - published);
             }
           }
-          pending = (q + 2 >= q_end) ? 0u : 1u;
+          ++issued;                                        // (warp-uniform bookkeeping)
+          if (issued > published + kInFlight) published = issued - kInFlight;
         }
         if (++s == S) { s = 0; ++k; }
       }
     }
+    // (the last kInFlight rows of conv5's second chunk are never announced: nobody polls for them, the next launch
+    //  waits for the whole grid; the staging tiles must have been read before the CTA releases its shared memory)
     if (lane == 0) bulk_wait_read0_f();
   }
 
@@ -696,14 +728,14 @@ cudaError_t rdb_fused_prepare() {
 // One CTA per SM, all co-resident (the progress-counter waits rely on it); 0 if the kernel cannot be resident.
 int rdb_fused_max_ctas_per_sm() {
   int n = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, rdb_fused_kernel, kStreamThreads, kSmemBytes) != cudaSuccess) return 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, rdb_fused_kernel, kRdbThreads, kSmemBytes) != cudaSuccess) return 0;
   return n;
 }
 
 cudaError_t rdb_fused_launch(const RdbParams& p, int grid, cudaStream_t stream, bool pdl) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(kStreamThreads);
+  cfg.blockDim = dim3(kRdbThreads);
   cfg.dynamicSmemBytes = kSmemBytes;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];

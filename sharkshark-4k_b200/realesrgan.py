@@ -63,22 +63,23 @@ class _NativeNet(nn.Module):
 
     arch = None
 
-    def __init__(self, state_dict, scale, depth, device=0, act_mode=L.ACT_F16, tile=0, tile_pad=10,
+    def __init__(self, state_dict, scale, depth, device=0, act_mode=L.ACT_F16, tile=0, tile_pad=10, pre_pad=0,
                  out_dtype=torch.float32, use_graph=True, max_plans=12):
         super().__init__()
         self.engine = Engine.get(device)
         self.scale, self.depth, self.act_mode = scale, depth, act_mode
-        self.tile, self.tile_pad = tile, tile_pad
-        self.tile_batch = 16   # crops of one shape per engine run (memory bound: 16 x 1024^2 x4 crops fit 180 GB easily)
+        # RealESRGANer options (factory.py:93-95): applied inside the engine plan (csrc/engine.cu create_tiled_plan)
+        self.tile, self.tile_pad, self.pre_pad = tile, tile_pad, pre_pad
         self.out_dtype = out_dtype
         self.use_graph = use_graph
         self.net_id = self.engine.new_net(state_dict)
         self._plans = PlanCache(max_plans)
 
     def _plan(self, n, h, w, in_fmt, out_fmt):
-        return self._plans.get((n, h, w, in_fmt, out_fmt), lambda: self.engine.plan(
-            self.net_id, self.arch, n, h, w, scale=self.scale, depth=self.depth, tile=0, tile_pad=self.tile_pad,
-            act_mode=self.act_mode, in_fmt=in_fmt, out_fmt=out_fmt, use_graph=self.use_graph))
+        key = (n, h, w, in_fmt, out_fmt, self.tile, self.tile_pad, self.pre_pad)
+        return self._plans.get(key, lambda: self.engine.plan(
+            self.net_id, self.arch, n, h, w, scale=self.scale, depth=self.depth, tile=self.tile or 0, tile_pad=self.tile_pad,
+            act_mode=self.act_mode, in_fmt=in_fmt, out_fmt=out_fmt, use_graph=self.use_graph, pre_pad=self.pre_pad or 0))
 
     def plan_for(self, x):
         n, _, h, w = x.shape
@@ -92,39 +93,7 @@ class _NativeNet(nn.Module):
         if x.dtype not in (torch.float16, torch.float32):
             x = x.float()
         x = x.contiguous()
-        if self.tile and self.tile > 0:
-            return self._forward_tiled(x)
         return self.plan_for(x).run(x)
-
-    def _forward_tiled(self, x):
-        """RealESRGANer.tile_process semantics: tiles_x = ceil(W/tile), padded
-        crop clamped to the image, paste of the un-padded centre, no blending.
-
-        Tiles are independent images, so all padded crops of one shape (interior tiles, and each border class) go
-        through the engine as ONE batch: at tile 256..512 a single crop is only a few rows of work per SM and the
-        per-kernel prologue / tail would dominate."""
-        import math
-        b, c, h, w = x.shape
-        s, tile, pad = self.scale, self.tile, self.tile_pad
-        out = torch.zeros(b, c, h * s, w * s, device=x.device, dtype=self.out_dtype)
-        groups = {}  # padded crop shape -> list of tile boxes
-        for ty in range(math.ceil(h / tile)):
-            for tx in range(math.ceil(w / tile)):
-                sx, sy = tx * tile, ty * tile
-                ex, ey = min(sx + tile, w), min(sy + tile, h)
-                sxp, exp_ = max(sx - pad, 0), min(ex + pad, w)
-                syp, eyp = max(sy - pad, 0), min(ey + pad, h)
-                groups.setdefault((eyp - syp, exp_ - sxp), []).append((sx, sy, ex, ey, sxp, syp, exp_, eyp))
-        max_batch = max(1, self.tile_batch // b)
-        for boxes in groups.values():
-            for g0 in range(0, len(boxes), max_batch):
-                part = boxes[g0:g0 + max_batch]
-                crops = torch.cat([x[:, :, syp:eyp, sxp:exp_] for (_, _, _, _, sxp, syp, exp_, eyp) in part], dim=0).contiguous()
-                o = self.plan_for(crops).run(crops)
-                for i, (sx, sy, ex, ey, sxp, syp, _, _) in enumerate(part):
-                    ox0, oy0 = (sx - sxp) * s, (sy - syp) * s
-                    out[:, :, sy * s:ey * s, sx * s:ex * s] = o[i * b:(i + 1) * b, :, oy0:oy0 + (ey - sy) * s, ox0:ox0 + (ex - sx) * s]
-        return out
 
     # weights are not nn.Parameters: these keep callers such as ``model.eval().to(device)`` working
     def half(self):
@@ -213,7 +182,7 @@ def build_model(factor=4, device=0, input_shape=(720, 1280), batch_size=8, denoi
         convs = [k for k, v in state_dict.items() if k.startswith('body.') and k.endswith('.weight') and v.ndim == 4]
         depth = len(convs) - 2 if len(convs) >= 2 else depth
     cls = NativeSRVGG if arch == L.ARCH_SRVGG else NativeRRDBNet
-    kw = dict(device=device, act_mode=act_mode, tile=args.tile, tile_pad=args.tile_pad)
+    kw = dict(device=device, act_mode=act_mode, tile=args.tile, tile_pad=args.tile_pad, pre_pad=args.pre_pad)
     if arch == L.ARCH_SRVGG:
         model = cls(state_dict, num_conv=depth, upscale=netscale, **kw)
     else:

@@ -140,22 +140,21 @@ def test_run_host_async_matches_run_host(engine):
 
 
 def test_fused_rdb_equals_conv_by_conv(model, net, monkeypatch):
-    """The fused residual-dense-block launch (csrc/rdb_fused.cu: five convs per launch, cross-CTA progress counters
-    instead of kernel boundaries) performs the same arithmetic in the same order as the conv-by-conv trunk: the frames
-    must be bit-identical, run after run (a missed dependency shows up as a stale row somewhere in 69 blocks)."""
+    """The fused residual-dense-block launch (csrc/rdb_fused.cu, opt-in with SS4K_RDB_FUSE=1: six phases per launch,
+    cross-CTA progress counters instead of kernel boundaries, half-band shifted schedule, weight ring) performs the same
+    arithmetic in the same order as the conv-by-conv trunk: the frames must be bit-identical, run after run (a missed
+    dependency shows up as a stale row somewhere in 69 blocks)."""
     x = _frames(2, seed=11).cuda()
-    plan = model._plan(1, H, W, L.FMT_F32_NCHW, L.FMT_F16_NCHW)
-    assert plan.fused_blocks == 69 and plan.launches == plan.steps - 4 * 69
-    fused = [plan.run(x[i:i + 1].contiguous()).clone() for i in range(2)]
-    again = [plan.run(x[i:i + 1].contiguous()).clone() for i in range(2)]
-    monkeypatch.setenv("SS4K_NO_RDB_FUSE", "1")
-    m2 = realesrgan.NativeRRDBNet(net.state_dict(), scale=2, num_block=23, device=0)
-    p2 = m2._plan(1, H, W, L.FMT_F32_NCHW, L.FMT_F16_NCHW)
+    p2 = model._plan(1, H, W, L.FMT_F32_NCHW, L.FMT_F16_NCHW)
     assert p2.fused_blocks == 0 and p2.launches == p2.steps
-    for i in range(2):
-        want = p2.run(x[i:i + 1].contiguous())
-        assert torch.equal(fused[i], want)
-        assert torch.equal(again[i], want)
+    want = [p2.run(x[i:i + 1].contiguous()).clone() for i in range(2)]
+    monkeypatch.setenv("SS4K_RDB_FUSE", "1")
+    m2 = realesrgan.NativeRRDBNet(net.state_dict(), scale=2, num_block=23, device=0)
+    plan = m2._plan(1, H, W, L.FMT_F32_NCHW, L.FMT_F16_NCHW)
+    assert plan.fused_blocks == 69 and plan.launches == plan.steps - 4 * 69
+    for rep in range(3):
+        for i in range(2):
+            assert torch.equal(plan.run(x[i:i + 1].contiguous()), want[i])
     m2.close()
 
 
@@ -164,7 +163,6 @@ def test_early_activation_loads_are_sound(net, monkeypatch):
     the engine checks the occupancy when it sets the mask, and the result must not depend on it: conv-by-conv trunk
     with and without the early loads, bit for bit at full size (small shapes never take this path)."""
     x = _frames(1, seed=13).cuda()
-    monkeypatch.setenv("SS4K_NO_RDB_FUSE", "1")
     a = realesrgan.NativeRRDBNet(net.state_dict(), scale=2, num_block=23, device=0)
     ya = a._plan(1, H, W, L.FMT_F32_NCHW, L.FMT_F16_NCHW).run(x).clone()
     monkeypatch.setenv("SS4K_NO_EARLY_LOAD", "1")

@@ -72,8 +72,9 @@ def test_rrdbnet(engine, scale, blocks, h, w):
 
 
 def test_rrdbnet_tiled_matches_oracle_tiles(engine):
-    """tile / tile_pad option (RealESRGANer.tile_process semantics): compare with the oracle run
-    through the SAME tiling (tiled vs untiled cannot meet 50 dB)."""
+    """tile / tile_pad option (RealESRGANer.tile_process semantics), applied inside the engine plan (crop gather, one
+    batch per crop-shape class, paste: csrc/engine.cu create_tiled_plan): compare with the oracle run through the SAME
+    tiling (tiled vs untiled cannot meet 50 dB)."""
     torch.manual_seed(0)
     net = rrdbnet.RRDBNet(3, 3, 2, 64, 3, 32).eval()
     x = torch.rand(1, 3, 80, 112)
@@ -93,7 +94,6 @@ def test_rrdbnet_tiled_batched_groups(engine):
     with torch.no_grad():
         want = rrdbnet.tile_process(net, x, 4, 32, 6)
     model = realesrgan.NativeRRDBNet(net.state_dict(), scale=4, num_block=2, device=0, tile=32, tile_pad=6)
-    model.tile_batch = 8
     got = model(x.cuda())
     assert tuple(got.shape) == (2, 3, 400, 600)
     psnr, maxabs = gate(got, want)
@@ -156,3 +156,63 @@ def test_rrdbnet_uint8_frames_ragged_width(engine):
     d = (got.permute(0, 3, 1, 2).float() - want * 255.0)
     # truncating quantisation (fsrcnn_upscaler.py:233): got == floor(255 * y) up to the fp16 error of y
     assert d.max().item() <= 0.6 and d.min().item() >= -1.6, (d.min().item(), d.max().item())
+
+
+def test_rrdbnet_1080p_tile512_every_shape_class(engine):
+    """BASELINE.json configs[3] geometry: 1920x1080 frame, tile 512, tile_pad 10 (the reference defaults,
+    realesrgan/factory.py:93-94) -> 4 x 3 tiles in 9 padded-crop shape classes (522/532/406 x 522/532/76 ...), every
+    class a batch of its own inside ONE engine run.  RRDBNet x2 with 2 blocks (the tiling, not the depth, is under
+    test) against the oracle's tile_process on the whole frame; uint8 frames in and out as the service passes them."""
+    torch.manual_seed(2)
+    net = rrdbnet.RRDBNet(3, 3, 2, 64, 2, 32).eval()
+    g = torch.Generator().manual_seed(4)
+    base = torch.rand(1, 3, 135, 240, generator=g)
+    x = (torch.nn.functional.interpolate(base, size=(1080, 1920), mode="bilinear") + 0.03 * torch.randn(1, 3, 1080, 1920, generator=g)).clamp(0, 1)
+    with torch.no_grad():
+        want = rrdbnet.tile_process(net, x, 2, 512, 10)
+    model = realesrgan.NativeRRDBNet(net.state_dict(), scale=2, num_block=2, device=0, tile=512, tile_pad=10)
+    got = model(x.cuda())
+    assert tuple(got.shape) == (1, 3, 2160, 3840)
+    psnr, maxabs = gate(got, want)
+    print(f"RRDBNet-2 x2 1920x1080 tile 512 / pad 10: PSNR {psnr:.1f} dB, max|err| {maxabs:.3f}/255")
+    assert psnr >= 50 and maxabs <= 2.0
+    plan = model.plan_for(x.cuda())
+    assert plan.launches > 9 * 2          # nine classes: gather + paste each, plus the nets
+    # the same through the uint8 frame boundary
+    u8 = (x * 255).round().to(torch.uint8).permute(0, 2, 3, 1).contiguous()
+    pu = model._plan(1, 1080, 1920, L.FMT_U8_NHWC, L.FMT_U8_NHWC)
+    out = pu.run(u8.cuda()).cpu()
+    with torch.no_grad():
+        want_u8 = rrdbnet.tile_process(net, u8.permute(0, 3, 1, 2).float() / 255.0, 2, 512, 10).clamp(0, 1) * 255
+    d = out.permute(0, 3, 1, 2).float() - want_u8
+    assert d.max().item() <= 0.6 and d.min().item() >= -1.6
+
+
+@pytest.mark.parametrize("h,w,tile,pre_pad", [(45, 71, 0, 0), (44, 70, 0, 6), (45, 71, 32, 5), (60, 90, 40, 4), (45, 70, 32, 0)])
+def test_rrdbnet_x2_pre_pad_and_mod_pad(engine, h, w, tile, pre_pad):
+    """RealESRGANer.pre_process / post_process: reflect pre_pad on the right / bottom, reflect
+    mod-2 pad of the x2 net for odd sizes (upstream pads, it does not refuse), both cropped off the output.  (Tile sizes
+    whose padded crops are even: an odd crop fails in upstream's pixel_unshuffle as it does here.)"""
+    torch.manual_seed(3)
+    net = rrdbnet.RRDBNet(3, 3, 2, 64, 2, 32).eval()
+    x = torch.rand(2, 3, h, w)
+    with torch.no_grad():
+        want = rrdbnet.enhance_tensor(net, x, 2, tile=tile, tile_pad=6, pre_pad=pre_pad)
+    model = realesrgan.NativeRRDBNet(net.state_dict(), scale=2, num_block=2, device=0, tile=tile, tile_pad=6, pre_pad=pre_pad)
+    got = model(x.cuda())
+    assert tuple(got.shape) == (2, 3, 2 * h, 2 * w) == tuple(want.shape)
+    psnr, maxabs = gate(got, want)
+    assert psnr >= 50 and maxabs <= 2.0
+
+
+def test_srvgg_x4_tiled_with_pre_pad(engine):
+    torch.manual_seed(4)
+    net = srvgg.SRVGGNetCompact(3, 3, 64, 16, 4).eval()
+    x = torch.rand(1, 3, 50, 77)
+    with torch.no_grad():
+        want = rrdbnet.enhance_tensor(net, x, 4, tile=24, tile_pad=4, pre_pad=3)
+    model = realesrgan.NativeSRVGG(net.state_dict(), num_conv=16, upscale=4, device=0, tile=24, tile_pad=4, pre_pad=3)
+    got = model(x.cuda())
+    assert tuple(got.shape) == (1, 3, 200, 308)
+    psnr, maxabs = gate(got, want)
+    assert psnr >= 50 and maxabs <= 2.0

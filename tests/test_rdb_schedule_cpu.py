@@ -2,7 +2,7 @@
 
 The kernel cuts the frame into column strips x row bands (same band boundaries in every strip), one CTA per band, and
 keeps a CTA on its band through six phases (conv1..4, conv5 as two chunks).  What a phase reads from an earlier one is
-guarded by per-epilogue-warp progress counters; every other phase shifts the bands by half a band (the rows that fall
+guarded by per-epilogue-warp progress counters (a warp announces a row once two newer stores of its own are in flight); every other phase shifts the bands by half a band (the rows that fall
 off the top wrap to the bottom of the strip and are taken last) so that nobody has to wait for them.  This test
 re-states the kernel's integer arithmetic (band split, shift / wrap / rotation, row -> owner CTA and processing
 position, "positions < V are complete" from the eight counters, the verified-row cache) in Python and checks
@@ -98,45 +98,54 @@ class Cta:
 
 
 def poll(geo, ctas, c, p, r, written, visible_ctr=None):
-    """the producer's dependency check for input row r of phase p; returns False if it has to wait"""
+    """the producer's dependency check for input row r of phase p; returns False if it has to wait.  The bands are
+    aligned across strips, so the owners in the strip and its two neighbours sit at the same band / position: one poll
+    reads all three counter sets and the verified range is the smallest of the three."""
     dep = DEP[p]
     if dep < 0:
         return True
-    for s2 in (c.strip - 1, c.strip, c.strip + 1):
-        if s2 < 0 or s2 >= geo.strips:
-            continue
-        lo, hi = c.ok.get((p, s2), (0, 0))
-        if lo <= r < hi:
-            continue
-        j, q, follow, nj = geo.owner(dep, c.n, s2, r)
-        ctr = visible_ctr(j) if visible_ctr else ctas[j].ctr
-        V = min(2 * min(ctr[0:4]), 2 * min(ctr[4:8]) + 1)
+    lo, hi = c.ok.get(p, (0, 0))
+    if not lo <= r < hi:
+        V, q, follow = None, None, None
+        for s2 in (c.strip - 1, c.strip, c.strip + 1):
+            if s2 < 0 or s2 >= geo.strips:
+                continue
+            j, q, follow, nj = geo.owner(dep, c.n, s2, r)
+            ctr = visible_ctr(j) if visible_ctr else ctas[j].ctr
+            Vd = min(2 * min(ctr[0:4]), 2 * min(ctr[4:8]) + 1)
+            V = Vd if V is None else min(V, Vd)
         if not q < V:
             return False
-        c.ok[(p, s2)] = (r, min(r + min(V - q, follow), geo.H))
+        c.ok[p] = (r, min(r + min(V - q, follow), geo.H))
     for s2 in (c.strip - 1, c.strip, c.strip + 1):
         if 0 <= s2 < geo.strips:
             assert (dep, c.n, s2, r) in written, ("stale read", c.idx, p, s2, r)
     return True
 
 
+IN_FLIGHT = 2   # kInFlight of the kernel: TMA stores per epilogue warp that may still be in flight
+
+
 def compute_row(c, written):
+    """the epilogue of the next row of CTA c: store it, announce every row of the warp except the IN_FLIGHT newest"""
     q = c.done
     p, y = c.rows[q]
     par = q & 1
-    for quarter in range(4):
-        w = par * 4 + quarter
-        c.ctr[w] += c.pending[w]       # the warp's previous store is complete: publish it
-        c.pending[w] = 0
     written.add((p, c.n, c.strip, y))
-    last_of_phase = q + 2 >= (p + 1) * c.nrows
     for quarter in range(4):
         w = par * 4 + quarter
-        if last_of_phase:
-            c.ctr[w] += 1
-        else:
-            c.pending[w] = 1
+        c.pending[w] += 1                       # issued
+        if c.pending[w] > IN_FLIGHT:
+            c.ctr[w] += c.pending[w] - IN_FLIGHT
+            c.pending[w] = IN_FLIGHT
     c.done += 1
+
+
+def flush(c):
+    """a warp that runs dry (its next accumulator is not ready) waits for its stores in flight and announces them"""
+    for w in range(8):
+        c.ctr[w] += c.pending[w]
+        c.pending[w] = 0
 
 
 @pytest.mark.parametrize("n_img,strips,H,sms,seed", [
@@ -176,10 +185,13 @@ def test_protocol_is_safe_and_live(n_img, strips, H, sms, seed):
                     compute_row(c, written)
                     done_rows += 1
                     progressed = True
+                elif any(c.pending):
+                    flush(c)
+                    progressed = True
         idle = 0 if progressed else idle + 1
         assert idle < 50, "deadlock: no CTA can make progress"
-    for c in ctas:
-        assert c.ctr[0:4] == [(len(c.rows) + 1) // 2] * 4 and c.ctr[4:8] == [len(c.rows) // 2] * 4
+    for c in ctas:   # announced + still in flight == rows of the warp's parity class
+        assert [a + b for a, b in zip(c.ctr, c.pending)] == [(len(c.rows) + 1) // 2] * 4 + [len(c.rows) // 2] * 4
 
 
 def lockstep_makespan(geo, lag):
@@ -215,18 +227,21 @@ def lockstep_makespan(geo, lag):
                 pos[c.idx] += 1
             if not stalled:
                 compute_row(c, written)
+            else:
+                flush(c)
         for c in ctas:
             history[c.idx].append((tick, list(c.ctr)))
     return tick
 
 
 def test_half_band_shift_hides_the_publication_latency():
-    """720p trunk (5 strips x 29 bands of 12-13 rows), counters visible 3 row-times late: with the half-band shift the
-    six phases take exactly 6 x 13 row-times -- nobody ever waits for data, only for the 13-row bands -- while the
-    un-shifted schedule pays the latency at every phase change."""
+    """720p trunk (5 strips x 29 bands of 12-13 rows); a warp announces a row only when two newer stores of its own are
+    in flight (store completion takes a few row-times) and the counter is seen one more row-time later: with the
+    half-band shift the six phases take exactly 6 x 13 row-times -- nobody ever waits for data, only for the 13-row
+    bands -- while the un-shifted schedule pays the latency at every phase change."""
     ideal = 6 * 13
-    shifted = lockstep_makespan(Geometry(1, 5, 360, 148, shifted=True), lag=3)
-    plain = lockstep_makespan(Geometry(1, 5, 360, 148, shifted=False), lag=3)
+    shifted = lockstep_makespan(Geometry(1, 5, 360, 148, shifted=True), lag=1)
+    plain = lockstep_makespan(Geometry(1, 5, 360, 148, shifted=False), lag=1)
     print(f"row-times for six phases: ideal {ideal}, shifted {shifted}, un-shifted {plain}")
     assert shifted == ideal
     assert plain >= ideal + 5
