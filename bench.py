@@ -384,7 +384,7 @@ def run_native_cfg3(args, rank, world, local_rank):
     e2e_fps = T_all * args.steps / e2e_s
 
     # ---- per-kernel-class shares: un-graphed plan runs with CUDA events between the steps
-    den_plan = pipe.den_plan(T)
+    den_plan = pipe.den_plan(T, ch.lo - ch.load_lo, ch.hi - ch.load_lo)
     den_out = den_plan.new_output()
     prof_den = den_plan.profile(chunks_dev[0], den_out)
     lr0 = pipe._lr[F][0:1]
@@ -421,8 +421,8 @@ def run_native_cfg3(args, rank, world, local_rank):
                        "weights": "random init: BSVD reference constructor (kaiming_normal_), RRDBNet upstream basicsr init, seed 0",
                        "noise_map": NOISE,
                        "l2": "no flush: every step streams > 100 GB through HBM (BSVD clip tensors of %d frames, 13.5 GB per upscaled frame), >> 126 MB L2; %d input chunks rotated" % (T, n_in),
-                       "parallelism": f"contiguous frame chunks x{world}, 16-frame BSVD halo per side (sharding.bsvd_chunks), NCCL gather of uint8 frames to rank 0 inside the step",
-                       "ms_per_frame": {"bsvd_per_denoised_frame": den_ms / T, "rrdb_per_upscaled_frame": sr_ms,
+                       "parallelism": f"contiguous frame chunks x{world}, 16-frame BSVD halo per side (sharding.bsvd_chunks; every BSVD layer runs only on the halo frames the owned outputs depend on), NCCL gather of uint8 frames to rank 0 inside the step",
+                       "ms_per_frame": {"bsvd_per_owned_frame": den_ms / F, "rrdb_per_upscaled_frame": sr_ms,
                                         "note": "un-graphed profile runs (serialised launches)"},
                        "launch": "BSVD clip: %d kernels per chunk, RRDBNet: %d per frame, CUDA graphs; programmatic dependent launch %s"
                                  % (den_plan.launches, pipe.sr_plan.launches, "off" if os.environ.get("SS4K_NO_PDL") else "on")},

@@ -76,18 +76,24 @@ class NativeBSVD(nn.Module):
         self.net_id = self.engine.new_net(state_dict)
         self._plans = PlanCache(max_plans)
 
-    def _plan(self, t, h, w, in_fmt, out_fmt, noise=0.0):
-        return self._plans.get((t, h, w, in_fmt, out_fmt, float(noise)), lambda: self.engine.plan(
+    def _plan(self, t, h, w, in_fmt, out_fmt, noise=0.0, own=None):
+        """own = (lo, hi): only frames [lo, hi) of the t-frame clip are wanted (the others are the temporal halo of a
+        sharded stream, sharding.bsvd_chunks): every layer then runs only on the frames the owned outputs depend on
+        (csrc/bsvd_program.cpp) and the plan returns hi - lo frames."""
+        if own is not None and tuple(own) == (0, t):
+            own = None
+        key = (t, h, w, in_fmt, out_fmt, float(noise), tuple(own) if own is not None else None)
+        return self._plans.get(key, lambda: self.engine.plan(
             self.net_id, L.ARCH_BSVD, t, h, w, act_mode=self.act_mode, in_fmt=in_fmt, out_fmt=out_fmt,
-            use_graph=self.use_graph, bsvd_noise=noise))
+            use_graph=self.use_graph, bsvd_noise=noise, own=own))
 
-    def denoise_frames(self, frames, h, w, noise, nv12=False):
+    def denoise_frames(self, frames, h, w, noise, nv12=False, own=None):
         """Frame-format entry: a clip of uint8 NHWC RGB frames ``[T,h,w,3]`` or NV12 frames ``[T, h*w*3/2]`` (CUDA) ->
-        ``[T,3,h,w]``; /255, NV12 -> RGB and the constant noise map (0.1 * denoise_rate, fsrcnn_upscaler.py:262) are
-        produced by the engine's layout kernel."""
+        ``[T,3,h,w]`` (``[hi-lo,3,h,w]`` with ``own=(lo, hi)``); /255, NV12 -> RGB and the constant noise map
+        (0.1 * denoise_rate, fsrcnn_upscaler.py:262) are produced by the engine's layout kernel."""
         t = frames.shape[0]
         out_fmt = L.FMT_F16_NCHW if self.out_dtype == torch.float16 else L.FMT_F32_NCHW
-        return self._plan(t, h, w, L.FMT_NV12 if nv12 else L.FMT_U8_NHWC, out_fmt, noise).run(frames.contiguous())
+        return self._plan(t, h, w, L.FMT_NV12 if nv12 else L.FMT_U8_NHWC, out_fmt, noise, own=own).run(frames.contiguous())
 
     def forward(self, x, noise_map=None):
         if noise_map is not None:

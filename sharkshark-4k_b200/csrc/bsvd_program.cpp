@@ -13,6 +13,7 @@
 // [fold, 2 fold) into frame t+1's, so the consumer's TMA loader reads one contiguous pixel row.
 #include "program.h"
 
+#include <algorithm>
 #include <vector>
 
 #include "conv_params.h"
@@ -145,6 +146,38 @@ std::string build_bsvd_clip(const PlanCfgLite& c, Program* P) {
   };
   den_block("temp1.", in16, 16, 4, mid, false);
   den_block("temp2.", t1out, mid, mid, 3, true);
+
+  // ---- owned frames + temporal halo: run every step only on the frames the owned outputs depend on.
+  // Each shift conv reads its input at frames t-1, t, t+1, so a tensor is needed on the owned range widened by the
+  // number of shift convs between it and the output: 16 for the first layers, 0 for the last -- about half the
+  // halo work of a chunk with a 16-frame halo on each side (sharding.bsvd_chunks) falls away.
+  const int own_lo = c.own_hi > c.own_lo ? c.own_lo : 0, own_hi = c.own_hi > c.own_lo ? c.own_hi : T;
+  if (own_lo < 0 || own_hi > T) return "BSVD: owned frame range outside the clip";
+  if (!c.bsvd_stream && (own_lo > 0 || own_hi < T)) {
+    const int nb = static_cast<int>(P->bufs.size());
+    std::vector<int> need(nb, -1), shifted(nb, 0);
+    for (const Step& st : P->steps)
+      if (st.kind == 1 && st.conv.out_buf >= 0 && st.conv.tshift) shifted[st.conv.out_buf] = 1;
+    auto widen = [&](int buf, int r) { if (buf >= 0 && r > need[buf]) need[buf] = r; };
+    for (int si = static_cast<int>(P->steps.size()) - 1; si >= 0; --si) {
+      Step& st = P->steps[si];
+      const int outb = st.kind == 1 ? st.conv.out_buf : st.prep.out_buf;
+      const int R = outb >= 0 ? std::max(need[outb], 0) : 0;   // frames beyond the owned range this step must produce
+      const int n0 = std::max(0, own_lo - R), n1 = std::min(T, own_hi + R);
+      if (st.kind == 1) {
+        ConvSpec& v = st.conv;
+        P->flops -= v.flops();
+        v.n0 = n0; v.n = n1 - n0; v.n_total = T;
+        P->flops += v.flops();
+        widen(v.in_buf, R + (shifted[v.in_buf] ? 1 : 0));
+        widen(v.res1_buf, R);
+        widen(v.res2_buf, R);
+      } else {
+        st.prep.n0 = n0; st.prep.n = n1 - n0;
+      }
+    }
+    P->out_n = own_hi - own_lo;   // the result holds the owned frames only
+  }
   return "";
 }
 

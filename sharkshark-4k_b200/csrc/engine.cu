@@ -534,7 +534,15 @@ void fill_epilogue(const ConvSpec& cs, bool bf16, BufPtr bufptr, float* d_bias, 
   E.slope_const = cs.const_slope;
   E.res1_nch = cs.res1_nch;
   E.up2_store = cs.up2_store;
-  E.t0 = 0; E.t_count = cs.n;
+  E.t0 = cs.n0; E.t_count = cs.n_total > 0 ? cs.n_total : cs.n;
+  if (cs.n0 > 0) {
+    // the kernels index images from 0: a step that starts at frame n0 of the clip gets its tensors' frame n0 as base
+    auto adv = [&](const void* p, int64_t frame_elems) { return p ? static_cast<const void*>(reinterpret_cast<const uint16_t*>(p) + cs.n0 * frame_elems) : p; };
+    const int64_t fo = static_cast<int64_t>(cs.out_h) * cs.out_w * cs.out_pitch;
+    if (cs.out_buf >= 0) { E.out = const_cast<void*>(adv(E.out, fo)); E.out_lo = const_cast<void*>(adv(E.out_lo, fo)); }
+    E.res1 = adv(E.res1, static_cast<int64_t>(cs.out_h) * cs.out_w * cs.res1_pitch);
+    E.res2 = adv(E.res2, static_cast<int64_t>(cs.out_h) * cs.out_w * cs.res2_pitch);
+  }
   E.off_prev = E.off_next = 0;
   E.res1_lo_off = E.res2_lo_off = 0;
   if (cs.res1_buf >= 0 && cs.res1_lo_buf >= 0)
@@ -577,7 +585,7 @@ int materialize_stream(ss4k_ctx* ctx, const ConvSpec& cs, const HostTensor& W, c
     cuuint64_t dims[5] = {static_cast<cuuint64_t>(s2 ? 64 : (nkb0 == 1 ? std::min(64, avail) : 64)),
                           static_cast<cuuint64_t>(s2 ? cs.in_w / 2 : cs.in_w),
                           static_cast<cuuint64_t>(nkb0), static_cast<cuuint64_t>(cs.in_h),
-                          static_cast<cuuint64_t>(cs.in_ring ? cs.in_ring : cs.n)};
+                          static_cast<cuuint64_t>(cs.in_ring ? cs.in_ring : (cs.n_total > 0 ? cs.n_total : cs.n))};
     cuuint64_t strides[4] = {(s2 ? 2 : 1) * cs.in_pitch * eb, 128, static_cast<cuuint64_t>(cs.in_w) * cs.in_pitch * eb,
                              static_cast<cuuint64_t>(cs.in_h) * cs.in_w * cs.in_pitch * eb};
     cuuint32_t box[5] = {64, static_cast<cuuint32_t>(kBoxW), 1, 1, 1};
@@ -624,8 +632,9 @@ int materialize_stream(ss4k_ctx* ctx, const ConvSpec& cs, const HostTensor& W, c
       (pk.nout == 16 || pk.nout == 32 || pk.nout == 64) && getenv("SS4K_NO_FAST_STORE") == nullptr) {
     const cuuint64_t eb = 2;
     const int cavail = std::min(cs.out_pitch - cs.out_coff, pk.npad_total);
+    const int out_imgs = cs.out_ring ? cs.out_ring : (cs.n_total > 0 ? cs.n_total : cs.n);
     cuuint64_t dims[4] = {static_cast<cuuint64_t>(cavail), static_cast<cuuint64_t>(cs.out_w), static_cast<cuuint64_t>(cs.out_h),
-                          static_cast<cuuint64_t>(cs.out_ring ? cs.out_ring : cs.n)};
+                          static_cast<cuuint64_t>(out_imgs)};
     cuuint64_t strides[3] = {cs.out_pitch * eb, static_cast<cuuint64_t>(cs.out_w) * cs.out_pitch * eb,
                              static_cast<cuuint64_t>(cs.out_h) * cs.out_w * cs.out_pitch * eb};
     cuuint32_t box[4] = {static_cast<cuuint32_t>(pk.nout), 32, 1, 1};
@@ -637,7 +646,7 @@ int materialize_stream(ss4k_ctx* ctx, const ConvSpec& cs, const HostTensor& W, c
       // nearest-x2 upsample in the store: destination viewed as (C, b, W, a, N*H): pixel (2y+a, 2x+b) of the 2H x 2W image
       const cuuint64_t pb = cs.out_pitch * eb;
       cuuint64_t d5[5] = {static_cast<cuuint64_t>(cavail), 2, static_cast<cuuint64_t>(cs.out_w), 2,
-                          static_cast<cuuint64_t>(cs.out_h) * (cs.out_ring ? cs.out_ring : cs.n)};
+                          static_cast<cuuint64_t>(cs.out_h) * out_imgs};
       cuuint64_t s5[4] = {pb, 2 * pb, 2 * static_cast<cuuint64_t>(cs.out_w) * pb, 4 * static_cast<cuuint64_t>(cs.out_w) * pb};
       cuuint32_t b5[5] = {static_cast<cuuint32_t>(pk.nout), 1, 32, 1, 1};
       r = ctx->encode(&p.tmO, dt, 5, base, d5, s5, b5, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_NONE,
@@ -651,6 +660,7 @@ int materialize_stream(ss4k_ctx* ctx, const ConvSpec& cs, const HostTensor& W, c
   }
   p.nkb = pk.nkb;
   for (int kb = 0; kb < pk.nkb; ++kb) { p.a_kb[kb] = pk.src_kb[kb]; p.a_tm[kb] = pk.src_tm[kb]; p.nks[kb] = pk.nks[kb]; }
+  p.n_in0 = cs.n0; p.n_out0 = cs.n0;   // TMA image coordinates of a step that starts inside the clip
   p.stride2 = pk.stride2; p.nkx = pk.nkx;
   for (int kb = 0; kb < pk.nkb; ++kb) { p.ksm[kb][0] = pk.ksm[kb][0]; p.ksm[kb][1] = pk.ksm[kb][1]; }
   p.n_img = cs.n; p.H = pk.stride2 ? cs.in_h / 2 : cs.in_h; p.W = pk.stride2 ? cs.in_w / 2 : cs.in_w;  // the output grid
@@ -732,7 +742,7 @@ int materialize_conv(ss4k_ctx* ctx, const ConvSpec& cs, const HostTensor& W, con
   CK(ctx, cudaMemcpy(ex->d_slope, pw.slope.data(), pw.slope.size() * 4, cudaMemcpyHostToDevice));
   // tensor maps
   const int box_w = ctx->desc_mode == 2 ? kTileW : kBoxW;
-  const int in_imgs = cs.in_ring ? cs.in_ring : cs.n;
+  const int in_imgs = cs.in_ring ? cs.in_ring : (cs.n_total > 0 ? cs.n_total : cs.n);
   e = encode_act_map(ctx, &p.tmA[0], bufptr(cs.in_buf), in_imgs, cs.in_h, cs.in_w, cs.in_pitch, cs.mode, bf16, box_w);
   if (!e.empty()) return fail(ctx, SS4K_E_CUDA, e);
   if (cs.split) {
@@ -750,6 +760,7 @@ int materialize_conv(ss4k_ctx* ctx, const ConvSpec& cs, const HostTensor& W, con
   for (int i = 0; i < pw.nkb; ++i)
     for (int j = 0; j < kMaxTaps; ++j) p.ksmask[i][j] = pw.mask[static_cast<size_t>(i) * kMaxTaps + j];
   p.n_img = cs.n; p.H = AH; p.W = AW; p.R = t.R;
+  p.n_in0 = cs.n0;
   p.tiles_x = t.tiles_x; p.tiles_y = t.tiles_y; p.n_chunks = t.n_chunks; p.n_tiles = t.n_tiles;
   p.n_cta = t.n_cta; p.acc_stride = t.acc_stride;
   p.a_slots = t.a_slots; p.a_slot_bytes = t.a_slot_bytes; p.a_sub_bytes = t.a_sub_bytes;
@@ -832,9 +843,13 @@ int run_step(ss4k_plan* pl, int si, const void* in_dev, void* out_dev, cudaStrea
   if (s.kind == 0) {
     const PrepSpec& p = s.prep;
     const bool bf16 = pl->cfg.act_mode == SS4K_ACT_BF16;
-    CK(ctx, prep_launch(p.in_fmt, in_dev, pl->bufs[p.out_buf], p.out_lo_buf >= 0 ? pl->bufs[p.out_lo_buf] : nullptr,
-                        p.n, p.c, p.h, p.w, pl->prog.bufs[p.out_buf].pitch, p.unshuffle, p.fill_ch, p.fill_val,
-                        bf16 ? 1 : 0, st));
+    // (a BSVD chunk with a temporal halo converts only the frames [n0, n0 + n) the owned outputs depend on)
+    const BufSpec& ob = pl->prog.bufs[p.out_buf];
+    const size_t in_off = static_cast<size_t>(fmt_bytes(p.in_fmt, 1, pl->prog.in_c, p.h, p.w)) * p.n0;
+    const size_t out_off = static_cast<size_t>(ob.h) * ob.w * ob.pitch * 2 * p.n0;
+    CK(ctx, prep_launch(p.in_fmt, reinterpret_cast<const uint8_t*>(in_dev) + in_off, reinterpret_cast<uint8_t*>(pl->bufs[p.out_buf]) + out_off,
+                        p.out_lo_buf >= 0 ? reinterpret_cast<uint8_t*>(pl->bufs[p.out_lo_buf]) + out_off : nullptr,
+                        p.n, p.c, p.h, p.w, ob.pitch, p.unshuffle, p.fill_ch, p.fill_val, bf16 ? 1 : 0, st));
     ctx->launches++;
   } else {
     ConvExec& c = pl->convs[pl->step_conv[si]];
@@ -1118,6 +1133,7 @@ static PlanCfgLite lite(const ss4k_plan_cfg* c) {
   l.arch = c->arch; l.n = c->n; l.h = c->h; l.w = c->w; l.scale = c->scale; l.depth = c->depth;
   l.tile = c->tile; l.tile_pad = c->tile_pad; l.act_mode = c->act_mode; l.in_fmt = c->in_fmt; l.out_fmt = c->out_fmt;
   memcpy(&l.bsvd_noise, &c->reserved[0], 4);
+  l.own_lo = c->reserved[2]; l.own_hi = c->reserved[3];
   return l;
 }
 

@@ -242,14 +242,14 @@ std::string Program::to_json() const {
     if (s.kind == 0) {
       const PrepSpec& p = s.prep;
       js_ks(o, "kind", "prep"); js_kv(o, "in_fmt", p.in_fmt); js_kv(o, "c", p.c); js_kv(o, "h", p.h);
-      js_kv(o, "w", p.w); js_kv(o, "n", p.n); js_kv(o, "unshuffle", p.unshuffle);
+      js_kv(o, "w", p.w); js_kv(o, "n", p.n); js_kv(o, "n0", p.n0); js_kv(o, "unshuffle", p.unshuffle);
       js_kv(o, "out_buf", p.out_buf); js_kv(o, "out_lo_buf", p.out_lo_buf);
       js_kv(o, "fill_ch", p.fill_ch); js_kv(o, "fill_val", p.fill_val, true);
     } else {
       const ConvSpec& c = s.conv;
       js_ks(o, "kind", "conv"); js_ks(o, "name", c.name); js_ks(o, "wname", c.wname);
       js_ks(o, "bname", c.bname); js_ks(o, "sname", c.sname); js_kv(o, "const_slope", c.const_slope);
-      js_kv(o, "mode", c.mode); js_kv(o, "n", c.n); js_kv(o, "cin", c.cin); js_kv(o, "cout", c.cout);
+      js_kv(o, "mode", c.mode); js_kv(o, "n", c.n); js_kv(o, "n0", c.n0); js_kv(o, "n_total", c.n_total); js_kv(o, "cin", c.cin); js_kv(o, "cout", c.cout);
       js_kv(o, "in_buf", c.in_buf); js_kv(o, "in_lo_buf", c.in_lo_buf); js_kv(o, "in_h", c.in_h);
       js_kv(o, "in_w", c.in_w); js_kv(o, "in_pitch", c.in_pitch); js_kv(o, "in_coff", c.in_coff);
       js_kv(o, "act", c.act); js_kv(o, "alpha", c.alpha); js_kv(o, "beta1", c.beta1);

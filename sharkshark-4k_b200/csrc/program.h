@@ -26,6 +26,7 @@ struct PrepSpec {
   int c = 3;            // source channels
   int h = 0, w = 0;     // source frame size
   int n = 1;
+  int n0 = 0;           // first frame of the clip this step processes (BSVD chunks with a temporal halo, bsvd_program.cpp)
   int unshuffle = 1;    // pixel_unshuffle factor
   int out_buf = kBufNone, out_lo_buf = kBufNone;
   int fill_ch = -1;     // channel receiving a constant (BSVD noise map), or -1
@@ -38,6 +39,7 @@ struct ConvSpec {
   float const_slope = 0.f;          // LeakyReLU slope when act == 1 and sname is empty
   int mode = 0;                     // ConvMode
   int n = 1;
+  int n0 = 0, n_total = 0;          // BSVD chunk with halo: this step runs frames [n0, n0 + n) of the n_total-frame tensors (0: n0 = 0, all)
   int cin = 0, cout = 0;
   int in_buf = kBufNone, in_lo_buf = kBufNone;
   int in_h = 0, in_w = 0, in_pitch = 0, in_coff = 0;
@@ -100,6 +102,7 @@ struct Program {
 struct PlanCfgLite {
   int arch, n, h, w, scale, depth, tile, tile_pad, act_mode, in_fmt, out_fmt;
   int bsvd_stream = 0;
+  int own_lo = 0, own_hi = 0;  // BSVD: frames of the clip whose result is wanted (0, 0: all); the others are temporal halo
   float bsvd_noise = 0.f;  // noise-map value for 3-channel frame inputs (uint8 NHWC / NV12)  // 1: BSVD program for the streaming engine (separate buffers for temp1 / temp2)
 };
 

@@ -65,10 +65,12 @@ class Engine:
             self.lib.ss4k_clear_weights(self.h, net_id)
 
     def plan(self, net_id, arch, n, h, w, scale=4, depth=0, tile=0, tile_pad=10, act_mode=L.ACT_F16,
-             in_fmt=L.FMT_F32_NCHW, out_fmt=L.FMT_F32_NCHW, use_graph=True, bsvd_noise=0.0, pre_pad=0):
+             in_fmt=L.FMT_F32_NCHW, out_fmt=L.FMT_F32_NCHW, use_graph=True, bsvd_noise=0.0, pre_pad=0, own=None):
         cfg = make_cfg(net_id, arch, n, h, w, scale, depth, tile, tile_pad, act_mode, in_fmt, out_fmt, use_graph)
         cfg.reserved[0] = struct.unpack("<i", struct.pack("<f", float(bsvd_noise)))[0]
         cfg.reserved[1] = int(pre_pad)
+        if own is not None:   # BSVD: frames [lo, hi) of the clip are wanted, the rest is temporal halo
+            cfg.reserved[2], cfg.reserved[3] = int(own[0]), int(own[1])
         return Plan(self, cfg)
 
     def rgb_to_nv12(self, frames):

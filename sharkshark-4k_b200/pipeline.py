@@ -36,9 +36,11 @@ class DenoiseUpscalePipeline:
         self._calls = 0
 
     # ------------------------------------------------------------------ plans
-    def den_plan(self, t):
+    def den_plan(self, t, lo=0, hi=None):
+        """BSVD plan for a t-frame chunk of which frames [lo, hi) are owned (the rest is temporal halo: each layer runs
+        only on the frames the owned outputs depend on); returns the owned frames."""
         in_fmt = L.FMT_NV12 if self.nv12 else L.FMT_U8_NHWC
-        return self.den._plan(t, self.h, self.w, in_fmt, L.FMT_F16_NCHW, self.noise)
+        return self.den._plan(t, self.h, self.w, in_fmt, L.FMT_F16_NCHW, self.noise, own=(lo, t if hi is None else hi))
 
     def frame_bytes_in(self):
         return self.h * self.w * 3 // 2 if self.nv12 else self.h * self.w * 3
@@ -50,11 +52,6 @@ class DenoiseUpscalePipeline:
         dt = {L.FMT_U8_NHWC: torch.uint8, L.FMT_F16_NCHW: torch.float16, L.FMT_F32_NCHW: torch.float32}[self.out_fmt]
         return torch.empty((n_own,) + self.out_frame_shape(), device=self.device, dtype=dt)
 
-    def flops(self, t, n_own):
-        return self.den_plan(t).flops + n_own * self.sr_plan.flops
-
-    def launches(self, t, n_own):
-        return self.den_plan(t).launches + n_own * self.sr_plan.launches
 
     # ------------------------------------------------------------------ device-resident path
     def run(self, frames, own=None, out=None, after_frame=None):
@@ -64,7 +61,7 @@ class DenoiseUpscalePipeline:
         own = own if own is not None else slice(0, t)
         lo, hi, _ = own.indices(t)
         frames = frames.contiguous()
-        den = self.den_plan(t).run(frames)                        # [T,3,H,W] half
+        den = self.den_plan(t, lo, hi).run(frames)                # [n_own,3,H,W] half: the owned frames
         if out is None:
             out = self.new_output(hi - lo)
         n_own = hi - lo
@@ -74,7 +71,7 @@ class DenoiseUpscalePipeline:
         # denoised -> 3x3 reflect sharpen(2e-5) + clamp -> 0.8 * . + 0.2 * original frame (fsrcnn_upscaler.py:278-281)
         st = ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
         src = frames[lo:hi]
-        L.check(self.lib.ss4k_glue_sharpen_blend(ctypes.c_void_p(den[lo:hi].data_ptr()), 1, n_own, 3, self.h, self.w,
+        L.check(self.lib.ss4k_glue_sharpen_blend(ctypes.c_void_p(den.data_ptr()), 1, n_own, 3, self.h, self.w,
                                                  0.00002, 0.8, ctypes.c_void_p(src.data_ptr()), 3 if self.nv12 else 2,
                                                  ctypes.c_void_p(lr.data_ptr()), st), self.den.engine.h)
         for i in range(n_own):

@@ -103,15 +103,18 @@ def run_program(prog, sd, x, quant=None):
                 src = x.reshape(-1, *x.shape[2:])
             if us > 1:
                 src = F.pixel_unshuffle(x, us)
+            n0, nn = st.get("n0", 0), st["n"]          # frames [n0, n0 + n) of the clip (BSVD chunk with a temporal halo)
             dst = bufs[st["out_buf"]]
             dst.zero_()
-            dst[..., :src.shape[1]] = q(_nhwc(src))
+            dst[n0:n0 + nn, ..., :src.shape[1]] = q(_nhwc(src[n0:n0 + nn]))
             if st["fill_ch"] >= 0:
-                dst[..., st["fill_ch"]] = q(torch.tensor(st["fill_val"]))
+                dst[n0:n0 + nn, ..., st["fill_ch"]] = q(torch.tensor(st["fill_val"]))
             continue
         c = st
         cin, cout = c["cin"], c["cout"]
-        src = _nchw(bufs[c["in_buf"]][..., c["in_coff"]:c["in_coff"] + cin])
+        n0, nn = c.get("n0", 0), c["n"]
+        fr = slice(n0, n0 + nn)                          # the frames this step processes
+        src = _nchw(bufs[c["in_buf"]][fr][..., c["in_coff"]:c["in_coff"] + cin])
         w, b = sd[c["wname"]], sd[c["bname"]]
         if c.get("neg_first", 0):
             w, b = w.clone(), b.clone()
@@ -139,9 +142,9 @@ def run_program(prog, sd, x, quant=None):
                 if k == 1 and c.get("res1_nch", 0):
                     nch = c["res1_nch"]
                     r = torch.zeros_like(v)
-                    r[:, :nch] = _nchw(bufs[rb][..., c["res1_coff"]:c["res1_coff"] + nch])
+                    r[:, :nch] = _nchw(bufs[rb][fr][..., c["res1_coff"]:c["res1_coff"] + nch])
                 else:
-                    r = _nchw(bufs[rb][..., c[f"res{k}_coff"]:c[f"res{k}_coff"] + oc])
+                    r = _nchw(bufs[rb][fr][..., c[f"res{k}_coff"]:c[f"res{k}_coff"] + oc])
                 v = v + c[f"beta{k}"] * r
         if om in (0, 3):
             dst = bufs[c["out_buf"]]
@@ -155,12 +158,17 @@ def run_program(prog, sd, x, quant=None):
             vv = q(_nhwc(v))
             if c.get("tshift", 0):   # temporal-shift scatter: time == batch index, out-of-clip slices dropped
                 fold, o = c["fold"], c["out_coff"]
-                dst[:-1, ..., o:o + fold] = vv[1:, ..., :fold]
-                dst[1:, ..., o + fold:o + 2 * fold] = vv[:-1, ..., fold:2 * fold]
-                dst[..., o + 2 * fold:o + oc] = vv[..., 2 * fold:]
+                T = dst.shape[0]
+                for i in range(nn):
+                    t = n0 + i
+                    if t > 0:
+                        dst[t - 1, ..., o:o + fold] = vv[i, ..., :fold]
+                    if t < T - 1:
+                        dst[t + 1, ..., o + fold:o + 2 * fold] = vv[i, ..., fold:2 * fold]
+                dst[fr][..., o + 2 * fold:o + oc] = vv[..., 2 * fold:]
             else:
-                dst[..., c["out_coff"]:c["out_coff"] + npad] = 0
-                dst[..., c["out_coff"]:c["out_coff"] + oc] = vv
+                dst[fr][..., c["out_coff"]:c["out_coff"] + npad] = 0
+                dst[fr][..., c["out_coff"]:c["out_coff"] + oc] = vv
         elif om == 4:    # temporal-shift scatter
             fold = c["fold"]
             vv = q(_nhwc(v))

@@ -88,6 +88,36 @@ def test_bsvd_program(lib, frames):
     assert abs(p720["flops"] / 2e9 - 271.99) < 0.05
 
 
+@pytest.mark.parametrize("T,lo,hi", [(40, 16, 24), (30, 0, 14), (30, 14, 30), (9, 3, 6)])
+def test_bsvd_program_owned_frames_with_halo(lib, T, lo, hi):
+    """A chunk of a sharded stream: frames [lo, hi) are owned, the rest is temporal halo (sharding.bsvd_chunks).  Every
+    layer then runs only on the frames the owned outputs depend on (owned range widened by the number of shift convs
+    between the layer and the output): the result must equal the owned frames of the whole-chunk program exactly, and
+    with a full 16-frame halo on both sides about half of the halo work must be gone."""
+    from oracle import bsvd
+    sd = bsvd.build_bsvd32(0)
+    x = torch.rand(1, T, 4, 8, 16, generator=torch.Generator().manual_seed(7))
+    x[:, :, 3] = 0.075
+    full_cfg = ss4k_b200.make_cfg(0, L.ARCH_BSVD, T, 8, 16)
+    full = ss4k_b200.plan_dry(full_cfg)
+    cfg = ss4k_b200.make_cfg(0, L.ARCH_BSVD, T, 8, 16)
+    cfg.reserved[2], cfg.reserved[3] = lo, hi
+    prog = ss4k_b200.plan_dry(cfg)
+    assert prog["out_n"] == hi - lo and prog["in_n"] == T
+    want = run_program(full, sd, x)[lo:hi]
+    got = run_program(prog, sd, x)
+    assert got.shape == want.shape
+    assert torch.equal(got, want)
+    convs = [s for s in prog["steps"] if s["kind"] == "conv"]
+    assert convs[-1]["n0"] == lo and convs[-1]["n"] == hi - lo               # the last conv: owned frames only
+    assert convs[0]["n0"] == max(0, lo - 16) and convs[0]["n0"] + convs[0]["n"] == min(T, hi + 16)   # 16 shift convs to the output
+    assert all(a["n"] >= b["n"] for a, b in zip(convs, convs[1:]))           # the ranges only shrink towards the output
+    if (T, lo, hi) == (40, 16, 24):
+        halo_full = full["flops"] * (T - (hi - lo)) / T
+        halo_now = prog["flops"] - full["flops"] * (hi - lo) / T
+        assert 0.4 < halo_now / halo_full < 0.6
+
+
 def test_rrdb_memory_management_is_sound(lib):
     """L2 management of the dense block checked against a liveness analysis of the program:
     * a conv that DISCARDS 128-byte lines of a slab (discard_buf / discard_mask: line l = channels [64 l, 64 l + 64))
