@@ -181,6 +181,12 @@ struct StreamParams {
   // Vertically, input row r feeds output row r/2 (ky = 1) when r is even and output rows (r-1)/2 (ky = 2), (r+1)/2
   // (ky = 0) when r is odd: the weight tile stacks its N blocks as [ky2 | ky0 | ky1] so that both cases are one MMA.
   // H, W are the OUTPUT grid; the activation tensor map has 2 H rows of W pairs.
+  // Weight tile group (nkx tiles) read by K block i.  Plain convs: wt[i] = i.  Split precision: the three K blocks of a
+  // 64-channel source block are A_hi*W_hi, A_hi*W_lo, A_lo*W_hi -- the first and the third multiply with the SAME weight
+  // tiles, which are held once (nwt = 2 groups per source block instead of 3: a third less shared memory for weights,
+  // i.e. wider output chunks).
+  uint8_t wt[kMaxSKB];
+  int32_t nwt;                // distinct weight tile groups of one output chunk
   int32_t stride2;
   int32_t nkx;                // weight tiles (horizontal shifts) per K block: 3, or 2 for stride 2
   uint8_t ksm[kMaxSKB][2];    // stride 2: 4-bit mask of the 16-channel k-steps to issue per (K block, shift)

@@ -142,7 +142,7 @@ conv3x3_stream_kernel(const __grid_constant__ StreamParams P) {
   // after the weights: fp32 bias of every chunk (tcgen05.st initialisation), or bias tile + ones tile (bias MMA)
   constexpr bool kBiasMMA = stream_bias_mma(NOUT);
   constexpr uint32_t kBiasTile = NOUT * 128u;
-  const uint32_t bias_base = w_base + static_cast<uint32_t>(P.nkb * P.nkx) * kWTile;
+  const uint32_t bias_base = w_base + static_cast<uint32_t>(P.nwt * P.nkx) * kWTile;
   const uint32_t ones_base = bias_base + kBiasTile;
   const uint32_t a_base = kBiasMMA ? ones_base + kStreamOnesBytes : bias_base + kStreamBiasBytes;
   const uint32_t stage_base = a_base + static_cast<uint32_t>(P.a_slots) * kASlotBytes;
@@ -206,7 +206,7 @@ conv3x3_stream_kernel(const __grid_constant__ StreamParams P) {
       next_band(P, uu, u1, fb);
       early_chunk = fb.chunk;
       if (elect_one()) {
-        const int ntile = P.nkb * P.nkx;
+        const int ntile = P.nwt * P.nkx;
         mbar_expect_tx(w_full, static_cast<uint32_t>(ntile) * kWTile + (kBiasMMA ? kBiasTile : 0u));
         for (int t = 0; t < ntile; ++t)
           tma_load_2d(w_base + t * kWTile, &P.tmW, w_full, 0, (fb.chunk * ntile + t) * 3 * NOUT);
@@ -284,7 +284,7 @@ conv3x3_stream_kernel(const __grid_constant__ StreamParams P) {
         if (b.chunk == early_chunk) {
           early_chunk = -1;  // already requested in the prologue
         } else if (elect_one()) {
-          const int ntile = P.nkb * P.nkx;
+          const int ntile = P.nwt * P.nkx;
           mbar_expect_tx(w_full, static_cast<uint32_t>(ntile) * kWTile + (kBiasMMA ? kBiasTile : 0u));
           for (int t = 0; t < ntile; ++t)
             tma_load_2d(w_base + t * kWTile, &P.tmW, w_full, 0, (b.chunk * ntile + t) * 3 * NOUT);
@@ -477,7 +477,7 @@ conv3x3_stream_kernel(const __grid_constant__ StreamParams P) {
           }
           // descriptor low words (address >> 4): per-MMA offsets are compile-time constants
           const uint32_t a_lo = (a_base + as * kASlotBytes) >> 4;
-          const uint32_t w_lo = (w_base + static_cast<uint32_t>(kb * P.nkx) * kWTile) >> 4;
+          const uint32_t w_lo = (w_base + static_cast<uint32_t>(P.wt[kb] * P.nkx) * kWTile) >> 4;
           const uint32_t wA_lo = w_lo + woffA, wB_lo = w_lo + woffB;
           const int nks = P.nks[kb];
           const uint32_t as_cur = as;

@@ -277,6 +277,8 @@ struct StreamPacked {
   uint8_t src_kb[kMaxSKB];  // 64-channel block of the source tensor read by K block i
   uint8_t src_tm[kMaxSKB];  // 0: the tensor itself (high halves in split mode), 1: its low-half twin
   uint8_t whalf[kMaxSKB];   // 0: weights (high halves), 1: low halves of the weights
+  uint8_t wt[kMaxSKB];      // weight tile group read by K block i (split mode: A_hi*W_hi and A_lo*W_hi share W_hi's tiles)
+  int nwt = 0;              // distinct weight tile groups per output chunk
   int stride2 = 0, nkx = 3;
   uint8_t ksm[kMaxSKB][2];  // stride 2: k-step masks per (K block, horizontal shift)
 };
@@ -296,6 +298,7 @@ bool stream_config(const ConvSpec& cs, StreamPacked* sp) {
   const int nsplit = cs.split ? 3 : 1;
   const int nkb0 = s2 ? 2 * cs.in_pitch / 64 : (cs.cin + 63) / 64;
   const int nkb = nkb0 * nsplit;
+  const int nwt = nkb0 * (cs.split ? 2 : 1);   // W_hi (shared by A_hi and A_lo) and W_lo tile groups per source block
   const int nkx = s2 ? 2 : 3;
   if (nkb > kMaxSKB) return false;
   int cand[4], nc = 0;
@@ -306,13 +309,15 @@ bool stream_config(const ConvSpec& cs, StreamPacked* sp) {
   for (int i = 0; i < nc; ++i) {
     const int nout = cand[i];
     if (npad % nout) continue;
-    const int wbytes = nkb * nkx * 3 * nout * 128 + (stream_bias_mma(nout) ? nout * 128 + kStreamOnesBytes : kStreamBiasBytes);
+    const int wbytes = nwt * nkx * 3 * nout * 128 + (stream_bias_mma(nout) ? nout * 128 + kStreamOnesBytes : kStreamBiasBytes);
     const int stage = kStreamEpiWarps * round_up(32 * nout * 2, 1024);
     const int left = kSmemBytes - 3072 - wbytes - stage;  // 1 KB alignment slack + barriers, row records, row_ready ring
     const int slots = std::min(kMaxSASlots, left / kASlotBytes);
-    if (slots < 3) continue;
+    // a wider chunk is worth it only with enough slabs in flight (experiments: SS4K_MIN_SLOTS)
+    static const int min_slots = getenv("SS4K_MIN_SLOTS") ? std::max(3, atoi(getenv("SS4K_MIN_SLOTS"))) : 3;
+    if (slots < (nout > 16 ? min_slots : 3)) continue;
     sp->nout = nout; sp->chunks = npad / nout; sp->nkb = nkb; sp->npad_total = npad;
-    sp->stride2 = s2 ? 1 : 0; sp->nkx = nkx;
+    sp->stride2 = s2 ? 1 : 0; sp->nkx = nkx; sp->nwt = nwt;
     sp->a_slots = slots; sp->acc_slots = std::min(kMaxAccSlots, kTmemCols / nout) & ~1;  // even: rows alternate between two epilogue warp groups
     for (int kb = 0; kb < nkb; ++kb) {
       const int b0 = kb / nsplit, part = kb % nsplit;
@@ -320,6 +325,7 @@ bool stream_config(const ConvSpec& cs, StreamPacked* sp) {
       sp->src_kb[kb] = static_cast<uint8_t>(b0);
       sp->src_tm[kb] = part == 2 ? 1 : 0;
       sp->whalf[kb] = part == 1 ? 1 : 0;
+      sp->wt[kb] = static_cast<uint8_t>(cs.split ? 2 * b0 + (part == 1 ? 1 : 0) : b0);
       sp->ksm[kb][0] = sp->ksm[kb][1] = 0;
       if (s2) {
         // merged channel m = b0*64 + cc of the pair view: half = m / pitch (0 even pixel, 1 odd pixel), c = m % pitch.
@@ -361,7 +367,8 @@ std::string pack_weights_stream(const ConvSpec& cs, const HostTensor& W, const H
   // weight tiles, then (bias-MMA variant) one bias tile per chunk: row = output channel, K column 0 = high half,
   // column 1 = low half of the bias (the "ones" operand has 1 there)
   const int nkx = out->nkx;
-  const size_t wrows = static_cast<size_t>(out->chunks) * nkb * nkx * 3 * nout;
+  const int nwt = out->nwt;
+  const size_t wrows = static_cast<size_t>(out->chunks) * nwt * nkx * 3 * nout;
   out->bias_row0 = static_cast<int>(wrows);
   out->w.assign((wrows + (stream_bias_mma(nout) ? npad : 0)) * 64, 0);
   // vertical tap of N block `blk`: stride 1 stacks [ky2 | ky1 | ky0] (block = 2 - ky); stride 2 stacks [ky2 | ky0 | ky1]
@@ -373,7 +380,8 @@ std::string pack_weights_stream(const ConvSpec& cs, const HostTensor& W, const H
           for (int co = 0; co < nout; ++co) {
             const int n = orow[ch * nout + co];
             if (n < 0) continue;
-            const size_t row = ((((static_cast<size_t>(ch) * nkb + kb) * nkx + kx) * 3 + blk) * nout + co);
+            if (kb > 0 && out->wt[kb] <= out->wt[kb - 1] && out->whalf[kb] == 0 && cs.split) continue;   // A_lo * W_hi: W_hi's tiles are already there
+            const size_t row = ((((static_cast<size_t>(ch) * nwt + out->wt[kb]) * nkx + kx) * 3 + blk) * nout + co);
             for (int cc = 0; cc < 64; ++cc) {
               int c, wkx;
               if (out->stride2) {
@@ -659,7 +667,8 @@ int materialize_stream(ss4k_ctx* ctx, const ConvSpec& cs, const HostTensor& W, c
     p.fast_store = cs.up2_store ? 2 : 1;
   }
   p.nkb = pk.nkb;
-  for (int kb = 0; kb < pk.nkb; ++kb) { p.a_kb[kb] = pk.src_kb[kb]; p.a_tm[kb] = pk.src_tm[kb]; p.nks[kb] = pk.nks[kb]; }
+  for (int kb = 0; kb < pk.nkb; ++kb) { p.a_kb[kb] = pk.src_kb[kb]; p.a_tm[kb] = pk.src_tm[kb]; p.nks[kb] = pk.nks[kb]; p.wt[kb] = pk.wt[kb]; }
+  p.nwt = pk.nwt;
   p.n_in0 = cs.n0; p.n_out0 = cs.n0;   // TMA image coordinates of a step that starts inside the clip
   p.stride2 = pk.stride2; p.nkx = pk.nkx;
   for (int kb = 0; kb < pk.nkb; ++kb) { p.ksm[kb][0] = pk.ksm[kb][0]; p.ksm[kb][1] = pk.ksm[kb][1]; }
@@ -1654,6 +1663,8 @@ int ss4k_debug_pack(const ss4k_conv_desc* d, int in_pitch, int in_coff, int wper
     for (int i = 0; i < sp.nkb; ++i) js += fmt("%s%d", i ? "," : "", sp.nks[i]);
     js += fmt("],\"stride2\":%d,\"nkx\":%d,\"ksm\":[", sp.stride2, sp.nkx);
     for (int i = 0; i < sp.nkb; ++i) js += fmt("%s[%d,%d]", i ? "," : "", sp.ksm[i][0], sp.ksm[i][1]);
+    js += fmt("],\"nwt\":%d,\"wt\":[", sp.nwt);
+    for (int i = 0; i < sp.nkb; ++i) js += fmt("%s%d", i ? "," : "", sp.wt[i]);
     js += "],\"src_kb\":[";
     for (int i = 0; i < sp.nkb; ++i) js += fmt("%s%d", i ? "," : "", sp.src_kb[i]);
     js += "],\"bias\":[";

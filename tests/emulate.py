@@ -211,7 +211,8 @@ def debug_pack_stream(lib, L, w, bias=None, slope=None, in_pitch=None, in_coff=0
     meta = json.loads(ctypes.string_at(js).decode())
     arr = (ctypes.c_float * cnt.value).from_address(pk.value)
     flat = torch.tensor(list(arr), dtype=torch.float32).reshape(-1, 64)
-    packed = flat[:meta["w_rows"]].reshape(meta["chunks"], meta["nkb"], meta["nkx"], 3, meta["nout"], 64)
+    # weight tile groups: one per K block, except that the A_hi*W_hi and A_lo*W_hi K blocks of the split mode share one
+    packed = flat[:meta["w_rows"]].reshape(meta["chunks"], meta["nwt"], meta["nkx"], 3, meta["nout"], 64)[:, meta["wt"]]
     # (the 64-wide variant appends one bias tile per chunk: bias hi / lo halves in K columns 0 / 1, for its bias MMA)
     meta["bias_tiles"] = flat[meta["w_rows"]:]
     # meta["bias_f"]: fp32 bias with alpha folded in, [chunks * nout] -- the accumulators' initial value

@@ -196,5 +196,6 @@ def test_stream_stride2_split_blocks(lib):
     wt = _exact_weights(64, 32, 41)
     meta, packed = debug_pack_stream(lib, L, wt, mode=2, in_pitch=32, act_mode=L.ACT_F16_SPLIT)
     assert meta["nkb"] == 3 and meta["src_kb"] == [0, 0, 0] and meta["ksm"] == [[12, 15]] * 3
-    assert torch.equal(packed[0, 0], packed[0, 2])          # A_hi*W_hi and A_lo*W_hi share the weight tile
+    assert meta["nwt"] == 2 and meta["wt"] == [0, 1, 0]      # A_hi*W_hi and A_lo*W_hi share ONE weight tile group
+    assert torch.equal(packed[0, 0], packed[0, 2])
     assert torch.count_nonzero(packed[0, 1]) == 0             # exactly representable weights: the low halves are zero
