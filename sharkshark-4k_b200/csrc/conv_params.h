@@ -142,9 +142,11 @@ struct StreamParams {
   CUtensorMap tmW;      // 2-D (64, rows), box (64, 3*NOUT): rows = [chunk][kb][kx][2-ky][NOUT], then bias tiles (NOUT == 64)
   CUtensorMap tmB;      // same tensor, box (64, NOUT): the per-chunk bias tile (bias hi/lo in K columns 0/1; NOUT == 64)
   CUtensorMap tmO;      // NHWC output, 4-D (C, W, H, N), box (NOUT, 32, 1, 1), swizzled: TMA store of the fast path
+  CUtensorMap tmO2;     // split precision: the same map over the low-half twin of the output tensor
   Epilogue ep;
   int32_t fast_store;   // 1: plain NHWC output -> registers -> swizzled smem tile -> TMA store;
                         // 2: the same tile stored four times through a 5-D (C, b, W, a, N*H) map: nearest-x2 upsample
+                        // 3: split precision (hi + lo twins): two staging tiles per warp, two TMA stores
   const float* bias_f;  // [chunks * NOUT] fp32 bias with alpha folded in: the accumulators' initial value
   int32_t bias_row0;    // first row of the bias tiles inside the weight tensor (NOUT == 64)
   uint8_t a_kb[kMaxSKB];  // source 64-channel block of K block i

@@ -146,7 +146,9 @@ conv3x3_stream_kernel(const __grid_constant__ StreamParams P) {
   const uint32_t ones_base = bias_base + kBiasTile;
   const uint32_t a_base = kBiasMMA ? ones_base + kStreamOnesBytes : bias_base + kStreamBiasBytes;
   const uint32_t stage_base = a_base + static_cast<uint32_t>(P.a_slots) * kASlotBytes;
-  const uint32_t bar_base = stage_base + kStreamEpiWarps * ((kStageWarp + 1023u) & ~1023u);
+  // (split-precision fast store: a second tile per warp for the low halves)
+  const uint32_t stage_stride = ((P.fast_store == 3 ? 2u * kStageWarp : kStageWarp) + 1023u) & ~1023u;
+  const uint32_t bar_base = stage_base + kStreamEpiWarps * stage_stride;
   const uint32_t a_full = bar_base;
   const uint32_t a_empty = a_full + 8 * kMaxSASlots;
   const uint32_t acc_full = a_empty + 8 * kMaxSASlots;
@@ -559,7 +561,8 @@ conv3x3_stream_kernel(const __grid_constant__ StreamParams P) {
     const int qd = warp & 3;       // TMEM lane quarter this warp may access
     const int par = ew >> 2;       // this warp takes the CTA's output rows with (row counter & 1) == par
     const int m = qd * 32 + lane;  // accumulator row == pixel inside the strip
-    const uint32_t stage = stage_base + static_cast<uint32_t>(ew) * ((kStageWarp + 1023u) & ~1023u);
+    const uint32_t stage = stage_base + static_cast<uint32_t>(ew) * stage_stride;
+    const bool split_store = P.fast_store == 3;
     const bool bf16 = E.is_bf16 != 0;
     const bool fast = P.fast_store != 0;
     const uint64_t pol_out = l2_policy(P.l2_out);
@@ -708,6 +711,26 @@ conv3x3_stream_kernel(const __grid_constant__ StreamParams P) {
                   }
                   sts128(srow + ((static_cast<uint32_t>(j) ^ sxor) << 4), h2(v[0], v[1]), h2(v[2], v[3]), h2(v[4], v[5]), h2(v[6], v[7]));
                 }
+              } else if (split_store) {
+                // split precision (BSVD, SS4K_ACT_F16_SPLIT): value = hi + lo with hi = fp16(v), lo = fp16(v - hi); ReLU6 or
+                // linear, no residuals (the planner sends everything else through the general path)
+                const bool relu6 = E.act == kActRelu6;
+#pragma unroll
+                for (int j = 0; j < NOUT / 8; ++j) {
+                  uint32_t hi[4], lo[4];
+#pragma unroll
+                  for (int i = 0; i < 4; ++i) {
+                    float a = __uint_as_float(raw[8 * j + 2 * i]), c = __uint_as_float(raw[8 * j + 2 * i + 1]);
+                    if (relu6) { a = fminf(fmaxf(a, 0.f), 6.f); c = fminf(fmaxf(c, 0.f), 6.f); }
+                    const __half2 h = __floats2half2_rn(a, c);
+                    const float2 back = __half22float2(h);
+                    hi[i] = *reinterpret_cast<const uint32_t*>(&h);
+                    lo[i] = h2(a - back.x, c - back.y);
+                  }
+                  const uint32_t off = (static_cast<uint32_t>(j) ^ sxor) << 4;
+                  sts128(srow + off, hi[0], hi[1], hi[2], hi[3]);
+                  sts128(srow + kStageWarp + off, lo[0], lo[1], lo[2], lo[3]);
+                }
               } else if (emode == 4) {
 #pragma unroll
                 for (int j = 0; j < NOUT / 8; ++j) {
@@ -805,6 +828,7 @@ conv3x3_stream_kernel(const __grid_constant__ StreamParams P) {
                     tma_store_5d(&P.tmO, stage, b.chunk * NOUT, ab & 1, b.strip * kTileW + qd * 32, ab >> 1, (b.n + P.n_out0) * P.H + y, pol_out);
                 } else {
                   tma_store_4d(&P.tmO, stage, b.chunk * NOUT, b.strip * kTileW + qd * 32, y, b.n + P.n_out0, pol_out);
+                  if (split_store) tma_store_4d(&P.tmO2, stage + kStageWarp, b.chunk * NOUT, b.strip * kTileW + qd * 32, y, b.n + P.n_out0, pol_out);
                 }
                 bulk_commit();
               }

@@ -281,7 +281,20 @@ struct StreamPacked {
   int nwt = 0;              // distinct weight tile groups per output chunk
   int stride2 = 0, nkx = 3;
   uint8_t ksm[kMaxSKB][2];  // stride 2: k-step masks per (K block, horizontal shift)
+  int split_fast = 0;       // split precision with the hi / lo twin staging tiles and two TMA stores (StreamParams::fast_store 3)
 };
+
+// Output side of a conv that can leave through the swizzled staging tile + TMA store.
+static bool stream_fast_store_ok(const ConvSpec& cs, int nout) {
+  return cs.out_mode == kOutNHWC && cs.out_buf >= 0 && cs.out_coff % 8 == 0 && cs.out_pitch % 8 == 0 && !cs.tshift &&
+         (cs.res1_nch == 0 || (cs.res1_nch <= 8 && cs.res1_pitch >= 8 && cs.res1_coff % 8 == 0 && cs.res1_lo_buf < 0)) &&
+         (nout == 16 || nout == 32 || nout == 64) && getenv("SS4K_NO_FAST_STORE") == nullptr;
+}
+// ... and, for the hi / lo output pair of split precision: ReLU6 or linear, no residual, nothing folded behind the activation
+static bool stream_split_fast_ok(const ConvSpec& cs, int nout) {
+  return cs.out_lo_buf >= 0 && stream_fast_store_ok(cs, nout) && cs.res1_buf < 0 && cs.res2_buf < 0 && !cs.up2_store &&
+         (cs.act == kActNone || cs.act == kActRelu6) && cs.alpha == 1.f && getenv("SS4K_NO_SPLIT_FAST") == nullptr;
+}
 
 bool stream_config(const ConvSpec& cs, StreamPacked* sp) {
   const bool s2 = cs.mode == kModeS2;
@@ -310,14 +323,18 @@ bool stream_config(const ConvSpec& cs, StreamPacked* sp) {
     const int nout = cand[i];
     if (npad % nout) continue;
     const int wbytes = nwt * nkx * 3 * nout * 128 + (stream_bias_mma(nout) ? nout * 128 + kStreamOnesBytes : kStreamBiasBytes);
-    const int stage = kStreamEpiWarps * round_up(32 * nout * 2, 1024);
-    const int left = kSmemBytes - 3072 - wbytes - stage;  // 1 KB alignment slack + barriers, row records, row_ready ring
+    int stage = kStreamEpiWarps * round_up(32 * nout * 2, 1024);
+    int left = kSmemBytes - 3072 - wbytes - stage;  // 1 KB alignment slack + barriers, row records, row_ready ring
+    int split_fast = 0;
+    if (stream_split_fast_ok(cs, nout) && (left - stage) / kASlotBytes >= 3) {  // twin tiles only where three slabs still fit
+      left -= stage; stage *= 2; split_fast = 1;
+    }
     const int slots = std::min(kMaxSASlots, left / kASlotBytes);
     // a wider chunk is worth it only with enough slabs in flight (experiments: SS4K_MIN_SLOTS)
     static const int min_slots = getenv("SS4K_MIN_SLOTS") ? std::max(3, atoi(getenv("SS4K_MIN_SLOTS"))) : 3;
     if (slots < (nout > 16 ? min_slots : 3)) continue;
     sp->nout = nout; sp->chunks = npad / nout; sp->nkb = nkb; sp->npad_total = npad;
-    sp->stride2 = s2 ? 1 : 0; sp->nkx = nkx; sp->nwt = nwt;
+    sp->stride2 = s2 ? 1 : 0; sp->nkx = nkx; sp->nwt = nwt; sp->split_fast = split_fast;
     sp->a_slots = slots; sp->acc_slots = std::min(kMaxAccSlots, kTmemCols / nout) & ~1;  // even: rows alternate between two epilogue warp groups
     for (int kb = 0; kb < nkb; ++kb) {
       const int b0 = kb / nsplit, part = kb % nsplit;
@@ -635,9 +652,7 @@ int materialize_stream(ss4k_ctx* ctx, const ConvSpec& cs, const HostTensor& W, c
   }
   // fast epilogue: plain NHWC 16-bit output -> swizzled shared-memory tile -> TMA store
   p.fast_store = 0;
-  if (cs.out_mode == kOutNHWC && cs.out_buf >= 0 && cs.out_lo_buf < 0 && cs.out_coff % 8 == 0 && cs.out_pitch % 8 == 0 &&
-      !cs.tshift && (cs.res1_nch == 0 || (cs.res1_nch <= 8 && cs.res1_pitch >= 8 && cs.res1_coff % 8 == 0 && cs.res1_lo_buf < 0)) &&
-      (pk.nout == 16 || pk.nout == 32 || pk.nout == 64) && getenv("SS4K_NO_FAST_STORE") == nullptr) {
+  if (stream_fast_store_ok(cs, pk.nout) && (cs.out_lo_buf < 0 || pk.split_fast)) {
     const cuuint64_t eb = 2;
     const int cavail = std::min(cs.out_pitch - cs.out_coff, pk.npad_total);
     const int out_imgs = cs.out_ring ? cs.out_ring : (cs.n_total > 0 ? cs.n_total : cs.n);
@@ -663,8 +678,13 @@ int materialize_stream(ss4k_ctx* ctx, const ConvSpec& cs, const HostTensor& W, c
       r = ctx->encode(&p.tmO, dt, 4, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
                       CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     }
+    if (r == CUDA_SUCCESS && pk.split_fast) {
+      void* base_lo = reinterpret_cast<uint8_t*>(bufptr(cs.out_lo_buf)) + static_cast<size_t>(cs.out_coff) * 2;
+      r = ctx->encode(&p.tmO2, dt, 4, base_lo, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                      CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    }
     if (r != CUDA_SUCCESS) return fail(ctx, SS4K_E_CUDA, fmt("cuTensorMapEncodeTiled(stream output, %s) failed: %d", cs.name.c_str(), (int)r));
-    p.fast_store = cs.up2_store ? 2 : 1;
+    p.fast_store = pk.split_fast ? 3 : (cs.up2_store ? 2 : 1);
   }
   p.nkb = pk.nkb;
   for (int kb = 0; kb < pk.nkb; ++kb) { p.a_kb[kb] = pk.src_kb[kb]; p.a_tm[kb] = pk.src_tm[kb]; p.nks[kb] = pk.nks[kb]; p.wt[kb] = pk.wt[kb]; }
