@@ -111,11 +111,11 @@ class NativeBSVD(nn.Module):
         out = self._plan(n * f, h, w, in_fmt, out_fmt).run(x)
         return out.reshape(n, f, 3, h, w)
 
-    def stream(self, h, w):
-        if self.act_mode == L.ACT_F16_SPLIT:
-            raise L.Ss4kError("the ring-buffer streaming engine runs single-MMA fp16/bf16 only; "
-                              "use forward() (clip mode) with the split precision mode")
-        return BSVDStream(self, h, w)
+    def stream(self, h, w, in_fmt=L.FMT_F32_NCHW, noise=0.0):
+        """A frame-at-a-time stream in this model's precision mode (the split precision mode included).  ``in_fmt``:
+        ``FMT_F32_NCHW`` frames ``[4,h,w]`` (RGB + noise map, the reference layout) or ``FMT_U8_NHWC`` / ``FMT_NV12``
+        frames with the constant noise map ``noise`` filled in by the layout kernel."""
+        return BSVDStream(self, h, w, in_fmt, noise)
 
     def streaming_forward(self, input_seq):
         """BSVD.streaming_forward (model.py:526-580) through the ring-buffer engine: feed, drain, reset."""
@@ -158,11 +158,11 @@ class BSVDStream:
     ``push(frame)`` returns the denoised frame t-16 once the 16-stage pipeline is full, else None; ``flush()``
     yields the remaining frames (the reference feeds ``None``, model.py:555-569); ``reset()`` starts a new clip."""
 
-    def __init__(self, model, h, w):
+    def __init__(self, model, h, w, in_fmt=L.FMT_F32_NCHW, noise=0.0):
         import ctypes
-        self.model, self.h, self.w = model, h, w
+        self.model, self.h, self.w, self.in_fmt = model, h, w, in_fmt
         self.lib = model.engine.lib
-        self.plan = model._plan(1, h, w, L.FMT_F32_NCHW, L.FMT_F32_NCHW)
+        self.plan = model._plan(1, h, w, in_fmt, L.FMT_F32_NCHW, noise)
         hdl = ctypes.c_void_p()
         L.check(self.lib.ss4k_bsvd_stream_open(self.plan.h, ctypes.byref(hdl)), model.engine.h)
         self.hdl = hdl
@@ -174,7 +174,12 @@ class BSVDStream:
 
     def push(self, frame):
         import ctypes
-        x = frame.reshape(4, self.h, self.w).float().contiguous()
+        if self.in_fmt == L.FMT_F32_NCHW:
+            x = frame.reshape(4, self.h, self.w).float().contiguous()
+        else:  # uint8 RGB [h,w,3] or NV12 [h*3/2, w]: decoded, normalised and extended by the noise map on the device
+            if frame.dtype != torch.uint8:
+                raise ValueError("frame-format streams take uint8 frames")
+            x = frame.contiguous()
         out = torch.empty(1, 3, self.h, self.w, device=x.device, dtype=torch.float32)
         got = ctypes.c_int(0)
         L.check(self.lib.ss4k_bsvd_stream_push(self.hdl, ctypes.c_void_p(x.data_ptr()), ctypes.c_void_p(out.data_ptr()),

@@ -31,9 +31,9 @@ std::string build_bsvd_clip(const PlanCfgLite& c, Program* P) {
   const int c0 = 32, c1 = 64, c2 = 128, mid = 32, interm = 30;
   // fp16 hi/lo split precision (SS4K_ACT_F16_SPLIT): every activation tensor has a low-half twin, every product is
   // three MMAs (hi*hi + hi*lo + lo*hi).  Needed for parity with ill-conditioned weights such as the reference
-  // constructor's kaiming init (fp32 outputs span +-14); clip mode only.
+  // constructor's kaiming init (fp32 outputs span +-14); clip and streaming layouts alike
+  // (a twin is one more ring of frames with the same geometry, bsvd_stream.inc).
   const bool split = c.act_mode == 2;
-  if (split && c.bsvd_stream) return "BSVD: the split precision mode is available in clip mode only";
   P->in_n = T; P->in_c = 4; P->in_h = H; P->in_w = W;
   P->out_n = T; P->out_c = 3; P->out_h = H; P->out_w = W;
   const int in16 = P->add_buf("in16", T, H, W, 16);

@@ -162,7 +162,7 @@ conv3x3_stream_kernel(const __grid_constant__ StreamParams P) {
 
   const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);  // warp-uniform for ptxas
   const int lane = threadIdx.x & 31;
-  long long* const trace = P.trace != nullptr ? P.trace + blockIdx.x * 64 : nullptr;
+  long long* const trace = P.trace != nullptr ? P.trace + blockIdx.x * 128 : nullptr;
 #define SS4K_TRACE(i) do { if (trace != nullptr && lane == 0) trace[i] = clock64(); } while (0)
   if (warp == 0) SS4K_TRACE(0);
 
@@ -276,6 +276,7 @@ conv3x3_stream_kernel(const __grid_constant__ StreamParams P) {
     const uint64_t pol_in = l2_policy(P.l2_in);
     Band b, nb;
     bool dep_ready = false;
+    int prow = 0;        // traced rows
     int sL = 0, kL = 0;  // accumulator ring position (slot, wrap count) of output row y_lo
     bool has = next_band(P, u, u1, b);
     while (has) {
@@ -317,6 +318,8 @@ conv3x3_stream_kernel(const __grid_constant__ StreamParams P) {
       const int x0 = b.strip * kTileW - 1;
       int y_lo = b.yb;
       for (int r = r0; r <= r1; ++r) {
+        const bool ptr8 = trace != nullptr && lane == 0 && prow == 8;
+        if (trace != nullptr && lane == 0 && prow < 16) trace[64 + prow++] = clock64();
         // ---- the row's record: output rows [y_lo, y_hi] receive this input row, the first through weight block b_lo
         int y_first, y_hi, b_lo, f_lo;
         bool done_lo;  // this input row completes output row y_lo
@@ -368,6 +371,7 @@ conv3x3_stream_kernel(const __grid_constant__ StreamParams P) {
         const uint32_t flags = static_cast<uint32_t>(nB) | ((r == r1 && !has_next) ? kRecLast : 0u) |
                                ((r == r0 && new_chunk) ? kRecNewChunk : 0u) |
                                ((r == r1 && has_next && nb.chunk != b.chunk) ? kRecFreeW : 0u);
+        if (ptr8) trace[112] = clock64();
         for (int kb = 0; kb < P.nkb; ++kb) {
           if (!dep_ready && !((P.early_kb_mask >> kb) & 1u)) {
             SS4K_TRACE(12);
@@ -376,6 +380,7 @@ conv3x3_stream_kernel(const __grid_constant__ StreamParams P) {
             SS4K_TRACE(13);
           }
           mbar_wait_u(a_empty + 8 * as, aph ^ 1);
+          if (ptr8) trace[113] = clock64();
           if (elect_one()) {
             if (kb == 0) {
               const uint32_t ra = rec_base + as * (kRecWords * 4u);
@@ -390,8 +395,10 @@ conv3x3_stream_kernel(const __grid_constant__ StreamParams P) {
               tma_load_5d_hint(a_base + as * kASlotBytes, &P.tmA[P.a_tm[kb]], a_full + 8 * as, 0, x0, P.a_kb[kb], r, b.n + P.n_in0, pol_in);
             }
           }
+          if (ptr8) trace[114] = clock64();
           __syncwarp();
           if (++as == static_cast<uint32_t>(P.a_slots)) { as = 0; aph ^= 1; }
+          if (ptr8) trace[115] = clock64();
         }
       }
       // ring position of the next band's first output row
@@ -659,8 +666,12 @@ conv3x3_stream_kernel(const __grid_constant__ StreamParams P) {
 #pragma unroll
             for (int j = 0; j < NOUT / 8; ++j) r2v[j] = rp[j];
           }
+          const bool trow = trace != nullptr && warp == 2 && lane == 0 && q < 16;
+          long long* const trw = trace + 80 + 4 * (q >> 1);
+          if (trow) trw[0] = clock64();
           mbar_wait_u(acc_full + 8 * s, k & 1);
           tcgen05_after_sync();
+          if (trow) trw[1] = clock64();
           if (warp == 2 && q == 0) SS4K_TRACE(5);
           const uint32_t taddr = tmem_base + (static_cast<uint32_t>(qd * 32) << 16) + static_cast<uint32_t>(s * NOUT);
           uint32_t raw[NOUT];
@@ -673,6 +684,7 @@ conv3x3_stream_kernel(const __grid_constant__ StreamParams P) {
             const int ut = u - (b.ye - y) + S;
             if (ut < u1) init_slot(s, ut / upc);
           }
+          if (trow) trw[2] = clock64();
           if (!(P.dbg_flags & 4)) {
             if (fast) {
               // ---- activation, residuals, 16-bit pack into the warp's swizzled staging tile, TMA store
@@ -960,6 +972,7 @@ conv3x3_stream_kernel(const __grid_constant__ StreamParams P) {
               }
             }
           }
+          if (trow) trw[3] = clock64();
         }
         if (++s == S) { s = 0; ++k; }
       }

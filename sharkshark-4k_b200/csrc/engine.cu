@@ -1782,8 +1782,8 @@ int ss4k_debug_bench_conv(ss4k_ctx* ctx, const ss4k_conv_desc* d, int slab_pitch
   if (rc == SS4K_OK) {
     long long* d_trace = nullptr;
     if (ex.stream && d->reserved[7] == 1) {
-      cudaMalloc(&d_trace, sizeof(long long) * 64 * 148);
-      cudaMemset(d_trace, 0, sizeof(long long) * 64 * 148);
+      cudaMalloc(&d_trace, sizeof(long long) * 128 * 148);
+      cudaMemset(d_trace, 0, sizeof(long long) * 128 * 148);
     }
     if (ex.stream) {
       ex.sp.dbg_flags = dbg_flags;
@@ -1816,18 +1816,18 @@ int ss4k_debug_bench_conv(ss4k_ctx* ctx, const ss4k_conv_desc* d, int slab_pitch
     ctx->launches += iters + 3;
     std::string trace_js;
     if (d_trace != nullptr) {  // one extra traced launch: clock64 stamps of CTA 0 and the last CTA, relative to entry
-      cudaMemset(d_trace, 0, sizeof(long long) * 64 * 148);
+      cudaMemset(d_trace, 0, sizeof(long long) * 128 * 148);
       ex.sp.trace = d_trace;
       launch_exec(ex, nullptr, ctx->stream);
       cudaStreamSynchronize(ctx->stream);
       ex.sp.trace = nullptr;
-      std::vector<long long> h(64 * 148);
-      cudaMemcpy(h.data(), d_trace, sizeof(long long) * 64 * 148, cudaMemcpyDeviceToHost);
+      std::vector<long long> h(128 * 148);
+      cudaMemcpy(h.data(), d_trace, sizeof(long long) * 128 * 148, cudaMemcpyDeviceToHost);
       cudaFree(d_trace);
       trace_js = ",\"trace\":[";
       for (int b : {0, ex.grid / 2, ex.grid - 1}) {
         trace_js += (b == 0 ? "[" : ",[");
-        for (int i = 0; i < 64; ++i) trace_js += fmt("%s%lld", i ? "," : "", h[b * 64 + i] ? h[b * 64 + i] - h[b * 64] : -1LL);
+        for (int i = 0; i < 128; ++i) trace_js += fmt("%s%lld", i ? "," : "", h[b * 128 + i] ? h[b * 128 + i] - h[b * 128] : -1LL);
         trace_js += "]";
       }
       trace_js += "]";

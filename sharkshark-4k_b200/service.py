@@ -11,6 +11,7 @@ All arithmetic runs in libss4k.so: the convnets (tcgen05 kernels) and the servic
 pooling, low-res gaussian, finalising pass, bicubic, sharpen: csrc/glue.cu).  torch is used for device buffers
 and streams only.
 """
+import collections
 import ctypes
 import math
 import time
@@ -68,7 +69,7 @@ class FsrcnnUpscalerService:
     def __init__(self, lr_level=3, device=0, on_queue=None, denoising=True, denoise_rate=1.0,
                  upscaler_model='realesrgan', batch_size=1, jit_mode=None, lr_hr_resize=True,
                  model_name=None, state_dict=None, denoise_state_dict=None, act_mode=L.ACT_F16,
-                 denoise_act_mode="auto", single_mode=None):
+                 denoise_act_mode="auto", single_mode=None, temporal_denoise=False):
         self.lr_shape = self.LR_SHAPES[lr_level]
         self.scale = 4
         self.denoise_rate = denoise_rate
@@ -91,6 +92,10 @@ class FsrcnnUpscalerService:
         self.denoise_state_dict = denoise_state_dict
         self.act_mode = act_mode
         self.denoise_act_mode = denoise_act_mode   # 'auto': fp16, or fp16 hi/lo split for kaiming-magnitude weights
+        # temporal_denoise: upscale_single feeds BSVD's persistent ring buffers (BSVD.feedin_one_element, bsvd/model.py:
+        # 510-513) instead of one F = 1 clip per frame (fsrcnn_upscaler.py:277): every frame is denoised with its +-16
+        # temporal neighbours and leaves the service 16 frames late (jobs are delayed as a whole, see proc_job_recieved)
+        self.temporal_denoise = bool(temporal_denoise)
         self.model = None
 
     # ------------------------------------------------------------------ life cycle (fsrcnn_upscaler.py:118-142)
@@ -116,13 +121,19 @@ class FsrcnnUpscalerService:
             self._build_denoiser()
         self.match_blur = gaussian_kernel(8 * 2 + 1, 8.0).to(self.device)     # :138
         self._sums = {}
+        self._den_stream = None      # temporal mode: the BSVD ring-buffer stream, the LR frames in flight, delayed jobs
+        self._lr_fifo = collections.deque()
+        self._jobs = collections.deque()
+        self._ready = collections.deque()
 
     def _build_denoiser(self):
         self.denoise_model = native_bsvd.build_model(device=self.device.index or 0, input_shape=self.lr_shape,
                                                      state_dict=self.denoise_state_dict, act_mode=self.denoise_act_mode)
 
     def proc_cleanup(self):
-        pass
+        if self._den_stream is not None:
+            self._den_stream.close()
+            self._den_stream = None
 
     def proc_job_recieved(self, job):
         """src/upscale/upscaler_base.py:40-55"""
@@ -134,8 +145,41 @@ class FsrcnnUpscalerService:
         self.profiler.end('upscaler.upscale')
         elapsed = time.time() - t
         self.profiler.start('upscaler.output')
+        if self._temporal():
+            # delay line of whole jobs: the entry returned for this job carries the frames, step and audio segment of the
+            # oldest job whose frames have all left the 16-frame pipeline (an entry without frames while it fills)
+            self._ready.extend(frames_up[i] for i in range(frames_up.shape[0]))
+            self._jobs.append((job, job.frames.shape[0]))
+            return self._pop_delayed(elapsed)
         return UpscalerQueueEntry(frames=frames_up, step=job.step, audio_segment=job.audio_segment, elapsed=elapsed,
                                   last_modified=time.time(), profiler=job.profiler)
+
+    def _temporal(self):
+        return self.temporal_denoise and self.denoising and self.single_mode
+
+    def _pop_delayed(self, elapsed=0.0):
+        if self._jobs and len(self._ready) >= self._jobs[0][1]:
+            old, n = self._jobs.popleft()
+            frames = torch.stack([self._ready.popleft() for _ in range(n)], dim=0)
+            return UpscalerQueueEntry(frames=frames, step=old.step, audio_segment=old.audio_segment, elapsed=elapsed,
+                                      last_modified=time.time(), profiler=old.profiler)
+        oh, ow = self.output_shape if self.output_shape is not None else (0, 0)
+        return UpscalerQueueEntry(frames=torch.empty(0, oh, ow, 3, dtype=torch.uint8, device=self.device), step=-1,
+                                  audio_segment=None, elapsed=elapsed, last_modified=time.time(), profiler=None)
+
+    def flush(self):
+        """End of the stream (temporal mode): drains BSVD's pipeline (the reference feeds None, bsvd/model.py:555-569) and
+        returns the entries of the jobs still in flight, oldest first; the next frame starts a new clip."""
+        if not self._temporal() or self._den_stream is None:
+            return []
+        for den in self._den_stream.flush():
+            self._ready.append(self._finish_single(den, self._lr_fifo.popleft()))
+        self._den_stream.reset()
+        self.lr_prev = None
+        out = []
+        while self._jobs:
+            out.append(self._pop_delayed())
+        return out
 
     # ------------------------------------------------------------------ glue helpers (csrc/glue.cu)
     def _stream(self):
@@ -191,9 +235,38 @@ class FsrcnnUpscalerService:
             raise Exception(frames.shape)
         assert frames.shape[-1] == 3
         frames = frames.contiguous()
+        if self._temporal():
+            return self.upscale_temporal(frames)
         if self.single_mode:
             return torch.stack([self.upscale_single(frames[i]) for i in range(frames.shape[0])], dim=0)
         return self.upscale_multi(frames)
+
+    def upscale_temporal(self, frames):
+        """upscale_single with BSVD as a temporal stream: pushes every frame into the ring-buffer engine and returns the
+        frames that left it (none for the first 16 pushes, then one per push; flush() returns the tail)."""
+        lh, lw = self.lr_shape
+        if self._den_stream is None:
+            if self.denoise_model is None:
+                self._build_denoiser()
+            self._den_stream = self.denoise_model.stream(lh, lw)
+        done = []
+        for i in range(frames.shape[0]):
+            ih, iw, _ = frames[i].shape
+            lr_before = self._area(frames[i].unsqueeze(0), 1, 3, ih, iw, lh, lw)
+            x = torch.empty(4, lh, lw, dtype=torch.float32, device=self.device)
+            x[:3].copy_(lr_before[0])
+            x[3].fill_(0.05 if self.lr_prev is None else 0.1 * self.denoise_rate)   # :262,269
+            self.lr_prev = lr_before
+            self._lr_fifo.append(lr_before)
+            self.profiler.start('fsrcnn.denoise')
+            den = self._den_stream.push(x)
+            self.profiler.end('fsrcnn.denoise')
+            if den is not None:
+                done.append(self._finish_single(den, self._lr_fifo.popleft()))
+        if done:
+            return torch.stack(done, dim=0)
+        oh, ow = self.output_shape if self.output_shape is not None else (0, 0)
+        return torch.empty(0, oh, ow, 3, dtype=torch.uint8, device=self.device)
 
     def upscale_multi(self, img):
         """fsrcnn_upscaler.py:168-233"""
@@ -225,7 +298,7 @@ class FsrcnnUpscalerService:
         ih, iw, _ = img.shape
         lh, lw = self.lr_shape
         lr_before = self._area(img.unsqueeze(0), 1, 3, ih, iw, lh, lw)        # :237-241 (always area-resized)
-        lr = lr_before
+        den = None
         if self.denoising:
             x = torch.empty(1, 1, 4, lh, lw, dtype=torch.float32, device=self.device)
             first = self.lr_prev is None
@@ -235,16 +308,23 @@ class FsrcnnUpscalerService:
             if self.denoise_model is None:
                 self._build_denoiser()
             den = self.denoise_model(x)[:, -1]                                 # :277  (F = 1 clip)
+            self.profiler.end('fsrcnn.denoise')
+            self.lr_prev_diff_map = x[0, 0, 3]
+        return self._finish_single(den, lr_before)
+
+    def _finish_single(self, den, lr_before):
+        """The rest of upscale_single for one frame: den [1,3,lh,lw] is BSVD's output for it (None: denoising off)."""
+        lh, lw = self.lr_shape
+        lr = lr_before
+        if den is not None:
             lr = torch.empty(1, 3, lh, lw, dtype=torch.float32, device=self.device)
             L.check(self.lib.ss4k_glue_sharpen_blend(_ptr(den), _fmt(den), 1, 3, lh, lw, 0.00002, 0.8, _ptr(lr_before), 0,
                                                      _ptr(lr), self._stream()))   # :278-281
-            self.profiler.end('fsrcnn.denoise')
             self.lr_prev = lr
-            self.lr_prev_diff_map = x[0, 0, 3]
         self.profiler.start('fsrcnn.model')
         hr = self.model(lr)                                                     # :293-295
         h, w = hr.shape[-2], hr.shape[-1]
-        if self.denoising:
+        if den is not None:
             hs_in = hr
             hr = torch.empty(1, 3, h, w, dtype=torch.float32, device=self.device)
             L.check(self.lib.ss4k_glue_sharpen_blend(_ptr(hs_in), _fmt(hs_in), 1, 3, h, w, 0.00007, 1.0, None, 0, _ptr(hr),

@@ -114,3 +114,53 @@ def test_bsvd_streaming_equals_clip(engine):
     got2 = torch.cat([o for o in (s.push(x2[0, i]) for i in range(3)) if o is not None] + list(s.flush()), dim=0)
     assert (got2 - model(x2)[0]).abs().max().item() <= 1e-3
     assert (model.streaming_forward(x2[0]) - got2).abs().max().item() == 0.0
+
+
+def test_bsvd_streaming_split_precision(engine):
+    """The ring-buffer engine in the split precision mode (every ring has a low-half twin): reference constructor init
+    (fp32 outputs span +-14), frame-at-a-time == the clip program bit for bit, and the north-star gate against the
+    oracle's BSVD.forward over the whole clip (model.py:515-580: streaming_forward == forward)."""
+    sd = bsvd.build_bsvd32(0)
+    model = native_bsvd.NativeBSVD(sd, device=0, act_mode=L.ACT_F16_SPLIT)
+    x = _clip(19, 32, 136, seed=21)
+    clip = model(x.cuda())[0]
+    s = model.stream(32, 136)
+    outs = []
+    for i in range(19):
+        o = s.push(x[0, i].cuda())
+        assert (o is None) == (i < 16)
+        if o is not None:
+            outs.append(o)
+    outs += list(s.flush())
+    got = torch.cat(outs, dim=0)
+    assert tuple(got.shape) == (19, 3, 32, 136)
+    assert torch.equal(got, clip)
+    psnr, maxabs = gate(got, bsvd.bsvd_forward(sd, x)[0])
+    print(f"BSVD-32 streaming, split precision, F=19: PSNR {psnr:.1f} dB, max|err| {maxabs:.3f}/255")
+    assert psnr >= 50 and maxabs <= 2.0
+    s.reset()   # a second, shorter clip (T < 16: the drain alone produces every frame)
+    x2 = _clip(3, 32, 136, seed=22).cuda()
+    got2 = torch.cat([o for o in (s.push(x2[0, i]) for i in range(3)) if o is not None] + list(s.flush()), dim=0)
+    assert torch.equal(got2, model(x2)[0])
+    s.close()
+
+
+@pytest.mark.parametrize("nv12", [False, True])
+def test_bsvd_streaming_frame_formats(engine, nv12):
+    """uint8 RGB / NV12 frames pushed one at a time (the layout kernel decodes, normalises and appends the noise map)
+    == the frame-format clip entry denoise_frames() on the same frames."""
+    sd = bsvd.build_bsvd32(0, weight_scale=0.5)
+    model = native_bsvd.NativeBSVD(sd, device=0)
+    h, w, t = 32, 128, 18
+    g = torch.Generator().manual_seed(5)
+    if nv12:
+        frames = torch.randint(16, 236, (t, h * 3 // 2, w), generator=g, dtype=torch.uint8).cuda()
+    else:
+        frames = torch.randint(0, 256, (t, h, w, 3), generator=g, dtype=torch.uint8).cuda()
+    clip = model.denoise_frames(frames, h, w, 0.075, nv12=nv12)
+    s = model.stream(h, w, in_fmt=L.FMT_NV12 if nv12 else L.FMT_U8_NHWC, noise=0.075)
+    outs = [o for o in (s.push(frames[i]) for i in range(t)) if o is not None] + list(s.flush())
+    s.close()
+    got = torch.cat(outs, dim=0)
+    assert tuple(got.shape) == tuple(clip.shape) == (t, 3, h, w)
+    assert (got - clip.float()).abs().max().item() <= 1e-3

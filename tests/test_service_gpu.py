@@ -100,6 +100,59 @@ def test_upscale_single_denoise_then_rrdb(engine):
     _cmp(got[1], want1)
 
 
+def test_upscale_temporal_ring_buffers(engine):
+    """temporal_denoise=True: upscale_single fed through BSVD's persistent ring buffers (bsvd/model.py:510-513) -- every
+    frame denoised with its temporal neighbours, jobs delayed as a whole by the 16-frame pipeline, flush() at the end.
+    Oracle: BSVD.forward over the WHOLE clip (== streaming_forward, model.py:515-580) on the per-frame inputs the service
+    builds (noise map 0.05 on the first frame), then the reference's per-frame glue on each denoised frame."""
+    torch.manual_seed(0)
+    net = rrdbnet.RRDBNet(3, 3, 2, 64, 1, 32).eval()
+    sd = bsvd.build_bsvd32(0, weight_scale=0.5)
+    t, lh, lw = 18, 360, 640
+    frames = _frames(t, lh, lw, 9)
+    x = torch.empty(1, t, 4, lh, lw)
+    x[0, :, :3] = frames.permute(0, 3, 1, 2) / 255.0        # lr_shape == frame size: the area resize is the identity
+    x[0, :, 3] = 0.075
+    x[0, 0, 3] = 0.05
+    clip = bsvd.bsvd_forward(sd, x)
+    svc = service.FsrcnnUpscalerService(lr_level=0, device=0, denoising=True, denoise_rate=0.75, batch_size=4,
+                                        model_name='RealESRGAN_x2plus', state_dict=net.state_dict(),
+                                        denoise_state_dict=sd, single_mode=True, temporal_denoise=True)
+    svc.proc_init()
+    svc.output_shape = (720, 1280)
+    entries = []
+    jobs = [(k, frames[4 * k: 4 * k + 4]) for k in range((t + 3) // 4)]
+    for k, fr in jobs:
+        e = svc.proc_job_recieved(service.UpscalerQueueEntry(frames=fr.cuda(), step=100 + k, audio_segment=("audio", k)))
+        if k < 4:   # 16 frames of latency: nothing can leave before the 17th push (job 4)
+            assert e.frames.shape[0] == 0 and e.step == -1 and e.audio_segment is None
+        entries.append(e)
+    entries += svc.flush()
+    done = [e for e in entries if e.frames.shape[0]]
+    assert [e.step for e in done] == [100 + k for k, _ in jobs]                 # in order, step / audio of the delayed job
+    assert [e.audio_segment for e in done] == [("audio", k) for k, _ in jobs]
+    assert [e.frames.shape[0] for e in done] == [fr.shape[0] for _, fr in jobs]
+    got = torch.cat([e.frames for e in done], dim=0)
+    assert tuple(got.shape) == (t, 720, 1280, 3)
+    for i in (0, 7, t - 1):
+        want = glue.upscale_single(frames[i], net, (lh, lw), (720, 1280), lambda _x, i=i: clip[:, i:i + 1], 0.75, i == 0,
+                                   return_float=True)
+        _cmp(got[i], want)
+    # a frame inside the stream differs from the same frame denoised alone (the F = 1 path of the reference)
+    alone = service.FsrcnnUpscalerService(lr_level=0, device=0, denoising=True, denoise_rate=0.75,
+                                          model_name='RealESRGAN_x2plus', state_dict=net.state_dict(),
+                                          denoise_state_dict=sd, single_mode=True)
+    alone.proc_init()
+    alone.output_shape = (720, 1280)
+    alone.lr_prev = 1     # not the first frame: noise map 0.075
+    assert (alone.upscale(frames[7:8].cuda())[0].int() - got[7].int()).abs().max().item() > 0
+    # a new clip after flush(): same result as the first time
+    e = [svc.proc_job_recieved(service.UpscalerQueueEntry(frames=fr.cuda(), step=k)) for k, fr in jobs]
+    got2 = torch.cat([q.frames for q in e + svc.flush() if q.frames.shape[0]], dim=0)
+    assert torch.equal(got2, got)
+    svc.proc_cleanup()
+
+
 def test_proc_job_recieved_roundtrip(engine):
     torch.manual_seed(0)
     net = srvgg.SRVGGNetCompact(3, 3, 64, 16, 4).eval()
