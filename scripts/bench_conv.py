@@ -11,11 +11,12 @@ import ss4k_b200  # noqa: E402
 from ss4k_b200 import _lib as L  # noqa: E402
 
 
-def bench(eng, cin, cout, h, w, n=1, mode=0, pitch=0, flags=0, iters=20, R=0, slots=0, act=1, beta=0.0, acc=0, grid=0, trace=0):
+def bench(eng, cin, cout, h, w, n=1, mode=0, pitch=0, flags=0, iters=20, R=0, slots=0, act=1, beta=0.0, acc=0, grid=0, trace=0, src=0):
     d = L.ConvDesc()
     d.struct_size = ctypes.sizeof(L.ConvDesc)
     d.n, d.h, d.w, d.cin, d.cout, d.mode, d.act = n, h, w, cin, cout, mode, act
     d.alpha, d.beta = 1.0, beta
+    d.reserved[1] = src
     d.reserved[2], d.reserved[3], d.reserved[4], d.reserved[5], d.reserved[7] = R, slots, acc, grid, trace
     ms = ctypes.c_float()
     js = ctypes.c_void_p()

@@ -12,13 +12,18 @@ F = int(sys.argv[1]) if len(sys.argv) > 1 else 8
 SPLIT = len(sys.argv) > 2 and sys.argv[2] == "split"
 sd = obsvd.build_bsvd32(0, weight_scale=1.0 if SPLIT else 0.5)
 den = nbsvd.NativeBSVD(sd, device=0, act_mode=L.ACT_F16_SPLIT if SPLIT else L.ACT_F16, out_dtype=torch.float16)
-x = torch.rand(1, F, 4, 720, 1280, device="cuda")
-y = den(x); torch.cuda.synchronize()
+NV12 = len(sys.argv) > 3 and sys.argv[3] == "nv12"   # frame-format entry: the first conv's loader decodes the frames
+if NV12:
+    x = torch.randint(16, 236, (F, 1080, 1280), dtype=torch.uint8, device="cuda")
+    y = den.denoise_frames(x, 720, 1280, 0.075, nv12=True); torch.cuda.synchronize()
+else:
+    x = torch.rand(1, F, 4, 720, 1280, device="cuda")
+    y = den(x); torch.cuda.synchronize()
 plan = list(den._plans._d.values())[0]
 cfg = plan.cfg
 dry = E.plan_dry(cfg)
 steps = dry["steps"]
-xin = x[0].contiguous() if x.dtype == torch.float32 else x[0].float().contiguous()
+xin = x if NV12 else (x[0].contiguous() if x.dtype == torch.float32 else x[0].float().contiguous())
 prof = None
 for _ in range(3):
     prof = plan.profile(xin)

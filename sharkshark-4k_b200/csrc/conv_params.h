@@ -135,6 +135,8 @@ constexpr int kStreamOnesBytes = 128 * 128;  // "ones" operand tile of the bias 
 
 constexpr int kStreamEpiWarps = 8;  // two per TMEM lane quarter, alternating output rows
 constexpr int kStreamThreads = 32 * (2 + kStreamEpiWarps);
+constexpr int kStreamSrcWarps = 2;  // frame-format source (StreamParams::src_fmt): decoder warps on top, alternating input rows
+constexpr int kStreamThreadsMax = kStreamThreads + 32 * kStreamSrcWarps;
 constexpr int kRdbThreads = kStreamThreads;                 // fused residual dense block kernel: same warp roles
 
 struct StreamParams {
@@ -144,6 +146,17 @@ struct StreamParams {
   CUtensorMap tmO;      // NHWC output, 4-D (C, W, H, N), box (NOUT, 32, 1, 1), swizzled: TMA store of the fast path
   CUtensorMap tmO2;     // split precision: the same map over the low-half twin of the output tensor
   Epilogue ep;
+  // Frame-format source (first layer of the BSVD clip program, north-star part 4): the producer warp decodes the
+  // caller's uint8 RGB / NV12 frames itself (/255 or BT.709 limited range, + the constant noise-map channel) straight into
+  // the swizzled activation slabs -- no layout kernel, no 16-bit copy of the input read back -- and leaves the decoded
+  // rows it owns in src_out (+ src_out_lo) for the DenBlock's residual (out[:, :3] = in[:, :3] - ..., model.py:436-442).
+  const uint8_t* src;     // the caller's frames (patched per run)
+  int32_t src_fmt;        // 0: activations come through tmA; SS4K_FMT_U8_NHWC (2) or SS4K_FMT_NV12 (3): decoded from src by
+                          // kStreamSrcWarps extra warps (launched with kStreamThreadsMax threads)
+  int32_t src_fill_ch;    // channel that holds src_fill (3), or -1
+  float src_fill;
+  uint16_t* src_out;      // [n_total, H, W, 16] 16-bit NHWC, channels 0..7 written
+  uint16_t* src_out_lo;   // split precision: low halves, or null
   int32_t fast_store;   // 1: plain NHWC output -> registers -> swizzled smem tile -> TMA store;
                         // 2: the same tile stored four times through a 5-D (C, b, W, a, N*H) map: nearest-x2 upsample
                         // 3: split precision (hi + lo twins): two staging tiles per warp, two TMA stores

@@ -131,8 +131,96 @@ __device__ __forceinline__ bool next_band(const StreamParams& P, int& u, int u1,
 
 static_assert(kMaxSASlots <= 16 && kMaxAccSlots <= 16, "barrier set-up assigns one lane per ring slot");
 
+// ---- frame-format source of the first layer (StreamParams::src): same arithmetic as prep_kernel (elementwise.cu).
+// A lane owns four consecutive interior pixels of the 130-pixel halo row (slab pixels 1 + 4 lane + i, aligned 32-bit
+// loads: W % 4 == 0) and lanes 0 / 31 the left / right halo pixel on top.
+struct SrcPix { uint32_t hi[2], lo[2]; };   // channels 0..3 as 16-bit pairs (value = hi + lo)
+struct SrcRow { uint32_t w[3], extra; };    // raw bytes: NV12 {Y x4, UV x2 pairs, -}, RGB {12 bytes}; extra: the halo pixel's three
+                                            // bytes (Y | U << 8 | V << 16 or R | G << 8 | B << 16) | bit 24: it exists | bit 25: the interior group exists
+constexpr uint32_t kSrcNone = 0xFFFFFFFFu;  // pixel outside the frame (zero padding)
+__device__ __forceinline__ SrcRow src_load_row(const StreamParams& P, int n, int r, int x4, int xe) {
+  SrcRow o;
+  o.w[0] = o.w[1] = o.w[2] = 0u;
+  o.extra = 0u;
+  const bool in4 = x4 < P.W, ine = xe >= 0 && xe < P.W;
+  if (P.src_fmt == 3) {
+    const uint8_t* frame = P.src + static_cast<size_t>(n) * (static_cast<size_t>(P.H) * P.W * 3 / 2);
+    const uint8_t* yrow = frame + static_cast<size_t>(r) * P.W;
+    const uint8_t* uvrow = frame + static_cast<size_t>(P.H) * P.W + static_cast<size_t>(r >> 1) * P.W;
+    if (in4) {
+      o.w[0] = __ldg(reinterpret_cast<const uint32_t*>(yrow + x4));
+      o.w[1] = __ldg(reinterpret_cast<const uint32_t*>(uvrow + x4));
+    }
+    if (ine)
+      o.extra = static_cast<uint32_t>(__ldg(yrow + xe)) | (static_cast<uint32_t>(__ldg(reinterpret_cast<const uint16_t*>(uvrow + (xe & ~1)))) << 8);
+  } else {
+    const uint8_t* row = P.src + (static_cast<size_t>(n) * P.H + r) * P.W * 3;
+    if (in4) {
+      const uint32_t* q = reinterpret_cast<const uint32_t*>(row + static_cast<size_t>(x4) * 3);
+      o.w[0] = __ldg(q); o.w[1] = __ldg(q + 1); o.w[2] = __ldg(q + 2);
+    }
+    if (ine) {
+      const uint8_t* px = row + static_cast<size_t>(xe) * 3;
+      o.extra = static_cast<uint32_t>(__ldg(px)) | (static_cast<uint32_t>(__ldg(px + 1)) << 8) | (static_cast<uint32_t>(__ldg(px + 2)) << 16);
+    }
+  }
+  o.extra |= (ine ? 1u << 24 : 0u) | (in4 ? 1u << 25 : 0u);
+  return o;
+}
+__device__ __forceinline__ SrcPix src_decode(const StreamParams& P, uint32_t raw) {   // raw: three bytes, or kSrcNone
+  SrcPix o;
+  o.hi[0] = o.hi[1] = o.lo[0] = o.lo[1] = 0u;
+  if (raw == kSrcNone) return o;
+  float v[4];
+  const float b0 = static_cast<float>(raw & 0xFFu), b1 = static_cast<float>((raw >> 8) & 0xFFu), b2 = static_cast<float>((raw >> 16) & 0xFFu);
+  if (P.src_fmt == 3) {  // BT.709 limited range, nearest chroma
+    const float yy = (b0 - 16.f) * (1.f / 219.f);
+    const float cb = (b1 - 128.f) * (1.f / 224.f);
+    const float cr = (b2 - 128.f) * (1.f / 224.f);
+    v[0] = fminf(fmaxf(yy + 1.5748f * cr, 0.f), 1.f);
+    v[1] = fminf(fmaxf(yy - 0.187324f * cb - 0.468124f * cr, 0.f), 1.f);
+    v[2] = fminf(fmaxf(yy + 1.8556f * cb, 0.f), 1.f);
+  } else {
+    v[0] = b0 / 255.0f; v[1] = b1 / 255.0f; v[2] = b2 / 255.0f;
+  }
+  v[3] = P.src_fill_ch == 3 ? P.src_fill : 0.f;
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const __half2 h = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+    const float2 back = __half22float2(h);
+    const __half2 l = __floats2half2_rn(v[2 * i] - back.x, v[2 * i + 1] - back.y);
+    o.hi[i] = *reinterpret_cast<const uint32_t*>(&h);
+    o.lo[i] = *reinterpret_cast<const uint32_t*>(&l);
+  }
+  return o;
+}
+// the three source bytes of interior pixel i (0..3) of a lane's row / of its halo pixel, or kSrcNone
+__device__ __forceinline__ uint32_t src_px(const StreamParams& P, const SrcRow& R, int i) {
+  if (!(R.extra & (1u << 25))) return kSrcNone;
+  if (P.src_fmt == 3) return ((R.w[0] >> (8 * i)) & 0xFFu) | (((R.w[1] >> (16 * (i >> 1))) & 0xFFFFu) << 8);
+  const uint64_t lo = (static_cast<uint64_t>(R.w[1]) << 32) | R.w[0];
+  const uint64_t hi = (static_cast<uint64_t>(R.w[2]) << 32) | R.w[1];
+  return i < 2 ? static_cast<uint32_t>(lo >> (24 * i)) & 0xFFFFFFu : static_cast<uint32_t>(hi >> (24 * i - 32)) & 0xFFFFFFu;
+}
+__device__ __forceinline__ uint32_t src_px_extra(const SrcRow& R) { return (R.extra & (1u << 24)) ? (R.extra & 0xFFFFFFu) : kSrcNone; }
+
+// L2 prefetch of the source bytes of input row r of a strip (lane l < 3 takes one 128-byte line): the decoder warps'
+// register prefetch (one of their rows ahead) then hits L2 instead of paying a DRAM round trip per row
+__device__ __forceinline__ void src_prefetch_row(const StreamParams& P, int n, int r, int xs, int l) {
+  const uint8_t* p;
+  if (P.src_fmt == 3) {
+    if (l >= 2) return;
+    const uint8_t* frame = P.src + static_cast<size_t>(n) * (static_cast<size_t>(P.H) * P.W * 3 / 2);
+    p = l == 0 ? frame + static_cast<size_t>(r) * P.W + xs : frame + static_cast<size_t>(P.H) * P.W + static_cast<size_t>(r >> 1) * P.W + xs;
+  } else {
+    if (l >= 3) return;
+    p = P.src + ((static_cast<size_t>(n) * P.H + r) * P.W + xs) * 3 + 128 * l;
+  }
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+
 template <int NOUT>
-__global__ void __launch_bounds__(kStreamThreads, 1)
+__global__ void __launch_bounds__(kStreamThreadsMax, 1)
 conv3x3_stream_kernel(const __grid_constant__ StreamParams P) {
   extern __shared__ uint8_t smem_raw[];
   constexpr uint32_t kWTile = 3u * NOUT * 128u;      // one (K block, horizontal tap) weight tile
@@ -191,7 +279,7 @@ conv3x3_stream_kernel(const __grid_constant__ StreamParams P) {
       mbar_init(w_empty, 1);
     }
     if (lane < kMaxSASlots) {
-      mbar_init(a_full + 8 * lane, 1);
+      mbar_init(a_full + 8 * lane, P.src_fmt != 0 ? 2 : 1);   // frame-format source: the row record (this warp) + the decoded slab
       mbar_init(a_empty + 8 * lane, 1);
     }
     if (lane >= 16 && lane < 16 + kMaxAccSlots) {
@@ -232,7 +320,7 @@ conv3x3_stream_kernel(const __grid_constant__ StreamParams P) {
       // "ones" operand of the accumulator-init MMA: 128 rows x 64 channels, swizzle-128B K-major, value 1 in K
       // columns 0 and 1 (they meet the hi / lo halves of the bias in the bias tile), 0 elsewhere
       const uint32_t one2 = P.ep.is_bf16 ? 0x3F803F80u : 0x3C003C00u;
-      if (warp != 0)
+      if (warp != 0 && warp < 2 + kStreamEpiWarps)
         for (uint32_t ci = threadIdx.x - 32; ci < 1024u; ci += kStreamThreads - 32) {
           const uint32_t r = ci >> 3, pc = ci & 7u;
           sts128(ones_base + ci * 16u, pc == (r & 7u) ? one2 : 0u, 0u, 0u, 0u);
@@ -241,7 +329,7 @@ conv3x3_stream_kernel(const __grid_constant__ StreamParams P) {
     } else {
       float* sb = reinterpret_cast<float*>(smem_gen + (bias_base - smem_base));
       const int nb = P.chunks * NOUT;
-      if (warp != 0)
+      if (warp != 0 && warp < 2 + kStreamEpiWarps)
         for (int i = threadIdx.x - 32; i < nb; i += kStreamThreads - 32) sb[i] = __ldg(P.bias_f + i);
     }
     if (warp == 2) SS4K_TRACE(11);
@@ -250,10 +338,10 @@ conv3x3_stream_kernel(const __grid_constant__ StreamParams P) {
   // straight on to its loads -- it needs neither the TMEM allocation nor the bias copy, and its first activation
   // load is the head of the per-launch critical path.
   if (warp == 0) {
-    asm volatile("bar.arrive 1, %0;" ::"n"(kStreamThreads) : "memory");
+    asm volatile("bar.arrive 1, %0;" ::"r"(blockDim.x) : "memory");
   } else {
     tcgen05_before_sync();
-    asm volatile("bar.sync 1, %0;" ::"n"(kStreamThreads) : "memory");
+    asm volatile("bar.sync 1, %0;" ::"r"(blockDim.x) : "memory");
     tcgen05_after_sync();
     // this CTA owns all 512 TMEM columns (one CTA per SM), so the allocation starts at column 0 / lane 0;
     // using the constant keeps TMEM addresses in uniform registers
@@ -279,6 +367,7 @@ conv3x3_stream_kernel(const __grid_constant__ StreamParams P) {
     int prow = 0;        // traced rows
     int sL = 0, kL = 0;  // accumulator ring position (slot, wrap count) of output row y_lo
     bool has = next_band(P, u, u1, b);
+    const bool from_src = P.src_fmt != 0;   // the slabs are filled by the decoder warps; this warp sends the row records
     while (has) {
       const bool has_next = next_band(P, u, u1, nb);
       const bool new_chunk = b.chunk != loaded_chunk;
@@ -381,7 +470,17 @@ conv3x3_stream_kernel(const __grid_constant__ StreamParams P) {
           }
           mbar_wait_u(a_empty + 8 * as, aph ^ 1);
           if (ptr8) trace[113] = clock64();
-          if (elect_one()) {
+          if (from_src) {
+            if (lane == 0) {
+              if (kb == 0) {
+                const uint32_t ra = rec_base + as * (kRecWords * 4u);
+                sts128(ra, static_cast<uint32_t>(sL * NOUT), P.idesc[nA - 1], P.idesc[nB > 0 ? nB - 1 : 0],
+                       static_cast<uint32_t>(b_lo * NOUT * 128) >> 4);
+                sts128(ra + 16, static_cast<uint32_t>((b_lo + nA) * NOUT * 128) >> 4, flags, c0 | (c1 << 8), fresh);
+              }
+              mbar_arrive(a_full + 8 * as);
+            }
+          } else if (elect_one()) {
             if (kb == 0) {
               const uint32_t ra = rec_base + as * (kRecWords * 4u);
               sts128(ra, static_cast<uint32_t>(sL * NOUT), P.idesc[nA - 1], P.idesc[nB > 0 ? nB - 1 : 0],
@@ -561,6 +660,80 @@ conv3x3_stream_kernel(const __grid_constant__ StreamParams P) {
       }
     }
     SS4K_TRACE(4);
+  } else if (warp >= 2 + kStreamEpiWarps) {
+    // ======================================================= frame decoders (frame-format source only)
+    // Warp d of kStreamSrcWarps takes every kStreamSrcWarps-th input row of the producer's sequence: loads the row's
+    // bytes (the next one of its rows is in flight meanwhile), converts, writes the row's activation slabs -- the same
+    // swizzled layout a TMA box load produces, one per K block (split precision: high, high, low halves) -- and the
+    // 16-bit copy for the DenBlock's residual.
+    const int dw = warp - (2 + kStreamEpiWarps);
+    const int src_xe_off = lane == 0 ? -1 : (lane == 31 ? kTileW : -(1 << 20));   // halo pixel of this lane, relative to the strip
+    // (the 16-byte chunk of channels 8..15 of every slab pixel stays zero: k-step 0 reads 16 channels)
+    for (int sl = 0; sl < P.a_slots; ++sl)
+#pragma unroll
+      for (int j = 0; j < 5; ++j) {
+        const uint32_t p = lane + 32u * j;
+        if (p < static_cast<uint32_t>(kBoxW)) sts128(a_base + sl * kASlotBytes + p * 128u + ((1u ^ (p & 7u)) << 4), 0u, 0u, 0u, 0u);
+      }
+    pdl_wait();   // the frames (and src_out's last readers) belong to earlier work
+    uint32_t as = 0, aph = 0;
+    int u = u0, rowc = 0;
+    Band b;
+    SrcRow row_next;
+    bool have_next = false;
+    while (next_band(P, u, u1, b)) {
+      const int r0 = b.yb > 0 ? b.yb - 1 : b.yb, r1 = b.ye < P.H ? b.ye : b.ye - 1;
+      const int n_abs = b.n + P.n_in0;
+      const int xs = b.strip * kTileW, x4 = xs + 4 * lane;
+      have_next = false;
+      constexpr int kAhead = 8;   // rows between the L2 prefetch and the load
+      if (dw == 0 && lane < 4 * kAhead && r0 + (lane >> 2) <= r1) src_prefetch_row(P, n_abs, r0 + (lane >> 2), xs, lane & 3);
+      for (int r = r0; r <= r1; ++r, ++rowc) {
+        if (dw == (r & 1) && r + kAhead <= r1) src_prefetch_row(P, n_abs, r + kAhead, xs, lane);
+        if (rowc % kStreamSrcWarps != dw) {
+          for (int kb = 0; kb < P.nkb; ++kb)
+            if (++as == static_cast<uint32_t>(P.a_slots)) { as = 0; aph ^= 1; }
+          continue;
+        }
+        const bool trow = trace != nullptr && dw == 0 && lane == 0 && rowc < 16;
+        long long* const trw = trace + 96 + 2 * (rowc >> 1);
+        if (trow) trw[0] = clock64();
+        const SrcRow row = have_next ? row_next : src_load_row(P, n_abs, r, x4, xs + src_xe_off);
+        have_next = r + kStreamSrcWarps <= r1;
+        if (have_next) row_next = src_load_row(P, n_abs, r + kStreamSrcWarps, x4, xs + src_xe_off);
+        SrcPix pix[5];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) pix[i] = src_decode(P, src_px(P, row, i));
+        pix[4] = src_decode(P, src_px_extra(row));
+        if (r >= b.yb && r < b.ye && x4 < P.W) {   // this CTA's own rows: the decoded pixels for the DenBlock's residual
+          const size_t off = ((static_cast<size_t>(n_abs) * P.H + r) * P.W + x4) * 16;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            *reinterpret_cast<uint4*>(P.src_out + off + 16 * i) = make_uint4(pix[i].hi[0], pix[i].hi[1], 0u, 0u);
+            if (P.src_out_lo != nullptr) *reinterpret_cast<uint4*>(P.src_out_lo + off + 16 * i) = make_uint4(pix[i].lo[0], pix[i].lo[1], 0u, 0u);
+          }
+        }
+        if (trow) trw[1] = clock64();
+        for (int kb = 0; kb < P.nkb; ++kb) {
+          mbar_wait_u(a_empty + 8 * as, aph ^ 1);
+          const uint32_t slab = a_base + as * kASlotBytes;
+          const bool low = P.a_tm[kb] != 0;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const uint32_t p = 1u + 4u * lane + i;
+            sts128(slab + p * 128u + ((p & 7u) << 4), low ? pix[i].lo[0] : pix[i].hi[0], low ? pix[i].lo[1] : pix[i].hi[1], 0u, 0u);
+          }
+          if (lane == 0 || lane == 31) {
+            const uint32_t p = lane == 0 ? 0u : static_cast<uint32_t>(kBoxW - 1);
+            sts128(slab + p * 128u + ((p & 7u) << 4), low ? pix[4].lo[0] : pix[4].hi[0], low ? pix[4].lo[1] : pix[4].hi[1], 0u, 0u);
+          }
+          fence_proxy_async();   // generic-proxy writes -> visible to the tensor pipe's operand reads
+          __syncwarp();
+          if (lane == 0) mbar_arrive(a_full + 8 * as);
+          if (++as == static_cast<uint32_t>(P.a_slots)) { as = 0; aph ^= 1; }
+        }
+      }
+    }
   } else {
     // ======================================================= epilogue (warps 2..9)
     const Epilogue& E = P.ep;
@@ -1026,7 +1199,7 @@ template <int NOUT>
 static cudaError_t launch_one(const StreamParams& p, int grid, cudaStream_t stream, bool pdl) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(kStreamThreads);
+  cfg.blockDim = dim3(p.src_fmt != 0 ? kStreamThreadsMax : kStreamThreads);   // + the frame decoder warps
   cfg.dynamicSmemBytes = kSmemBytes;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];

@@ -118,6 +118,8 @@ struct ConvExec {
   float* d_bias = nullptr;
   float* d_slope = nullptr;
   bool ext_out = false;  // ep.out is the caller's output pointer (patched per run)
+  bool src_ext = false;  // sp.src is the caller's input pointer (frame-format source decoded by the producer warp, patched per run)
+  size_t src_off = 0;    //   byte offset of the step's first frame in it
   std::string name;
 };
 
@@ -827,6 +829,7 @@ struct ss4k_plan {
   std::vector<int> step_conv;   // step index -> conv index (or -1)
   cudaGraphExec_t graph = nullptr;
   int graph_first = -1, graph_last = -1;  // [first, last] step range inside the graph
+  int fused_prep = -1;   // step index of a layout (prep) step whose work the following conv's loader does, or -1
   uint32_t* d_ctr = nullptr;  // progress counters of the fused residual dense blocks (3 rotating buffers)
   long long* d_rdb_trace = nullptr;  // SS4K_RDB_TRACE=1: producer statistics of every fused launch [n_fused][nsm][16]
   int n_fused = 0;
@@ -870,6 +873,7 @@ int run_step(ss4k_plan* pl, int si, const void* in_dev, void* out_dev, cudaStrea
   ss4k_ctx* ctx = pl->ctx;
   const Step& s = pl->prog.steps[si];
   if (s.kind == 0) {
+    if (si == pl->fused_prep) return SS4K_OK;   // decoded by the first conv's producer warp (StreamParams::src)
     const PrepSpec& p = s.prep;
     const bool bf16 = pl->cfg.act_mode == SS4K_ACT_BF16;
     // (a BSVD chunk with a temporal halo converts only the frames [n0, n0 + n) the owned outputs depend on)
@@ -883,6 +887,7 @@ int run_step(ss4k_plan* pl, int si, const void* in_dev, void* out_dev, cudaStrea
   } else {
     ConvExec& c = pl->convs[pl->step_conv[si]];
     if (c.skip) return SS4K_OK;
+    if (c.src_ext) c.sp.src = reinterpret_cast<const uint8_t*>(in_dev) + c.src_off;
     CK(ctx, launch_exec(c, out_dev, st));
     ctx->launches++;
   }
@@ -1047,6 +1052,43 @@ int fuse_rdbs(ss4k_plan* pl) {
 bool step_is_external(const Step& s) {
   if (s.kind == 0) return true;  // prep reads the caller's pointer
   return s.conv.out_buf == kBufExternalOut;
+}
+
+// North-star part 4 (colour conversion in the first layer's load): a BSVD clip plan fed with uint8 RGB / NV12 frames
+// does not run its layout step; the first conv's producer warp decodes the frames into its activation slabs and leaves
+// the 16-bit rows for the DenBlock's residual (StreamParams::src).  Streaming convs of the <32> kernel only.
+void fuse_prep(ss4k_plan* pl) {
+  Program& P = pl->prog;
+  if (getenv("SS4K_NO_FUSED_PREP") != nullptr || P.steps.size() < 2) return;
+  const Step& s0 = P.steps[0];
+  const Step& s1 = P.steps[1];
+  if (s0.kind != 0 || s1.kind != 1) return;
+  const PrepSpec& pp = s0.prep;
+  const ConvSpec& cs = s1.conv;
+  if ((pp.in_fmt != SS4K_FMT_U8_NHWC && pp.in_fmt != SS4K_FMT_NV12) || pp.unshuffle != 1 || pp.c != 3) return;
+  if (cs.in_buf != pp.out_buf || cs.mode != kModeConv3 || cs.in_pitch != 16 || cs.in_coff != 0 || cs.cin > 8) return;
+  if (pl->cfg.act_mode == SS4K_ACT_BF16) return;
+  if (pp.fill_ch >= 0 && pp.fill_ch != 3) return;
+  ConvExec& c = pl->convs[pl->step_conv[1]];
+  if (!c.stream || c.fused || c.skip) return;
+  // the conv must cover every frame the layout step would have converted for other readers (the residual of the block's
+  // last conv): its frame range contains theirs by construction (bsvd_program.cpp), check it anyway
+  const int c0 = cs.n0, c1 = cs.n0 + cs.n;
+  for (size_t si = 2; si < P.steps.size(); ++si) {
+    if (P.steps[si].kind != 1) continue;
+    const ConvSpec& o = P.steps[si].conv;
+    const bool reads = o.in_buf == pp.out_buf || o.res1_buf == pp.out_buf || o.res2_buf == pp.out_buf;
+    if (reads && (o.n0 < c0 || o.n0 + o.n > c1)) return;
+  }
+  StreamParams& sp = c.sp;
+  sp.src_fmt = pp.in_fmt;
+  sp.src_fill_ch = pp.fill_ch;
+  sp.src_fill = pp.fill_val;
+  sp.src_out = reinterpret_cast<uint16_t*>(pl->bufs[pp.out_buf]);
+  sp.src_out_lo = pp.out_lo_buf >= 0 ? reinterpret_cast<uint16_t*>(pl->bufs[pp.out_lo_buf]) : nullptr;
+  c.src_ext = true;
+  c.src_off = 0;   // (sp.n_in0 carries the step's first frame)
+  pl->fused_prep = 0;
 }
 
 }  // namespace
@@ -1269,6 +1311,7 @@ int ss4k_plan_create(ss4k_ctx* ctx, const ss4k_plan_cfg* cfg, ss4k_plan** out_pl
     int rc = fuse_rdbs(pl.get());
     if (rc != SS4K_OK) { ss4k_plan_destroy(pl.release()); return rc; }
   }
+  fuse_prep(pl.get());
   // Early activation loads (StreamParams::early_kb_mask): K blocks that only read channels written at least two steps
   // ago are requested before the dependency wait.  Needs this conv and the two launches before it to be streaming convs
   // that fill every SM (see conv_params.h).
@@ -1309,11 +1352,14 @@ int ss4k_plan_create(ss4k_ctx* ctx, const ss4k_plan_cfg* cfg, ss4k_plan** out_pl
   // CUDA graph over the internal (non-external) middle of the program
   if (cfg->use_graph) {
     int first = -1, last = -1;
+    auto external = [&](size_t si) {
+      return step_is_external(P.steps[si]) || (P.steps[si].kind == 1 && pl->convs[pl->step_conv[si]].src_ext);
+    };
     for (size_t si = 0; si < P.steps.size(); ++si) {
-      if (!step_is_external(P.steps[si])) { if (first < 0) first = (int)si; last = (int)si; }
+      if (!external(si)) { if (first < 0) first = (int)si; last = (int)si; }
     }
     bool contiguous = first >= 0;
-    for (int si = first; contiguous && si <= last; ++si) if (step_is_external(P.steps[si])) contiguous = false;
+    for (int si = first; contiguous && si <= last; ++si) if (external(si)) contiguous = false;
     if (contiguous && last - first >= 1) {
       cudaGraph_t g = nullptr;
       int64_t saved = ctx->launches;
@@ -1421,7 +1467,7 @@ double ss4k_plan_flops(const ss4k_plan* pl) { return pl ? pl->prog.flops : 0.0; 
 static int live_steps(const ss4k_plan* pl, int first, int last) {
   int n = 0;
   for (int si = first; si <= last; ++si)
-    if (!(pl->prog.steps[si].kind == 1 && pl->convs[pl->step_conv[si]].skip)) ++n;
+    if (!(pl->prog.steps[si].kind == 1 && pl->convs[pl->step_conv[si]].skip) && si != pl->fused_prep) ++n;
   return n;
 }
 // kernels one run launches (a fused residual dense block is one launch for five convs)
@@ -1569,7 +1615,7 @@ int ss4k_plan_profile(ss4k_plan* pl, const void* in_dev, void* out_dev, void* cu
     cudaEventElapsedTime(&ms[si], ev[si], ev[si + 1]);
     const Step& s = pl->prog.steps[si];
     flops[si] = s.kind == 1 ? s.conv.flops() : 0.0;
-    kind[si] = s.kind == 0 ? 0 : (pl->convs[pl->step_conv[si]].stream ? 1 : 2);
+    kind[si] = s.kind == 0 ? (si == pl->fused_prep ? 4 : 0) : (pl->convs[pl->step_conv[si]].stream ? 1 : 2);
     if (s.kind == 1) {
       const ConvExec& c = pl->convs[pl->step_conv[si]];
       if (c.fused) { kind[si] = 3; flops[si] = c.fused_flops; }   // one launch for the block's five convs
@@ -1785,6 +1831,16 @@ int ss4k_debug_bench_conv(ss4k_ctx* ctx, const ss4k_conv_desc* d, int slab_pitch
       cudaMalloc(&d_trace, sizeof(long long) * 128 * 148);
       cudaMemset(d_trace, 0, sizeof(long long) * 128 * 148);
     }
+    void* d_src = nullptr;
+    if (ex.stream && d->reserved[1] != 0 && in_pitch == 16 && d->mode == kModeConv3) {  // frame-format source decoded by the kernel
+      const size_t sb = static_cast<size_t>(d->n) * d->h * d->w * 3;
+      cudaMalloc(&d_src, sb);
+      cudaMemset(d_src, 128, sb);
+      ex.sp.src = reinterpret_cast<const uint8_t*>(d_src);
+      ex.sp.src_fmt = d->reserved[1]; ex.sp.src_fill_ch = 3; ex.sp.src_fill = 0.075f;
+      ex.sp.src_out = reinterpret_cast<uint16_t*>(b[0]);
+      ex.sp.src_out_lo = nullptr;
+    }
     if (ex.stream) {
       ex.sp.dbg_flags = dbg_flags;
       if (d->reserved[3] > 0) ex.sp.a_slots = std::min(ex.sp.a_slots, d->reserved[3]);
@@ -1844,6 +1900,7 @@ int ss4k_debug_bench_conv(ss4k_ctx* ctx, const ss4k_conv_desc* d, int slab_pitch
       *out_json = static_cast<char*>(malloc(js.size() + 1));
       memcpy(*out_json, js.c_str(), js.size() + 1);
     }
+    if (d_src) cudaFree(d_src);
   }
   free_conv(ex);
   for (void* q : b) if (q) cudaFree(q);

@@ -164,3 +164,32 @@ def test_bsvd_streaming_frame_formats(engine, nv12):
     got = torch.cat(outs, dim=0)
     assert tuple(got.shape) == tuple(clip.shape) == (t, 3, h, w)
     assert (got - clip.float()).abs().max().item() <= 1e-3
+
+
+@pytest.mark.parametrize("nv12", [False, True])
+@pytest.mark.parametrize("split", [False, True])
+def test_bsvd_first_layer_decodes_frames(engine, nv12, split, monkeypatch):
+    """North-star part 4: with uint8 RGB / NV12 frames the clip plan has no layout kernel -- the first conv's producer
+    warp decodes the frames (BT.709 / 255, noise-map channel) into its activation slabs and leaves the 16-bit rows for the
+    DenBlock's residual.  Must equal the plan with the stand-alone layout kernel (SS4K_NO_FUSED_PREP=1) bit for bit:
+    ragged width (three strips, the last one partial), several row bands per CTA, owned-range plans with a temporal halo."""
+    sd = bsvd.build_bsvd32(0) if split else bsvd.build_bsvd32(0, weight_scale=0.5)
+    mode = L.ACT_F16_SPLIT if split else L.ACT_F16
+    t, h, w = 6, 36, 264
+    g = torch.Generator().manual_seed(31)
+    if nv12:
+        frames = torch.randint(16, 236, (t, h * 3 // 2, w), generator=g, dtype=torch.uint8).cuda()
+    else:
+        frames = torch.randint(0, 256, (t, h, w, 3), generator=g, dtype=torch.uint8).cuda()
+    fused = native_bsvd.NativeBSVD(sd, device=0, act_mode=mode)
+    a = fused.denoise_frames(frames, h, w, 0.075, nv12=nv12).clone()
+    a_own = fused.denoise_frames(frames, h, w, 0.075, nv12=nv12, own=(2, 5)).clone()
+    monkeypatch.setenv("SS4K_NO_FUSED_PREP", "1")
+    plain = native_bsvd.NativeBSVD(sd, device=0, act_mode=mode)
+    b = plain.denoise_frames(frames, h, w, 0.075, nv12=nv12)
+    b_own = plain.denoise_frames(frames, h, w, 0.075, nv12=nv12, own=(2, 5))
+    torch.cuda.synchronize()
+    assert fused._plan(t, h, w, L.FMT_NV12 if nv12 else L.FMT_U8_NHWC, L.FMT_F32_NCHW, 0.075).launches == \
+        plain._plan(t, h, w, L.FMT_NV12 if nv12 else L.FMT_U8_NHWC, L.FMT_F32_NCHW, 0.075).launches - 1
+    assert torch.equal(a, b)
+    assert torch.equal(a_own, b_own) and torch.equal(a_own, a[2:5])
