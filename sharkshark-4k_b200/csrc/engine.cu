@@ -1146,16 +1146,12 @@ int ss4k_create(int device_id, ss4k_ctx** out_ctx) {
   } else {
     int rc = SS4K_E_SELFTEST;
     std::string log;
-    // (a second round before giving up: seen once -- a worker process starting while two other processes kept the GPU
-    //  busy got the same wrong result in all three modes, and passed on every later start)
-    for (int attempt = 0; attempt < 2 && rc == SS4K_E_SELFTEST; ++attempt) {
-      for (int mode = 0; mode < 3; ++mode) {
-        ctx->desc_mode = mode;
-        rc = self_probe(ctx.get());
-        if (rc == SS4K_OK) break;
-        log += fmt("[mode %d: %s] ", mode, ctx->err.c_str());
-        if (rc != SS4K_E_SELFTEST) break;  // CUDA error: context is likely poisoned
-      }
+    for (int mode = 0; mode < 3; ++mode) {
+      ctx->desc_mode = mode;
+      rc = self_probe(ctx.get());
+      if (rc == SS4K_OK) break;
+      log += fmt("[mode %d: %s] ", mode, ctx->err.c_str());
+      if (rc != SS4K_E_SELFTEST) break;  // CUDA error: context is likely poisoned
     }
     if (rc != SS4K_OK) return fail(nullptr, rc, "tcgen05 self-probe failed: " + log);
   }
@@ -1384,6 +1380,8 @@ int ss4k_plan_create(ss4k_ctx* ctx, const ss4k_plan_cfg* cfg, ss4k_plan** out_pl
       cudaGetLastError();
     }
   }
+  // weight uploads (pageable cudaMemcpy) and buffer memsets ran on the NULL stream; the plan runs on the caller's stream
+  { cudaError_t ce = cudaDeviceSynchronize(); if (ce != cudaSuccess) { int rc = check_kernel_health(ctx, ce, "ss4k_plan_create"); ss4k_plan_destroy(pl.release()); return rc; } }
   *out_plan = pl.release();
   return SS4K_OK;
 }
@@ -1451,6 +1449,7 @@ static int create_tiled_plan(ss4k_ctx* ctx, const ss4k_plan_cfg* cfg, ss4k_plan*
   }
   pl->in_bytes = fmt_bytes(P.in_fmt, P.in_n, P.in_c, P.in_h, P.in_w);
   pl->out_bytes = fmt_bytes(P.out_fmt, P.out_n, P.out_c, P.out_h, P.out_w);
+  cudaDeviceSynchronize();   // the tile boxes were uploaded on the NULL stream
   *out_plan = pl.release();
   return SS4K_OK;
 }
@@ -1693,7 +1692,8 @@ int ss4k_conv3x3(ss4k_ctx* ctx, const ss4k_conv_desc* d, const float* x, const f
   auto bufptr = [&](int id) -> void* { return id >= 0 ? b[id] : nullptr; };
   int rc = materialize_conv(ctx, cs, W, bias ? &B : nullptr, slope ? &S : nullptr, d->act_mode, bufptr, &ex);
   if (rc != SS4K_OK) { free_conv(ex); cleanup(); return rc; }
-  cudaError_t ce = launch_exec(ex, y, st);
+  cudaError_t ce = cudaDeviceSynchronize();   // packed weights were uploaded on the NULL stream
+  if (ce == cudaSuccess) ce = launch_exec(ex, y, st);
   ctx->launches++;
   if (ce == cudaSuccess && !ex.ext_out) {
     ce = unprep_launch(b[2], b[4], y, d->n, res_c, ooh, oow, out_ch_pitch, 0, bf16, st);
@@ -1934,6 +1934,9 @@ static int self_probe(ss4k_ctx* ctx) {
   CK(ctx, cudaMemcpy(dx, hx.data(), hx.size() * 4, cudaMemcpyHostToDevice));
   CK(ctx, cudaMemcpy(dw, hw.data(), hw.size() * 4, cudaMemcpyHostToDevice));
   CK(ctx, cudaMemcpy(db, hb.data(), hb.size() * 4, cudaMemcpyHostToDevice));
+  // cudaMemcpy from pageable memory returns once the data is staged: its DMA runs on the NULL stream, which the engine's
+  // non-blocking stream does not wait for (seen as wrong probe results when other processes keep the copy engine busy)
+  CK(ctx, cudaDeviceSynchronize());
   ss4k_conv_desc d;
   memset(&d, 0, sizeof(d));
   d.struct_size = sizeof(d); d.n = N; d.h = H; d.w = W; d.cin = C; d.cout = C; d.alpha = 1.f;
