@@ -387,10 +387,21 @@ def run_native_cfg3(args, rank, world, local_rank):
     den_plan = pipe.den_plan(T, ch.lo - ch.load_lo, ch.hi - ch.load_lo)
     den_out = den_plan.new_output()
     prof_den = den_plan.profile(chunks_dev[0], den_out)
-    lr0 = pipe._lr[F][0:1]
+    lr0 = torch.rand(1, 3, FRAME_H, FRAME_W, device=dev)
     prof_sr = pipe.sr_plan.profile(lr0, out_dev[0:1])
     prof_sr = pipe.sr_plan.profile(lr0, out_dev[0:1])
     torch.cuda.synchronize()
+    glue_ms = None
+    if pipe._act is not None:
+        # the product path never runs the upscaler plan's layout step: the glue between the nets (sharpen + clamp + blend
+        # with the decoded NV12 frame) writes conv_first's activation tensor itself -- time that kernel in its place
+        import ctypes
+        ptr, pitch, us, bf = pipe._act
+        st = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        glue_ms = timed_kernel(lambda: eng.lib.ss4k_glue_sharpen_blend_act(
+            ctypes.c_void_p(den_out.data_ptr()), 1, 1, 3, FRAME_H, FRAME_W, 0.00002, 0.8, ctypes.c_void_p(chunks_dev[0].data_ptr()), 3,
+            ctypes.c_void_p(ptr), us, pitch, bf, st))
+        prof_sr = [(glue_ms, 0.0, 0) if i == 0 and kd == 0 else (m, f, kd) for i, (m, f, kd) in enumerate(prof_sr)]
     den_ms = sum(m for m, _, _ in prof_den)
     sr_ms = sum(m for m, _, _ in prof_sr)
 
@@ -405,6 +416,11 @@ def run_native_cfg3(args, rank, world, local_rank):
             nb_ = T * (FRAME_H * FRAME_W * 3 // 2) + T * FRAME_H * FRAME_W * 16 * 2 * (2 if den.act_mode == L.ACT_F16_SPLIT else 1)
             hbm_kernels.append({"kernel": "prep_kernel<NV12>", "bytes_per_launch": nb_, "us": 1000 * lay[0], "GB/s": nb_ / lay[0] / 1e6,
                                 "what": f"NV12 -> RGB (BT.709) + noise map -> 16-channel fp16 NHWC ({'hi + lo twins, ' if den.act_mode == L.ACT_F16_SPLIT else ''}{T} frames per launch): 1.5 B/px read, 32 B/px written per twin"})
+        if glue_ms is not None:
+            nb_ = FRAME_H * FRAME_W * (3 * 2 + 1.5 + 8)
+            hbm_kernels.append({"kernel": "sharpen_blend_act_kernel", "bytes_per_launch": nb_, "us": 1000 * glue_ms, "GB/s": nb_ / glue_ms / 1e6,
+                                "what": "glue between the nets, one frame per launch: 3x3 reflect sharpen + clamp of the denoised frame (fp16 NCHW, 6 B/px), "
+                                        "0.8/0.2 blend with the NV12 frame decoded in place (1.5 B/px) -> RRDBNet conv_first's pixel-unshuffled fp16 NHWC input (8 B/px)"})
         t_nv = timed_kernel(lambda: eng.rgb_to_nv12(out_dev[:8]))
         nbytes = out_dev[:8].numel() * 1.5
         hbm_kernels.append({"kernel": "rgb_to_nv12_kernel", "bytes_per_launch": nbytes, "us": 1000 * t_nv, "GB/s": nbytes / t_nv / 1e6,
@@ -424,7 +440,9 @@ def run_native_cfg3(args, rank, world, local_rank):
                        "parallelism": f"contiguous frame chunks x{world}, 16-frame BSVD halo per side (sharding.bsvd_chunks; every BSVD layer runs only on the halo frames the owned outputs depend on), NCCL gather of uint8 frames to rank 0 inside the step",
                        "ms_per_frame": {"bsvd_per_owned_frame": den_ms / F, "rrdb_per_upscaled_frame": sr_ms,
                                         "note": "un-graphed profile runs (serialised launches)"},
-                       "launch": "BSVD clip: %d kernels per chunk, RRDBNet: %d per frame, CUDA graphs; programmatic dependent launch %s"
+                       "colour": "NV12 -> RGB (BT.709), /255 and the noise map are decoded by the first BSVD conv's loader warps (no layout kernel); "
+                                 "the sharpen / blend glue between the nets writes RRDBNet's first activation tensor; the last conv stores uint8 RGB",
+                       "launch": "BSVD clip: %d kernels per chunk, RRDBNet: %d per frame (+ 1 glue kernel, - its layout kernel), CUDA graphs; programmatic dependent launch %s"
                                  % (den_plan.launches, pipe.sr_plan.launches, "off" if os.environ.get("SS4K_NO_PDL") else "on")},
             "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": chunks_host[0].numel(), "d2h_bytes_per_step": d2h_bytes,
                     "note": "per rank: pinned NV12 chunk H2D -> BSVD -> RRDBNet -> (N>1: NCCL gather ->) D2H of the uint8 frames on rank 0"},

@@ -209,6 +209,16 @@ int ss4k_glue_bicubic_u8(const float* in, int n, int c, int h, int w, uint8_t* o
  * (fsrcnn_upscaler.py:54-84,278-281,298-299) */
 int ss4k_glue_sharpen_blend(const void* x, int fmt, int n, int c, int h, int w, float strength, float opacity,
                             const void* other, int other_fmt, float* out, void* cuda_stream);
+/* the same, written as an upscaler plan's first-layer activation tensor (ss4k_plan_input_act: 16-bit NHWC, channel
+ * pitch `pitch`, pixel_unshuffle(`unshuffle`) channel order): the denoise -> upscale hand-over of upscale_single
+ * (fsrcnn_upscaler.py:278-295) without a float image and without a layout kernel in front of conv_first */
+int ss4k_glue_sharpen_blend_act(const void* x, int fmt, int n, int c, int h, int w, float strength, float opacity,
+                                const void* other, int other_fmt, void* act_out, int unshuffle, int pitch, int is_bf16,
+                                void* cuda_stream);
+/* device pointer / layout of the tensor a plan's layout step writes (fails for tiled, split-precision and frame-decoding
+ * plans, which have no plain layout step), and ss4k_run without that step: the caller has filled the tensor itself */
+int ss4k_plan_input_act(ss4k_plan* plan, void** act_dev, int32_t* pitch, int32_t* unshuffle, int32_t* is_bf16);
+int ss4k_run_act(ss4k_plan* plan, void* out_dev, void* cuda_stream);
 
 /* operator-level entry (kernel parity tests) -------------------------------------------- */
 typedef struct ss4k_conv_desc {

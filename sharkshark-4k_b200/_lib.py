@@ -71,6 +71,10 @@ SYMBOLS = {
                                            _i, _i, _i, _vp]),
     "ss4k_glue_bicubic_u8": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _i, _i, _vp]),
     "ss4k_glue_sharpen_blend": (_i, [_vp, _i, _i, _i, _i, _i, ctypes.c_float, ctypes.c_float, _vp, _i, _vp, _vp]),
+    "ss4k_glue_sharpen_blend_act": (_i, [_vp, _i, _i, _i, _i, _i, ctypes.c_float, ctypes.c_float, _vp, _i, _vp, _i, _i, _i, _vp]),
+    "ss4k_plan_input_act": (_i, [_vp, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_int32),
+                                ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32)]),
+    "ss4k_run_act": (_i, [_vp, _vp, _vp]),
     "ss4k_conv3x3": (_i, [_vp, ctypes.POINTER(ConvDesc), _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "ss4k_debug_bench_conv": (_i, [_vp, ctypes.POINTER(ConvDesc), _i, _i, _i, ctypes.POINTER(ctypes.c_float),
                                    ctypes.POINTER(_vp)]),

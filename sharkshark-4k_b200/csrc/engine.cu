@@ -1535,6 +1535,43 @@ int ss4k_run(ss4k_plan* pl, const void* in_dev, void* out_dev, void* cuda_stream
   return SS4K_OK;
 }
 
+// The plan's first-layer activation tensor: where its layout step would write.  A producer that already has the frame
+// on the device in float form (the service glue between denoiser and upscaler) writes it here itself and calls
+// ss4k_run_act, which runs the plan without the layout step.
+int ss4k_plan_input_act(ss4k_plan* pl, void** act_dev, int32_t* pitch, int32_t* unshuffle, int32_t* is_bf16) {
+  if (!pl || !act_dev) return fail(pl ? pl->ctx : nullptr, SS4K_E_INVALID, "null argument to ss4k_plan_input_act");
+  const Program& P = pl->prog;
+  if (pl->tiled || P.steps.empty() || P.steps[0].kind != 0 || P.steps[0].prep.out_lo_buf >= 0 || pl->fused_prep >= 0)
+    return fail(pl->ctx, SS4K_E_INVALID, "ss4k_plan_input_act: the plan has no plain layout step in front (tiled / split precision / frame-decoding plans)");
+  const PrepSpec& p = P.steps[0].prep;
+  *act_dev = pl->bufs[p.out_buf];
+  if (pitch) *pitch = P.bufs[p.out_buf].pitch;
+  if (unshuffle) *unshuffle = p.unshuffle;
+  if (is_bf16) *is_bf16 = pl->cfg.act_mode == SS4K_ACT_BF16 ? 1 : 0;
+  return SS4K_OK;
+}
+
+int ss4k_run_act(ss4k_plan* pl, void* out_dev, void* cuda_stream) {
+  if (!pl || !out_dev) return fail(pl ? pl->ctx : nullptr, SS4K_E_INVALID, "null argument to ss4k_run_act");
+  ss4k_ctx* ctx = pl->ctx;
+  void* act = nullptr;
+  int rc = ss4k_plan_input_act(pl, &act, nullptr, nullptr, nullptr);
+  if (rc != SS4K_OK) return rc;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(cuda_stream);
+  const int ns = static_cast<int>(pl->prog.steps.size());
+  for (int si = 1; si < ns; ++si) {
+    if (pl->graph && si == pl->graph_first) {
+      CK(ctx, cudaGraphLaunch(pl->graph, st));
+      ctx->launches += live_steps(pl, pl->graph_first, pl->graph_last);
+      si = pl->graph_last;
+      continue;
+    }
+    rc = run_step(pl, si, nullptr, out_dev, st);
+    if (rc != SS4K_OK) return rc;
+  }
+  return SS4K_OK;
+}
+
 int ss4k_run_host(ss4k_plan* pl, const void* in_host, void* out_host) {
   if (!pl || !in_host || !out_host) return fail(pl ? pl->ctx : nullptr, SS4K_E_INVALID, "null argument to ss4k_run_host");
   ss4k_ctx* ctx = pl->ctx;

@@ -11,6 +11,7 @@
 // The reference runs ~10 separate ATen passes over the HR frame; here: one statistics pass, one pooling pass,
 // a tiny low-resolution blur and ONE finalising pass that applies the affine match, subtracts the bilinearly
 // upsampled colour difference, clamps and writes uint8 NHWC.
+#include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -465,6 +466,45 @@ __global__ void sharpen_blend_kernel(Img x, float k_center, float k_side, float 
   out[idx] = v;
 }
 
+// The same arithmetic, written as the upscaler's first-layer activation tensor: 16-bit NHWC [N, H/us, W/us, pitch] with
+// torch pixel_unshuffle(us) channel order (ch = c*us*us + iy*us + jx), zero channel padding -- what the plan's layout
+// kernel would produce from the float image (prep_kernel, elementwise.cu), without the float image.
+__global__ void sharpen_blend_act_kernel(Img x, float k_center, float k_side, float opacity, Img other, uint16_t* __restrict__ out,
+                                         int us, int pitch, int bf16) {
+  const int OH = x.H / us, OW = x.W / us;
+  const size_t total = static_cast<size_t>(x.N) * OH * OW;
+  const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int ox = static_cast<int>(idx % OW);
+  const int oy = static_cast<int>((idx / OW) % OH);
+  const int n = static_cast<int>(idx / (static_cast<size_t>(OW) * OH));
+  const int creal = x.C * us * us;
+  uint16_t* o = out + idx * pitch;
+  for (int c8 = 0; c8 < pitch; c8 += 8) {
+    uint16_t v8[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int ch = c8 + i;
+      float v = 0.f;
+      if (ch < creal) {
+        const int c = ch / (us * us), rem = ch - c * us * us;
+        const int py = oy * us + rem / us, px = ox * us + rem % us;
+        float acc = 0.f;
+#pragma unroll
+        for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+          for (int dx = -1; dx <= 1; ++dx)
+            acc += ((dy == 0 && dx == 0) ? k_center : k_side) * x.at(n, c, reflect(py + dy, x.H), reflect(px + dx, x.W));
+        v = fminf(fmaxf(acc, 0.f), 1.f);
+        if (other.p != nullptr) v = opacity * v + (1.f - opacity) * other.at(n, c, py, px);
+      }
+      if (bf16) { const __nv_bfloat16 h = __float2bfloat16_rn(v); v8[i] = *reinterpret_cast<const uint16_t*>(&h); }
+      else { const __half h = __float2half_rn(v); v8[i] = *reinterpret_cast<const uint16_t*>(&h); }
+    }
+    *reinterpret_cast<uint4*>(o + c8) = *reinterpret_cast<const uint4*>(v8);
+  }
+}
+
 inline unsigned blocks_for(size_t total, int threads) { return static_cast<unsigned>((total + threads - 1) / threads); }
 
 }  // namespace
@@ -545,6 +585,22 @@ int ss4k_glue_sharpen_blend(const void* x, int fmt, int n, int c, int h, int w, 
   const size_t total = static_cast<size_t>(n) * c * h * w;
   sharpen_blend_kernel<<<blocks_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       Img{x, fmt, n, c, h, w}, center / sum, side / sum, opacity, Img{other, other_fmt, n, c, h, w}, out);
+  return cudaGetLastError() == cudaSuccess ? SS4K_OK : SS4K_E_CUDA;
+}
+
+// ss4k_glue_sharpen_blend with the result written as a plan's first-layer activation tensor (ss4k_plan_input_act): the glue
+// between the denoiser and the upscaler (fsrcnn_upscaler.py:278-281) then feeds conv_first directly -- no float image, no
+// layout kernel in the upscaler's plan (ss4k_run_act).
+int ss4k_glue_sharpen_blend_act(const void* x, int fmt, int n, int c, int h, int w, float strength, float opacity, const void* other,
+                                int other_fmt, void* act_out, int unshuffle, int pitch, int bf16, void* stream) {
+  if (!x || !act_out || fmt < 0 || fmt > 2 || (other && (other_fmt < 0 || other_fmt > 3))) return SS4K_E_INVALID;
+  if (unshuffle < 1 || h % unshuffle || w % unshuffle || pitch % 8 || pitch < c * unshuffle * unshuffle) return SS4K_E_INVALID;
+  const float center = 9.f * strength + (1.f - strength), side = -strength;
+  const float sum = center + 8.f * side;
+  const size_t total = static_cast<size_t>(n) * (h / unshuffle) * (w / unshuffle);
+  sharpen_blend_act_kernel<<<blocks_for(total, 128), 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      Img{x, fmt, n, c, h, w}, center / sum, side / sum, opacity, Img{other, other_fmt, n, c, h, w},
+      reinterpret_cast<uint16_t*>(act_out), unshuffle, pitch, bf16);
   return cudaGetLastError() == cudaSuccess ? SS4K_OK : SS4K_E_CUDA;
 }
 

@@ -205,6 +205,20 @@ class Plan:
                 self.engine.h)
         return out
 
+    def input_act(self):
+        """(device pointer, channel pitch, pixel-unshuffle factor, is_bf16) of the tensor the plan's layout step writes
+        (ss4k_plan_input_act); raises for plans without a plain layout step."""
+        ptr, pitch, us, bf = ctypes.c_void_p(), ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32()
+        L.check(self.lib.ss4k_plan_input_act(self.h, ctypes.byref(ptr), ctypes.byref(pitch), ctypes.byref(us), ctypes.byref(bf)),
+                self.engine.h)
+        return ptr.value, pitch.value, us.value, bf.value
+
+    def run_act(self, out):
+        """The plan without its layout step: the caller has written the first-layer activation tensor (input_act())."""
+        st = ctypes.c_void_p(torch.cuda.current_stream(out.device).cuda_stream)
+        L.check(self.lib.ss4k_run_act(self.h, ctypes.c_void_p(out.data_ptr()), st), self.engine.h)
+        return out
+
     def profile(self, x, out=None):
         """One un-graphed run with a CUDA event between every step: list of (ms, flops, kind) per step
         (kind 0 layout/colour kernel, 1 row-streaming conv kernel, 2 tile conv kernel, 3 fused residual dense block =

@@ -29,6 +29,12 @@ class DenoiseUpscalePipeline:
         self.device = denoiser.engine.device
         self.sr_plan = upscaler._plan(1, h, w, L.FMT_F32_NCHW, out_fmt)
         self.lib = denoiser.engine.lib
+        # the glue between the nets writes the upscaler's first-layer activation tensor itself (no float image, no layout
+        # kernel in the upscaler's plan) unless the plan has no plain layout step (tiled plans)
+        try:
+            self._act = self.sr_plan.input_act()
+        except L.Ss4kError:
+            self._act = None
         self._lr = {}
         self._den_out_dtype = denoiser.out_dtype
         self._copy_stream = None
@@ -65,12 +71,25 @@ class DenoiseUpscalePipeline:
         if out is None:
             out = self.new_output(hi - lo)
         n_own = hi - lo
-        lr = self._lr.get(n_own)
-        if lr is None:
-            lr = self._lr[n_own] = torch.empty(n_own, 3, self.h, self.w, dtype=torch.float32, device=self.device)
         # denoised -> 3x3 reflect sharpen(2e-5) + clamp -> 0.8 * . + 0.2 * original frame (fsrcnn_upscaler.py:278-281)
         st = ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
         src = frames[lo:hi]
+        if self._act is not None:
+            ptr, pitch, us, bf = self._act
+            den_frame = den.stride(0) * den.element_size()
+            src_frame = src.stride(0) * src.element_size()
+            for i in range(n_own):
+                L.check(self.lib.ss4k_glue_sharpen_blend_act(
+                    ctypes.c_void_p(den.data_ptr() + i * den_frame), 1, 1, 3, self.h, self.w, 0.00002, 0.8,
+                    ctypes.c_void_p(src.data_ptr() + i * src_frame), 3 if self.nv12 else 2,
+                    ctypes.c_void_p(ptr), us, pitch, bf, st), self.den.engine.h)
+                self.sr_plan.run_act(out[i:i + 1])
+                if after_frame is not None:
+                    after_frame(i)
+            return out
+        lr = self._lr.get(n_own)
+        if lr is None:
+            lr = self._lr[n_own] = torch.empty(n_own, 3, self.h, self.w, dtype=torch.float32, device=self.device)
         L.check(self.lib.ss4k_glue_sharpen_blend(ctypes.c_void_p(den.data_ptr()), 1, n_own, 3, self.h, self.w,
                                                  0.00002, 0.8, ctypes.c_void_p(src.data_ptr()), 3 if self.nv12 else 2,
                                                  ctypes.c_void_p(lr.data_ptr()), st), self.den.engine.h)

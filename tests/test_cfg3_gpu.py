@@ -119,3 +119,21 @@ def test_cfg3_host_path_equals_device_path(nets):
     pipe.host_sync()
     for a, b in zip(want, outs):
         assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("nv12", [True, False])
+def test_cfg3_glue_writes_the_upscalers_first_tensor(nets, nv12):
+    """The hand-over between the nets: the sharpen / clamp / blend glue writes RRDBNet's pixel-unshuffled fp16 activation
+    tensor itself (ss4k_glue_sharpen_blend_act + ss4k_run_act: no float image, no layout kernel in the upscaler's plan).
+    Must equal the two-step path (float NCHW image -> the plan's own layout kernel) bit for bit."""
+    rr, bsd, sr, den = nets
+    h, w, T = 72, 136, 5
+    g = torch.Generator().manual_seed(13)
+    shape = (T, h * w * 3 // 2) if nv12 else (T, h, w, 3)
+    frames = torch.randint(16, 236, shape, dtype=torch.uint8, generator=g).cuda()
+    pipe = DenoiseUpscalePipeline(den, sr, h, w, NOISE, nv12=nv12, out_fmt=L.FMT_U8_NHWC)
+    assert pipe._act is not None
+    direct = pipe.run(frames, slice(1, 4)).clone()
+    pipe._act = None
+    two_step = pipe.run(frames, slice(1, 4))
+    assert torch.equal(direct, two_step)
