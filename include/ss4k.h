@@ -165,6 +165,21 @@ int ss4k_plan_profile(ss4k_plan* plan, const void* in_dev, void* out_dev, void* 
  * point, chroma = mean of the 2x2 block.  h % 2 == 0, w % 4 == 0.  Device pointers. */
 int ss4k_rgb_to_nv12(ss4k_ctx* ctx, const void* rgb_dev, void* nv12_dev, int n, int h, int w, void* cuda_stream);
 
+/* ingest / egress surfaces.  A hardware decoder hands out, and a hardware encoder takes, PITCHED
+ * NV12 device surfaces, one allocation per frame: luma rows `pitch` bytes apart, the interleaved chroma plane at its own
+ * pointer (cuvidMapVideoFrame: base + pitch * coded_height; NvEncRegisterResource: base + pitch * height).  These two
+ * entries move n such surfaces into / out of the packed frame chunk the plans read (in_fmt SS4K_FMT_NV12:
+ * [n, h*3/2, w] bytes) with 2-D DMA copies on `cuda_stream` -- no kernel, no host round trip.  They replace the rgb24 OS
+ * pipes of src/stream/twitch_realtime_handler/twitchgrabber.py:91-102 and src/stream/twitch_stream/output_stream.py:115-191.
+ * `surfaces` is a HOST array; all pointers in it are device pointers. */
+typedef struct ss4k_nv12_surface {
+  void* y;             /* luma plane: h rows of w bytes, pitch_y bytes apart                    */
+  void* uv;            /* interleaved chroma plane: h/2 rows of w bytes, pitch_uv bytes apart   */
+  int32_t pitch_y, pitch_uv;
+} ss4k_nv12_surface;
+int ss4k_nv12_pack(ss4k_ctx* ctx, const ss4k_nv12_surface* surfaces, int n, int h, int w, void* packed_dev, void* cuda_stream);
+int ss4k_nv12_unpack(ss4k_ctx* ctx, const void* packed_dev, const ss4k_nv12_surface* surfaces, int n, int h, int w, void* cuda_stream);
+
 /* BSVD streaming (persistent per-stream ring buffers) ----------------------------------- */
 /* open: plan must be an SS4K_ARCH_BSVD plan (its n is ignored; frames are pushed one at a time) */
 int ss4k_bsvd_stream_open(ss4k_plan* plan, ss4k_bsvd_stream** out_stream);

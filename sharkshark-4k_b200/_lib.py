@@ -19,6 +19,11 @@ class PlanCfg(ctypes.Structure):
         "act_mode", "in_fmt", "out_fmt", "use_graph")] + [("reserved", ctypes.c_int32 * 8)]
 
 
+class Nv12Surface(ctypes.Structure):
+    """ss4k_nv12_surface (include/ss4k.h): one pitched NV12 frame of a hardware decoder / encoder"""
+    _fields_ = [("y", ctypes.c_void_p), ("uv", ctypes.c_void_p), ("pitch_y", ctypes.c_int32), ("pitch_uv", ctypes.c_int32)]
+
+
 class ConvDesc(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int32) for n in (
         "struct_size", "n", "h", "w", "cin", "cout", "mode", "act", "act_mode", "pixel_shuffle")] + [
@@ -62,6 +67,8 @@ SYMBOLS = {
     "ss4k_bsvd_stream_latency": (_i, [_vp]),
     "ss4k_bsvd_stream_close": (_i, [_vp]),
     "ss4k_rgb_to_nv12": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
+    "ss4k_nv12_pack": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
+    "ss4k_nv12_unpack": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
     "ss4k_glue_chan_stats": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "ss4k_glue_area_pool": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _i, _i, _vp]),
     "ss4k_glue_blur_diff": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, ctypes.c_double, ctypes.c_double, _vp]),

@@ -1036,7 +1036,7 @@ conv3x3_stream_kernel(const __grid_constant__ StreamParams P) {
                 reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(E.out) + pix0 * 3)[lane] = static_cast<uint32_t>(two >> (8 * sh));
               }
             } else if (NOUT == 16 && (E.out_mode == kOutNCHWF16 || E.out_mode == kOutNCHWF32) && E.cout <= 4 &&
-                       E.act == kActNone && E.alpha == 1.0f && E.res2 == nullptr && E.res1_lo_off == 0 && !bf16) {
+                       E.act == kActNone && E.alpha == 1.0f && E.res2 == nullptr && !bf16) {
               // few-channel planar output (last conv of RRDBNet / BSVD at the model boundary, optional residual on the
               // first res1_nch channels: BSVD none_minus, bsvd/model.py:436-442): one coalesced store per channel
               if (valid) {
@@ -1048,7 +1048,12 @@ conv3x3_stream_kernel(const __grid_constant__ StreamParams P) {
                 for (int c = 0; c < 4; ++c) {
                   if (c < E.cout) {
                     float v = __uint_as_float(raw[c]);
-                    if (c < nres) v = fmaf(E.beta1, __half2float(*reinterpret_cast<const __half*>(rp + c)), v);
+                    if (c < nres) {
+                      // (split precision: + the residual's low half; same association as epilogue_chunk)
+                      float r = E.beta1 * __half2float(*reinterpret_cast<const __half*>(rp + c));
+                      if (E.res1_lo_off != 0) r = fmaf(E.beta1, __half2float(*reinterpret_cast<const __half*>(rp + c + E.res1_lo_off)), r);
+                      v += r;
+                    }
                     if (E.out_mode == kOutNCHWF16) reinterpret_cast<__half*>(E.out)[o0 + c * plane] = __float2half_rn(v);
                     else reinterpret_cast<float*>(E.out)[o0 + c * plane] = v;
                   }
@@ -1082,7 +1087,7 @@ conv3x3_stream_kernel(const __grid_constant__ StreamParams P) {
                 }
               }
             } else if ((E.out_mode == kOutNHWC || E.out_mode == kOutPS2NHWC) && !E.up2_store && E.alpha == 1.0f &&
-                       E.res2 == nullptr && E.res1_nch == 0 && E.out_lo == nullptr && E.res1_lo_off == 0 && !bf16 &&
+                       E.res2 == nullptr && E.res1_nch <= 8 && !bf16 &&
                        (E.act == kActRelu6 || E.act == kActNone) && (E.res1 == nullptr || E.beta1 == 1.0f)) {
               // BSVD stores (bsvd/model.py:43-52, 231-323): ReLU6 or linear, optional PixelShuffle(2) (weights'
               // output channels pre-permuted to (a, b, c)), optional skip add at the output pixel, optional temporal-
@@ -1112,14 +1117,40 @@ conv3x3_stream_kernel(const __grid_constant__ StreamParams P) {
                     const float a = __uint_as_float(raw[8 * j + i]);
                     v[i] = relu6 ? fminf(fmaxf(a, 0.f), 6.f) : a;
                   }
-                  if (E.res1 != nullptr) {
-                    const uint4 r = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(E.res1) + po * E.res1_pitch + E.res1_coff + oc);
+                  if (E.res1 != nullptr && (E.res1_nch == 0 || oc == 0)) {
+                    // (split precision: the residual tensor has a low-half twin res1_lo_off elements further on;
+                    //  res1_nch > 0: only the first channels take part -- BSVD none_minus, model.py:436-442)
+                    const uint16_t* const rp = reinterpret_cast<const uint16_t*>(E.res1) + po * E.res1_pitch + E.res1_coff + oc;
+                    const uint4 r = *reinterpret_cast<const uint4*>(rp);
                     const uint32_t w4[4] = {r.x, r.y, r.z, r.w};
+                    float rs[8];
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                       const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w4[i]));
-                      v[2 * i] += f.x;
-                      v[2 * i + 1] += f.y;
+                      rs[2 * i] = f.x;
+                      rs[2 * i + 1] = f.y;
+                    }
+                    float rl[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                    if (E.res1_lo_off != 0) {
+                      const uint4 q = *reinterpret_cast<const uint4*>(rp + E.res1_lo_off);
+                      const uint32_t l4[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                      for (int i = 0; i < 4; ++i) {
+                        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&l4[i]));
+                        rl[2 * i] = f.x;
+                        rl[2 * i + 1] = f.y;
+                      }
+                    }
+                    if (E.res1_nch > 0) {
+#pragma unroll
+                      for (int i = 0; i < 8; ++i)
+                        if (i < E.res1_nch) v[i] += (E.res1_lo_off != 0 ? rs[i] + rl[i] : rs[i]);
+                    } else {
+#pragma unroll
+                      for (int i = 0; i < 8; ++i) {
+                        v[i] += rs[i];
+                        if (E.res1_lo_off != 0) v[i] += rl[i];
+                      }
                     }
                   }
                   int64_t delta = 0;
@@ -1131,7 +1162,18 @@ conv3x3_stream_kernel(const __grid_constant__ StreamParams P) {
                   if (ok) {
                     uint4 q4;
                     q4.x = pack2(v[0], v[1], false); q4.y = pack2(v[2], v[3], false); q4.z = pack2(v[4], v[5], false); q4.w = pack2(v[6], v[7], false);
-                    *reinterpret_cast<uint4*>(o16 + static_cast<int64_t>(po * E.out_pitch + E.out_coff + oc) + delta) = q4;
+                    const int64_t off = static_cast<int64_t>(po * E.out_pitch + E.out_coff + oc) + delta;
+                    *reinterpret_cast<uint4*>(o16 + off) = q4;
+                    if (E.out_lo != nullptr) {   // split precision: lo = fp16(v - hi) into the low-half twin
+                      const uint32_t h4[4] = {q4.x, q4.y, q4.z, q4.w};
+                      uint32_t l4[4];
+#pragma unroll
+                      for (int i = 0; i < 4; ++i) {
+                        const float2 back = __half22float2(*reinterpret_cast<const __half2*>(&h4[i]));
+                        l4[i] = pack2(v[2 * i] - back.x, v[2 * i + 1] - back.y, false);
+                      }
+                      *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(E.out_lo) + off) = make_uint4(l4[0], l4[1], l4[2], l4[3]);
+                    }
                   }
                 }
               }

@@ -1454,6 +1454,33 @@ static int create_tiled_plan(ss4k_ctx* ctx, const ss4k_plan_cfg* cfg, ss4k_plan*
   return SS4K_OK;
 }
 
+// Pitched NV12 surfaces (one allocation per frame, as a hardware decoder / encoder owns them) <-> the packed chunk
+// [n, h*3/2, w] the plans read: two 2-D DMA copies per frame, stream-ordered.
+static int nv12_surfaces(ss4k_ctx* ctx, const ss4k_nv12_surface* sf, int n, int h, int w, uint8_t* packed, bool pack, cudaStream_t st) {
+  if (!ctx || !sf || !packed || n <= 0 || h <= 0 || w <= 0 || (h % 2) || (w % 2)) return fail(ctx, SS4K_E_INVALID, "bad argument to ss4k_nv12_pack / ss4k_nv12_unpack");
+  const size_t frame = static_cast<size_t>(h) * w * 3 / 2;
+  for (int i = 0; i < n; ++i) {
+    if (!sf[i].y || !sf[i].uv || sf[i].pitch_y < w || sf[i].pitch_uv < w) return fail(ctx, SS4K_E_INVALID, fmt("NV12 surface %d: null plane or pitch < width", i));
+    uint8_t* py = packed + i * frame;
+    uint8_t* puv = py + static_cast<size_t>(h) * w;
+    if (pack) {
+      CK(ctx, cudaMemcpy2DAsync(py, w, sf[i].y, sf[i].pitch_y, w, h, cudaMemcpyDeviceToDevice, st));
+      CK(ctx, cudaMemcpy2DAsync(puv, w, sf[i].uv, sf[i].pitch_uv, w, h / 2, cudaMemcpyDeviceToDevice, st));
+    } else {
+      CK(ctx, cudaMemcpy2DAsync(sf[i].y, sf[i].pitch_y, py, w, w, h, cudaMemcpyDeviceToDevice, st));
+      CK(ctx, cudaMemcpy2DAsync(sf[i].uv, sf[i].pitch_uv, puv, w, w, h / 2, cudaMemcpyDeviceToDevice, st));
+    }
+  }
+  return SS4K_OK;
+}
+int ss4k_nv12_pack(ss4k_ctx* ctx, const ss4k_nv12_surface* surfaces, int n, int h, int w, void* packed_dev, void* cuda_stream) {
+  return nv12_surfaces(ctx, surfaces, n, h, w, reinterpret_cast<uint8_t*>(packed_dev), true, reinterpret_cast<cudaStream_t>(cuda_stream));
+}
+int ss4k_nv12_unpack(ss4k_ctx* ctx, const void* packed_dev, const ss4k_nv12_surface* surfaces, int n, int h, int w, void* cuda_stream) {
+  return nv12_surfaces(ctx, surfaces, n, h, w, const_cast<uint8_t*>(reinterpret_cast<const uint8_t*>(packed_dev)), false,
+                       reinterpret_cast<cudaStream_t>(cuda_stream));
+}
+
 int ss4k_rgb_to_nv12(ss4k_ctx* ctx, const void* rgb_dev, void* nv12_dev, int n, int h, int w, void* cuda_stream) {
   if (!ctx || !rgb_dev || !nv12_dev || n <= 0 || h <= 0 || w <= 0) return fail(ctx, SS4K_E_INVALID, "bad argument to ss4k_rgb_to_nv12");
   if (h % 2 || w % 4) return fail(ctx, SS4K_E_INVALID, "ss4k_rgb_to_nv12 needs h % 2 == 0 and w % 4 == 0");

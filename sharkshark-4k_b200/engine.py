@@ -84,6 +84,30 @@ class Engine:
                                           n, h, w, st), self.h)
         return out
 
+    def _surfaces(self, surfaces):
+        arr = (L.Nv12Surface * len(surfaces))()
+        for i, (y, uv) in enumerate(surfaces):   # 2-D uint8 CUDA views with unit inner stride: pitch = stride(0)
+            assert y.is_cuda and uv.is_cuda and y.dtype == uv.dtype == torch.uint8 and y.stride(1) == 1 and uv.stride(1) == 1
+            arr[i].y, arr[i].uv = y.data_ptr(), uv.data_ptr()
+            arr[i].pitch_y, arr[i].pitch_uv = y.stride(0), uv.stride(0)
+        return arr
+
+    def nv12_pack(self, surfaces, h, w, out=None):
+        """Pitched NV12 decoder surfaces [(y_plane, uv_plane), ...] -> the packed chunk [n, h*3/2, w] the plans read
+        (ss4k_nv12_pack: 2-D DMA copies, stream-ordered)."""
+        n = len(surfaces)
+        if out is None:
+            out = torch.empty(n, h * 3 // 2, w, dtype=torch.uint8, device=self.device)
+        st = ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        L.check(self.lib.ss4k_nv12_pack(self.h, self._surfaces(surfaces), n, h, w, ctypes.c_void_p(out.data_ptr()), st), self.h)
+        return out
+
+    def nv12_unpack(self, packed, surfaces, h, w):
+        """Packed NV12 frames -> pitched encoder input surfaces (ss4k_nv12_unpack)."""
+        st = ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        L.check(self.lib.ss4k_nv12_unpack(self.h, ctypes.c_void_p(packed.data_ptr()), self._surfaces(surfaces), len(surfaces), h, w, st),
+                self.h)
+
     def conv3x3(self, x, weight, bias=None, slope=None, residual=None, mode=L.MODE_CONV3, act=0,
                 act_mode=L.ACT_F16, pixel_shuffle=0, alpha=1.0, beta=1.0, direct_f32=False):
         """Operator-level entry (kernel parity tests): float NCHW CUDA tensors in / out."""

@@ -79,3 +79,30 @@ def test_bsvd_takes_nv12_and_u8_frames(engine):
         maxabs = (got - want).abs().max().item() * 255
         print(f"BSVD from {name} frames: PSNR {psnr:.1f} dB, max|err| {maxabs:.3f}/255")
         assert psnr >= 50 and maxabs <= 2.0
+
+
+def test_nv12_surfaces_in_and_out(engine):
+    """Ingest / egress surfaces: pitched per-frame NV12 surfaces as a hardware decoder hands them out
+    (luma pitch 1536 for 1280 columns, chroma plane after 736 coded rows) are packed into the chunk the plans read, and
+    packed NV12 frames are written into pitched encoder surfaces: byte-exact both ways, padding bytes untouched; the
+    denoiser run on the packed chunk equals the run on the same frames supplied packed from the start."""
+    from ss4k_b200 import bsvd as native_bsvd
+    from oracle import bsvd
+    h, w, n, pitch, coded_h = 72, 136, 5, 256, 80
+    g = torch.Generator().manual_seed(3)
+    packed = torch.randint(16, 236, (n, h * 3 // 2, w), dtype=torch.uint8, generator=g).cuda()
+    pool = [torch.full((coded_h * 3 // 2, pitch), 7, dtype=torch.uint8, device="cuda") for _ in range(n)]   # decoder-owned surfaces
+    surf = [(s[:h, :w], s[coded_h:coded_h + h // 2, :w]) for s in pool]
+    engine.nv12_unpack(packed, surf, h, w)                     # packed -> pitched (the encoder direction)
+    torch.cuda.synchronize()
+    for i, s in enumerate(pool):
+        assert torch.equal(s[:h, :w], packed[i, :h]) and torch.equal(s[coded_h:coded_h + h // 2, :w], packed[i, h:])
+        assert (s[:h, w:] == 7).all() and (s[h:coded_h] == 7).all() and (s[coded_h:, w:] == 7).all()   # padding untouched
+    again = engine.nv12_pack(surf, h, w)                       # pitched -> packed (the decoder direction)
+    assert torch.equal(again, packed)
+    den = native_bsvd.NativeBSVD(bsvd.build_bsvd32(0, weight_scale=0.5), device=0)
+    a = den.denoise_frames(again.reshape(n, -1), h, w, 0.075, nv12=True)
+    b = den.denoise_frames(packed.reshape(n, -1), h, w, 0.075, nv12=True)
+    assert torch.equal(a, b)
+    with pytest.raises(L.Ss4kError):
+        engine.nv12_pack([(pool[0][:h, :w - 8], pool[0][coded_h:coded_h + h // 2, :w])], h, w + 512)   # pitch < width
