@@ -193,3 +193,30 @@ def test_bsvd_first_layer_decodes_frames(engine, nv12, split, monkeypatch):
         plain._plan(t, h, w, L.FMT_NV12 if nv12 else L.FMT_U8_NHWC, L.FMT_F32_NCHW, 0.075).launches - 1
     assert torch.equal(a, b)
     assert torch.equal(a_own, b_own) and torch.equal(a_own, a[2:5])
+
+
+@pytest.mark.parametrize("split", [False, True])
+def test_bsvd_streaming_steady_state_graphs(engine, split, monkeypatch):
+    """A steady-state push (all layers active, no clip boundary in reach) is ONE graph launch between two copies: ring
+    lengths are powers of two, so the launch parameters depend only on t mod period and one graph per phase is captured
+    the first time the phase comes up.  60 frames: every phase is captured and re-used; equals the clip program and the
+    un-graphed stream (SS4K_NO_STREAM_GRAPH=1) bit for bit."""
+    sd = bsvd.build_bsvd32(0) if split else bsvd.build_bsvd32(0, weight_scale=0.5)
+    model = native_bsvd.NativeBSVD(sd, device=0, act_mode=L.ACT_F16_SPLIT if split else L.ACT_F16)
+    x = _clip(60, 32, 136, seed=41).cuda()
+    clip = model(x)[0]
+
+    def run_stream():
+        s = model.stream(32, 136)
+        before = engine.launch_count
+        outs = [o for o in (s.push(x[0, i]) for i in range(60)) if o is not None] + list(s.flush())
+        s.close()
+        return torch.cat(outs, dim=0), engine.launch_count - before
+
+    graphed, _ = run_stream()
+    monkeypatch.setenv("SS4K_NO_STREAM_GRAPH", "1")
+    plain, _ = run_stream()
+    assert torch.equal(graphed, plain)
+    assert (graphed - clip).abs().max().item() <= 1e-3
+    if split:
+        assert torch.equal(graphed, clip)
