@@ -235,7 +235,8 @@ conv3x3_stream_kernel(const __grid_constant__ StreamParams P) {
   const uint32_t a_base = kBiasMMA ? ones_base + kStreamOnesBytes : bias_base + kStreamBiasBytes;
   const uint32_t stage_base = a_base + static_cast<uint32_t>(P.a_slots) * kASlotBytes;
   // (split-precision fast store: a second tile per warp for the low halves)
-  const uint32_t stage_stride = ((P.fast_store == 3 ? 2u * kStageWarp : kStageWarp) + 1023u) & ~1023u;
+  const uint32_t stage_stride = P.fast_store == 0 ? P.stage_keep * ((kStageWarp + 1023u) & ~1023u)
+                                                  : (((P.fast_store == 3 ? 2u * kStageWarp : kStageWarp) + 1023u) & ~1023u);
   const uint32_t bar_base = stage_base + kStreamEpiWarps * stage_stride;
   const uint32_t a_full = bar_base;
   const uint32_t a_empty = a_full + 8 * kMaxSASlots;

@@ -325,11 +325,16 @@ bool stream_config(const ConvSpec& cs, StreamPacked* sp) {
     const int nout = cand[i];
     if (npad % nout) continue;
     const int wbytes = nwt * nkx * 3 * nout * 128 + (stream_bias_mma(nout) ? nout * 128 + kStreamOnesBytes : kStreamBiasBytes);
+    // epilogue staging tiles (one per epilogue warp; twin tiles for the hi / lo pair of split precision) exist only for
+    // convs that leave through TMA stores: the others keep the shared memory for slabs / a wider chunk
     int stage = kStreamEpiWarps * round_up(32 * nout * 2, 1024);
-    int left = kSmemBytes - 3072 - wbytes - stage;  // 1 KB alignment slack + barriers, row records, row_ready ring
+    int left = kSmemBytes - 3072 - wbytes;  // 1 KB alignment slack + barriers, row records, row_ready ring
     int split_fast = 0;
-    if (stream_split_fast_ok(cs, nout) && (left - stage) / kASlotBytes >= 3) {  // twin tiles only where three slabs still fit
-      left -= stage; stage *= 2; split_fast = 1;
+    const bool plain_fast = stream_fast_store_ok(cs, nout) && cs.out_lo_buf < 0;
+    if (stream_split_fast_ok(cs, nout) && (left - 2 * stage) / kASlotBytes >= 3) {  // twin tiles only where three slabs still fit
+      left -= 2 * stage; split_fast = 1;
+    } else if (plain_fast || getenv("SS4K_KEEP_STAGE") != nullptr) {
+      left -= stage;
     }
     const int slots = std::min(kMaxSASlots, left / kASlotBytes);
     // a wider chunk is worth it only with enough slabs in flight (experiments: SS4K_MIN_SLOTS)
@@ -654,6 +659,7 @@ int materialize_stream(ss4k_ctx* ctx, const ConvSpec& cs, const HostTensor& W, c
   }
   // fast epilogue: plain NHWC 16-bit output -> swizzled shared-memory tile -> TMA store
   p.fast_store = 0;
+  p.stage_keep = getenv("SS4K_KEEP_STAGE") != nullptr ? 1u : 0u;
   if (stream_fast_store_ok(cs, pk.nout) && (cs.out_lo_buf < 0 || pk.split_fast)) {
     const cuuint64_t eb = 2;
     const int cavail = std::min(cs.out_pitch - cs.out_coff, pk.npad_total);
