@@ -157,6 +157,8 @@ struct StreamParams {
   float src_fill;
   uint16_t* src_out;      // [n_total, H, W, 16] 16-bit NHWC, channels 0..7 written
   uint16_t* src_out_lo;   // split precision: low halves, or null
+  int32_t ps2;          // fast store of a PixelShuffle(2) conv (+ skip add): tmO / tmO2 are 5-D (C, b, W, a, N*H) maps over the
+                        // shuffled tensor, a chunk is (part of) one sub-pixel phase (a, b); residuals are read at the output pixel
   uint32_t stage_keep;  // fast_store == 0: 1 keeps the (unused) staging region in the shared-memory carve-up (experiments)
   int32_t fast_store;   // 1: plain NHWC output -> registers -> swizzled smem tile -> TMA store;
                         // 2: the same tile stored four times through a 5-D (C, b, W, a, N*H) map: nearest-x2 upsample

@@ -812,9 +812,29 @@ conv3x3_stream_kernel(const __grid_constant__ StreamParams P) {
         if ((q & 1) == par) {
           // residual prefetch (fast path): issued before the accumulator wait so the latency is hidden
           uint4 r1v[NOUT / 8], r2v[NOUT / 8];
+          constexpr bool kPs2 = NOUT <= 32;          // (the planner uses the PixelShuffle(2) fast store with chunks <= 32 only)
+          uint4 r1l[kPs2 ? NOUT / 8 : 1];            // split precision + PixelShuffle(2): low halves of the skip tensor
           const size_t pix = (static_cast<size_t>(b.n) * E.out_h + y) * E.out_w + ax;
           const bool has_r1 = fast && E.res1 != nullptr, has_r2 = fast && E.res2 != nullptr;
-          if (has_r1 && valid) {
+          // PixelShuffle(2) fast store: this chunk is (part of) sub-pixel phase ab of the shuffled tensor (channels
+          // pre-permuted to (a, b, c)); E.out_h / E.out_w are the shuffled sizes
+          int ps_ab = 0, ps_c0 = 0;
+          const bool ps2 = kPs2 && P.ps2 != 0;
+          if (ps2) {
+            const int cq = E.cout >> 2;
+            ps_ab = (b.chunk * NOUT) / cq;
+            ps_c0 = b.chunk * NOUT - ps_ab * cq;
+          }
+          if (ps2 && has_r1 && valid) {
+            const size_t po = (static_cast<size_t>(b.n) * E.out_h + 2 * y + (ps_ab >> 1)) * E.out_w + 2 * ax + (ps_ab & 1);
+            const uint16_t* const rb = reinterpret_cast<const uint16_t*>(E.res1) + po * E.res1_pitch + E.res1_coff + ps_c0;
+#pragma unroll
+            for (int j = 0; j < NOUT / 8; ++j) r1v[j] = reinterpret_cast<const uint4*>(rb)[j];
+            if (E.res1_lo_off != 0) {
+#pragma unroll
+              for (int j = 0; j < NOUT / 8; ++j) r1l[j] = reinterpret_cast<const uint4*>(rb + E.res1_lo_off)[j];
+            }
+          } else if (has_r1 && valid) {
             if (E.res1_nch > 0) {
               // residual on the first res1_nch (<= 8) channels of the conv only (BSVD none_minus, bsvd/model.py:436-442):
               // one 16-byte load for channel group 0 of chunk 0, the other channels' halves masked to +0
@@ -899,15 +919,27 @@ conv3x3_stream_kernel(const __grid_constant__ StreamParams P) {
                 }
               } else if (split_store) {
                 // split precision (BSVD, SS4K_ACT_F16_SPLIT): value = hi + lo with hi = fp16(v), lo = fp16(v - hi); ReLU6 or
-                // linear, no residuals (the planner sends everything else through the general path)
+                // linear; a residual only as the skip add of a PixelShuffle(2) conv (the planner sends everything else
+                // through the specialised / general per-thread paths)
                 const bool relu6 = E.act == kActRelu6;
 #pragma unroll
                 for (int j = 0; j < NOUT / 8; ++j) {
                   uint32_t hi[4], lo[4];
+                  const uint32_t rh4[4] = {r1v[j].x, r1v[j].y, r1v[j].z, r1v[j].w};
+                  const uint4 rlq = r1l[kPs2 ? j : 0];
+                  const uint32_t rl4[4] = {rlq.x, rlq.y, rlq.z, rlq.w};
 #pragma unroll
                   for (int i = 0; i < 4; ++i) {
                     float a = __uint_as_float(raw[8 * j + 2 * i]), c = __uint_as_float(raw[8 * j + 2 * i + 1]);
                     if (relu6) { a = fminf(fmaxf(a, 0.f), 6.f); c = fminf(fmaxf(c, 0.f), 6.f); }
+                    if (kPs2 && has_r1) {   // skip add of the PixelShuffle(2) convs: (v + hi) + lo, as the other store paths
+                      const float2 fh = __half22float2(*reinterpret_cast<const __half2*>(&rh4[i]));
+                      a += fh.x; c += fh.y;
+                      if (E.res1_lo_off != 0) {
+                        const float2 fl = __half22float2(*reinterpret_cast<const __half2*>(&rl4[i]));
+                        a += fl.x; c += fl.y;
+                      }
+                    }
                     const __half2 h = __floats2half2_rn(a, c);
                     const float2 back = __half22float2(h);
                     hi[i] = *reinterpret_cast<const uint32_t*>(&h);
@@ -1012,6 +1044,9 @@ conv3x3_stream_kernel(const __grid_constant__ StreamParams P) {
 #pragma unroll
                   for (int ab = 0; ab < 4; ++ab)
                     tma_store_5d(&P.tmO, stage, b.chunk * NOUT, ab & 1, b.strip * kTileW + qd * 32, ab >> 1, (b.n + P.n_out0) * P.H + y, pol_out);
+                } else if (ps2) {
+                  tma_store_5d(&P.tmO, stage, ps_c0, ps_ab & 1, b.strip * kTileW + qd * 32, ps_ab >> 1, (b.n + P.n_out0) * P.H + y, pol_out);
+                  if (split_store) tma_store_5d(&P.tmO2, stage + kStageWarp, ps_c0, ps_ab & 1, b.strip * kTileW + qd * 32, ps_ab >> 1, (b.n + P.n_out0) * P.H + y, pol_out);
                 } else {
                   tma_store_4d(&P.tmO, stage, b.chunk * NOUT, b.strip * kTileW + qd * 32, y, b.n + P.n_out0, pol_out);
                   if (split_store) tma_store_4d(&P.tmO2, stage + kStageWarp, b.chunk * NOUT, b.strip * kTileW + qd * 32, y, b.n + P.n_out0, pol_out);

@@ -288,13 +288,23 @@ struct StreamPacked {
 
 // Output side of a conv that can leave through the swizzled staging tile + TMA store.
 static bool stream_fast_store_ok(const ConvSpec& cs, int nout) {
-  return cs.out_mode == kOutNHWC && cs.out_buf >= 0 && cs.out_coff % 8 == 0 && cs.out_pitch % 8 == 0 && !cs.tshift &&
-         (cs.res1_nch == 0 || (cs.res1_nch <= 8 && cs.res1_pitch >= 8 && cs.res1_coff % 8 == 0 && cs.res1_lo_buf < 0)) &&
-         (nout == 16 || nout == 32 || nout == 64) && getenv("SS4K_NO_FAST_STORE") == nullptr;
+  if (getenv("SS4K_NO_FAST_STORE") != nullptr || !(nout == 16 || nout == 32 || nout == 64)) return false;
+  if (cs.out_buf < 0 || cs.out_coff % 8 || cs.out_pitch % 8 || cs.tshift) return false;
+  if (cs.out_mode == kOutPS2NHWC) {
+    // PixelShuffle(2) (+ skip add): a chunk must lie inside one sub-pixel phase of the (a, b, c)-permuted channels
+    const int cq = cs.cout / 4;
+    return getenv("SS4K_NO_PS2_FAST") == nullptr && nout <= 32 && cs.wperm == 1 && cs.cout % 4 == 0 && cq % nout == 0 && cs.act == kActNone &&
+           cs.alpha == 1.f && cs.res2_buf < 0 && cs.res1_nch == 0 && (cs.res1_buf < 0 || (cs.beta1 == 1.f && cs.res1_pitch % 8 == 0 && cs.res1_coff % 8 == 0)) &&
+           !cs.up2_store && cs.mode == kModeConv3;
+  }
+  return cs.out_mode == kOutNHWC &&
+         (cs.res1_nch == 0 || (cs.res1_nch <= 8 && cs.res1_pitch >= 8 && cs.res1_coff % 8 == 0 && cs.res1_lo_buf < 0));
 }
-// ... and, for the hi / lo output pair of split precision: ReLU6 or linear, no residual, nothing folded behind the activation
+// ... and, for the hi / lo output pair of split precision: ReLU6 or linear, nothing folded behind the activation, no residual
+// except the skip add of a PixelShuffle(2) conv
 static bool stream_split_fast_ok(const ConvSpec& cs, int nout) {
-  return cs.out_lo_buf >= 0 && stream_fast_store_ok(cs, nout) && cs.res1_buf < 0 && cs.res2_buf < 0 && !cs.up2_store &&
+  const bool ps2 = cs.out_mode == kOutPS2NHWC;
+  return cs.out_lo_buf >= 0 && stream_fast_store_ok(cs, nout) && (ps2 || cs.res1_buf < 0) && cs.res2_buf < 0 && !cs.up2_store &&
          (cs.act == kActNone || cs.act == kActRelu6) && cs.alpha == 1.f && getenv("SS4K_NO_SPLIT_FAST") == nullptr;
 }
 
@@ -321,9 +331,15 @@ bool stream_config(const ConvSpec& cs, StreamPacked* sp) {
   else if (npad % 64 == 0) cand[nc++] = 64;
   if (npad % 32 == 0 && npad > 32) cand[nc++] = 32;
   if (npad > 16) cand[nc++] = 16;
+  // a PixelShuffle(2) conv prefers the widest chunk that can still leave through TMA stores (its per-thread store path is
+  // the slower one); everything else takes the widest chunk that fits
+  bool want_fast = false;
+  if (cs.out_mode == kOutPS2NHWC)
+    for (int i = 0; i < nc; ++i) want_fast = want_fast || (npad % cand[i] == 0 && stream_fast_store_ok(cs, cand[i]));
   for (int i = 0; i < nc; ++i) {
     const int nout = cand[i];
     if (npad % nout) continue;
+    if (want_fast && !stream_fast_store_ok(cs, nout)) continue;
     const int wbytes = nwt * nkx * 3 * nout * 128 + (stream_bias_mma(nout) ? nout * 128 + kStreamOnesBytes : kStreamBiasBytes);
     // epilogue staging tiles (one per epilogue warp; twin tiles for the hi / lo pair of split precision) exist only for
     // convs that leave through TMA stores: the others keep the shared memory for slabs / a wider chunk
@@ -673,7 +689,24 @@ int materialize_stream(ss4k_ctx* ctx, const ConvSpec& cs, const HostTensor& W, c
     const CUtensorMapSwizzle sw = pk.nout == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (pk.nout == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
     void* base = reinterpret_cast<uint8_t*>(bufptr(cs.out_buf)) + static_cast<size_t>(cs.out_coff) * 2;
     CUresult r;
-    if (cs.up2_store) {
+    if (cs.out_mode == kOutPS2NHWC) {
+      // PixelShuffle(2) in the store: the shuffled tensor [N, 2H, 2W, pitch] viewed as (C, b, W, a, N*H); a chunk writes the
+      // 32-pixel row segment of one sub-pixel phase (a, b)
+      const cuuint64_t pb = cs.out_pitch * eb;
+      const int cw = cs.in_w, chh = cs.in_h;   // conv resolution
+      cuuint64_t d5[5] = {static_cast<cuuint64_t>(std::min(cs.out_pitch - cs.out_coff, cs.cout / 4)), 2, static_cast<cuuint64_t>(cw), 2,
+                          static_cast<cuuint64_t>(chh) * out_imgs};
+      cuuint64_t s5[4] = {pb, 2 * pb, 2 * static_cast<cuuint64_t>(cw) * pb, 4 * static_cast<cuuint64_t>(cw) * pb};
+      cuuint32_t b5[5] = {static_cast<cuuint32_t>(pk.nout), 1, 32, 1, 1};
+      r = ctx->encode(&p.tmO, dt, 5, base, d5, s5, b5, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r == CUDA_SUCCESS && pk.split_fast) {
+        void* base_lo = reinterpret_cast<uint8_t*>(bufptr(cs.out_lo_buf)) + static_cast<size_t>(cs.out_coff) * 2;
+        r = ctx->encode(&p.tmO2, dt, 5, base_lo, d5, s5, b5, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      }
+      p.ps2 = 1;
+    } else if (cs.up2_store) {
       // nearest-x2 upsample in the store: destination viewed as (C, b, W, a, N*H): pixel (2y+a, 2x+b) of the 2H x 2W image
       const cuuint64_t pb = cs.out_pitch * eb;
       cuuint64_t d5[5] = {static_cast<cuuint64_t>(cavail), 2, static_cast<cuuint64_t>(cs.out_w), 2,
@@ -686,7 +719,7 @@ int materialize_stream(ss4k_ctx* ctx, const ConvSpec& cs, const HostTensor& W, c
       r = ctx->encode(&p.tmO, dt, 4, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
                       CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     }
-    if (r == CUDA_SUCCESS && pk.split_fast) {
+    if (r == CUDA_SUCCESS && pk.split_fast && cs.out_mode != kOutPS2NHWC) {
       void* base_lo = reinterpret_cast<uint8_t*>(bufptr(cs.out_lo_buf)) + static_cast<size_t>(cs.out_coff) * 2;
       r = ctx->encode(&p.tmO2, dt, 4, base_lo, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
                       CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

@@ -105,3 +105,31 @@ def test_engine_reports_mode_and_launches(engine):
     x = torch.randn(1, 64, 4, 130).cuda()
     engine.conv3x3(x, torch.randn(64, 64, 3, 3).cuda() * 0.05, direct_f32=True)
     assert engine.launch_count >= before + 2
+
+
+@pytest.mark.parametrize("cin,cout,use_res,act_mode", [
+    (64, 128, True, L.ACT_F16), (64, 128, True, L.ACT_F16_SPLIT), (64, 128, False, L.ACT_F16),
+    (128, 256, True, L.ACT_F16_SPLIT),          # a 32-wide chunk is half of a 64-channel sub-pixel phase
+])
+def test_conv_pixelshuffle2_skip_tma_store(engine, cin, cout, use_res, act_mode, monkeypatch):
+    """BSVD up-convs (bsvd/model.py:290-323): conv + PixelShuffle(2) + skip add leaving through the staging tile and 5-D
+    TMA stores (one sub-pixel phase per chunk; twin hi / lo tiles in split precision).  Ragged width, two frames; against
+    the fp64 reference and against the per-thread store path (SS4K_NO_PS2_FAST=1: that plan may pick a 64-wide chunk, whose
+    bias enters through an MMA as hi + lo halves instead of the fp32 accumulator init -- equal to one fp16 rounding)."""
+    g = torch.Generator().manual_seed(cin + cout)
+    x = torch.randn(2, cin, 6, 140, generator=g)
+    wt = torch.randn(cout, cin, 3, 3, generator=g) * (2.0 / (cin * 9)) ** 0.5
+    b = torch.randn(cout, generator=g) * 0.1
+    res = torch.randn(2, cout // 4, 12, 280, generator=g) if use_res else None
+    want = _ref(x, wt, b, 0, 0, None, 1.0, 1.0, res, 2)
+
+    def run():
+        return engine.conv3x3(x.cuda(), wt.cuda(), b.cuda(), None, res.cuda() if use_res else None, act=0, pixel_shuffle=2,
+                              alpha=1.0, beta=1.0, act_mode=act_mode).cpu()
+
+    fast = run()
+    monkeypatch.setenv("SS4K_NO_PS2_FAST", "1")
+    slow = run()
+    assert fast.shape == want.shape
+    assert (fast - slow).abs().max().item() <= 2e-3 * max(1.0, want.abs().max().item())
+    assert (fast - want).abs().max().item() <= 4e-3 * max(1.0, want.abs().max().item())
