@@ -1,7 +1,7 @@
 #!/bin/bash
-# Final evidence of round 2 (tag r02_m): whole GPU suite, bench lines, BSVD profiles, streaming, launch list + ncu captures.
+# Final evidence of round 2 (tag r02_p): whole GPU suite, bench lines, BSVD profiles, streaming, launch list + ncu captures.
 mkdir -p gpurun_out
-T=r02_m
+T=r02_p
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/${T}_smi.txt 2>&1
 echo "=== pytest gpu"; timeout 2400 python -m pytest tests -m gpu -q -s --timeout 900 > gpurun_out/${T}_pytest_gpu.log 2>&1; grep -v "^\.*$" gpurun_out/${T}_pytest_gpu.log | tail -n 12
 echo "=== bench default (cfg3 split)"; timeout 1200 python bench.py > gpurun_out/${T}_bench_cfg3_n1.json 2> gpurun_out/${T}_bench_cfg3_n1.err; tail -n 1 gpurun_out/${T}_bench_cfg3_n1.json | cut -c1-300
