@@ -342,6 +342,8 @@ def run_native_cfg3(args, rank, world, local_rank):
         stage_in = [torch.empty_like(chunks_dev[0]) for _ in range(2)]
         copy_stream = torch.cuda.Stream(dev)
         host_all = [torch.empty((world, F) + pipe.out_frame_shape(), dtype=torch.uint8).pin_memory() for _ in range(2)] if rank == 0 else None
+        # two sets of gather buffers on the encoder rank: the D2H copy of step i overlaps the kernels AND the gather of step i+1
+        gather_lists = [gather_list, [torch.empty_like(out_dev) for _ in range(world)]] if rank == 0 else [None, None]
         copied = [None, None]
 
         def e2e_step(i):
@@ -350,19 +352,18 @@ def run_native_cfg3(args, rank, world, local_rank):
             stage_in[s].copy_(chunks_host[i % n_in], non_blocking=True)
             pipe.run(stage_in[s], ch.owned, out_dev)
             if rank == 0 and copied[s] is not None:
-                cur.wait_event(copied[s])
-            dist.gather(out_dev, gather_list, dst=0)
+                cur.wait_event(copied[s])     # slot s's frames of step i-2 have left the device
+            dist.gather(out_dev, gather_lists[s], dst=0)
             if rank == 0:
                 ev = torch.cuda.Event()
                 ev.record(cur)
                 copy_stream.wait_event(ev)
                 with torch.cuda.stream(copy_stream):
                     for r in range(world):
-                        host_all[s][r].copy_(gather_list[r], non_blocking=True)
+                        host_all[s][r].copy_(gather_lists[s][r], non_blocking=True)
                     done = torch.cuda.Event()
                     done.record(copy_stream)
                 copied[s] = done
-                cur.wait_event(done)      # gather_list is reused by the next step
 
         def e2e_sync():
             torch.cuda.synchronize()
