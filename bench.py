@@ -419,7 +419,7 @@ def run_native_cfg3(args, rank, world, local_rank):
                                 "what": f"NV12 -> RGB (BT.709) + noise map -> 16-channel fp16 NHWC ({'hi + lo twins, ' if den.act_mode == L.ACT_F16_SPLIT else ''}{T} frames per launch): 1.5 B/px read, 32 B/px written per twin"})
         if glue_ms is not None:
             nb_ = FRAME_H * FRAME_W * (3 * 2 + 1.5 + 8)
-            hbm_kernels.append({"kernel": "sharpen_blend_act_kernel", "bytes_per_launch": nb_, "us": 1000 * glue_ms, "GB/s": nb_ / glue_ms / 1e6,
+            hbm_kernels.append({"kernel": "sharpen_blend_act_us2_kernel", "bytes_per_launch": nb_, "us": 1000 * glue_ms, "GB/s": nb_ / glue_ms / 1e6,
                                 "what": "glue between the nets, one frame per launch: 3x3 reflect sharpen + clamp of the denoised frame (fp16 NCHW, 6 B/px), "
                                         "0.8/0.2 blend with the NV12 frame decoded in place (1.5 B/px) -> RRDBNet conv_first's pixel-unshuffled fp16 NHWC input (8 B/px)"})
         t_nv = timed_kernel(lambda: eng.rgb_to_nv12(out_dev[:8]))

@@ -14,6 +14,8 @@
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
+
+#include <cstdlib>
 #include <stdint.h>
 
 #include "../../include/ss4k.h"
@@ -505,6 +507,85 @@ __global__ void sharpen_blend_act_kernel(Img x, float k_center, float k_side, fl
   }
 }
 
+// Hot case of the cfg3 hand-over (RRDBNet x2: pixel_unshuffle(2), 3 channels, denoised frame as half NCHW, original
+// frame as NV12 or uint8 RGB): one thread per trunk pixel = a 2x2 block of the frame.  It loads the 4x4 patch of each
+// channel once (48 values instead of 108 gathers) and the block's four luma / one chroma sample(s); the arithmetic and
+// its order are those of sharpen_blend_act_kernel (same expressions -> bit-identical results, tests/test_cfg3_gpu.py).
+__global__ void sharpen_blend_act_us2_kernel(const __half* __restrict__ x, int N, int H, int W, float k_center, float k_side,
+                                             float opacity, const uint8_t* __restrict__ other, int other_fmt,
+                                             uint16_t* __restrict__ out, int pitch) {
+  const int OH = H >> 1, OW = W >> 1;
+  const size_t total = static_cast<size_t>(N) * OH * OW;
+  const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int ox = static_cast<int>(idx % OW);
+  const int oy = static_cast<int>((idx / OW) % OH);
+  const int n = static_cast<int>(idx / (static_cast<size_t>(OW) * OH));
+  int ry[4], rx[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    ry[i] = reflect(2 * oy - 1 + i, H);
+    rx[i] = reflect(2 * ox - 1 + i, W);
+  }
+  // the original frame's 2x2 block: [iy][jx][c]
+  float org[2][2][3];
+  if (other != nullptr) {
+    if (other_fmt == 3) {
+      const uint8_t* frame = other + static_cast<size_t>(n) * (static_cast<size_t>(H) * W * 3 / 2);
+      const uint8_t* uv = frame + static_cast<size_t>(H) * W + static_cast<size_t>(oy) * W + 2 * ox;
+      const float cb = (static_cast<float>(uv[0]) - 128.f) * (1.f / 224.f), cr = (static_cast<float>(uv[1]) - 128.f) * (1.f / 224.f);
+#pragma unroll
+      for (int iy = 0; iy < 2; ++iy)
+#pragma unroll
+        for (int jx = 0; jx < 2; ++jx) {
+          const float yy = (static_cast<float>(frame[static_cast<size_t>(2 * oy + iy) * W + 2 * ox + jx]) - 16.f) * (1.f / 219.f);
+          org[iy][jx][0] = fminf(fmaxf(yy + 1.5748f * cr, 0.f), 1.f);
+          org[iy][jx][1] = fminf(fmaxf(yy - 0.187324f * cb - 0.468124f * cr, 0.f), 1.f);
+          org[iy][jx][2] = fminf(fmaxf(yy + 1.8556f * cb, 0.f), 1.f);
+        }
+    } else {
+#pragma unroll
+      for (int iy = 0; iy < 2; ++iy)
+#pragma unroll
+        for (int jx = 0; jx < 2; ++jx)
+#pragma unroll
+          for (int c = 0; c < 3; ++c)
+            org[iy][jx][c] = static_cast<float>(other[((static_cast<size_t>(n) * H + 2 * oy + iy) * W + 2 * ox + jx) * 3 + c]) / 255.0f;
+    }
+  }
+  uint16_t v16[16];
+#pragma unroll
+  for (int i = 12; i < 16; ++i) v16[i] = 0;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const __half* plane = x + (static_cast<size_t>(n) * 3 + c) * H * W;
+    float p[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) p[i][j] = __half2float(plane[static_cast<size_t>(ry[i]) * W + rx[j]]);
+#pragma unroll
+    for (int iy = 0; iy < 2; ++iy)
+#pragma unroll
+      for (int jx = 0; jx < 2; ++jx) {
+        float acc = 0.f;
+#pragma unroll
+        for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+          for (int dx = -1; dx <= 1; ++dx)
+            acc += ((dy == 0 && dx == 0) ? k_center : k_side) * p[iy + dy + 1][jx + dx + 1];
+        float v = fminf(fmaxf(acc, 0.f), 1.f);
+        if (other != nullptr) v = opacity * v + (1.f - opacity) * org[iy][jx][c];
+        const __half h = __float2half_rn(v);
+        v16[c * 4 + iy * 2 + jx] = *reinterpret_cast<const uint16_t*>(&h);
+      }
+  }
+  uint16_t* o = out + idx * pitch;
+  *reinterpret_cast<uint4*>(o) = *reinterpret_cast<const uint4*>(v16);
+  *reinterpret_cast<uint4*>(o + 8) = *reinterpret_cast<const uint4*>(v16 + 8);
+  for (int c8 = 16; c8 < pitch; c8 += 8) *reinterpret_cast<uint4*>(o + c8) = make_uint4(0u, 0u, 0u, 0u);
+}
+
 inline unsigned blocks_for(size_t total, int threads) { return static_cast<unsigned>((total + threads - 1) / threads); }
 
 }  // namespace
@@ -598,6 +679,13 @@ int ss4k_glue_sharpen_blend_act(const void* x, int fmt, int n, int c, int h, int
   const float center = 9.f * strength + (1.f - strength), side = -strength;
   const float sum = center + 8.f * side;
   const size_t total = static_cast<size_t>(n) * (h / unshuffle) * (w / unshuffle);
+  if (unshuffle == 2 && c == 3 && fmt == 1 && !bf16 && pitch >= 16 && (!other || other_fmt == 2 || other_fmt == 3) &&
+      getenv("SS4K_GLUE_GENERIC") == nullptr) {
+    sharpen_blend_act_us2_kernel<<<blocks_for(total, 128), 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const __half*>(x), n, h, w, center / sum, side / sum, opacity, reinterpret_cast<const uint8_t*>(other), other_fmt,
+        reinterpret_cast<uint16_t*>(act_out), pitch);
+    return cudaGetLastError() == cudaSuccess ? SS4K_OK : SS4K_E_CUDA;
+  }
   sharpen_blend_act_kernel<<<blocks_for(total, 128), 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       Img{x, fmt, n, c, h, w}, center / sum, side / sum, opacity, Img{other, other_fmt, n, c, h, w},
       reinterpret_cast<uint16_t*>(act_out), unshuffle, pitch, bf16);
