@@ -157,6 +157,12 @@ struct StreamParams {
   float src_fill;
   uint16_t* src_out;      // [n_total, H, W, 16] 16-bit NHWC, channels 0..7 written
   uint16_t* src_out_lo;   // split precision: low halves, or null
+  // Masked canvases (tiled inference, engine.cu::create_tiled_plan): image n of the launch is a crop of mask_hw[2n] x
+  // mask_hw[2n+1] pixels (at the plan's input resolution; this conv works at that resolution shifted by mask_shift: > 0
+  // left, < 0 right) in the top-left corner of the H x W canvas.  Outputs outside the crop are forced to zero, which is
+  // what the next conv's zero padding at the crop's own border needs -- crops of different shapes share one batch.
+  const int32_t* mask_hw;
+  int32_t mask_shift;
   int32_t ps2;          // fast store of a PixelShuffle(2) conv (+ skip add): tmO / tmO2 are 5-D (C, b, W, a, N*H) maps over the
                         // shuffled tensor, a chunk is (part of) one sub-pixel phase (a, b); residuals are read at the output pixel
   uint32_t stage_keep;  // fast_store == 0: 1 keeps the (unused) staging region in the shared-memory carve-up (experiments)

@@ -808,6 +808,12 @@ conv3x3_stream_kernel(const __grid_constant__ StreamParams P) {
     while (next_band(P, u, u1, b)) {
       const int ax = b.strip * kTileW + m;
       const bool valid = ax < P.W;
+      int mask_h = 0x7fffffff, mask_w = 0x7fffffff;   // masked canvases: the crop of image b.n at this conv's resolution
+      if (P.mask_hw != nullptr) {
+        const int hh = __ldg(P.mask_hw + 2 * b.n), ww = __ldg(P.mask_hw + 2 * b.n + 1);
+        mask_h = P.mask_shift >= 0 ? hh << P.mask_shift : hh >> -P.mask_shift;
+        mask_w = P.mask_shift >= 0 ? ww << P.mask_shift : ww >> -P.mask_shift;
+      }
       for (int y = b.yb; y < b.ye; ++y, ++q) {
         if ((q & 1) == par) {
           // residual prefetch (fast path): issued before the accumulator wait so the latency is hidden
@@ -872,6 +878,10 @@ conv3x3_stream_kernel(const __grid_constant__ StreamParams P) {
 #pragma unroll
           for (int c = 0; c < NOUT; c += 16) tmem_ld16p(taddr + c, &raw[c]);
           tmem_ld_wait();
+          if (y >= mask_h || ax >= mask_w) {   // outside the crop: bias included, every store path starts from raw
+#pragma unroll
+            for (int c = 0; c < NOUT; ++c) raw[c] = 0u;
+          }
           {
             // slot drained: re-initialise it with the bias of the output row that reuses it (S rows ahead in this
             // CTA's unit order, possibly the next chunk) and release it to the MMA stream

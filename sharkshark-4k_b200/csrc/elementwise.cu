@@ -374,6 +374,11 @@ __global__ void tile_gather_kernel(const uint8_t* __restrict__ in, uint8_t* __re
     int c, y, x;
     if (nhwc) { c = static_cast<int>(r % C); r /= C; x = static_cast<int>(r % wc); y = static_cast<int>(r / wc); }
     else { x = static_cast<int>(r % wc); r /= wc; y = static_cast<int>(r % hc); c = static_cast<int>(r / hc); }
+    if (y >= boxes[k].crop_h || x >= boxes[k].crop_w) {   // canvas outside this crop
+#pragma unroll
+      for (int b = 0; b < ES; ++b) out[idx * ES + b] = 0;
+      continue;
+    }
     const int sy = reflect2(boxes[k].src_y + y, H, H1), sx = reflect2(boxes[k].src_x + x, W, W1);
     const size_t si = nhwc ? ((static_cast<size_t>(n) * H + sy) * W + sx) * C + c
                            : ((static_cast<size_t>(n) * C + c) * H + sy) * W + sx;

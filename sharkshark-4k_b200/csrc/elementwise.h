@@ -26,6 +26,7 @@ struct TileBox {
   int32_t off_y, off_x;       // top-left of the un-padded centre inside the net's output for the crop (pixels of the output grid)
   int32_t dst_y, dst_x;       // where it goes in the output frame
   int32_t paste_h, paste_w;   // its size (clipped to the output frame by the kernel)
+  int32_t crop_h, crop_w;     // size of the padded crop (<= the batch's canvas hc x wc: the rest of the canvas is zero)
 };
 // fmt: SS4K_FMT_F32_NCHW / F16_NCHW / U8_NHWC; crops are stored as a batch [box * N + n] of hc x wc images in the same format
 cudaError_t tile_gather_launch(int fmt, const void* in, void* out, const TileBox* boxes_dev, int nbox, int N, int C, int H,

@@ -869,6 +869,7 @@ struct ss4k_plan {
   cudaGraphExec_t graph = nullptr;
   int graph_first = -1, graph_last = -1;  // [first, last] step range inside the graph
   int fused_prep = -1;   // step index of a layout (prep) step whose work the following conv's loader does, or -1
+  int32_t* d_mask = nullptr;  // masked canvases (cfg.reserved[5]): crop size (h, w) of every image of the batch at the input resolution
   uint32_t* d_ctr = nullptr;  // progress counters of the fused residual dense blocks (3 rotating buffers)
   long long* d_rdb_trace = nullptr;  // SS4K_RDB_TRACE=1: producer statistics of every fused launch [n_fused][nsm][16]
   int n_fused = 0;
@@ -1283,6 +1284,7 @@ int ss4k_plan_destroy(ss4k_plan* pl) {
   if (pl->stage_out) cudaFree(pl->stage_out);
   if (pl->d_ctr) cudaFree(pl->d_ctr);
   if (pl->d_rdb_trace) cudaFree(pl->d_rdb_trace);
+  if (pl->d_mask) cudaFree(pl->d_mask);
   delete pl;
   return SS4K_OK;
 }
@@ -1352,6 +1354,31 @@ int ss4k_plan_create(ss4k_ctx* ctx, const ss4k_plan_cfg* cfg, ss4k_plan** out_pl
     if (rc != SS4K_OK) { ss4k_plan_destroy(pl.release()); return rc; }
   }
   fuse_prep(pl.get());
+  if (cfg->reserved[5] == 1) {
+    // masked canvases (tiled inference): every conv zeroes its output outside the image's crop; needs every conv on the
+    // streaming kernel, at a power-of-two multiple of the input resolution
+    std::vector<int32_t> hw(static_cast<size_t>(2) * P.in_n);
+    for (int i = 0; i < P.in_n; ++i) { hw[2 * i] = P.in_h; hw[2 * i + 1] = P.in_w; }
+    cudaError_t ce = cudaMalloc(&pl->d_mask, hw.size() * sizeof(int32_t));
+    if (ce == cudaSuccess) ce = cudaMemcpy(pl->d_mask, hw.data(), hw.size() * sizeof(int32_t), cudaMemcpyHostToDevice);
+    if (ce != cudaSuccess) { ss4k_plan_destroy(pl.release()); return fail(ctx, SS4K_E_NOMEM, "mask table"); }
+    for (size_t si = 0; si < P.steps.size(); ++si) {
+      if (P.steps[si].kind != 1) continue;
+      const ConvSpec& cs = P.steps[si].conv;
+      ConvExec& c = pl->convs[pl->step_conv[si]];
+      int shift = 0, hh = P.in_h;
+      bool ok = c.stream && !c.fused && !c.skip && cs.mode == kModeConv3 && cs.n == P.in_n;
+      if (ok) {
+        while (hh < cs.in_h && shift < 4) { hh *= 2; ++shift; }
+        while (hh > cs.in_h && shift > -4) { if (hh & 1) { ok = false; break; } hh /= 2; --shift; }
+        ok = ok && hh == cs.in_h &&
+             (shift >= 0 ? (P.in_w << shift) == cs.in_w : (P.in_w >> -shift) == cs.in_w && (P.in_w & ((1 << -shift) - 1)) == 0);
+      }
+      if (!ok) { ss4k_plan_destroy(pl.release()); return fail(ctx, SS4K_E_INVALID, "masked canvases: conv " + cs.name + " is not a streaming conv at a power-of-two multiple of the input size"); }
+      c.sp.mask_hw = pl->d_mask;
+      c.sp.mask_shift = shift;
+    }
+  }
   // Early activation loads (StreamParams::early_kb_mask): K blocks that only read channels written at least two steps
   // ago are requested before the dependency wait.  Needs this conv and the two launches before it to be streaming convs
   // that fill every SM (see conv_params.h).
@@ -1462,19 +1489,76 @@ static int create_tiled_plan(ss4k_ctx* ctx, const ss4k_plan_cfg* cfg, ss4k_plan*
       b.paste_h = (ey - sy) * s; b.paste_w = (ex - sx) * s;
       classes[std::make_pair(eyp - syp, exp_ - sxp)].push_back(b);
     }
-  for (auto& kv : classes) {
+  // Crops of different shapes share a batch as MASKED CANVASES: each crop sits in the top-left corner of the group's
+  // canvas (the largest height x the largest width of the group), the rest of the canvas is zero on the way in and is
+  // forced back to zero by every conv's epilogue (StreamParams::mask_hw), so each crop sees exactly the zero padding
+  // at its own border that a run of its own would give it -- bit-identical, but 2-3 batches per frame instead of one per
+  // shape class (1080p, tile 512: nine classes), i.e. 4-8 times the rows per launch.  Greedy grouping, tallest first: a
+  // crop joins the open group while the canvas area stays within 20 % of the crops' own area.
+  struct Group { int hc = 0, wc = 0; long long area = 0; std::vector<TileBox> boxes; };
+  std::vector<Group> groups;
+  {
+    std::vector<std::pair<std::pair<int, int>, TileBox>> all;
+    bool even = true;
+    for (auto& kv : classes)
+      for (const TileBox& b : kv.second) {
+        all.push_back(std::make_pair(kv.first, b));
+        even = even && (kv.first.first % 2 == 0) && (kv.first.second % 2 == 0);
+      }
+    const bool merge = getenv("SS4K_TILE_EXACT_CLASSES") == nullptr && (even || !(cfg->arch == SS4K_ARCH_RRDB && s == 2));
+    std::stable_sort(all.begin(), all.end(), [](const std::pair<std::pair<int, int>, TileBox>& a, const std::pair<std::pair<int, int>, TileBox>& b) {
+      return a.first.first != b.first.first ? a.first.first > b.first.first : a.first.second > b.first.second; });
+    for (auto& e : all) {
+      TileBox b = e.second;
+      b.crop_h = e.first.first; b.crop_w = e.first.second;
+      const long long a = static_cast<long long>(b.crop_h) * b.crop_w;
+      bool placed = false;
+      if (!groups.empty()) {
+        Group& g = groups.back();
+        const int nh = std::max(g.hc, b.crop_h), nw = std::max(g.wc, b.crop_w);
+        const long long canvas = static_cast<long long>(nh) * nw * (static_cast<long long>(g.boxes.size()) + 1);
+        const bool same = nh == g.hc && nw == g.wc && b.crop_h == g.hc && b.crop_w == g.wc && g.area == static_cast<long long>(g.hc) * g.wc * static_cast<long long>(g.boxes.size());
+        if (same || (merge && canvas * 100 <= (g.area + a) * 120)) {
+          g.hc = nh; g.wc = nw; g.area += a; g.boxes.push_back(b);
+          placed = true;
+        }
+      }
+      if (!placed) {
+        groups.emplace_back();
+        Group& g = groups.back();
+        g.hc = b.crop_h; g.wc = b.crop_w; g.area = a; g.boxes.push_back(b);
+      }
+    }
+  }
+  for (auto& g : groups) {
     ss4k_plan::TileClass tc;
-    tc.hc = kv.first.first; tc.wc = kv.first.second; tc.count = static_cast<int>(kv.second.size());
+    tc.hc = g.hc; tc.wc = g.wc; tc.count = static_cast<int>(g.boxes.size());
+    bool uniform = true;
+    for (const TileBox& b : g.boxes) uniform = uniform && b.crop_h == g.hc && b.crop_w == g.wc;
     ss4k_plan_cfg sub = *cfg;
     sub.tile = 0; sub.reserved[1] = 0;
+    sub.reserved[5] = uniform ? 0 : 1;
     sub.n = cfg->n * tc.count; sub.h = tc.hc; sub.w = tc.wc;
     pl->tiles.push_back(tc);
     ss4k_plan::TileClass& t = pl->tiles.back();
+    struct KV { std::vector<TileBox>& second; } kv{g.boxes};
     int rc = ss4k_plan_create(ctx, &sub, &t.sub);
     if (rc != SS4K_OK) {
       const std::string why = ctx->err;
       ss4k_plan_destroy(pl.release());
-      return fail(ctx, rc, fmt("tile class %dx%d: %s", tc.hc, tc.wc, why.c_str()));
+      return fail(ctx, rc, fmt("tile group %dx%d: %s", tc.hc, tc.wc, why.c_str()));
+    }
+    if (!uniform) {   // crop sizes of the batch's images (image index = box * N + n)
+      std::vector<int32_t> hw(static_cast<size_t>(2) * sub.n);
+      for (int k = 0; k < tc.count; ++k)
+        for (int n = 0; n < cfg->n; ++n) {
+          hw[2 * (static_cast<size_t>(k) * cfg->n + n)] = g.boxes[k].crop_h;
+          hw[2 * (static_cast<size_t>(k) * cfg->n + n) + 1] = g.boxes[k].crop_w;
+        }
+      if (cudaMemcpy(t.sub->d_mask, hw.data(), hw.size() * sizeof(int32_t), cudaMemcpyHostToDevice) != cudaSuccess) {
+        ss4k_plan_destroy(pl.release());
+        return fail(ctx, SS4K_E_CUDA, "mask table upload");
+      }
     }
     cudaError_t ce = cudaMalloc(&t.d_boxes, kv.second.size() * sizeof(TileBox));
     if (ce == cudaSuccess) ce = cudaMemcpy(t.d_boxes, kv.second.data(), kv.second.size() * sizeof(TileBox), cudaMemcpyHostToDevice);

@@ -160,8 +160,8 @@ def test_rrdbnet_uint8_frames_ragged_width(engine):
 
 def test_rrdbnet_1080p_tile512_every_shape_class(engine):
     """BASELINE.json configs[3] geometry: 1920x1080 frame, tile 512, tile_pad 10 (the reference defaults,
-    realesrgan/factory.py:93-94) -> 4 x 3 tiles in 9 padded-crop shape classes (522/532/406 x 522/532/76 ...), every
-    class a batch of its own inside ONE engine run.  RRDBNet x2 with 2 blocks (the tiling, not the depth, is under
+    realesrgan/factory.py:93-94) -> 4 x 3 tiles in 9 padded-crop shape classes (522/532/394 x 522/532/66), run as two
+    batches of masked canvases (eight crops on 532 x 532, four on 66 x 532) inside ONE engine run.  RRDBNet x2 with 2 blocks (the tiling, not the depth, is under
     test) against the oracle's tile_process on the whole frame; uint8 frames in and out as the service passes them."""
     torch.manual_seed(2)
     net = rrdbnet.RRDBNet(3, 3, 2, 64, 2, 32).eval()
@@ -177,7 +177,7 @@ def test_rrdbnet_1080p_tile512_every_shape_class(engine):
     print(f"RRDBNet-2 x2 1920x1080 tile 512 / pad 10: PSNR {psnr:.1f} dB, max|err| {maxabs:.3f}/255")
     assert psnr >= 50 and maxabs <= 2.0
     plan = model.plan_for(x.cuda())
-    assert plan.launches > 9 * 2          # nine classes: gather + paste each, plus the nets
+    assert plan.launches > 2 * 2          # two canvas groups: gather + paste each, plus the nets
     # the same through the uint8 frame boundary
     u8 = (x * 255).round().to(torch.uint8).permute(0, 2, 3, 1).contiguous()
     pu = model._plan(1, 1080, 1920, L.FMT_U8_NHWC, L.FMT_U8_NHWC)
@@ -216,3 +216,27 @@ def test_srvgg_x4_tiled_with_pre_pad(engine):
     assert tuple(got.shape) == (1, 3, 200, 308)
     psnr, maxabs = gate(got, want)
     assert psnr >= 50 and maxabs <= 2.0
+
+
+@pytest.mark.parametrize("arch", ["rrdb_x2", "rrdb_x4", "srvgg_x4"])
+def test_tiled_masked_canvases_equal_exact_classes(engine, arch, monkeypatch):
+    """Crops of different shapes share a batch as masked canvases (every conv forces its output back to zero outside the
+    image's own crop, so each crop sees the zero padding at its own border): must equal the one-batch-per-shape-class run
+    (SS4K_TILE_EXACT_CLASSES=1) bit for bit and launch fewer batches.  Ragged frame, small tiles: nine shape classes."""
+    torch.manual_seed(3)
+    if arch == "srvgg_x4":
+        net = srvgg.SRVGGNetCompact(3, 3, 64, 4, 4).eval()
+        mk = lambda: realesrgan.NativeSRVGG(net.state_dict(), num_conv=4, upscale=4, device=0, tile=40, tile_pad=6)  # noqa: E731
+    else:
+        sc = 2 if arch == "rrdb_x2" else 4
+        net = rrdbnet.RRDBNet(3, 3, sc, 64, 1, 32).eval()
+        mk = lambda: realesrgan.NativeRRDBNet(net.state_dict(), scale=sc, num_block=1, device=0, tile=40, tile_pad=6)  # noqa: E731
+    x = torch.rand(2, 3, 98, 150, generator=torch.Generator().manual_seed(8)).cuda()
+    merged = mk()
+    a = merged(x).clone()
+    n_merged = merged.plan_for(x).launches
+    monkeypatch.setenv("SS4K_TILE_EXACT_CLASSES", "1")
+    exact = mk()
+    b = exact(x)
+    assert torch.equal(a, b)
+    assert n_merged < exact.plan_for(x).launches
