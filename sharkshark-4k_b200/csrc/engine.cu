@@ -1495,7 +1495,7 @@ static int create_tiled_plan(ss4k_ctx* ctx, const ss4k_plan_cfg* cfg, ss4k_plan*
   // at its own border that a run of its own would give it -- bit-identical, but 2-3 batches per frame instead of one per
   // shape class (1080p, tile 512: nine classes), i.e. 4-8 times the rows per launch.  Greedy grouping, tallest first: a
   // crop joins the open group while the canvas area stays within 20 % of the crops' own area.
-  struct Group { int hc = 0, wc = 0; long long area = 0; std::vector<TileBox> boxes; };
+  struct Group { int hc = 0, wc = 0; long long area = 0; bool small = false; std::vector<TileBox> boxes; };
   std::vector<Group> groups;
   {
     std::vector<std::pair<std::pair<int, int>, TileBox>> all;
@@ -1506,6 +1506,13 @@ static int create_tiled_plan(ss4k_ctx* ctx, const ss4k_plan_cfg* cfg, ss4k_plan*
         even = even && (kv.first.first % 2 == 0) && (kv.first.second % 2 == 0);
       }
     const bool merge = getenv("SS4K_TILE_EXACT_CLASSES") == nullptr && (even || !(cfg->arch == SS4K_ARCH_RRDB && s == 2));
+    // only shape classes whose own batch would be a small launch (fewer than ~12 trunk rows per SM: set-up, tail and halo
+    // rows dominate) are merged; a class that fills the GPU on its own gains nothing and would pay the canvas waste
+    const int tdiv = (cfg->arch == SS4K_ARCH_RRDB && s == 2) ? 2 : 1;   // trunk resolution = input / tdiv
+    auto small_class = [&](const std::pair<int, int>& hw) {
+      const long long units = static_cast<long long>(classes[hw].size()) * cfg->n * ((hw.second / tdiv + kTileW - 1) / kTileW) * (hw.first / tdiv);
+      return units < 12LL * ctx->nsm;
+    };
     std::stable_sort(all.begin(), all.end(), [](const std::pair<std::pair<int, int>, TileBox>& a, const std::pair<std::pair<int, int>, TileBox>& b) {
       return a.first.first != b.first.first ? a.first.first > b.first.first : a.first.second > b.first.second; });
     for (auto& e : all) {
@@ -1518,7 +1525,7 @@ static int create_tiled_plan(ss4k_ctx* ctx, const ss4k_plan_cfg* cfg, ss4k_plan*
         const int nh = std::max(g.hc, b.crop_h), nw = std::max(g.wc, b.crop_w);
         const long long canvas = static_cast<long long>(nh) * nw * (static_cast<long long>(g.boxes.size()) + 1);
         const bool same = nh == g.hc && nw == g.wc && b.crop_h == g.hc && b.crop_w == g.wc && g.area == static_cast<long long>(g.hc) * g.wc * static_cast<long long>(g.boxes.size());
-        if (same || (merge && canvas * 100 <= (g.area + a) * 120)) {
+        if (same || (merge && g.small && small_class(e.first) && canvas * 100 <= (g.area + a) * 120)) {
           g.hc = nh; g.wc = nw; g.area += a; g.boxes.push_back(b);
           placed = true;
         }
@@ -1527,6 +1534,7 @@ static int create_tiled_plan(ss4k_ctx* ctx, const ss4k_plan_cfg* cfg, ss4k_plan*
         groups.emplace_back();
         Group& g = groups.back();
         g.hc = b.crop_h; g.wc = b.crop_w; g.area = a; g.boxes.push_back(b);
+        g.small = small_class(e.first);
       }
     }
   }
