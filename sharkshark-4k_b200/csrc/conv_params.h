@@ -135,6 +135,8 @@ constexpr int kStreamOnesBytes = 128 * 128;  // "ones" operand tile of the bias 
 
 constexpr int kStreamEpiWarps = 8;  // two per TMEM lane quarter, alternating output rows
 constexpr int kStreamThreads = 32 * (2 + kStreamEpiWarps);
+constexpr int kMaskRects = 16;                 // crops per atlas image
+constexpr int kMaskStride = 1 + 3 * kMaskRects;  // int32 words per image in StreamParams::mask_hw
 constexpr int kStreamSrcWarps = 2;  // frame-format source (StreamParams::src_fmt): decoder warps on top, alternating input rows
 constexpr int kStreamThreadsMax = kStreamThreads + 32 * kStreamSrcWarps;
 constexpr int kRdbThreads = kStreamThreads;                 // fused residual dense block kernel: same warp roles
@@ -157,10 +159,11 @@ struct StreamParams {
   float src_fill;
   uint16_t* src_out;      // [n_total, H, W, 16] 16-bit NHWC, channels 0..7 written
   uint16_t* src_out_lo;   // split precision: low halves, or null
-  // Masked canvases (tiled inference, engine.cu::create_tiled_plan): image n of the launch is a crop of mask_hw[2n] x
-  // mask_hw[2n+1] pixels (at the plan's input resolution; this conv works at that resolution shifted by mask_shift: > 0
-  // left, < 0 right) in the top-left corner of the H x W canvas.  Outputs outside the crop are forced to zero, which is
-  // what the next conv's zero padding at the crop's own border needs -- crops of different shapes share one batch.
+  // Masked canvases / crop atlases (tiled inference, engine.cu::create_tiled_plan): image n of the launch holds up to
+  // kMaskRects crops side by side (zero gap columns between them); mask_hw + n * kMaskStride = {count, (x0, w, h) x count}
+  // at the plan's input resolution (this conv works at that resolution shifted by mask_shift: > 0 left, < 0 right).
+  // Outputs outside every crop are forced to zero, which is what the next conv's zero padding at each crop's own border
+  // needs -- crops of different shapes share one image.
   const int32_t* mask_hw;
   int32_t mask_shift;
   int32_t ps2;          // fast store of a PixelShuffle(2) conv (+ skip add): tmO / tmO2 are 5-D (C, b, W, a, N*H) maps over the

@@ -808,11 +808,17 @@ conv3x3_stream_kernel(const __grid_constant__ StreamParams P) {
     while (next_band(P, u, u1, b)) {
       const int ax = b.strip * kTileW + m;
       const bool valid = ax < P.W;
-      int mask_h = 0x7fffffff, mask_w = 0x7fffffff;   // masked canvases: the crop of image b.n at this conv's resolution
+      int mask_h = 0x7fffffff;   // crop atlases: rows of this thread's pixel column that lie inside a crop of image b.n
       if (P.mask_hw != nullptr) {
-        const int hh = __ldg(P.mask_hw + 2 * b.n), ww = __ldg(P.mask_hw + 2 * b.n + 1);
-        mask_h = P.mask_shift >= 0 ? hh << P.mask_shift : hh >> -P.mask_shift;
-        mask_w = P.mask_shift >= 0 ? ww << P.mask_shift : ww >> -P.mask_shift;
+        const int32_t* mt = P.mask_hw + static_cast<size_t>(b.n) * kMaskStride;
+        const int cnt = __ldg(mt);
+        const int sh = P.mask_shift;
+        mask_h = 0;
+        for (int k = 0; k < cnt; ++k) {
+          const int x0 = __ldg(mt + 1 + 3 * k), w = __ldg(mt + 2 + 3 * k), h = __ldg(mt + 3 + 3 * k);
+          const int cx0 = sh >= 0 ? x0 << sh : x0 >> -sh, cw = sh >= 0 ? w << sh : w >> -sh, chh = sh >= 0 ? h << sh : h >> -sh;
+          if (ax >= cx0 && ax < cx0 + cw) mask_h = chh;
+        }
       }
       for (int y = b.yb; y < b.ye; ++y, ++q) {
         if ((q & 1) == par) {
@@ -878,7 +884,7 @@ conv3x3_stream_kernel(const __grid_constant__ StreamParams P) {
 #pragma unroll
           for (int c = 0; c < NOUT; c += 16) tmem_ld16p(taddr + c, &raw[c]);
           tmem_ld_wait();
-          if (y >= mask_h || ax >= mask_w) {   // outside the crop: bias included, every store path starts from raw
+          if (y >= mask_h) {   // outside every crop: bias included, every store path starts from raw
 #pragma unroll
             for (int c = 0; c < NOUT; ++c) raw[c] = 0u;
           }

@@ -363,23 +363,26 @@ __device__ __forceinline__ int reflect2(int i, int n, int n1) { return reflect_h
 // elements of ES bytes; NCHW planes (nhwc == 0) or NHWC pixels of C elements (nhwc == 1)
 template <int ES>
 __global__ void tile_gather_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, const TileBox* __restrict__ boxes,
-                                   int nbox, int N, int C, int H, int W, int H1, int W1, int hc, int wc, int nhwc) {
+                                   int nbox, int nimg, int N, int C, int H, int W, int H1, int W1, int hc, int wc, int nhwc) {
   const size_t per = static_cast<size_t>(C) * hc * wc;
-  const size_t total = static_cast<size_t>(nbox) * N * per;
+  const size_t total = static_cast<size_t>(nimg) * N * per;
   for (size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
        idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    const size_t img = idx / per;           // crop index k * N + n
+    const size_t img = idx / per;           // atlas image index a * N + n
     size_t r = idx - img * per;
-    const int k = static_cast<int>(img / N), n = static_cast<int>(img - static_cast<size_t>(k) * N);
+    const int a = static_cast<int>(img / N), n = static_cast<int>(img - static_cast<size_t>(a) * N);
     int c, y, x;
     if (nhwc) { c = static_cast<int>(r % C); r /= C; x = static_cast<int>(r % wc); y = static_cast<int>(r / wc); }
     else { x = static_cast<int>(r % wc); r /= wc; y = static_cast<int>(r % hc); c = static_cast<int>(r / hc); }
-    if (y >= boxes[k].crop_h || x >= boxes[k].crop_w) {   // canvas outside this crop
+    int k = -1;                             // the crop of this atlas image that covers (y, x), if any
+    for (int j = 0; j < nbox; ++j)
+      if (boxes[j].img == a && x >= boxes[j].atlas_x && x < boxes[j].atlas_x + boxes[j].crop_w && y < boxes[j].crop_h) k = j;
+    if (k < 0) {                            // gap column / canvas below a shorter crop
 #pragma unroll
       for (int b = 0; b < ES; ++b) out[idx * ES + b] = 0;
       continue;
     }
-    const int sy = reflect2(boxes[k].src_y + y, H, H1), sx = reflect2(boxes[k].src_x + x, W, W1);
+    const int sy = reflect2(boxes[k].src_y + y, H, H1), sx = reflect2(boxes[k].src_x + (x - boxes[k].atlas_x), W, W1);
     const size_t si = nhwc ? ((static_cast<size_t>(n) * H + sy) * W + sx) * C + c
                            : ((static_cast<size_t>(n) * C + c) * H + sy) * W + sx;
 #pragma unroll
@@ -389,21 +392,21 @@ __global__ void tile_gather_kernel(const uint8_t* __restrict__ in, uint8_t* __re
 
 template <int ES>
 __global__ void tile_paste_kernel(const uint8_t* __restrict__ crops, uint8_t* __restrict__ out, const TileBox* __restrict__ boxes,
-                                  int N, int C, int hco, int wco, int OH, int OW, int nhwc) {
+                                  int N, int C, int hco, int wco, int scale, int OH, int OW, int nhwc) {
   const int k = blockIdx.y / N, n = blockIdx.y - k * N;
   const TileBox bx = boxes[k];
   // the pasted rectangle, clipped to the output frame (the pre_pad / mod-pad margin is cropped off, RealESRGANer.post_process)
   const int ph = min(bx.paste_h, OH - bx.dst_y), pw = min(bx.paste_w, OW - bx.dst_x);
   if (ph <= 0 || pw <= 0) return;
   const size_t total = static_cast<size_t>(C) * ph * pw;
-  const size_t img = static_cast<size_t>(k) * N + n;
+  const size_t img = static_cast<size_t>(bx.img) * N + n;
   for (size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
        idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
     size_t r = idx;
     int c, y, x;
     if (nhwc) { c = static_cast<int>(r % C); r /= C; x = static_cast<int>(r % pw); y = static_cast<int>(r / pw); }
     else { x = static_cast<int>(r % pw); r /= pw; y = static_cast<int>(r % ph); c = static_cast<int>(r / ph); }
-    const int cy = bx.off_y + y, cx = bx.off_x + x, oy = bx.dst_y + y, ox = bx.dst_x + x;
+    const int cy = bx.off_y + y, cx = bx.atlas_x * scale + bx.off_x + x, oy = bx.dst_y + y, ox = bx.dst_x + x;
     const size_t si = nhwc ? ((img * hco + cy) * wco + cx) * C + c : ((img * C + c) * hco + cy) * wco + cx;
     const size_t di = nhwc ? ((static_cast<size_t>(n) * OH + oy) * OW + ox) * C + c
                            : ((static_cast<size_t>(n) * C + c) * OH + oy) * OW + ox;
@@ -416,32 +419,32 @@ int fmt_elem_size(int fmt) { return fmt == 0 ? 4 : (fmt == 1 ? 2 : (fmt == 2 ? 1
 
 }  // namespace
 
-cudaError_t tile_gather_launch(int fmt, const void* in, void* out, const TileBox* boxes_dev, int nbox, int N, int C, int H,
+cudaError_t tile_gather_launch(int fmt, const void* in, void* out, const TileBox* boxes_dev, int nbox, int nimg, int N, int C, int H,
                                int W, int pre_pad, int hc, int wc, cudaStream_t s) {
   const int H1 = H + pre_pad, W1 = W + pre_pad;
   const int es = fmt_elem_size(fmt);
   if (es == 0) return cudaErrorInvalidValue;
-  const size_t total = static_cast<size_t>(nbox) * N * C * hc * wc;
+  const size_t total = static_cast<size_t>(nimg) * N * C * hc * wc;
   const unsigned blocks = static_cast<unsigned>(std::min<size_t>((total + 255) / 256, 148 * 16));
   const uint8_t* i8 = reinterpret_cast<const uint8_t*>(in);
   uint8_t* o8 = reinterpret_cast<uint8_t*>(out);
-  if (es == 4) tile_gather_kernel<4><<<blocks, 256, 0, s>>>(i8, o8, boxes_dev, nbox, N, C, H, W, H1, W1, hc, wc, 0);
-  else if (es == 2) tile_gather_kernel<2><<<blocks, 256, 0, s>>>(i8, o8, boxes_dev, nbox, N, C, H, W, H1, W1, hc, wc, 0);
-  else tile_gather_kernel<1><<<blocks, 256, 0, s>>>(i8, o8, boxes_dev, nbox, N, C, H, W, H1, W1, hc, wc, 1);
+  if (es == 4) tile_gather_kernel<4><<<blocks, 256, 0, s>>>(i8, o8, boxes_dev, nbox, nimg, N, C, H, W, H1, W1, hc, wc, 0);
+  else if (es == 2) tile_gather_kernel<2><<<blocks, 256, 0, s>>>(i8, o8, boxes_dev, nbox, nimg, N, C, H, W, H1, W1, hc, wc, 0);
+  else tile_gather_kernel<1><<<blocks, 256, 0, s>>>(i8, o8, boxes_dev, nbox, nimg, N, C, H, W, H1, W1, hc, wc, 1);
   return cudaGetLastError();
 }
 
 cudaError_t tile_paste_launch(int fmt, const void* crops, void* out, const TileBox* boxes_dev, int nbox, int N, int C, int hco,
-                              int wco, int OH, int OW, cudaStream_t s) {
+                              int wco, int scale, int OH, int OW, cudaStream_t s) {
   const int es = fmt_elem_size(fmt);
   if (es == 0) return cudaErrorInvalidValue;
   const size_t per = static_cast<size_t>(C) * hco * wco;
   dim3 grid(static_cast<unsigned>(std::min<size_t>((per + 255) / 256, 256)), static_cast<unsigned>(nbox * N));
   const uint8_t* i8 = reinterpret_cast<const uint8_t*>(crops);
   uint8_t* o8 = reinterpret_cast<uint8_t*>(out);
-  if (es == 4) tile_paste_kernel<4><<<grid, 256, 0, s>>>(i8, o8, boxes_dev, N, C, hco, wco, OH, OW, 0);
-  else if (es == 2) tile_paste_kernel<2><<<grid, 256, 0, s>>>(i8, o8, boxes_dev, N, C, hco, wco, OH, OW, 0);
-  else tile_paste_kernel<1><<<grid, 256, 0, s>>>(i8, o8, boxes_dev, N, C, hco, wco, OH, OW, 1);
+  if (es == 4) tile_paste_kernel<4><<<grid, 256, 0, s>>>(i8, o8, boxes_dev, N, C, hco, wco, scale, OH, OW, 0);
+  else if (es == 2) tile_paste_kernel<2><<<grid, 256, 0, s>>>(i8, o8, boxes_dev, N, C, hco, wco, scale, OH, OW, 0);
+  else tile_paste_kernel<1><<<grid, 256, 0, s>>>(i8, o8, boxes_dev, N, C, hco, wco, scale, OH, OW, 1);
   return cudaGetLastError();
 }
 

@@ -26,13 +26,16 @@ struct TileBox {
   int32_t off_y, off_x;       // top-left of the un-padded centre inside the net's output for the crop (pixels of the output grid)
   int32_t dst_y, dst_x;       // where it goes in the output frame
   int32_t paste_h, paste_w;   // its size (clipped to the output frame by the kernel)
-  int32_t crop_h, crop_w;     // size of the padded crop (<= the batch's canvas hc x wc: the rest of the canvas is zero)
+  int32_t crop_h, crop_w;     // size of the padded crop
+  int32_t img, atlas_x;       // atlas image of the group it is packed into and its column there (crops sit side by side,
+                              // top-aligned, zero gap columns between them; the rest of the hc x wc canvas is zero)
 };
-// fmt: SS4K_FMT_F32_NCHW / F16_NCHW / U8_NHWC; crops are stored as a batch [box * N + n] of hc x wc images in the same format
-cudaError_t tile_gather_launch(int fmt, const void* in, void* out, const TileBox* boxes_dev, int nbox, int N, int C, int H,
+// fmt: SS4K_FMT_F32_NCHW / F16_NCHW / U8_NHWC; the crops are packed into nimg atlas images per frame, stored as a batch
+// [img * N + n] of hc x wc images in the same format
+cudaError_t tile_gather_launch(int fmt, const void* in, void* out, const TileBox* boxes_dev, int nbox, int nimg, int N, int C, int H,
                                int W, int pre_pad, int hc, int wc, cudaStream_t s);
 cudaError_t tile_paste_launch(int fmt, const void* crops, void* out, const TileBox* boxes_dev, int nbox, int N, int C, int hco,
-                              int wco, int OH, int OW, cudaStream_t s);
+                              int wco, int scale, int OH, int OW, cudaStream_t s);
 
 // elementwise.cu
 // in_fmt: SS4K_FMT_* ; out: [N, H/us, W/us, pitch] 16-bit NHWC (out_lo: low halves for split mode or null)

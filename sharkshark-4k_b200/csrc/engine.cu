@@ -887,7 +887,8 @@ struct ss4k_plan {
   int64_t in_bytes = 0, out_bytes = 0;
   // tiled inference (cfg.tile / tile_pad / pre_pad, RealESRGANer semantics): one sub-plan per padded-crop shape class
   struct TileClass {
-    int hc = 0, wc = 0, count = 0;
+    int hc = 0, wc = 0, count = 0;   // canvas of the group's atlas images, number of crops
+    int nimg = 1;                    // atlas images per frame
     ss4k_plan* sub = nullptr;
     TileBox* d_boxes = nullptr;
     void* d_in = nullptr;
@@ -1357,8 +1358,11 @@ int ss4k_plan_create(ss4k_ctx* ctx, const ss4k_plan_cfg* cfg, ss4k_plan** out_pl
   if (cfg->reserved[5] == 1) {
     // masked canvases (tiled inference): every conv zeroes its output outside the image's crop; needs every conv on the
     // streaming kernel, at a power-of-two multiple of the input resolution
-    std::vector<int32_t> hw(static_cast<size_t>(2) * P.in_n);
-    for (int i = 0; i < P.in_n; ++i) { hw[2 * i] = P.in_h; hw[2 * i + 1] = P.in_w; }
+    std::vector<int32_t> hw(static_cast<size_t>(kMaskStride) * P.in_n, 0);
+    for (int i = 0; i < P.in_n; ++i) {   // default: one crop = the whole canvas (the tiled plan fills in its atlases)
+      int32_t* e = hw.data() + static_cast<size_t>(i) * kMaskStride;
+      e[0] = 1; e[1] = 0; e[2] = P.in_w; e[3] = P.in_h;
+    }
     cudaError_t ce = cudaMalloc(&pl->d_mask, hw.size() * sizeof(int32_t));
     if (ce == cudaSuccess) ce = cudaMemcpy(pl->d_mask, hw.data(), hw.size() * sizeof(int32_t), cudaMemcpyHostToDevice);
     if (ce != cudaSuccess) { ss4k_plan_destroy(pl.release()); return fail(ctx, SS4K_E_NOMEM, "mask table"); }
@@ -1489,64 +1493,71 @@ static int create_tiled_plan(ss4k_ctx* ctx, const ss4k_plan_cfg* cfg, ss4k_plan*
       b.paste_h = (ey - sy) * s; b.paste_w = (ex - sx) * s;
       classes[std::make_pair(eyp - syp, exp_ - sxp)].push_back(b);
     }
-  // Crops of different shapes share a batch as MASKED CANVASES: each crop sits in the top-left corner of the group's
-  // canvas (the largest height x the largest width of the group), the rest of the canvas is zero on the way in and is
-  // forced back to zero by every conv's epilogue (StreamParams::mask_hw), so each crop sees exactly the zero padding
-  // at its own border that a run of its own would give it -- bit-identical, but 2-3 batches per frame instead of one per
-  // shape class (1080p, tile 512: nine classes), i.e. 4-8 times the rows per launch.  Greedy grouping, tallest first: a
-  // crop joins the open group while the canvas area stays within 20 % of the crops' own area.
-  struct Group { int hc = 0, wc = 0; long long area = 0; bool small = false; std::vector<TileBox> boxes; };
+  // Crops of different shapes share an image as a CROP ATLAS: the crops of a group sit side by side (top-aligned, zero gap
+  // columns between them) in atlas images of the group's canvas, everything outside the crops is zero on the way in and is
+  // forced back to zero by every conv's epilogue (StreamParams::mask_hw), so each crop sees exactly the zero padding at its
+  // own border that a run of its own would give it -- bit-identical, but the frame's tiles are one or two large launches
+  // per conv instead of one small launch per shape class (1080p, tile 512: nine classes), and a row of the atlas fills
+  // the kernel's 128-pixel strips instead of leaving every crop's last strip partly empty.  Groups collect crops of similar
+  // height (tallest first; a crop joins while it is at least 90 % of the group's height); a group is cut into images of at
+  // most kMaskRects crops.
+  struct Group { int hc = 0, wc = 0, nimg = 1; std::vector<TileBox> boxes; };
   std::vector<Group> groups;
   {
     std::vector<std::pair<std::pair<int, int>, TileBox>> all;
-    bool even = true;
     for (auto& kv : classes)
-      for (const TileBox& b : kv.second) {
-        all.push_back(std::make_pair(kv.first, b));
-        even = even && (kv.first.first % 2 == 0) && (kv.first.second % 2 == 0);
-      }
-    const bool merge = getenv("SS4K_TILE_EXACT_CLASSES") == nullptr && (even || !(cfg->arch == SS4K_ARCH_RRDB && s == 2));
-    // only shape classes whose own batch would be a small launch (fewer than ~12 trunk rows per SM: set-up, tail and halo
-    // rows dominate) are merged; a class that fills the GPU on its own gains nothing and would pay the canvas waste
-    const int tdiv = (cfg->arch == SS4K_ARCH_RRDB && s == 2) ? 2 : 1;   // trunk resolution = input / tdiv
-    auto small_class = [&](const std::pair<int, int>& hw) {
-      const long long units = static_cast<long long>(classes[hw].size()) * cfg->n * ((hw.second / tdiv + kTileW - 1) / kTileW) * (hw.first / tdiv);
-      return units < 12LL * ctx->nsm;
-    };
+      for (const TileBox& b : kv.second) all.push_back(std::make_pair(kv.first, b));
+    const int tdiv = (cfg->arch == SS4K_ARCH_RRDB && s == 2) ? 2 : 1;   // coarsest conv resolution = input / tdiv
+    bool aligned = true;
+    for (auto& e : all) aligned = aligned && e.first.first % tdiv == 0 && e.first.second % tdiv == 0;
+    const bool merge = getenv("SS4K_TILE_EXACT_CLASSES") == nullptr && aligned;
     std::stable_sort(all.begin(), all.end(), [](const std::pair<std::pair<int, int>, TileBox>& a, const std::pair<std::pair<int, int>, TileBox>& b) {
       return a.first.first != b.first.first ? a.first.first > b.first.first : a.first.second > b.first.second; });
     for (auto& e : all) {
       TileBox b = e.second;
-      b.crop_h = e.first.first; b.crop_w = e.first.second;
-      const long long a = static_cast<long long>(b.crop_h) * b.crop_w;
+      b.crop_h = e.first.first; b.crop_w = e.first.second; b.img = 0; b.atlas_x = 0;
       bool placed = false;
       if (!groups.empty()) {
         Group& g = groups.back();
-        const int nh = std::max(g.hc, b.crop_h), nw = std::max(g.wc, b.crop_w);
-        const long long canvas = static_cast<long long>(nh) * nw * (static_cast<long long>(g.boxes.size()) + 1);
-        const bool same = nh == g.hc && nw == g.wc && b.crop_h == g.hc && b.crop_w == g.wc && g.area == static_cast<long long>(g.hc) * g.wc * static_cast<long long>(g.boxes.size());
-        if (same || (merge && g.small && small_class(e.first) && canvas * 100 <= (g.area + a) * 120)) {
-          g.hc = nh; g.wc = nw; g.area += a; g.boxes.push_back(b);
-          placed = true;
-        }
+        const bool same = b.crop_h == g.boxes[0].crop_h && b.crop_w == g.boxes[0].crop_w && g.boxes.back().crop_w == b.crop_w && g.boxes.back().crop_h == b.crop_h;
+        if (merge ? b.crop_h * 10 >= g.hc * 9 : same) { g.boxes.push_back(b); placed = true; }
       }
       if (!placed) {
         groups.emplace_back();
-        Group& g = groups.back();
-        g.hc = b.crop_h; g.wc = b.crop_w; g.area = a; g.boxes.push_back(b);
-        g.small = small_class(e.first);
+        groups.back().hc = b.crop_h;
+        groups.back().boxes.push_back(b);
+      }
+    }
+    for (Group& g : groups) {
+      const int cnt = static_cast<int>(g.boxes.size());
+      if (!merge) {   // one image per crop, no atlas (the classes are uniform)
+        g.nimg = cnt; g.wc = g.boxes[0].crop_w;
+        for (int k = 0; k < cnt; ++k) { g.boxes[k].img = k; g.boxes[k].atlas_x = 0; }
+        continue;
+      }
+      g.nimg = (cnt + kMaskRects - 1) / kMaskRects;
+      const int per = (cnt + g.nimg - 1) / g.nimg;
+      const int gap = tdiv;   // one zero column at the coarsest resolution
+      g.wc = 0;
+      for (int k = 0; k < cnt; ++k) {
+        const int im = k / per;
+        const bool first = k % per == 0;
+        g.boxes[k].img = im;
+        g.boxes[k].atlas_x = first ? 0 : g.boxes[k - 1].atlas_x + g.boxes[k - 1].crop_w + gap;
+        g.wc = std::max(g.wc, g.boxes[k].atlas_x + g.boxes[k].crop_w);
       }
     }
   }
   for (auto& g : groups) {
     ss4k_plan::TileClass tc;
-    tc.hc = g.hc; tc.wc = g.wc; tc.count = static_cast<int>(g.boxes.size());
-    bool uniform = true;
-    for (const TileBox& b : g.boxes) uniform = uniform && b.crop_h == g.hc && b.crop_w == g.wc;
+    tc.hc = g.hc; tc.wc = g.wc; tc.count = static_cast<int>(g.boxes.size()); tc.nimg = g.nimg;
+    bool uniform = true;   // every image is exactly one crop of the canvas size: no mask needed
+    for (const TileBox& b : g.boxes) uniform = uniform && b.crop_h == g.hc && b.crop_w == g.wc && b.atlas_x == 0;
+    uniform = uniform && g.nimg == tc.count;
     ss4k_plan_cfg sub = *cfg;
     sub.tile = 0; sub.reserved[1] = 0;
     sub.reserved[5] = uniform ? 0 : 1;
-    sub.n = cfg->n * tc.count; sub.h = tc.hc; sub.w = tc.wc;
+    sub.n = cfg->n * tc.nimg; sub.h = tc.hc; sub.w = tc.wc;
     pl->tiles.push_back(tc);
     ss4k_plan::TileClass& t = pl->tiles.back();
     struct KV { std::vector<TileBox>& second; } kv{g.boxes};
@@ -1556,12 +1567,13 @@ static int create_tiled_plan(ss4k_ctx* ctx, const ss4k_plan_cfg* cfg, ss4k_plan*
       ss4k_plan_destroy(pl.release());
       return fail(ctx, rc, fmt("tile group %dx%d: %s", tc.hc, tc.wc, why.c_str()));
     }
-    if (!uniform) {   // crop sizes of the batch's images (image index = box * N + n)
-      std::vector<int32_t> hw(static_cast<size_t>(2) * sub.n);
-      for (int k = 0; k < tc.count; ++k)
+    if (!uniform) {   // the crops of every atlas image of the batch (image index = img * N + n)
+      std::vector<int32_t> hw(static_cast<size_t>(kMaskStride) * sub.n, 0);
+      for (const TileBox& b : g.boxes)
         for (int n = 0; n < cfg->n; ++n) {
-          hw[2 * (static_cast<size_t>(k) * cfg->n + n)] = g.boxes[k].crop_h;
-          hw[2 * (static_cast<size_t>(k) * cfg->n + n) + 1] = g.boxes[k].crop_w;
+          int32_t* e = hw.data() + (static_cast<size_t>(b.img) * cfg->n + n) * kMaskStride;
+          const int k = e[0]++;
+          e[1 + 3 * k] = b.atlas_x; e[2 + 3 * k] = b.crop_w; e[3 + 3 * k] = b.crop_h;
         }
       if (cudaMemcpy(t.sub->d_mask, hw.data(), hw.size() * sizeof(int32_t), cudaMemcpyHostToDevice) != cudaSuccess) {
         ss4k_plan_destroy(pl.release());
@@ -1670,11 +1682,11 @@ int ss4k_run(ss4k_plan* pl, const void* in_dev, void* out_dev, void* cuda_stream
   if (pl->tiled) {
     const Program& P = pl->prog;
     for (auto& t : pl->tiles) {
-      CK(ctx, tile_gather_launch(P.in_fmt, in_dev, t.d_in, t.d_boxes, t.count, P.in_n, 3, P.in_h, P.in_w, pl->cfg.reserved[1], t.hc, t.wc, st));
+      CK(ctx, tile_gather_launch(P.in_fmt, in_dev, t.d_in, t.d_boxes, t.count, t.nimg, P.in_n, 3, P.in_h, P.in_w, pl->cfg.reserved[1], t.hc, t.wc, st));
       int rc = ss4k_run(t.sub, t.d_in, t.d_out, cuda_stream);
       if (rc != SS4K_OK) return rc;
       CK(ctx, tile_paste_launch(P.out_fmt, t.d_out, out_dev, t.d_boxes, t.count, P.in_n, 3, t.sub->prog.out_h, t.sub->prog.out_w,
-                                P.out_h, P.out_w, st));
+                                pl->cfg.scale, P.out_h, P.out_w, st));
       ctx->launches += 2;
     }
     return SS4K_OK;
