@@ -161,7 +161,7 @@ def test_rrdbnet_uint8_frames_ragged_width(engine):
 def test_rrdbnet_1080p_tile512_every_shape_class(engine):
     """BASELINE.json configs[3] geometry: 1920x1080 frame, tile 512, tile_pad 10 (the reference defaults,
     realesrgan/factory.py:93-94) -> 4 x 3 tiles in 9 padded-crop shape classes (522/532/394 x 522/532/66), run as two
-    batches of masked canvases (eight crops on 532 x 532, four on 66 x 532) inside ONE engine run.  RRDBNet x2 with 2 blocks (the tiling, not the depth, is under
+    crop atlases (eight crops side by side in one 3974 x 532 image, the four short ones in a 2000 x 66 image) inside ONE engine run.  RRDBNet x2 with 2 blocks (the tiling, not the depth, is under
     test) against the oracle's tile_process on the whole frame; uint8 frames in and out as the service passes them."""
     torch.manual_seed(2)
     net = rrdbnet.RRDBNet(3, 3, 2, 64, 2, 32).eval()
