@@ -181,9 +181,13 @@ int ss4k_nv12_pack(ss4k_ctx* ctx, const ss4k_nv12_surface* surfaces, int n, int 
 int ss4k_nv12_unpack(ss4k_ctx* ctx, const void* packed_dev, const ss4k_nv12_surface* surfaces, int n, int h, int w, void* cuda_stream);
 
 /* BSVD streaming (persistent per-stream ring buffers) ----------------------------------- */
-/* open: plan must be an SS4K_ARCH_BSVD plan (its n is ignored; frames are pushed one at a time) */
+/* open: plan must be an SS4K_ARCH_BSVD plan (its n is ignored; frames are pushed one at a time).  Every precision mode
+ * streams (split precision: every ring has a low-half twin).  Ring lengths are powers of two, so a steady-state push (all
+ * layers active, no clip boundary in reach) replays one captured CUDA graph per phase of the longest ring between a copy
+ * into and a copy out of stream-owned staging buffers (plan cfg use_graph = 0 or SS4K_NO_STREAM_GRAPH: per-layer launches). */
 int ss4k_bsvd_stream_open(ss4k_plan* plan, ss4k_bsvd_stream** out_stream);
-/* push frame t (in_dev: one frame in the plan's in_fmt with 4 channels: RGB + noise map).
+/* push frame t (in_dev: one frame in the plan's in_fmt: 4 channels RGB + noise map for the float / half NCHW formats, a
+ * uint8 RGB or NV12 frame for the frame formats -- the noise map is then the plan's reserved[0] level).
  * *got_output = 1 when the denoised frame t-16 was written to out_dev (3 channels). */
 int ss4k_bsvd_stream_push(ss4k_bsvd_stream* s, const void* in_dev, void* out_dev,
                           int* got_output, void* cuda_stream);
