@@ -103,6 +103,20 @@ int round_up(int a, int b) { return (a + b - 1) / b * b; }
 
 // ------------------------------------------------------------------------------------------------
 // A materialised convolution: packed weights on the device + kernel parameter block + grid.
+// Binds the calling thread to the engine's GPU for the duration of an entry point and restores the previous device: the
+// caller (a PyTorch process that drives several engines, a worker whose current device is still 0) need not have it set.
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    if (dev < 0) return;
+    int cur = -1;
+    if (cudaGetDevice(&cur) == cudaSuccess && cur != dev && cudaSetDevice(dev) == cudaSuccess) prev = cur;
+  }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+  DeviceGuard(const DeviceGuard&) = delete;
+  DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+
 struct ConvExec {
   ConvParams p;
   StreamParams sp;      // row-streaming kernel (conv_stream.cu) when `stream` is set
@@ -1295,7 +1309,7 @@ static int create_tiled_plan(ss4k_ctx* ctx, const ss4k_plan_cfg* cfg, ss4k_plan*
 int ss4k_plan_create(ss4k_ctx* ctx, const ss4k_plan_cfg* cfg, ss4k_plan** out_plan) {
   if (!ctx || !cfg || !out_plan) return fail(ctx, SS4K_E_INVALID, "null argument");
   *out_plan = nullptr;
-  CK(ctx, cudaSetDevice(ctx->device));
+  DeviceGuard dev_guard(ctx->device);
   if (cfg->arch != SS4K_ARCH_BSVD) {
     // RealESRGANer options (factory.py:93-95): tile / tile_pad / pre_pad, and the reflect mod-pad of the x2 nets
     const int pre_pad = cfg->reserved[1];
@@ -1600,6 +1614,7 @@ static int create_tiled_plan(ss4k_ctx* ctx, const ss4k_plan_cfg* cfg, ss4k_plan*
 // Pitched NV12 surfaces (one allocation per frame, as a hardware decoder / encoder owns them) <-> the packed chunk
 // [n, h*3/2, w] the plans read: two 2-D DMA copies per frame, stream-ordered.
 static int nv12_surfaces(ss4k_ctx* ctx, const ss4k_nv12_surface* sf, int n, int h, int w, uint8_t* packed, bool pack, cudaStream_t st) {
+  DeviceGuard dev_guard(ctx ? ctx->device : -1);
   if (!ctx || !sf || !packed || n <= 0 || h <= 0 || w <= 0 || (h % 2) || (w % 2)) return fail(ctx, SS4K_E_INVALID, "bad argument to ss4k_nv12_pack / ss4k_nv12_unpack");
   const size_t frame = static_cast<size_t>(h) * w * 3 / 2;
   for (int i = 0; i < n; ++i) {
@@ -1625,6 +1640,7 @@ int ss4k_nv12_unpack(ss4k_ctx* ctx, const void* packed_dev, const ss4k_nv12_surf
 }
 
 int ss4k_rgb_to_nv12(ss4k_ctx* ctx, const void* rgb_dev, void* nv12_dev, int n, int h, int w, void* cuda_stream) {
+  DeviceGuard dev_guard(ctx ? ctx->device : -1);
   if (!ctx || !rgb_dev || !nv12_dev || n <= 0 || h <= 0 || w <= 0) return fail(ctx, SS4K_E_INVALID, "bad argument to ss4k_rgb_to_nv12");
   if (h % 2 || w % 4) return fail(ctx, SS4K_E_INVALID, "ss4k_rgb_to_nv12 needs h % 2 == 0 and w % 4 == 0");
   CK(ctx, rgb_to_nv12_launch(rgb_dev, nv12_dev, n, h, w, static_cast<cudaStream_t>(cuda_stream)));
@@ -1678,6 +1694,7 @@ int ss4k_plan_io_bytes(const ss4k_plan* pl, int64_t* in_bytes, int64_t* out_byte
 int ss4k_run(ss4k_plan* pl, const void* in_dev, void* out_dev, void* cuda_stream) {
   if (!pl || !in_dev || !out_dev) return fail(pl ? pl->ctx : nullptr, SS4K_E_INVALID, "null argument to ss4k_run");
   ss4k_ctx* ctx = pl->ctx;
+  DeviceGuard dev_guard(ctx->device);   // launches go to the engine's GPU whatever the calling thread's current device is
   cudaStream_t st = reinterpret_cast<cudaStream_t>(cuda_stream);
   if (pl->tiled) {
     const Program& P = pl->prog;
@@ -1724,6 +1741,7 @@ int ss4k_plan_input_act(ss4k_plan* pl, void** act_dev, int32_t* pitch, int32_t* 
 int ss4k_run_act(ss4k_plan* pl, void* out_dev, void* cuda_stream) {
   if (!pl || !out_dev) return fail(pl ? pl->ctx : nullptr, SS4K_E_INVALID, "null argument to ss4k_run_act");
   ss4k_ctx* ctx = pl->ctx;
+  DeviceGuard dev_guard(ctx->device);
   void* act = nullptr;
   int rc = ss4k_plan_input_act(pl, &act, nullptr, nullptr, nullptr);
   if (rc != SS4K_OK) return rc;
@@ -1745,6 +1763,7 @@ int ss4k_run_act(ss4k_plan* pl, void* out_dev, void* cuda_stream) {
 int ss4k_run_host(ss4k_plan* pl, const void* in_host, void* out_host) {
   if (!pl || !in_host || !out_host) return fail(pl ? pl->ctx : nullptr, SS4K_E_INVALID, "null argument to ss4k_run_host");
   ss4k_ctx* ctx = pl->ctx;
+  DeviceGuard dev_guard(ctx->device);
   if (!pl->stage_in) CK(ctx, cudaMalloc(&pl->stage_in, pl->in_bytes + 256));
   if (!pl->stage_out) CK(ctx, cudaMalloc(&pl->stage_out, pl->out_bytes + 256));
   CK(ctx, cudaMemcpyAsync(pl->stage_in, in_host, pl->in_bytes, cudaMemcpyHostToDevice, ctx->stream));
@@ -1761,6 +1780,7 @@ int ss4k_run_host(ss4k_plan* pl, const void* in_host, void* out_host) {
 int ss4k_run_host_async(ss4k_plan* pl, const void* in_host, void* out_host) {
   if (!pl || !in_host || !out_host) return fail(pl ? pl->ctx : nullptr, SS4K_E_INVALID, "null argument to ss4k_run_host_async");
   ss4k_ctx* ctx = pl->ctx;
+  DeviceGuard dev_guard(ctx->device);
   auto& pp = pl->pipe;
   if (!pp.init) {
     CK(ctx, cudaStreamCreateWithFlags(&pp.h2d, cudaStreamNonBlocking));
@@ -1809,6 +1829,7 @@ int ss4k_plan_profile(ss4k_plan* pl, const void* in_dev, void* out_dev, void* cu
                       int32_t* kind, int cap) {
   if (!pl || !in_dev || !out_dev || !ms || !flops || !kind) return fail(pl ? pl->ctx : nullptr, SS4K_E_INVALID, "null argument to ss4k_plan_profile");
   ss4k_ctx* ctx = pl->ctx;
+  DeviceGuard dev_guard(ctx->device);
   if (pl->tiled) return fail(ctx, SS4K_E_INVALID, "ss4k_plan_profile: profile the tile classes' shapes as plans of their own");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(cuda_stream);
   const int ns = static_cast<int>(pl->prog.steps.size());
@@ -1842,6 +1863,7 @@ int ss4k_plan_profile(ss4k_plan* pl, const void* in_dev, void* out_dev, void* cu
 int ss4k_conv3x3(ss4k_ctx* ctx, const ss4k_conv_desc* d, const float* x, const float* weight, const float* bias,
                  const float* slope, const float* residual, float* y, void* cuda_stream) {
   if (!ctx || !d || !x || !weight || !y) return fail(ctx, SS4K_E_INVALID, "null argument to ss4k_conv3x3");
+  DeviceGuard dev_guard(ctx->device);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(cuda_stream);
   const bool bf16 = d->act_mode == SS4K_ACT_BF16;
   const bool split = d->act_mode == SS4K_ACT_F16_SPLIT;
@@ -2001,6 +2023,7 @@ int ss4k_debug_pack(const ss4k_conv_desc* d, int in_pitch, int in_coff, int wper
 int ss4k_debug_bench_conv(ss4k_ctx* ctx, const ss4k_conv_desc* d, int slab_pitch, int dbg_flags, int iters,
                           float* ms_per_launch, char** out_json) {
   if (!ctx || !d || !ms_per_launch) return fail(ctx, SS4K_E_INVALID, "null argument");
+  DeviceGuard dev_guard(ctx->device);
   const bool bf16 = d->act_mode == SS4K_ACT_BF16;
   const int in_pitch = slab_pitch > 0 ? slab_pitch : round_up(d->cin, 16);
   const int npad = round_up(d->cout, 16);

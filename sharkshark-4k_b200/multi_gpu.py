@@ -23,6 +23,7 @@ import threading
 import time
 import traceback
 
+import torch
 import torch.multiprocessing as mp
 
 
@@ -33,6 +34,8 @@ def _default_factory(device, **kw):
 
 def _worker_main(factory, device, kwargs, output_shape, job_q, result_q, cmd_q):
     try:
+        if isinstance(device, int) and torch.cuda.is_available():
+            torch.cuda.set_device(device)   # allocations and kernel launches of this process go to its own GPU
         svc = factory(device, **kwargs)
         if output_shape is not None:
             svc.output_shape = output_shape

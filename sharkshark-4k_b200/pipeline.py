@@ -63,6 +63,10 @@ class DenoiseUpscalePipeline:
     def run(self, frames, own=None, out=None, after_frame=None):
         """frames: CUDA uint8 chunk [T, h*w*3/2] (NV12) or [T,h,w,3]; own: slice of the chunk whose frames are
         upscaled (default: all); returns [n_own, sH, sW, 3] uint8 (stream-ordered, no sync)."""
+        with torch.cuda.device(self.device):     # the glue kernel launches on the current device's stream
+            return self._run(frames, own, out, after_frame)
+
+    def _run(self, frames, own, out, after_frame):
         t = frames.shape[0]
         own = own if own is not None else slice(0, t)
         lo, hi, _ = own.indices(t)

@@ -172,6 +172,10 @@ class FsrcnnUpscalerService:
         returns the entries of the jobs still in flight, oldest first; the next frame starts a new clip."""
         if not self._temporal() or self._den_stream is None:
             return []
+        with torch.cuda.device(self.device):
+            return self._flush()
+
+    def _flush(self):
         for den in self._den_stream.flush():
             self._ready.append(self._finish_single(den, self._lr_fifo.popleft()))
         self._den_stream.reset()
@@ -228,6 +232,10 @@ class FsrcnnUpscalerService:
 
     # ------------------------------------------------------------------ upscale (fsrcnn_upscaler.py:144-166)
     def upscale(self, frames):
+        with torch.cuda.device(self.device):     # the glue kernels launch on the current device's stream
+            return self._upscale(frames)
+
+    def _upscale(self, frames):
         assert isinstance(frames, torch.Tensor)
         if frames.device != self.device:
             frames = frames.to(self.device, non_blocking=True)
