@@ -239,6 +239,10 @@ int ss4k_glue_sharpen_blend_act(const void* x, int fmt, int n, int c, int h, int
 int ss4k_plan_input_act(ss4k_plan* plan, void** act_dev, int32_t* pitch, int32_t* unshuffle, int32_t* is_bf16);
 int ss4k_run_act(ss4k_plan* plan, void* out_dev, void* cuda_stream);
 
+/* host-only: the tile grid of a plan configuration (tile, tile_pad, reserved[1] = pre_pad) and its packing into crop
+ * atlases as JSON; free with ss4k_free */
+int ss4k_debug_tile_layout(const ss4k_plan_cfg* cfg, char** out_json);
+
 /* operator-level entry (kernel parity tests) -------------------------------------------- */
 typedef struct ss4k_conv_desc {
   int32_t struct_size;

@@ -1475,23 +1475,20 @@ int ss4k_plan_create(ss4k_ctx* ctx, const ss4k_plan_cfg* cfg, ss4k_plan** out_pl
 // ceil(W/tile) x ceil(H/tile) tiles, each crop expanded by tile_pad and clamped to the padded frame, un-padded centre
 // pasted, no blending) and post_process (pads cropped off) -- SURVEY.md Appendix B; reached from
 // realesrgan/factory.py:93-95,160-169.  Crops of one shape are independent images: they run as ONE batch per class.
-static int create_tiled_plan(ss4k_ctx* ctx, const ss4k_plan_cfg* cfg, ss4k_plan** out_plan) {
-  if (cfg->in_fmt == SS4K_FMT_NV12) return fail(ctx, SS4K_E_INVALID, "tiled inference takes RGB frames (float / half NCHW or uint8 NHWC)");
+struct TileGroup { int hc = 0, wc = 0, nimg = 1; std::vector<TileBox> boxes; };
+
+// Host-only: RealESRGANer's tile grid for a frame and its packing into crop atlases (see create_tiled_plan).
+static std::string layout_tiles(const ss4k_plan_cfg* cfg, std::vector<TileGroup>* out_groups) {
+  std::vector<TileGroup>& groups = *out_groups;
+  groups.clear();
+  if (cfg->in_fmt == SS4K_FMT_NV12) return "tiled inference takes RGB frames (float / half NCHW or uint8 NHWC)";
   const int s = cfg->scale;
   const int pre_pad = cfg->reserved[1];
   int Hp = cfg->h + pre_pad, Wp = cfg->w + pre_pad;
   if (cfg->arch == SS4K_ARCH_RRDB && s == 2) { Hp += Hp & 1; Wp += Wp & 1; }
-  if (Hp - cfg->h >= cfg->h || Wp - cfg->w >= cfg->w) return fail(ctx, SS4K_E_INVALID, "pre_pad must be smaller than the frame (reflect padding)");
+  if (Hp - cfg->h >= cfg->h || Wp - cfg->w >= cfg->w) return "pre_pad must be smaller than the frame (reflect padding)";
   const int tile = cfg->tile > 0 ? cfg->tile : std::max(Hp, Wp);
   const int pad = cfg->tile > 0 ? cfg->tile_pad : 0;
-  std::unique_ptr<ss4k_plan> pl(new ss4k_plan());
-  pl->ctx = ctx;
-  pl->cfg = *cfg;
-  pl->tiled = true;
-  Program& P = pl->prog;
-  P.in_fmt = cfg->in_fmt; P.out_fmt = cfg->out_fmt;
-  P.in_n = cfg->n; P.in_c = 3; P.in_h = cfg->h; P.in_w = cfg->w;
-  P.out_n = cfg->n; P.out_c = 3; P.out_h = cfg->h * s; P.out_w = cfg->w * s;
   std::map<std::pair<int, int>, std::vector<TileBox>> classes;
   const int tx = (Wp + tile - 1) / tile, ty = (Hp + tile - 1) / tile;
   for (int y = 0; y < ty; ++y)
@@ -1501,6 +1498,7 @@ static int create_tiled_plan(ss4k_ctx* ctx, const ss4k_plan_cfg* cfg, ss4k_plan*
       const int sxp = std::max(sx - pad, 0), exp_ = std::min(ex + pad, Wp);
       const int syp = std::max(sy - pad, 0), eyp = std::min(ey + pad, Hp);
       TileBox b;
+      memset(&b, 0, sizeof(b));
       b.src_y = syp; b.src_x = sxp;
       b.off_y = (sy - syp) * s; b.off_x = (sx - sxp) * s;
       b.dst_y = sy * s; b.dst_x = sx * s;
@@ -1515,53 +1513,67 @@ static int create_tiled_plan(ss4k_ctx* ctx, const ss4k_plan_cfg* cfg, ss4k_plan*
   // the kernel's 128-pixel strips instead of leaving every crop's last strip partly empty.  Groups collect crops of similar
   // height (tallest first; a crop joins while it is at least 90 % of the group's height); a group is cut into images of at
   // most kMaskRects crops.
-  struct Group { int hc = 0, wc = 0, nimg = 1; std::vector<TileBox> boxes; };
-  std::vector<Group> groups;
-  {
-    std::vector<std::pair<std::pair<int, int>, TileBox>> all;
-    for (auto& kv : classes)
-      for (const TileBox& b : kv.second) all.push_back(std::make_pair(kv.first, b));
-    const int tdiv = (cfg->arch == SS4K_ARCH_RRDB && s == 2) ? 2 : 1;   // coarsest conv resolution = input / tdiv
-    bool aligned = true;
-    for (auto& e : all) aligned = aligned && e.first.first % tdiv == 0 && e.first.second % tdiv == 0;
-    const bool merge = getenv("SS4K_TILE_EXACT_CLASSES") == nullptr && aligned;
-    std::stable_sort(all.begin(), all.end(), [](const std::pair<std::pair<int, int>, TileBox>& a, const std::pair<std::pair<int, int>, TileBox>& b) {
-      return a.first.first != b.first.first ? a.first.first > b.first.first : a.first.second > b.first.second; });
-    for (auto& e : all) {
-      TileBox b = e.second;
-      b.crop_h = e.first.first; b.crop_w = e.first.second; b.img = 0; b.atlas_x = 0;
-      bool placed = false;
-      if (!groups.empty()) {
-        Group& g = groups.back();
-        const bool same = b.crop_h == g.boxes[0].crop_h && b.crop_w == g.boxes[0].crop_w && g.boxes.back().crop_w == b.crop_w && g.boxes.back().crop_h == b.crop_h;
-        if (merge ? b.crop_h * 10 >= g.hc * 9 : same) { g.boxes.push_back(b); placed = true; }
-      }
-      if (!placed) {
-        groups.emplace_back();
-        groups.back().hc = b.crop_h;
-        groups.back().boxes.push_back(b);
-      }
+  std::vector<std::pair<std::pair<int, int>, TileBox>> all;
+  for (auto& kv : classes)
+    for (const TileBox& b : kv.second) all.push_back(std::make_pair(kv.first, b));
+  const int tdiv = (cfg->arch == SS4K_ARCH_RRDB && s == 2) ? 2 : 1;   // coarsest conv resolution = input / tdiv
+  bool aligned = true;
+  for (auto& e : all) aligned = aligned && e.first.first % tdiv == 0 && e.first.second % tdiv == 0;
+  const bool merge = getenv("SS4K_TILE_EXACT_CLASSES") == nullptr && aligned;
+  std::stable_sort(all.begin(), all.end(), [](const std::pair<std::pair<int, int>, TileBox>& a, const std::pair<std::pair<int, int>, TileBox>& b) {
+    return a.first.first != b.first.first ? a.first.first > b.first.first : a.first.second > b.first.second; });
+  for (auto& e : all) {
+    TileBox b = e.second;
+    b.crop_h = e.first.first; b.crop_w = e.first.second; b.img = 0; b.atlas_x = 0;
+    bool placed = false;
+    if (!groups.empty()) {
+      TileGroup& g = groups.back();
+      const bool same = b.crop_h == g.boxes[0].crop_h && b.crop_w == g.boxes[0].crop_w && g.boxes.back().crop_w == b.crop_w && g.boxes.back().crop_h == b.crop_h;
+      if (merge ? b.crop_h * 10 >= g.hc * 9 : same) { g.boxes.push_back(b); placed = true; }
     }
-    for (Group& g : groups) {
-      const int cnt = static_cast<int>(g.boxes.size());
-      if (!merge) {   // one image per crop, no atlas (the classes are uniform)
-        g.nimg = cnt; g.wc = g.boxes[0].crop_w;
-        for (int k = 0; k < cnt; ++k) { g.boxes[k].img = k; g.boxes[k].atlas_x = 0; }
-        continue;
-      }
-      g.nimg = (cnt + kMaskRects - 1) / kMaskRects;
-      const int per = (cnt + g.nimg - 1) / g.nimg;
-      const int gap = tdiv;   // one zero column at the coarsest resolution
-      g.wc = 0;
-      for (int k = 0; k < cnt; ++k) {
-        const int im = k / per;
-        const bool first = k % per == 0;
-        g.boxes[k].img = im;
-        g.boxes[k].atlas_x = first ? 0 : g.boxes[k - 1].atlas_x + g.boxes[k - 1].crop_w + gap;
-        g.wc = std::max(g.wc, g.boxes[k].atlas_x + g.boxes[k].crop_w);
-      }
+    if (!placed) {
+      groups.emplace_back();
+      groups.back().hc = b.crop_h;
+      groups.back().boxes.push_back(b);
     }
   }
+  for (TileGroup& g : groups) {
+    const int cnt = static_cast<int>(g.boxes.size());
+    if (!merge) {   // one image per crop, no atlas (the classes are uniform)
+      g.nimg = cnt; g.wc = g.boxes[0].crop_w;
+      for (int k = 0; k < cnt; ++k) { g.boxes[k].img = k; g.boxes[k].atlas_x = 0; }
+      continue;
+    }
+    g.nimg = (cnt + kMaskRects - 1) / kMaskRects;
+    const int per = (cnt + g.nimg - 1) / g.nimg;
+    const int gap = tdiv;   // one zero column at the coarsest resolution
+    g.wc = 0;
+    for (int k = 0; k < cnt; ++k) {
+      const int im = k / per;
+      const bool first = k % per == 0;
+      g.boxes[k].img = im;
+      g.boxes[k].atlas_x = first ? 0 : g.boxes[k - 1].atlas_x + g.boxes[k - 1].crop_w + gap;
+      g.wc = std::max(g.wc, g.boxes[k].atlas_x + g.boxes[k].crop_w);
+    }
+  }
+  return "";
+}
+
+static int create_tiled_plan(ss4k_ctx* ctx, const ss4k_plan_cfg* cfg, ss4k_plan** out_plan) {
+  std::vector<TileGroup> groups;
+  {
+    const std::string e = layout_tiles(cfg, &groups);
+    if (!e.empty()) return fail(ctx, SS4K_E_INVALID, e);
+  }
+  const int s = cfg->scale;
+  std::unique_ptr<ss4k_plan> pl(new ss4k_plan());
+  pl->ctx = ctx;
+  pl->cfg = *cfg;
+  pl->tiled = true;
+  Program& P = pl->prog;
+  P.in_fmt = cfg->in_fmt; P.out_fmt = cfg->out_fmt;
+  P.in_n = cfg->n; P.in_c = 3; P.in_h = cfg->h; P.in_w = cfg->w;
+  P.out_n = cfg->n; P.out_c = 3; P.out_h = cfg->h * s; P.out_w = cfg->w * s;
   for (auto& g : groups) {
     ss4k_plan::TileClass tc;
     tc.hc = g.hc; tc.wc = g.wc; tc.count = static_cast<int>(g.boxes.size()); tc.nimg = g.nimg;
@@ -1608,6 +1620,30 @@ static int create_tiled_plan(ss4k_ctx* ctx, const ss4k_plan_cfg* cfg, ss4k_plan*
   pl->out_bytes = fmt_bytes(P.out_fmt, P.out_n, P.out_c, P.out_h, P.out_w);
   cudaDeviceSynchronize();   // the tile boxes were uploaded on the NULL stream
   *out_plan = pl.release();
+  return SS4K_OK;
+}
+
+// Host-only debug entry: the tile grid of a configuration and its crop atlases as JSON (tests/test_tiling_cpu.py).
+int ss4k_debug_tile_layout(const ss4k_plan_cfg* cfg, char** out_json) {
+  if (!cfg || !out_json) return fail(nullptr, SS4K_E_INVALID, "null argument");
+  std::vector<TileGroup> groups;
+  const std::string e = layout_tiles(cfg, &groups);
+  if (!e.empty()) return fail(nullptr, SS4K_E_INVALID, e);
+  std::string js = "{\"max_rects\":" + std::to_string(kMaskRects) + ",\"groups\":[";
+  for (size_t gi = 0; gi < groups.size(); ++gi) {
+    const TileGroup& g = groups[gi];
+    js += fmt("%s{\"hc\":%d,\"wc\":%d,\"nimg\":%d,\"boxes\":[", gi ? "," : "", g.hc, g.wc, g.nimg);
+    for (size_t k = 0; k < g.boxes.size(); ++k) {
+      const TileBox& b = g.boxes[k];
+      js += fmt("%s{\"src_y\":%d,\"src_x\":%d,\"off_y\":%d,\"off_x\":%d,\"dst_y\":%d,\"dst_x\":%d,\"paste_h\":%d,\"paste_w\":%d,"
+                "\"crop_h\":%d,\"crop_w\":%d,\"img\":%d,\"atlas_x\":%d}", k ? "," : "", b.src_y, b.src_x, b.off_y, b.off_x, b.dst_y, b.dst_x,
+                b.paste_h, b.paste_w, b.crop_h, b.crop_w, b.img, b.atlas_x);
+    }
+    js += "]}";
+  }
+  js += "]}";
+  *out_json = static_cast<char*>(malloc(js.size() + 1));
+  memcpy(*out_json, js.c_str(), js.size() + 1);
   return SS4K_OK;
 }
 

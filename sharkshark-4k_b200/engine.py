@@ -157,6 +157,18 @@ def plan_dry(cfg):
         lib.ss4k_free(out)
 
 
+def tile_layout(cfg):
+    """Host-only: RealESRGANer's tile grid for a configuration (tile, tile_pad, reserved[1] = pre_pad) and its packing into
+    crop atlases, as the engine's tiled plan would run it (works without a GPU)."""
+    lib = L.load()
+    out = ctypes.c_void_p()
+    L.check(lib.ss4k_debug_tile_layout(ctypes.byref(cfg), ctypes.byref(out)))
+    try:
+        return json.loads(ctypes.string_at(out).decode())
+    finally:
+        lib.ss4k_free(out)
+
+
 class PlanCache:
     """Shape-keyed LRU cache of engine plans.  A plan owns its workspaces (about 2 GB for RRDBNet at 720p), so a
     caller that sees arbitrary shapes -- the reference's still-image server drives the same service with one plan
